@@ -1,0 +1,107 @@
+/* mz_cuda_batch.h -- device-pointer batch API of the B200 DEFLATE + CRC-32 backend (C ABI).
+ *
+ * ADDITIVE to the reference: minizip-ng has no batch interface (SURVEY.md section 8b "Beyond the vtbl").
+ * It exists so that (a) the vtbl stream (mz_strm_cuda.h) has something to drive, (b) kernels can be
+ * measured on device-resident buffers against the HBM roofline, (c) chunks / zip entries can be sharded
+ * over GPUs. Plain pointers and sizes only; `stream` is a cudaStream_t passed as void* (NULL = default).
+ * All functions return MZ_OK (0) or a negative MZ_* code (mz.h:21-47); MZ_CUDA_ERROR details are
+ * available from mz_cuda_last_error().  Device pointers must belong to the CURRENT CUDA device.
+ */
+#ifndef MZ_CUDA_BATCH_H
+#define MZ_CUDA_BATCH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MZ_CUDA_CHUNK_MAX    65536u /* largest independent DEFLATE chunk */
+#define MZ_CUDA_FLAG_FINAL   1u     /* chunk ends its stream (BFINAL, no sync marker) */
+
+/* ---- runtime ---------------------------------------------------------------------------------- */
+int32_t mz_cuda_init(void);                 /* idempotent, thread-safe; MZ_SUPPORT_ERROR without a usable GPU */
+int32_t mz_cuda_device_count(void);
+int32_t mz_cuda_set_device(int32_t ordinal);
+const char *mz_cuda_last_error(void);
+int32_t mz_cuda_sm_count(void);
+
+void *mz_cuda_malloc(size_t bytes);         /* device memory; NULL on failure */
+void mz_cuda_free(void *dptr);
+void *mz_cuda_host_alloc(size_t bytes);     /* pinned host memory */
+void mz_cuda_host_free(void *hptr);
+int32_t mz_cuda_memcpy_h2d(void *dptr, const void *hptr, size_t bytes, void *stream);  /* async on stream */
+int32_t mz_cuda_memcpy_d2h(void *hptr, const void *dptr, size_t bytes, void *stream);  /* async on stream */
+int32_t mz_cuda_memcpy_d2d(void *dst, const void *src, size_t bytes, void *stream);
+int32_t mz_cuda_memset(void *dptr, int value, size_t bytes, void *stream);
+int32_t mz_cuda_host_is_pinned(const void *hptr);           /* 1 if page-locked and usable for async copies */
+int32_t mz_cuda_stream_sync(void *stream);
+void *mz_cuda_stream_create(void);
+void mz_cuda_stream_destroy(void *stream);
+void *mz_cuda_event_create(void);
+void mz_cuda_event_destroy(void *event);
+int32_t mz_cuda_event_record(void *event, void *stream);
+float mz_cuda_event_elapsed_ms(void *start, void *stop); /* syncs on stop */
+
+/* ---- K1: CRC-32 ---------------------------------------------------------------------------------
+ * Segments: either a uniform partition (d_off = d_len = NULL: segment i = bytes [i*seg_size, ...) of
+ * total_len) or explicit per-segment offsets/lengths (device arrays). d_residue[i] = pure residue
+ * R(segment) (init 0, no final xor) -- the linear quantity that folds; d_crc[i] (optional) = the value
+ * mz_crypt_crc32_update(0, segment, len) returns (mz_crypt.c:35). */
+int32_t mz_cuda_crc32_segments(const void *d_in, uint64_t total_len, uint64_t seg_size, const uint64_t *d_off,
+                               const uint32_t *d_len, uint32_t nseg, uint32_t *d_residue, uint32_t *d_crc, void *stream);
+/* fold the residues of a UNIFORM partition: d_out2[0] = residue of the whole buffer, d_out2[1] = crc32(0, buffer) */
+int32_t mz_cuda_crc32_fold(const uint32_t *d_residue, uint32_t nseg, uint64_t seg_size, uint64_t total_len, uint32_t *d_out2,
+                           void *stream);
+/* whole device buffer, synchronous: *crc = mz_crypt_crc32_update(value, buffer, len) */
+int32_t mz_cuda_crc32_device(const void *d_in, uint64_t len, uint32_t value, uint32_t *crc);
+/* host arithmetic: crc(A||B) from crc(A), crc(B), |B|  (the "polynomial combine" of the north star) */
+uint32_t mz_cuda_crc32_combine(uint32_t crc_a, uint32_t crc_b, uint64_t len_b);
+
+/* ---- K2+K3: DEFLATE encode of independent chunks --------------------------------------------------
+ * Chunk i (<= MZ_CUDA_CHUNK_MAX bytes) is compressed into slot i = d_slots + i*slot_stride
+ * (slot_stride >= mz_cuda_deflate_slot_bound(chunk size), multiple of 16; d_slots 16-byte aligned);
+ * d_out_len[i] = bytes written. Every slot is a byte-aligned piece of raw RFC1951 data: non-final
+ * chunks end with a sync-flush marker, chunks flagged FINAL end with BFINAL. Uniform partition when
+ * d_off == NULL (then only the last chunk gets `last_flags`). level 0 = stored, 1..9. */
+uint64_t mz_cuda_deflate_slot_bound(uint32_t chunk_size);
+int32_t mz_cuda_deflate_chunks(const void *d_in, uint64_t total_len, uint32_t chunk_size, const uint64_t *d_off,
+                               const uint32_t *d_len, const uint8_t *d_flags, uint32_t nchunks, uint32_t last_flags,
+                               int32_t level, void *d_slots, uint64_t slot_stride, uint32_t *d_out_len, void *stream);
+/* ---- K4: join slots into one contiguous stream ------------------------------------------------------
+ * d_offsets: nchunks+1 uint64 (scratch/out): d_offsets[i] = position of chunk i in d_dst, [nchunks] = total. */
+int32_t mz_cuda_concat(const void *d_slots, uint64_t slot_stride, const uint32_t *d_out_len, uint32_t nchunks,
+                       uint64_t *d_offsets, void *d_dst, void *stream);
+
+/* ---- K5: DEFLATE decode of independent raw streams (resumable) ---------------------------------------- */
+typedef struct mz_cuda_inflate_job {
+    const void *d_in;    /* d_in[0] = stream byte `in_base`; readable (zero padded) 16 bytes past in_avail */
+    uint64_t in_base;
+    uint64_t in_avail;
+    void *d_out;         /* d_out[0] = output byte `out_base`; keeps >= 32 KiB of history once out_pos > 0 */
+    uint64_t out_base;
+    uint64_t out_cap;
+    uint32_t in_final;   /* no more input will follow */
+    uint32_t reserved;
+} mz_cuda_inflate_job;
+
+typedef struct mz_cuda_inflate_state {
+    uint64_t in_bitpos;  /* consumed bits of the raw stream (TOTAL_IN = ceil(in_bitpos / 8) at END) */
+    uint64_t out_pos;    /* produced bytes (TOTAL_OUT) */
+    int32_t status;      /* 0 running, 1 end of stream, MZ_DATA_ERROR (-3), MZ_BUF_ERROR (-5) */
+    int32_t why;         /* when running: 1 needs input, 2 needs output space */
+    uint32_t phase, last_block, stored_remaining, nlit, ndist, blocks;
+    uint8_t lens[320];
+} mz_cuda_inflate_state;
+
+int32_t mz_cuda_inflate_streams(const mz_cuda_inflate_job *d_jobs, mz_cuda_inflate_state *d_states, uint32_t nstreams,
+                                void *stream);
+
+/* ---- bench/test support: synthetic enwik-style text on the device -------------------------- */
+int32_t mz_cuda_textgen(void *d_out, uint64_t nbytes, uint64_t seed, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

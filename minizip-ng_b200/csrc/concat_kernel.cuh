@@ -1,0 +1,115 @@
+/* concat_kernel.cuh -- K4: join per-chunk bitstreams (byte-aligned by construction) into one stream.
+ *
+ * Every chunk slot ends on a byte boundary (sync-flush marker or final padding, see deflate_kernel.cuh),
+ * so concatenation is an exclusive scan over out_len[] followed by a gather-copy. The result is one
+ * valid RFC1951 stream: what mz_stream_zlib_write + close hand to the base stream (mz_strm_zlib.c:196-201).
+ */
+#ifndef MZ_CONCAT_KERNEL_CUH
+#define MZ_CONCAT_KERNEL_CUH
+
+#include "mzcuda_common.cuh"
+
+namespace mzc {
+
+constexpr int SCAN_THREADS = 1024;
+
+/* exclusive scan of n 32-bit lengths into 64-bit offsets; offsets[n] = total. Single CTA. */
+__global__ void __launch_bounds__(SCAN_THREADS, 1) scan_lengths_kernel(const uint32_t *len, uint32_t n, uint64_t base, uint64_t *offsets) {
+    __shared__ uint64_t s_part[SCAN_THREADS];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t per = (n + SCAN_THREADS - 1) / SCAN_THREADS;
+    const uint64_t lo = (uint64_t)tid * per;
+    uint64_t sum = 0;
+    for (uint32_t k = 0; k < per; k++)
+        if (lo + k < n) sum += len[lo + k];
+    s_part[tid] = sum;
+    __syncthreads();
+    /* Hillis-Steele inclusive scan over the 1024 partial sums */
+    for (uint32_t d = 1; d < SCAN_THREADS; d <<= 1) {
+        uint64_t v = tid >= d ? s_part[tid - d] : 0;
+        __syncthreads();
+        s_part[tid] += v;
+        __syncthreads();
+    }
+    uint64_t run = base + s_part[tid] - sum;
+    for (uint32_t k = 0; k < per; k++)
+        if (lo + k < n) {
+            offsets[lo + k] = run;
+            run += len[lo + k];
+        }
+    if (tid == SCAN_THREADS - 1) offsets[n] = base + s_part[tid];
+}
+
+constexpr int GATHER_THREADS = 256;
+
+/* copy slot i (16-byte aligned source) to dst + offsets[i] (arbitrary alignment) */
+__global__ void __launch_bounds__(GATHER_THREADS) gather_slots_kernel(const uint8_t *slots, uint64_t slot_stride, const uint32_t *len,
+                                                                      const uint64_t *offsets, uint32_t n, uint8_t *dst) {
+    for (uint32_t c = blockIdx.x; c < n; c += gridDim.x) {
+        const uint8_t *src = slots + (uint64_t)c * slot_stride;
+        uint8_t *d = dst + offsets[c];
+        const uint32_t nbytes = len[c];
+        uint32_t head = (uint32_t)((4 - ((uintptr_t)d & 3)) & 3);
+        if (head > nbytes) head = nbytes;
+        if (threadIdx.x < head) d[threadIdx.x] = src[threadIdx.x];
+        const uint32_t nwords = (nbytes - head) >> 2;
+        uint32_t *dw = (uint32_t *)(d + head);
+        if ((((uintptr_t)(d + head)) & 15) == 0 && head == 0) {
+            /* fully aligned: 16-byte copies */
+            const uint32_t n16 = nwords >> 2;
+            for (uint32_t i = threadIdx.x; i < n16; i += GATHER_THREADS) ((uint4 *)dw)[i] = ((const uint4 *)src)[i];
+            for (uint32_t i = (n16 << 2) + threadIdx.x; i < nwords; i += GATHER_THREADS) dw[i] = ((const uint32_t *)src)[i];
+        } else {
+            const uint32_t *sw = (const uint32_t *)src; /* slot is padded: reading one word past is safe */
+            const uint32_t sh = (head & 3) * 8, wo = head >> 2;
+            for (uint32_t i = threadIdx.x; i < nwords; i += GATHER_THREADS) dw[i] = __funnelshift_r(sw[wo + i], sw[wo + i + 1], sh);
+        }
+        const uint32_t done = head + (nwords << 2);
+        if (threadIdx.x < nbytes - done) d[done + threadIdx.x] = src[done + threadIdx.x];
+    }
+}
+
+/* ---- synthetic "enwik-style" text generator (bench / test support) ----
+ * Zipf(1)-like draws from a fixed vocabulary joined by spaces, ~2% markup/newline/digit tokens.
+ * One thread fills one 256-byte piece, seeded by (seed, piece index): deterministic and position-independent. */
+constexpr int TEXT_PIECE = 256;
+__device__ __forceinline__ uint32_t tg_next(uint64_t &s) { /* splitmix-style */
+    s += 0x9E3779B97F4A7C15ull;
+    uint64_t z = s;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return (uint32_t)((z ^ (z >> 31)) >> 32);
+}
+__global__ void __launch_bounds__(256) textgen_kernel(uint8_t *out, uint64_t nbytes, uint64_t seed, const uint8_t *words,
+                                                      const uint32_t *word_off, uint32_t nwords) {
+    const float lnw = __log2f((float)nwords);
+    const uint64_t npieces = (nbytes + TEXT_PIECE - 1) / TEXT_PIECE;
+    for (uint64_t piece = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; piece < npieces; piece += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t s = seed * 0xD1342543DE82EF95ull + piece * 0x2545F4914F6CDD1Dull + 1;
+        uint8_t *p = out + piece * TEXT_PIECE;
+        uint32_t room = (uint32_t)(nbytes - piece * TEXT_PIECE < TEXT_PIECE ? nbytes - piece * TEXT_PIECE : TEXT_PIECE);
+        uint32_t pos = 0;
+        while (pos < room) {
+            uint32_t r = tg_next(s);
+            float u = (float)(r >> 8) * (1.0f / 16777216.0f);
+            uint32_t rank = (uint32_t)exp2f(u * lnw);
+            if (rank >= nwords) rank = nwords - 1;
+            uint32_t a = word_off[rank], b = word_off[rank + 1];
+            for (uint32_t i = a; i < b && pos < room; i++) p[pos++] = words[i];
+            uint32_t m = r & 255;
+            if (m < 3 && pos < room) p[pos++] = '.';
+            if (m == 0 && pos < room) p[pos++] = '\n';
+            else if (m == 1) {
+                uint32_t d = tg_next(s);
+                if (pos < room) p[pos++] = ' ';
+                if (pos < room) p[pos++] = '<';
+                for (int k = 0; k < 4 && pos < room; k++) { p[pos++] = (uint8_t)('0' + d % 10); d /= 10; }
+                if (pos < room) p[pos++] = '>';
+            }
+            if (pos < room) p[pos++] = ' ';
+        }
+    }
+}
+
+} // namespace mzc
+#endif

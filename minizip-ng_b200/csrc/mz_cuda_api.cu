@@ -1,0 +1,396 @@
+/* mz_cuda_api.cu -- the thin extern "C" shim between the C host side and the sm_100a kernels.
+ * Declares nothing new: every entry point is documented in include/mz_cuda_batch.h. */
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+#include <vector>
+
+#include "../../include/mz_cuda_batch.h"
+#include "concat_kernel.cuh"
+#include "crc32_kernel.cuh"
+#include "deflate_kernel.cuh"
+#include "inflate_kernel.cuh"
+
+#define MZ_OK 0
+#define MZ_MEM_ERROR (-4)
+#define MZ_PARAM_ERROR (-102)
+#define MZ_INTERNAL_ERROR (-104)
+#define MZ_SUPPORT_ERROR (-109)
+
+using namespace mzc;
+
+static_assert(sizeof(mz_cuda_inflate_job) == sizeof(InflateJob), "job layout");
+static_assert(sizeof(mz_cuda_inflate_state) == sizeof(InflateState), "state layout");
+
+namespace {
+
+struct DeviceCtx {
+    bool ready = false;
+    int sm_count = 0;
+    CrcConsts *d_consts = nullptr;
+    uint8_t *d_words = nullptr;
+    uint32_t *d_word_off = nullptr;
+    uint32_t nwords = 0;
+    uint32_t *d_crc_scratch = nullptr; /* residues for mz_cuda_crc32_device */
+    size_t crc_scratch_n = 0;
+};
+
+constexpr int kMaxDev = 16;
+DeviceCtx g_dev[kMaxDev];
+std::mutex g_mu;
+CrcConsts g_consts;
+bool g_consts_ready = false;
+thread_local char g_err[256] = "";
+
+int32_t fail(cudaError_t e, const char *what) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return e == cudaErrorMemoryAllocation ? MZ_MEM_ERROR : MZ_INTERNAL_ERROR;
+}
+#define CK(call)                                       \
+    do {                                               \
+        cudaError_t e_ = (call);                       \
+        if (e_ != cudaSuccess) return fail(e_, #call); \
+    } while (0)
+
+/* vocabulary for the text generator: 50k pseudo-words of 2..10 lowercase letters, fixed seed */
+void make_vocab(std::vector<uint8_t> &words, std::vector<uint32_t> &off, uint32_t n) {
+    uint64_t s = 1234;
+    off.resize(n + 1);
+    for (uint32_t i = 0; i < n; i++) {
+        off[i] = (uint32_t)words.size();
+        s = s * 6364136223846793005ull + 1442695040888963407ull;
+        uint32_t len = 2 + (uint32_t)((s >> 33) % 9);
+        for (uint32_t k = 0; k < len; k++) {
+            s = s * 6364136223846793005ull + 1442695040888963407ull;
+            /* skewed letter frequencies so words share n-grams like a natural language */
+            uint32_t r = (uint32_t)(s >> 40) % 100;
+            static const char alpha[] = "etaoinshrdlcumwfgypbvkjxqz";
+            uint32_t idx = r < 60 ? r % 8 : (r < 90 ? 8 + r % 10 : 18 + r % 8);
+            words.push_back((uint8_t)alpha[idx]);
+        }
+    }
+    off[n] = (uint32_t)words.size();
+}
+
+int32_t get_ctx(DeviceCtx **out) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        snprintf(g_err, sizeof(g_err), "no CUDA device: %s", cudaGetErrorString(e));
+        return MZ_SUPPORT_ERROR;
+    }
+    if (dev < 0 || dev >= kMaxDev) return MZ_PARAM_ERROR;
+    DeviceCtx &c = g_dev[dev];
+    if (!c.ready) {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (!c.ready) {
+            if (!g_consts_ready) {
+                crc_consts_init(g_consts);
+                g_consts_ready = true;
+            }
+            cudaDeviceProp prop;
+            CK(cudaGetDeviceProperties(&prop, dev));
+            if (prop.major < 10) {
+                snprintf(g_err, sizeof(g_err), "device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
+                return MZ_SUPPORT_ERROR;
+            }
+            c.sm_count = prop.multiProcessorCount;
+            CK(cudaMalloc(&c.d_consts, sizeof(CrcConsts)));
+            CK(cudaMemcpy(c.d_consts, &g_consts, sizeof(CrcConsts), cudaMemcpyHostToDevice));
+            std::vector<uint8_t> words;
+            std::vector<uint32_t> off;
+            make_vocab(words, off, 50000);
+            c.nwords = 50000;
+            CK(cudaMalloc(&c.d_words, words.size()));
+            CK(cudaMalloc(&c.d_word_off, off.size() * 4));
+            CK(cudaMemcpy(c.d_words, words.data(), words.size(), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(c.d_word_off, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
+            CK(cudaFuncSetAttribute(deflate_chunks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_SMEM_BYTES));
+            CK(cudaFuncSetAttribute(crc32_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CRC_SMEM_BYTES));
+            c.ready = true;
+        }
+    }
+    *out = &c;
+    return MZ_OK;
+}
+
+uint64_t pick_crc_seg(uint64_t len, int sm_count) {
+    /* aim for >= 4 segments per resident warp, segments between 4 KiB and 64 KiB */
+    uint64_t warps = (uint64_t)sm_count * (CRC_THREADS / 32);
+    uint64_t seg = 65536;
+    while (seg > 4096 && len / seg < warps * 2) seg >>= 1;
+    return seg;
+}
+
+} // namespace
+
+extern "C" {
+
+const char *mz_cuda_last_error(void) { return g_err; }
+
+int32_t mz_cuda_init(void) {
+    DeviceCtx *c;
+    return get_ctx(&c);
+}
+
+int32_t mz_cuda_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int32_t mz_cuda_set_device(int32_t ordinal) {
+    CK(cudaSetDevice(ordinal));
+    return MZ_OK;
+}
+
+int32_t mz_cuda_sm_count(void) {
+    DeviceCtx *c;
+    int32_t err = get_ctx(&c);
+    return err ? err : c->sm_count;
+}
+
+void *mz_cuda_malloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes ? bytes : 16) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void mz_cuda_free(void *p) {
+    if (p) cudaFree(p);
+}
+void *mz_cuda_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 16, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void mz_cuda_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+int32_t mz_cuda_memcpy_h2d(void *d, const void *h, size_t n, void *stream) {
+    CK(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    return MZ_OK;
+}
+int32_t mz_cuda_memcpy_d2h(void *h, const void *d, size_t n, void *stream) {
+    CK(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return MZ_OK;
+}
+int32_t mz_cuda_memcpy_d2d(void *d, const void *s, size_t n, void *stream) {
+    CK(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return MZ_OK;
+}
+int32_t mz_cuda_host_is_pinned(const void *h) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, h) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return a.type == cudaMemoryTypeHost ? 1 : 0;
+}
+int32_t mz_cuda_memset(void *d, int v, size_t n, void *stream) {
+    CK(cudaMemsetAsync(d, v, n, (cudaStream_t)stream));
+    return MZ_OK;
+}
+int32_t mz_cuda_stream_sync(void *stream) {
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return MZ_OK;
+}
+void *mz_cuda_stream_create(void) {
+    cudaStream_t s = nullptr;
+    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    return s;
+}
+void mz_cuda_stream_destroy(void *s) {
+    if (s) cudaStreamDestroy((cudaStream_t)s);
+}
+void *mz_cuda_event_create(void) {
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+    return e;
+}
+void mz_cuda_event_destroy(void *e) {
+    if (e) cudaEventDestroy((cudaEvent_t)e);
+}
+int32_t mz_cuda_event_record(void *e, void *stream) {
+    CK(cudaEventRecord((cudaEvent_t)e, (cudaStream_t)stream));
+    return MZ_OK;
+}
+float mz_cuda_event_elapsed_ms(void *a, void *b) {
+    float ms = -1.f;
+    if (cudaEventSynchronize((cudaEvent_t)b) != cudaSuccess) return -1.f;
+    if (cudaEventElapsedTime(&ms, (cudaEvent_t)a, (cudaEvent_t)b) != cudaSuccess) return -1.f;
+    return ms;
+}
+
+/* ---- CRC ------------------------------------------------------------------------------------------ */
+int32_t mz_cuda_crc32_segments(const void *d_in, uint64_t total_len, uint64_t seg_size, const uint64_t *d_off, const uint32_t *d_len,
+                               uint32_t nseg, uint32_t *d_residue, uint32_t *d_crc, void *stream) {
+    DeviceCtx *c;
+    int32_t err = get_ctx(&c);
+    if (err) return err;
+    if (nseg == 0) return MZ_OK;
+    if (!d_residue || (!d_off && seg_size == 0) || (d_off && !d_len)) return MZ_PARAM_ERROR;
+    CrcParams P;
+    P.in = (const uint8_t *)d_in;
+    P.in_off = d_off;
+    P.in_len = d_len;
+    P.total_len = total_len;
+    P.seg_size = seg_size;
+    P.nseg = nseg;
+    P.consts = c->d_consts;
+    P.out_residue = d_residue;
+    P.out_crc = d_crc;
+    uint32_t warps_per_cta = CRC_THREADS / 32;
+    uint32_t grid = (nseg + warps_per_cta - 1) / warps_per_cta;
+    if (grid > (uint32_t)c->sm_count) grid = (uint32_t)c->sm_count;
+    MZ_LAUNCH(crc32_segments_kernel, dim3(grid), dim3(CRC_THREADS), CRC_SMEM_BYTES, (cudaStream_t)stream, P);
+    CK(cudaGetLastError());
+    return MZ_OK;
+}
+
+int32_t mz_cuda_crc32_fold(const uint32_t *d_residue, uint32_t nseg, uint64_t seg_size, uint64_t total_len, uint32_t *d_out2, void *stream) {
+    DeviceCtx *c;
+    int32_t err = get_ctx(&c);
+    if (err) return err;
+    MZ_LAUNCH(crc32_fold_kernel, dim3(1), dim3(CRCF_THREADS), 0, (cudaStream_t)stream, d_residue, nseg, seg_size, total_len, c->d_consts, d_out2);
+    CK(cudaGetLastError());
+    return MZ_OK;
+}
+
+int32_t mz_cuda_crc32_device(const void *d_in, uint64_t len, uint32_t value, uint32_t *crc) {
+    DeviceCtx *c;
+    int32_t err = get_ctx(&c);
+    if (err) return err;
+    if (len == 0) {
+        *crc = value;
+        return MZ_OK;
+    }
+    uint64_t seg = pick_crc_seg(len, c->sm_count);
+    uint64_t nseg64 = (len + seg - 1) / seg;
+    while (nseg64 > 0x7fffffffull) {
+        seg <<= 1;
+        nseg64 = (len + seg - 1) / seg;
+    }
+    uint32_t nseg = (uint32_t)nseg64;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (c->crc_scratch_n < (size_t)nseg + 2) {
+            if (c->d_crc_scratch) cudaFree(c->d_crc_scratch);
+            c->d_crc_scratch = nullptr;
+            c->crc_scratch_n = 0;
+            CK(cudaMalloc(&c->d_crc_scratch, ((size_t)nseg + 2) * 4));
+            c->crc_scratch_n = (size_t)nseg + 2;
+        }
+    }
+    uint32_t *d_res = c->d_crc_scratch, *d_out2 = c->d_crc_scratch + nseg;
+    err = mz_cuda_crc32_segments(d_in, len, seg, nullptr, nullptr, nseg, d_res, nullptr, nullptr);
+    if (err) return err;
+    err = mz_cuda_crc32_fold(d_res, nseg, seg, len, d_out2, nullptr);
+    if (err) return err;
+    uint32_t h[2];
+    CK(cudaMemcpy(h, d_out2, 8, cudaMemcpyDeviceToHost));
+    /* chain the running value: crc(v, D) = ~((~v) x^(8|D|) + R(D)) */
+    *crc = ~(gf2_mulmod(~value, gf2_xpow(g_consts.x2n, 8ull * len)) ^ h[0]);
+    return MZ_OK;
+}
+
+uint32_t mz_cuda_crc32_combine(uint32_t crc_a, uint32_t crc_b, uint64_t len_b) {
+    if (!g_consts_ready) {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (!g_consts_ready) {
+            crc_consts_init(g_consts);
+            g_consts_ready = true;
+        }
+    }
+    if (len_b == 0) return crc_a; /* zlib's crc32_combine convention for the degenerate case */
+    /* crc(A||B) = crc(A) x^(8|B|) + crc(B): the init/xorout terms cancel (both sides carry them once) */
+    return gf2_mulmod(crc_a, gf2_xpow(g_consts.x2n, 8ull * len_b)) ^ crc_b;
+}
+
+/* ---- DEFLATE ---------------------------------------------------------------------------------------- */
+uint64_t mz_cuda_deflate_slot_bound(uint32_t chunk_size) { return deflate_slot_bound(chunk_size); }
+
+int32_t mz_cuda_deflate_chunks(const void *d_in, uint64_t total_len, uint32_t chunk_size, const uint64_t *d_off, const uint32_t *d_len,
+                               const uint8_t *d_flags, uint32_t nchunks, uint32_t last_flags, int32_t level, void *d_slots,
+                               uint64_t slot_stride, uint32_t *d_out_len, void *stream) {
+    DeviceCtx *c;
+    int32_t err = get_ctx(&c);
+    if (err) return err;
+    if (nchunks == 0) return MZ_OK;
+    if (level < 0 || level > 9 || !d_slots || !d_out_len || (slot_stride & 15) || ((uintptr_t)d_slots & 15)) return MZ_PARAM_ERROR;
+    if (!d_off) {
+        if (chunk_size == 0 || chunk_size > MZ_CUDA_CHUNK_MAX || slot_stride < deflate_slot_bound(chunk_size)) return MZ_PARAM_ERROR;
+        uint64_t need = total_len == 0 ? 1 : (total_len + chunk_size - 1) / chunk_size;
+        if (need != nchunks) return MZ_PARAM_ERROR;
+    } else if (!d_len) {
+        return MZ_PARAM_ERROR;
+    }
+    DeflateParams P;
+    P.in = (const uint8_t *)d_in;
+    P.in_off = d_off;
+    P.in_len = d_len;
+    P.flags = d_flags;
+    P.total_len = total_len;
+    P.chunk_size = chunk_size;
+    P.nchunks = nchunks;
+    P.last_flags = last_flags;
+    P.level = level;
+    P.out = (uint8_t *)d_slots;
+    P.slot_stride = slot_stride;
+    P.out_len = d_out_len;
+    uint32_t grid = nchunks < (uint32_t)c->sm_count ? nchunks : (uint32_t)c->sm_count;
+    MZ_LAUNCH(deflate_chunks_kernel, dim3(grid), dim3(DF_THREADS), DF_SMEM_BYTES, (cudaStream_t)stream, P);
+    CK(cudaGetLastError());
+    return MZ_OK;
+}
+
+int32_t mz_cuda_concat(const void *d_slots, uint64_t slot_stride, const uint32_t *d_out_len, uint32_t nchunks, uint64_t *d_offsets,
+                       void *d_dst, void *stream) {
+    DeviceCtx *c;
+    int32_t err = get_ctx(&c);
+    if (err) return err;
+    MZ_LAUNCH(scan_lengths_kernel, dim3(1), dim3(SCAN_THREADS), 0, (cudaStream_t)stream, d_out_len, nchunks, (uint64_t)0, d_offsets);
+    if (nchunks) {
+        uint32_t grid = nchunks < (uint32_t)c->sm_count * 16u ? nchunks : (uint32_t)c->sm_count * 16u;
+        MZ_LAUNCH(gather_slots_kernel, dim3(grid), dim3(GATHER_THREADS), 0, (cudaStream_t)stream, (const uint8_t *)d_slots, slot_stride,
+                  d_out_len, (const uint64_t *)d_offsets, nchunks, (uint8_t *)d_dst);
+    }
+    CK(cudaGetLastError());
+    return MZ_OK;
+}
+
+int32_t mz_cuda_inflate_streams(const mz_cuda_inflate_job *d_jobs, mz_cuda_inflate_state *d_states, uint32_t nstreams, void *stream) {
+    DeviceCtx *c;
+    int32_t err = get_ctx(&c);
+    if (err) return err;
+    if (nstreams == 0) return MZ_OK;
+    uint32_t maxgrid = (uint32_t)c->sm_count * 32u;
+    uint32_t grid = nstreams < maxgrid ? nstreams : maxgrid;
+    MZ_LAUNCH(inflate_streams_kernel, dim3(grid), dim3(INF_THREADS), 0, (cudaStream_t)stream, (const InflateJob *)d_jobs,
+              (InflateState *)d_states, nstreams);
+    CK(cudaGetLastError());
+    return MZ_OK;
+}
+
+int32_t mz_cuda_textgen(void *d_out, uint64_t nbytes, uint64_t seed, void *stream) {
+    DeviceCtx *c;
+    int32_t err = get_ctx(&c);
+    if (err) return err;
+    if (nbytes == 0) return MZ_OK;
+    uint64_t pieces = (nbytes + TEXT_PIECE - 1) / TEXT_PIECE;
+    uint64_t blocks = (pieces + 255) / 256;
+    uint32_t grid = blocks < (uint64_t)c->sm_count * 32 ? (uint32_t)blocks : (uint32_t)c->sm_count * 32u;
+    MZ_LAUNCH(textgen_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (uint8_t *)d_out, nbytes, seed, (const uint8_t *)c->d_words,
+              (const uint32_t *)c->d_word_off, c->nwords);
+    CK(cudaGetLastError());
+    return MZ_OK;
+}
+
+} /* extern "C" */

@@ -1,0 +1,779 @@
+/* mz_strm_cuda.c -- minizip-ng codec stream whose DEFLATE / inflate / CRC arithmetic runs on a B200.
+ *
+ * Host side in C, mirroring mz_strm_zlib.c function for function (citations at each entry point); the
+ * arithmetic lives in the sm_100a kernels behind include/mz_cuda_batch.h. There is no CPU codec here:
+ * if the GPU runtime cannot be initialised open() fails with MZ_SUPPORT_ERROR.
+ *
+ * Write path (mz_strm_zlib.c:203-264 equivalent): caller bytes accumulate in a pinned staging buffer;
+ * a full batch goes H2D, is cut into independent <=64 KiB chunks, compressed by K2+K3, joined by K4,
+ * comes back D2H and is handed to the base stream. Batches written before close() end with a sync
+ * marker; close() compresses what is left as the final batch (BFINAL) -- an empty one if need be --
+ * and appends the gzip / zlib trailer.
+ *
+ * Read path (mz_strm_zlib.c:116-193 equivalent): compressed bytes are pulled from the base stream
+ * into a pinned window, the resumable K5 decoder runs until it needs input or output space, decoded
+ * bytes come back into a host buffer from which read() calls are served. TOTAL_IN counts consumed
+ * compressed bytes exactly at end of stream, as mz_zip.c:2090-2112 relies on.
+ */
+#include "mz_strm_cuda.h"
+
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "mz_abi.h"
+#include "mz_cuda_batch.h"
+
+#define CU_CHUNK 65536u
+
+/* ---- workspaces: pinned + device buffers are expensive to create, so streams borrow them ---------- */
+typedef struct cu_ws_s {
+    struct cu_ws_s *next;
+    int kind; /* 1 write, 2 read */
+    size_t batch;
+    /* write */
+    uint8_t *h_in, *d_in, *d_slots, *d_out, *h_out;
+    uint32_t *d_out_len;
+    uint64_t *d_offsets;
+    uint64_t *h_total; /* pinned: offsets[nchunks] lands here */
+    uint32_t max_chunks;
+    uint64_t slot_stride;
+    /* read */
+    uint8_t *h_cin, *d_cin, *d_win, *h_dec;
+    size_t cin_cap, win_cap;
+    mz_cuda_inflate_job *h_job, *d_job;
+    mz_cuda_inflate_state *h_state, *d_state;
+} cu_ws;
+
+static pthread_mutex_t g_pool_mu = PTHREAD_MUTEX_INITIALIZER;
+static cu_ws *g_pool;
+
+static size_t env_size(const char *name, size_t dflt, size_t unit) {
+    const char *v = getenv(name);
+    if (!v || !*v)
+        return dflt;
+    long long n = atoll(v);
+    return n > 0 ? (size_t)n * unit : dflt;
+}
+
+static void ws_destroy(cu_ws *w) {
+    if (!w)
+        return;
+    mz_cuda_host_free(w->h_in);
+    mz_cuda_free(w->d_in);
+    mz_cuda_free(w->d_slots);
+    mz_cuda_free(w->d_out);
+    mz_cuda_host_free(w->h_out);
+    mz_cuda_free(w->d_out_len);
+    mz_cuda_free(w->d_offsets);
+    mz_cuda_host_free(w->h_total);
+    mz_cuda_host_free(w->h_cin);
+    mz_cuda_free(w->d_cin);
+    mz_cuda_free(w->d_win);
+    mz_cuda_host_free(w->h_dec);
+    mz_cuda_host_free(w->h_job);
+    mz_cuda_free(w->d_job);
+    mz_cuda_host_free(w->h_state);
+    mz_cuda_free(w->d_state);
+    free(w);
+}
+
+static cu_ws *ws_acquire(int kind) {
+    cu_ws *w = NULL, **pp;
+    size_t batch = env_size("MZ_CUDA_BATCH_KB", 32u << 20, 1024);
+    batch = (batch + CU_CHUNK - 1) / CU_CHUNK * CU_CHUNK;
+    pthread_mutex_lock(&g_pool_mu);
+    for (pp = &g_pool; *pp; pp = &(*pp)->next)
+        if ((*pp)->kind == kind && (*pp)->batch == batch) {
+            w = *pp;
+            *pp = w->next;
+            break;
+        }
+    pthread_mutex_unlock(&g_pool_mu);
+    if (w)
+        return w;
+    w = (cu_ws *)calloc(1, sizeof(cu_ws));
+    if (!w)
+        return NULL;
+    w->kind = kind;
+    w->batch = batch;
+    if (kind == 1) {
+        w->max_chunks = (uint32_t)(batch / CU_CHUNK);
+        w->slot_stride = mz_cuda_deflate_slot_bound(CU_CHUNK);
+        size_t slots = (size_t)w->max_chunks * w->slot_stride;
+        w->h_in = (uint8_t *)mz_cuda_host_alloc(batch);
+        w->d_in = (uint8_t *)mz_cuda_malloc(batch + 64);
+        w->d_slots = (uint8_t *)mz_cuda_malloc(slots);
+        w->d_out = (uint8_t *)mz_cuda_malloc(slots);
+        w->h_out = (uint8_t *)mz_cuda_host_alloc(slots);
+        w->d_out_len = (uint32_t *)mz_cuda_malloc((size_t)w->max_chunks * 4);
+        w->d_offsets = (uint64_t *)mz_cuda_malloc(((size_t)w->max_chunks + 1) * 8);
+        w->h_total = (uint64_t *)mz_cuda_host_alloc(8);
+        if (!w->h_in || !w->d_in || !w->d_slots || !w->d_out || !w->h_out || !w->d_out_len || !w->d_offsets || !w->h_total) {
+            ws_destroy(w);
+            return NULL;
+        }
+    } else {
+        w->cin_cap = batch / 4 > (1u << 20) ? batch / 4 : (1u << 20);
+        w->win_cap = 32768 + batch;
+        w->h_cin = (uint8_t *)mz_cuda_host_alloc(w->cin_cap + 64);
+        w->d_cin = (uint8_t *)mz_cuda_malloc(w->cin_cap + 64);
+        w->d_win = (uint8_t *)mz_cuda_malloc(w->win_cap + 512);
+        w->h_dec = (uint8_t *)mz_cuda_host_alloc(batch);
+        w->h_job = (mz_cuda_inflate_job *)mz_cuda_host_alloc(sizeof(mz_cuda_inflate_job));
+        w->d_job = (mz_cuda_inflate_job *)mz_cuda_malloc(sizeof(mz_cuda_inflate_job));
+        w->h_state = (mz_cuda_inflate_state *)mz_cuda_host_alloc(sizeof(mz_cuda_inflate_state));
+        w->d_state = (mz_cuda_inflate_state *)mz_cuda_malloc(sizeof(mz_cuda_inflate_state));
+        if (!w->h_cin || !w->d_cin || !w->d_win || !w->h_dec || !w->h_job || !w->d_job || !w->h_state || !w->d_state) {
+            ws_destroy(w);
+            return NULL;
+        }
+    }
+    return w;
+}
+
+static void ws_release(cu_ws *w) {
+    if (!w)
+        return;
+    pthread_mutex_lock(&g_pool_mu);
+    w->next = g_pool;
+    g_pool = w;
+    pthread_mutex_unlock(&g_pool_mu);
+}
+
+/* ---- the stream object ------------------------------------------------------------------------------ */
+typedef struct mz_stream_cuda_s {
+    mz_stream stream; /* must be first: mz_strm.h:69-72 */
+    int32_t error;
+    int8_t initialized;
+    int16_t level;
+    int32_t window_bits;
+    int32_t mode;
+    int64_t total_in;
+    int64_t total_out;
+    int64_t max_total_in;
+    cu_ws *ws;
+    /* write */
+    size_t in_len;      /* bytes staged in ws->h_in */
+    uint32_t crc;       /* running CRC-32 of the plaintext (gzip trailer) */
+    uint32_t adler_a, adler_b;
+    int8_t header_done;
+    /* read */
+    int8_t hdr_parsed, ended, base_eof;
+    int wrap;           /* 0 raw, 1 zlib, 2 gzip */
+    int64_t hdr_size;   /* framing bytes before the raw stream */
+    uint64_t cin_base;  /* raw-stream offset of ws->h_cin[0] */
+    size_t cin_len;     /* valid bytes in ws->h_cin */
+    uint64_t win_base;  /* output offset of ws->d_win[0] */
+    size_t dec_pos, dec_len; /* decoded bytes waiting in ws->h_dec */
+    uint64_t fed_in;    /* compressed bytes pulled from base (framing included) */
+} mz_stream_cuda;
+
+static mz_stream_vtbl mz_stream_cuda_vtbl = {
+    mz_stream_cuda_open,   mz_stream_cuda_is_open, mz_stream_cuda_read,           mz_stream_cuda_write,
+    mz_stream_cuda_tell,   mz_stream_cuda_seek,    mz_stream_cuda_close,          mz_stream_cuda_error,
+    mz_stream_cuda_create, mz_stream_cuda_delete,  mz_stream_cuda_get_prop_int64, mz_stream_cuda_set_prop_int64};
+
+static int valid_window_bits(int32_t wb) {
+    /* what zlib's deflateInit2 / inflateInit2 accept (zlib.h:539-572, 834-870); 8 is bumped to 9 by deflate */
+    return (wb >= -15 && wb <= -8) || (wb >= 8 && wb <= 15) || (wb >= 24 && wb <= 31);
+}
+
+static int wrap_of(int32_t wb) {
+    return wb < 0 ? 0 : (wb > 15 ? 2 : 1);
+}
+
+/* mz_strm_zlib.c:65-107. Does not touch `base` (minigzip.c:92-93 opens before set_base). */
+int32_t mz_stream_cuda_open(void *stream, const char *path, int32_t mode) {
+    mz_stream_cuda *cu = (mz_stream_cuda *)stream;
+    (void)path;
+    cu->total_in = 0;
+    cu->total_out = 0;
+    cu->error = 0;
+    if (mode & MZ_OPEN_MODE_WRITE) {
+#ifdef MZ_ZIP_NO_COMPRESSION
+        return MZ_SUPPORT_ERROR;
+#else
+        int lvl = (int8_t)cu->level; /* the reference passes (int8_t)level to deflateInit2, :87 */
+        if (lvl == -1)
+            lvl = 6;
+        if (lvl < 0 || lvl > 9 || !valid_window_bits(cu->window_bits)) {
+            cu->error = MZ_STREAM_ERROR; /* Z_STREAM_ERROR from deflateInit2 */
+            return MZ_OPEN_ERROR;
+        }
+#endif
+    } else if (mode & MZ_OPEN_MODE_READ) {
+#ifdef MZ_ZIP_NO_DECOMPRESSION
+        return MZ_SUPPORT_ERROR;
+#else
+        if (!valid_window_bits(cu->window_bits)) {
+            cu->error = MZ_STREAM_ERROR;
+            return MZ_OPEN_ERROR;
+        }
+#endif
+    }
+    if (mz_cuda_init() != MZ_OK) {
+        cu->error = MZ_SUPPORT_ERROR;
+        fprintf(stderr, "mz_strm_cuda: no usable sm_100 GPU (%s); there is no CPU fallback\n", mz_cuda_last_error());
+        return MZ_SUPPORT_ERROR;
+    }
+    cu->in_len = 0;
+    cu->crc = 0;
+    cu->adler_a = 1;
+    cu->adler_b = 0;
+    cu->header_done = 0;
+    cu->hdr_parsed = cu->ended = cu->base_eof = 0;
+    cu->wrap = wrap_of(cu->window_bits);
+    cu->hdr_size = 0;
+    cu->cin_base = 0;
+    cu->cin_len = 0;
+    cu->win_base = 0;
+    cu->dec_pos = cu->dec_len = 0;
+    cu->fed_in = 0;
+    cu->initialized = 1;
+    cu->mode = mode;
+    return MZ_OK;
+}
+
+/* mz_strm_zlib.c:109-114 */
+int32_t mz_stream_cuda_is_open(void *stream) {
+    mz_stream_cuda *cu = (mz_stream_cuda *)stream;
+    if (cu->initialized != 1)
+        return MZ_OPEN_ERROR;
+    return MZ_OK;
+}
+
+/* ---- write side --------------------------------------------------------------------------------------- */
+#ifndef MZ_ZIP_NO_COMPRESSION
+static int32_t cu_emit(mz_stream_cuda *cu, const uint8_t *p, uint64_t n) {
+    /* the base interface takes int32 sizes; mz_strm_zlib.c:196-201 maps a short write to MZ_WRITE_ERROR */
+    while (n > 0) {
+        int32_t part = n > (1u << 30) ? (int32_t)(1u << 30) : (int32_t)n;
+        if (mz_abi_base_write(cu->stream.base, p, part) != part)
+            return MZ_WRITE_ERROR;
+        p += part;
+        n -= (uint64_t)part;
+        cu->total_out += part;
+    }
+    return MZ_OK;
+}
+
+static int32_t cu_write_header(mz_stream_cuda *cu) {
+    int lvl = (int8_t)cu->level == -1 ? 6 : (int8_t)cu->level;
+    if (cu->header_done)
+        return MZ_OK;
+    cu->header_done = 1;
+    if (cu->wrap == 2) {
+        /* what zlib writes for windowBits 31 (RFC1952): no name, MTIME 0, XFL 2 for level 9, 4 for level < 2, OS 3 */
+        uint8_t h[10] = {0x1f, 0x8b, 8, 0, 0, 0, 0, 0, 0, 3};
+        h[8] = (uint8_t)(lvl == 9 ? 2 : (lvl < 2 ? 4 : 0));
+        return cu_emit(cu, h, 10);
+    }
+    if (cu->wrap == 1) {
+        /* RFC1950: CMF = deflate + window, FLG = level hint + check bits */
+        int wb = cu->window_bits < 9 ? 9 : cu->window_bits;
+        uint32_t cmf = 8u | ((uint32_t)(wb - 8) << 4);
+        uint32_t flevel = lvl < 2 ? 0 : (lvl < 6 ? 1 : (lvl == 6 ? 2 : 3));
+        uint32_t hdr = (cmf << 8) | (flevel << 6);
+        hdr += 31 - (hdr % 31);
+        uint8_t h[2] = {(uint8_t)(hdr >> 8), (uint8_t)hdr};
+        return cu_emit(cu, h, 2);
+    }
+    return MZ_OK;
+}
+
+static void cu_adler_update(mz_stream_cuda *cu, const uint8_t *p, size_t n) {
+    uint32_t a = cu->adler_a, b = cu->adler_b;
+    while (n > 0) {
+        size_t k = n > 5552 ? 5552 : n;
+        n -= k;
+        while (k--) {
+            a += *p++;
+            b += a;
+        }
+        a %= 65521u;
+        b %= 65521u;
+    }
+    cu->adler_a = a;
+    cu->adler_b = b;
+}
+
+/* compress the staged bytes as one batch of independent chunks and hand the joined stream to base */
+static int32_t cu_flush_batch(mz_stream_cuda *cu, int final) {
+    cu_ws *w = cu->ws;
+    size_t n = cu->in_len;
+    int lvl = (int8_t)cu->level == -1 ? 6 : (int8_t)cu->level;
+    uint32_t nchunks = n == 0 ? 1 : (uint32_t)((n + CU_CHUNK - 1) / CU_CHUNK);
+    int32_t err;
+    if (n == 0 && !final)
+        return MZ_OK;
+    if (n > 0) {
+        err = mz_cuda_memcpy_h2d(w->d_in, w->h_in, n, NULL);
+        if (err)
+            return err;
+    }
+    err = mz_cuda_deflate_chunks(w->d_in, n, CU_CHUNK, NULL, NULL, NULL, nchunks, final ? MZ_CUDA_FLAG_FINAL : 0, lvl, w->d_slots,
+                                 w->slot_stride, w->d_out_len, NULL);
+    if (err)
+        return err;
+    err = mz_cuda_concat(w->d_slots, w->slot_stride, w->d_out_len, nchunks, w->d_offsets, w->d_out, NULL);
+    if (err)
+        return err;
+    if (cu->wrap == 2 && n > 0) {
+        err = mz_cuda_crc32_device(w->d_in, n, cu->crc, &cu->crc); /* chained running value */
+        if (err)
+            return err;
+    } else if (cu->wrap == 1 && n > 0) {
+        cu_adler_update(cu, w->h_in, n); /* zlib framing is unused by minizip-ng callers; host Adler-32 */
+    }
+    err = mz_cuda_memcpy_d2h(w->h_total, w->d_offsets + nchunks, 8, NULL);
+    if (err)
+        return err;
+    err = mz_cuda_stream_sync(NULL);
+    if (err)
+        return err;
+    uint64_t total = *w->h_total;
+    err = mz_cuda_memcpy_d2h(w->h_out, w->d_out, total, NULL);
+    if (err)
+        return err;
+    err = mz_cuda_stream_sync(NULL);
+    if (err)
+        return err;
+    cu->in_len = 0;
+    return cu_emit(cu, w->h_out, total);
+}
+#endif
+
+/* mz_strm_zlib.c:243-264: all-or-error, total_in += size */
+int32_t mz_stream_cuda_write(void *stream, const void *buf, int32_t size) {
+#ifdef MZ_ZIP_NO_COMPRESSION
+    (void)stream; (void)buf; (void)size;
+    return MZ_SUPPORT_ERROR;
+#else
+    mz_stream_cuda *cu = (mz_stream_cuda *)stream;
+    const uint8_t *p = (const uint8_t *)buf;
+    int32_t left = size, err;
+    if (size < 0)
+        return MZ_PARAM_ERROR;
+    if (!cu->ws) {
+        cu->ws = ws_acquire(1);
+        if (!cu->ws) {
+            cu->error = MZ_MEM_ERROR;
+            return MZ_MEM_ERROR;
+        }
+    }
+    err = cu_write_header(cu);
+    if (err != MZ_OK)
+        return err;
+    while (left > 0) {
+        size_t room = cu->ws->batch - cu->in_len;
+        size_t k = (size_t)left < room ? (size_t)left : room;
+        memcpy(cu->ws->h_in + cu->in_len, p, k);
+        cu->in_len += k;
+        p += k;
+        left -= (int32_t)k;
+        if (cu->in_len == cu->ws->batch) {
+            err = cu_flush_batch(cu, 0);
+            if (err != MZ_OK) {
+                if (err != MZ_WRITE_ERROR)
+                    cu->error = err;
+                return err == MZ_WRITE_ERROR ? err : MZ_DATA_ERROR;
+            }
+        }
+    }
+    cu->total_in += size;
+    return size;
+#endif
+}
+
+/* ---- read side ------------------------------------------------------------------------------------------ */
+#ifndef MZ_ZIP_NO_DECOMPRESSION
+/* pull more compressed bytes from base into the pinned window; honours TOTAL_IN_MAX (mz_strm_zlib.c:140-144) */
+static int32_t cu_refill(mz_stream_cuda *cu) {
+    cu_ws *w = cu->ws;
+    while (cu->cin_len < w->cin_cap && !cu->base_eof) {
+        int64_t want = (int64_t)(w->cin_cap - cu->cin_len);
+        if (want > (1 << 20))
+            want = 1 << 20; /* like the reference, ask in bounded pieces */
+        if (cu->max_total_in > 0 && want > cu->max_total_in - (int64_t)cu->fed_in)
+            want = cu->max_total_in - (int64_t)cu->fed_in;
+        if (want <= 0) {
+            cu->base_eof = 1;
+            break;
+        }
+        int32_t got = mz_abi_base_read(cu->stream.base, w->h_cin + cu->cin_len, (int32_t)want);
+        if (got < 0)
+            return got;
+        if (got == 0) {
+            cu->base_eof = 1;
+            break;
+        }
+        cu->cin_len += (size_t)got;
+        cu->fed_in += (uint64_t)got;
+    }
+    return MZ_OK;
+}
+
+/* gzip / zlib framing in front of the raw stream (what inflateInit2's windowBits selects, :97) */
+static int32_t cu_parse_header(mz_stream_cuda *cu) {
+    cu_ws *w = cu->ws;
+    const uint8_t *p = w->h_cin;
+    size_t n = cu->cin_len, i;
+    if (cu->wrap == 0) {
+        cu->hdr_size = 0;
+    } else if (cu->wrap == 1) {
+        if (n < 2)
+            return MZ_BUF_ERROR;
+        if ((p[0] & 0x0f) != 8 || (p[0] >> 4) > 7 || (((uint32_t)p[0] << 8) | p[1]) % 31 != 0 || (p[1] & 0x20))
+            return MZ_DATA_ERROR;
+        cu->hdr_size = 2;
+    } else {
+        if (n < 10)
+            return n >= 2 && (p[0] != 0x1f || p[1] != 0x8b) ? MZ_DATA_ERROR : MZ_BUF_ERROR;
+        if (p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || (p[3] & 0xe0))
+            return MZ_DATA_ERROR;
+        i = 10;
+        if (p[3] & 4) {
+            if (i + 2 > n)
+                return MZ_BUF_ERROR;
+            i += 2 + ((size_t)p[i] | ((size_t)p[i + 1] << 8));
+        }
+        if (p[3] & 8) {
+            while (i < n && p[i])
+                i++;
+            i++;
+        }
+        if (p[3] & 16) {
+            while (i < n && p[i])
+                i++;
+            i++;
+        }
+        if (p[3] & 2)
+            i += 2;
+        if (i > n)
+            return MZ_BUF_ERROR;
+        cu->hdr_size = (int64_t)i;
+    }
+    /* drop the framing: h_cin[0] becomes raw-stream byte 0 */
+    memmove(w->h_cin, w->h_cin + cu->hdr_size, cu->cin_len - (size_t)cu->hdr_size);
+    cu->cin_len -= (size_t)cu->hdr_size;
+    cu->cin_base = 0;
+    cu->hdr_parsed = 1;
+    memset(w->h_state, 0, sizeof(*w->h_state));
+    return mz_cuda_memcpy_h2d(w->d_state, w->h_state, sizeof(*w->h_state), NULL);
+}
+
+/* run the decoder once; afterwards ws->h_dec[0..dec_len) holds fresh output (possibly none) */
+static int32_t cu_decode_more(mz_stream_cuda *cu) {
+    cu_ws *w = cu->ws;
+    mz_cuda_inflate_state *st = w->h_state;
+    int32_t err;
+    if (!cu->hdr_parsed) {
+        err = cu_refill(cu);
+        if (err != MZ_OK)
+            return err;
+        err = cu_parse_header(cu);
+        if (err != MZ_OK)
+            return err;
+    }
+    for (;;) {
+        /* slide the compressed window: keep only bytes at or after the decoder's position */
+        uint64_t pos_byte = st->in_bitpos >> 3;
+        if (pos_byte > cu->cin_base) {
+            size_t drop = (size_t)(pos_byte - cu->cin_base);
+            if (drop > cu->cin_len)
+                drop = cu->cin_len;
+            memmove(w->h_cin, w->h_cin + drop, cu->cin_len - drop);
+            cu->cin_len -= drop;
+            cu->cin_base += drop;
+        }
+        err = cu_refill(cu);
+        if (err != MZ_OK)
+            return err;
+        /* slide the output window when it is full: keep 32 KiB of history at the front */
+        uint64_t out_pos = st->out_pos;
+        if (out_pos - cu->win_base + 65536 > w->win_cap) {
+            uint64_t keep = out_pos - cu->win_base < 32768 ? out_pos - cu->win_base : 32768;
+            /* ranges cannot overlap: the window is much larger than 64 KiB */
+            err = mz_cuda_memcpy_d2d(w->d_win, w->d_win + (out_pos - cu->win_base - keep), keep, NULL);
+            if (err)
+                return err;
+            cu->win_base = out_pos - keep;
+        }
+        memset(w->h_cin + cu->cin_len, 0, 64); /* the kernel may read a few bytes past the end */
+        err = mz_cuda_memcpy_h2d(w->d_cin, w->h_cin, cu->cin_len + 64, NULL);
+        if (err)
+            return err;
+        w->h_job->d_in = w->d_cin;
+        w->h_job->in_base = cu->cin_base;
+        w->h_job->in_avail = cu->cin_len;
+        w->h_job->d_out = w->d_win;
+        w->h_job->out_base = cu->win_base;
+        /* at most one host buffer (`batch` bytes) of fresh output per launch */
+        w->h_job->out_cap = (out_pos - cu->win_base) + w->batch < w->win_cap ? (out_pos - cu->win_base) + w->batch : w->win_cap;
+        w->h_job->in_final = cu->base_eof ? 1u : 0u;
+        w->h_job->reserved = 0;
+        err = mz_cuda_memcpy_h2d(w->d_job, w->h_job, sizeof(*w->h_job), NULL);
+        if (err)
+            return err;
+        err = mz_cuda_inflate_streams(w->d_job, w->d_state, 1, NULL);
+        if (err)
+            return err;
+        err = mz_cuda_memcpy_d2h(st, w->d_state, sizeof(*st), NULL);
+        if (err)
+            return err;
+        err = mz_cuda_stream_sync(NULL);
+        if (err)
+            return err;
+        uint64_t produced = st->out_pos - out_pos;
+        if (produced > 0) {
+            if (cu->wrap == 2) {
+                err = mz_cuda_crc32_device(w->d_win + (out_pos - cu->win_base), produced, cu->crc, &cu->crc);
+                if (err)
+                    return err;
+            }
+            err = mz_cuda_memcpy_d2h(w->h_dec, w->d_win + (out_pos - cu->win_base), produced, NULL);
+            if (err)
+                return err;
+            err = mz_cuda_stream_sync(NULL);
+            if (err)
+                return err;
+            if (cu->wrap == 1)
+                cu_adler_update(cu, w->h_dec, produced);
+            cu->dec_pos = 0;
+            cu->dec_len = (size_t)produced;
+        }
+        if (st->status < 0)
+            return st->status; /* MZ_DATA_ERROR / MZ_BUF_ERROR, zlib-compatible */
+        if (st->status == 1) {
+            /* end of the raw stream: account for consumed bytes, verify the trailer */
+            uint64_t raw_bytes = (st->in_bitpos + 7) >> 3;
+            uint64_t tsize = cu->wrap == 2 ? 8 : (cu->wrap == 1 ? 4 : 0);
+            cu->ended = 1;
+            cu->total_in = cu->hdr_size + (int64_t)raw_bytes + (int64_t)tsize;
+            if (tsize) {
+                size_t off = (size_t)(raw_bytes - cu->cin_base);
+                if (off + tsize > cu->cin_len) {
+                    /* trailer not in the window yet: slide and pull */
+                    memmove(w->h_cin, w->h_cin + off, cu->cin_len - off);
+                    cu->cin_len -= off;
+                    cu->cin_base += off;
+                    off = 0;
+                    err = cu_refill(cu);
+                    if (err != MZ_OK)
+                        return err;
+                    if (tsize > cu->cin_len) {
+                        cu->total_in = cu->hdr_size + (int64_t)raw_bytes + (int64_t)cu->cin_len;
+                        return MZ_BUF_ERROR;
+                    }
+                }
+                const uint8_t *t = w->h_cin + off;
+                if (cu->wrap == 2) {
+                    uint32_t crc = t[0] | (t[1] << 8) | (t[2] << 16) | ((uint32_t)t[3] << 24);
+                    uint32_t isz = t[4] | (t[5] << 8) | (t[6] << 16) | ((uint32_t)t[7] << 24);
+                    if (crc != cu->crc || isz != (uint32_t)st->out_pos)
+                        return MZ_DATA_ERROR;
+                } else {
+                    uint32_t ad = ((uint32_t)t[0] << 24) | (t[1] << 16) | (t[2] << 8) | t[3];
+                    if (ad != ((cu->adler_b << 16) | cu->adler_a))
+                        return MZ_DATA_ERROR;
+                }
+            }
+            return MZ_OK;
+        }
+        cu->total_in = cu->hdr_size + (int64_t)(st->in_bitpos >> 3);
+        if (produced > 0)
+            return MZ_OK;
+        if (st->why == 1 && cu->base_eof && w->h_job->in_final)
+            return MZ_BUF_ERROR; /* decoder wants input that does not exist */
+        /* otherwise loop: more input was needed (refill) or the window had to slide */
+    }
+}
+#endif
+
+/* mz_strm_zlib.c:116-193: bytes produced, 0 at end of stream, negative zlib-compatible code on error */
+int32_t mz_stream_cuda_read(void *stream, void *buf, int32_t size) {
+#ifdef MZ_ZIP_NO_DECOMPRESSION
+    (void)stream; (void)buf; (void)size;
+    return MZ_SUPPORT_ERROR;
+#else
+    mz_stream_cuda *cu = (mz_stream_cuda *)stream;
+    uint8_t *out = (uint8_t *)buf;
+    int32_t done = 0;
+    if (size < 0)
+        return MZ_PARAM_ERROR;
+    if (cu->error != 0)
+        return cu->error; /* sticky, like zlib->error at :186-189 */
+    if (!cu->ws) {
+        cu->ws = ws_acquire(2);
+        if (!cu->ws) {
+            cu->error = MZ_MEM_ERROR;
+            return MZ_MEM_ERROR;
+        }
+    }
+    while (done < size) {
+        if (cu->dec_pos < cu->dec_len) {
+            size_t k = cu->dec_len - cu->dec_pos;
+            if (k > (size_t)(size - done))
+                k = (size_t)(size - done);
+            memcpy(out + done, cu->ws->h_dec + cu->dec_pos, k);
+            cu->dec_pos += k;
+            done += (int32_t)k;
+            continue;
+        }
+        if (cu->ended)
+            break;
+        int32_t err = cu_decode_more(cu);
+        if (err != MZ_OK) {
+            cu->error = err;
+            if (cu->dec_pos < cu->dec_len)
+                continue; /* deliver what decoded cleanly first; the error surfaces on the next call */
+            break;
+        }
+    }
+    if (done == 0 && cu->error != 0)
+        return cu->error;
+    cu->total_out += done;
+    return done;
+#endif
+}
+
+/* mz_strm_zlib.c:266-278 */
+int64_t mz_stream_cuda_tell(void *stream) {
+    (void)stream;
+    return MZ_TELL_ERROR;
+}
+
+int32_t mz_stream_cuda_seek(void *stream, int64_t offset, int32_t origin) {
+    (void)stream; (void)offset; (void)origin;
+    return MZ_SEEK_ERROR;
+}
+
+/* mz_strm_zlib.c:280-305: flush everything pending to base, keep totals readable, MZ_CLOSE_ERROR if an
+ * error was latched; like the reference, a failing final flush does not change the return value */
+int32_t mz_stream_cuda_close(void *stream) {
+    mz_stream_cuda *cu = (mz_stream_cuda *)stream;
+    if (cu->initialized == 1 && (cu->mode & MZ_OPEN_MODE_WRITE)) {
+#ifdef MZ_ZIP_NO_COMPRESSION
+        return MZ_SUPPORT_ERROR;
+#else
+        if (!cu->ws)
+            cu->ws = ws_acquire(1);
+        if (!cu->ws) {
+            cu->error = MZ_MEM_ERROR;
+        } else if (cu->error == 0) {
+            int32_t err = cu_write_header(cu);
+            if (err == MZ_OK)
+                err = cu_flush_batch(cu, 1);
+            if (err == MZ_OK && cu->wrap == 2) {
+                uint32_t isz = (uint32_t)cu->total_in; /* ISIZE is mod 2^32 */
+                uint8_t t[8] = {(uint8_t)cu->crc, (uint8_t)(cu->crc >> 8), (uint8_t)(cu->crc >> 16), (uint8_t)(cu->crc >> 24),
+                                (uint8_t)isz,     (uint8_t)(isz >> 8),     (uint8_t)(isz >> 16),     (uint8_t)(isz >> 24)};
+                err = cu_emit(cu, t, 8);
+            } else if (err == MZ_OK && cu->wrap == 1) {
+                uint32_t ad = (cu->adler_b << 16) | cu->adler_a;
+                uint8_t t[4] = {(uint8_t)(ad >> 24), (uint8_t)(ad >> 16), (uint8_t)(ad >> 8), (uint8_t)ad};
+                err = cu_emit(cu, t, 4);
+            }
+            if (err != MZ_OK && err != MZ_WRITE_ERROR)
+                cu->error = err;
+        }
+#endif
+    } else if (cu->initialized == 1 && (cu->mode & MZ_OPEN_MODE_READ)) {
+#ifdef MZ_ZIP_NO_DECOMPRESSION
+        return MZ_SUPPORT_ERROR;
+#endif
+    }
+    if (cu->ws) {
+        ws_release(cu->ws);
+        cu->ws = NULL;
+    }
+    cu->initialized = 0;
+    if (cu->error != 0)
+        return MZ_CLOSE_ERROR;
+    return MZ_OK;
+}
+
+/* mz_strm_zlib.c:307-310 */
+int32_t mz_stream_cuda_error(void *stream) {
+    mz_stream_cuda *cu = (mz_stream_cuda *)stream;
+    return cu->error;
+}
+
+/* mz_strm_zlib.c:312-334 */
+int32_t mz_stream_cuda_get_prop_int64(void *stream, int32_t prop, int64_t *value) {
+    mz_stream_cuda *cu = (mz_stream_cuda *)stream;
+    switch (prop) {
+    case MZ_STREAM_PROP_TOTAL_IN:
+        *value = cu->total_in;
+        break;
+    case MZ_STREAM_PROP_TOTAL_IN_MAX:
+        *value = cu->max_total_in;
+        break;
+    case MZ_STREAM_PROP_TOTAL_OUT:
+        *value = cu->total_out;
+        break;
+    case MZ_STREAM_PROP_HEADER_SIZE:
+        *value = 0;
+        break;
+    case MZ_STREAM_PROP_COMPRESS_WINDOW:
+        *value = cu->window_bits;
+        break;
+    default:
+        return MZ_EXIST_ERROR;
+    }
+    return MZ_OK;
+}
+
+/* mz_strm_zlib.c:336-355 */
+int32_t mz_stream_cuda_set_prop_int64(void *stream, int32_t prop, int64_t value) {
+    mz_stream_cuda *cu = (mz_stream_cuda *)stream;
+    switch (prop) {
+    case MZ_STREAM_PROP_COMPRESS_LEVEL:
+        if (value == MZ_COMPRESS_LEVEL_DEFAULT)
+            cu->level = -1;
+        else
+            cu->level = (int16_t)value;
+        break;
+    case MZ_STREAM_PROP_TOTAL_IN_MAX:
+        cu->max_total_in = value;
+        break;
+    case MZ_STREAM_PROP_COMPRESS_WINDOW:
+        cu->window_bits = (int32_t)value;
+        break;
+    default:
+        return MZ_EXIST_ERROR;
+    }
+    return MZ_OK;
+}
+
+/* mz_strm_zlib.c:357-365: level default, raw window (zip entries) */
+void *mz_stream_cuda_create(void) {
+    mz_stream_cuda *cu = (mz_stream_cuda *)calloc(1, sizeof(mz_stream_cuda));
+    if (cu) {
+        cu->stream.vtbl = &mz_stream_cuda_vtbl;
+        cu->level = -1;
+        cu->window_bits = -15;
+    }
+    return cu;
+}
+
+/* mz_strm_zlib.c:367-374 */
+void mz_stream_cuda_delete(void **stream) {
+    mz_stream_cuda *cu = NULL;
+    if (!stream)
+        return;
+    cu = (mz_stream_cuda *)*stream;
+    if (cu) {
+        if (cu->ws)
+            ws_release(cu->ws);
+        free(cu);
+    }
+    *stream = NULL;
+}
+
+/* mz_strm_zlib.c:376-378 */
+void *mz_stream_cuda_get_interface(void) {
+    return (void *)&mz_stream_cuda_vtbl;
+}

@@ -1,0 +1,105 @@
+/* mzcuda_common.cuh -- shared device helpers for the mz_strm_cuda kernels (sm_100a).
+ *
+ * Compiles two ways: with nvcc for the product (the only build that ships), and with g++ -DMZ_EMU
+ * against tests/emu/cuda_emu.h so the kernel logic can be exercised on the CPU by the unit tests.
+ */
+#ifndef MZCUDA_COMMON_CUH
+#define MZCUDA_COMMON_CUH
+
+#include <stdint.h>
+
+#ifdef MZ_EMU
+#include "cuda_emu.h"
+#define MZ_DYN_SMEM(name) uint8_t *name = emu_dyn_smem
+#else
+#include <cuda_runtime.h>
+#define MZ_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define MZ_DYN_SMEM(name) extern __shared__ __align__(128) uint8_t name[]
+#endif
+
+#define MZ_FULL_MASK 0xffffffffu
+
+namespace mzc {
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ unsigned warp_id() { return threadIdx.x >> 5; }
+
+/* unaligned little-endian 32-bit load from a byte buffer whose base is 4-byte aligned and which is
+ * readable for 4 bytes past (p & ~3) + 4 */
+__device__ __forceinline__ uint32_t load32u(const uint8_t *base, uint32_t p) {
+    const uint32_t *w = (const uint32_t *)(base + (p & ~3u));
+    return __funnelshift_r(w[0], w[1], (p & 3u) * 8u);
+}
+
+/* streaming 128-bit global load that does not pollute L1 */
+__device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
+#ifdef MZ_EMU
+    return *p;
+#else
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+#endif
+}
+
+/* warp inclusive scan (sum) */
+__device__ __forceinline__ uint32_t warp_incl_sum(uint32_t v) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t n = __shfl_up_sync(MZ_FULL_MASK, v, d);
+        if (lane_id() >= (unsigned)d) v += n;
+    }
+    return v;
+}
+
+__device__ __forceinline__ uint32_t warp_incl_max(uint32_t v) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t n = __shfl_up_sync(MZ_FULL_MASK, v, d);
+        if (lane_id() >= (unsigned)d) v = v > n ? v : n;
+    }
+    return v;
+}
+
+#ifndef MZ_EMU
+/* ---- mbarrier + TMA bulk copy (cp.async.bulk; SASS: UBLKCP) ------------------------------------ */
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+/* global -> shared bulk copy; dst, src 16-byte aligned, bytes multiple of 16 */
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+/* shared -> global bulk copy (bulk async-group completion) */
+__device__ __forceinline__ void tma_store_1d(void *gdst, const void *smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+#endif
+
+} // namespace mzc
+#endif

@@ -1,0 +1,135 @@
+/* emu_kernels.cc -- runs the product's kernel SOURCES on the CPU emulator (TEST INFRASTRUCTURE ONLY).
+ * Built as tests/emu/libmzemu.so by tests/emu/Makefile; used by tests/test_emu_*.py to debug kernel
+ * logic without a GPU. Never part of the product library. */
+#define MZ_EMU 1
+#include "../../minizip-ng_b200/csrc/concat_kernel.cuh"
+#include "../../minizip-ng_b200/csrc/crc32_kernel.cuh"
+#include "../../minizip-ng_b200/csrc/deflate_kernel.cuh"
+#include "../../minizip-ng_b200/csrc/inflate_kernel.cuh"
+
+using namespace mzc;
+
+static CrcConsts g_consts;
+static bool g_ready;
+static void ensure() {
+    if (!g_ready) {
+        crc_consts_init(g_consts);
+        g_ready = true;
+    }
+}
+
+extern "C" {
+
+uint64_t emu_deflate_slot_bound(uint32_t chunk) { return deflate_slot_bound(chunk); }
+
+/* uniform partition; returns total bytes written to dst (joined stream) or <0 */
+int64_t emu_deflate(const uint8_t *in, uint64_t len, uint32_t chunk_size, int level, uint32_t last_flags, uint8_t *dst, uint64_t dst_cap,
+                    uint32_t grid, uint32_t *out_len_opt) {
+    uint32_t nchunks = len == 0 ? 1 : (uint32_t)((len + chunk_size - 1) / chunk_size);
+    uint64_t stride = deflate_slot_bound(chunk_size);
+    std::vector<uint8_t> slots((size_t)(stride * nchunks + 64));
+    uint8_t *sl = (uint8_t *)(((uintptr_t)slots.data() + 15) & ~(uintptr_t)15);
+    std::vector<uint32_t> out_len(nchunks);
+    std::vector<uint64_t> offs(nchunks + 1);
+    /* input must be readable as uint4 when 16-byte aligned; copy into an aligned padded buffer */
+    std::vector<uint8_t> inbuf((size_t)len + 64);
+    uint8_t *ia = (uint8_t *)(((uintptr_t)inbuf.data() + 15) & ~(uintptr_t)15);
+    memcpy(ia, in, (size_t)len);
+    DeflateParams P;
+    memset(&P, 0, sizeof(P));
+    P.in = ia;
+    P.total_len = len;
+    P.chunk_size = chunk_size;
+    P.nchunks = nchunks;
+    P.last_flags = last_flags;
+    P.level = level;
+    P.out = sl;
+    P.slot_stride = stride;
+    P.out_len = out_len.data();
+    if (grid == 0 || grid > nchunks) grid = nchunks;
+    MZ_LAUNCH(deflate_chunks_kernel, dim3(grid), dim3(DF_THREADS), DF_SMEM_BYTES, 0, P);
+    MZ_LAUNCH(scan_lengths_kernel, dim3(1), dim3(SCAN_THREADS), 0, 0, (const uint32_t *)out_len.data(), nchunks, (uint64_t)0, offs.data());
+    if (offs[nchunks] > dst_cap) return -5;
+    MZ_LAUNCH(gather_slots_kernel, dim3(nchunks < 8 ? nchunks : 8), dim3(GATHER_THREADS), 0, 0, (const uint8_t *)sl, stride,
+              (const uint32_t *)out_len.data(), (const uint64_t *)offs.data(), nchunks, dst);
+    if (out_len_opt) memcpy(out_len_opt, out_len.data(), nchunks * 4);
+    return (int64_t)offs[nchunks];
+}
+
+/* per-segment CRCs + fold; misalign shifts the start address to exercise the head path */
+uint32_t emu_crc32(const uint8_t *in, uint64_t len, uint64_t seg_size, uint32_t misalign, uint32_t *seg_crcs_opt) {
+    ensure();
+    std::vector<uint8_t> buf((size_t)len + 96);
+    uint8_t *a = (uint8_t *)(((uintptr_t)buf.data() + 15) & ~(uintptr_t)15) + (misalign & 15);
+    memcpy(a, in, (size_t)len);
+    uint32_t nseg = len == 0 ? 0 : (uint32_t)((len + seg_size - 1) / seg_size);
+    std::vector<uint32_t> res(nseg + 1), crcs(nseg + 1);
+    uint32_t out2[2] = {0, 0};
+    if (nseg) {
+        CrcParams P;
+        memset(&P, 0, sizeof(P));
+        P.in = a;
+        P.total_len = len;
+        P.seg_size = seg_size;
+        P.nseg = nseg;
+        P.consts = &g_consts;
+        P.out_residue = res.data();
+        P.out_crc = crcs.data();
+        MZ_LAUNCH(crc32_segments_kernel, dim3(2), dim3(CRC_THREADS), CRC_SMEM_BYTES, 0, P);
+    }
+    MZ_LAUNCH(crc32_fold_kernel, dim3(1), dim3(CRCF_THREADS), 0, 0, (const uint32_t *)res.data(), nseg, seg_size, len, (const CrcConsts *)&g_consts, out2);
+    if (seg_crcs_opt) memcpy(seg_crcs_opt, crcs.data(), nseg * 4);
+    return out2[1];
+}
+
+uint32_t emu_crc32_combine(uint32_t a, uint32_t b, uint64_t len_b) {
+    ensure();
+    return gf2_mulmod(a, gf2_xpow(g_consts.x2n, 8ull * len_b)) ^ b;
+}
+
+/* Decode one raw stream, feeding it through bounded windows like the vtbl read path would.
+ * in_window / out_window = 0 means "everything at once". Returns status; *consumed, *produced filled. */
+int32_t emu_inflate(const uint8_t *in, uint64_t in_len, uint8_t *out, uint64_t out_cap, uint64_t in_window, uint64_t out_window,
+                    uint64_t *consumed, uint64_t *produced, uint32_t *blocks) {
+    InflateState st;
+    memset(&st, 0, sizeof(st));
+    std::vector<uint8_t> inbuf;
+    uint64_t fed = in_window ? (in_window < in_len ? in_window : in_len) : in_len;
+    uint64_t out_limit = out_window ? (out_window < out_cap ? out_window : out_cap) : out_cap;
+    for (int iter = 0; iter < 1000000; iter++) {
+        /* window of input starting at the byte holding the current bit position */
+        uint64_t base = st.in_bitpos >> 3;
+        inbuf.assign((size_t)(fed - base) + 32, 0);
+        memcpy(inbuf.data(), in + base, (size_t)(fed - base));
+        InflateJob job;
+        memset(&job, 0, sizeof(job));
+        job.in = inbuf.data();
+        job.in_base = base;
+        job.in_avail = fed - base;
+        job.out = out;
+        job.out_base = 0;
+        job.out_cap = out_limit;
+        job.in_final = fed == in_len;
+        MZ_LAUNCH(inflate_streams_kernel, dim3(1), dim3(INF_THREADS), 0, 0, (const InflateJob *)&job, &st, 1u);
+        if (st.status != INF_ST_RUN) break;
+        if (st.why == INF_WHY_INPUT) {
+            if (fed == in_len) { st.status = -99; break; }
+            fed = fed + in_window < in_len ? fed + in_window : in_len;
+        } else if (st.why == INF_WHY_OUTPUT) {
+            if (out_limit == out_cap) { st.status = INF_ST_BUF_ERROR; break; }
+            out_limit = out_limit + out_window < out_cap ? out_limit + out_window : out_cap;
+        } else {
+            st.status = -98;
+            break;
+        }
+    }
+    *consumed = (st.in_bitpos + 7) >> 3;
+    *produced = st.out_pos;
+    if (blocks) *blocks = st.blocks;
+    return st.status;
+}
+
+void emu_textgen(uint8_t *out, uint64_t n, uint64_t seed, const uint8_t *words, const uint32_t *word_off, uint32_t nwords) {
+    MZ_LAUNCH(textgen_kernel, dim3(4), dim3(256), 0, 0, out, n, seed, words, word_off, nwords);
+}
+}

@@ -1,0 +1,44 @@
+"""ctypes access to tests/emu/libmzemu.so: the product's kernel sources run on the CPU emulator."""
+import ctypes as C
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class EmuLib:
+    def __init__(self):
+        self.lib = L = C.CDLL(os.path.join(ROOT, "tests/emu/libmzemu.so"))
+        vp, u64, u32 = C.c_void_p, C.c_uint64, C.c_uint32
+        L.emu_deflate.restype = C.c_int64
+        L.emu_deflate.argtypes = [vp, u64, u32, C.c_int, u32, vp, u64, u32, vp]
+        L.emu_crc32.restype = u32
+        L.emu_crc32.argtypes = [vp, u64, u64, u32, vp]
+        L.emu_crc32_combine.restype = u32
+        L.emu_crc32_combine.argtypes = [u32, u32, u64]
+        L.emu_inflate.restype = C.c_int32
+        L.emu_inflate.argtypes = [vp, u64, vp, u64, u64, u64, C.POINTER(u64), C.POINTER(u64), C.POINTER(u32)]
+
+    def deflate(self, data, level=1, chunk=65536, final=True, grid=0):
+        data = bytes(data)
+        cap = len(data) + (len(data) // 16384 + 2) * 64 + 1024
+        out = C.create_string_buffer(cap)
+        nch = max(1, (len(data) + chunk - 1) // chunk)
+        lens = (C.c_uint32 * nch)()
+        n = self.lib.emu_deflate(data, len(data), chunk, level, 1 if final else 0, out, cap, grid, lens)
+        if n < 0:
+            raise ValueError(n)
+        return out.raw[:n], list(lens)
+
+    def crc32(self, data, seg=65536, misalign=0):
+        data = bytes(data)
+        nseg = (len(data) + seg - 1) // seg
+        segs = (C.c_uint32 * max(nseg, 1))()
+        v = self.lib.emu_crc32(data, len(data), seg, misalign, segs)
+        return v, list(segs)[:nseg]
+
+    def inflate(self, comp, out_cap, in_window=0, out_window=0):
+        comp = bytes(comp)
+        out = C.create_string_buffer(max(out_cap, 1) + 300)
+        cons, prod, blocks = C.c_uint64(0), C.c_uint64(0), C.c_uint32(0)
+        st = self.lib.emu_inflate(comp, len(comp), out, out_cap, in_window, out_window, C.byref(cons), C.byref(prod), C.byref(blocks))
+        return st, out.raw[:prod.value], cons.value, blocks.value

@@ -1,0 +1,116 @@
+"""CPU-side checks of the boundary: the C-ABI library loads, exports every symbol the headers declare, and the
+host logic that needs no GPU behaves like the reference (mz_strm_zlib.c:312-378). No compute calls here."""
+import ctypes as C
+import os
+import re
+
+import refshim
+
+
+def _pkg(built):
+    import cuharness
+    return cuharness.pkg()
+
+
+def _declared(header):
+    txt = open(header).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(mz_(?:stream_cuda|cuda|crypt)_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol(built):
+    p = _pkg(built)
+    lib = C.CDLL(p.LIB_PATH)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    names = _declared(os.path.join(root, "include/mz_strm_cuda.h")) + _declared(os.path.join(root, "include/mz_cuda_batch.h"))
+    assert len(names) >= 40
+    for n in names:
+        assert hasattr(lib, n), "missing export " + n
+    assert sorted(set(names)) == sorted(set(p.EXPORTS))
+
+
+def test_vtbl_slot_order_and_object_header(built):
+    p = _pkg(built)
+    lib = p.load()
+    vt = lib.mz_stream_cuda_get_interface()
+    slots = (C.c_void_p * 12).from_address(vt)
+    names = ["open", "is_open", "read", "write", "tell", "seek", "close", "error", "create", "delete", "get_prop_int64", "set_prop_int64"]
+    for i, n in enumerate(names):  # mz_strm.h:53-67 order
+        fn = C.cast(getattr(lib, "mz_stream_cuda_" + n), C.c_void_p).value
+        assert slots[i] == fn, n
+    s = lib.mz_stream_cuda_create()
+    hdr = (C.c_void_p * 2).from_address(s)
+    assert hdr[0] == vt and hdr[1] is None  # {vtbl, base} first (mz_strm.h:69-72)
+    ps = C.c_void_p(s)
+    lib.mz_stream_cuda_delete(C.byref(ps))
+    assert ps.value is None
+
+
+def test_props_and_lifecycle_without_gpu(built):
+    p = _pkg(built)
+    lib = p.load()
+    s = lib.mz_stream_cuda_create()
+    v = C.c_int64(0)
+    assert lib.mz_stream_cuda_is_open(s) == refshim.MZ_OPEN_ERROR
+    assert lib.mz_stream_cuda_set_prop_int64(s, refshim.PROP_COMPRESS_LEVEL, -1) == 0
+    assert lib.mz_stream_cuda_set_prop_int64(s, refshim.PROP_COMPRESS_WINDOW, 31) == 0
+    assert lib.mz_stream_cuda_set_prop_int64(s, refshim.PROP_TOTAL_IN_MAX, 1234) == 0
+    assert lib.mz_stream_cuda_get_prop_int64(s, refshim.PROP_TOTAL_IN_MAX, C.byref(v)) == 0 and v.value == 1234
+    assert lib.mz_stream_cuda_get_prop_int64(s, refshim.PROP_COMPRESS_WINDOW, C.byref(v)) == 0 and v.value == 31
+    assert lib.mz_stream_cuda_get_prop_int64(s, refshim.PROP_TOTAL_OUT_MAX, C.byref(v)) == refshim.MZ_EXIST_ERROR
+    assert lib.mz_stream_cuda_set_prop_int64(s, refshim.PROP_COMPRESS_METHOD, 8) == refshim.MZ_EXIST_ERROR
+    assert lib.mz_stream_cuda_tell(s) == refshim.MZ_TELL_ERROR
+    assert lib.mz_stream_cuda_seek(s, 0, 0) == refshim.MZ_SEEK_ERROR
+    # invalid parameters are rejected before the GPU is even looked at (zip_fuzzer.c feeds arbitrary levels)
+    lib.mz_stream_cuda_set_prop_int64(s, refshim.PROP_COMPRESS_LEVEL, 77)
+    assert lib.mz_stream_cuda_open(s, None, refshim.MZ_OPEN_MODE_WRITE) == refshim.MZ_OPEN_ERROR
+    assert lib.mz_stream_cuda_close(s) == refshim.MZ_CLOSE_ERROR  # latched error, like zlib->error (:302-304)
+    ps = C.c_void_p(s)
+    lib.mz_stream_cuda_delete(C.byref(ps))
+
+
+def test_no_gpu_means_support_error_not_a_fallback(built):
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("GPU present")
+    p = _pkg(built)
+    lib = p.load()
+    s = lib.mz_stream_cuda_create()
+    assert lib.mz_stream_cuda_open(s, None, refshim.MZ_OPEN_MODE_WRITE) == refshim.MZ_SUPPORT_ERROR
+    assert lib.mz_stream_cuda_is_open(s) == refshim.MZ_OPEN_ERROR
+    ps = C.c_void_p(s)
+    lib.mz_stream_cuda_delete(C.byref(ps))
+    assert lib.mz_cuda_init() == refshim.MZ_SUPPORT_ERROR
+
+
+def test_small_crc_calls_match_reference_semantics(built, orc):
+    """Below the size threshold mz_crypt_crc32_update is the mz_crypt.c:81-90 loop: byte-at-a-time chaining (pkcrypt)."""
+    p = _pkg(built)
+    lib = p.load()
+    data = b"The quick brown fox jumps over the lazy dog"
+    v = 0
+    for b in data:
+        v = lib.mz_crypt_crc32_update(v, bytes([b]), 1)
+    assert v == orc.crc32(0, data) == 0x414FA339
+    assert lib.mz_crypt_crc32_update(5, None, 0) == 5
+
+
+def test_crc_combine_host_arithmetic(built, orc):
+    p = _pkg(built)
+    lib = p.load()
+    import datagen
+    a, b = datagen.random_bytes(1000, 1), datagen.random_bytes(123457, 2)
+    assert lib.mz_cuda_crc32_combine(orc.crc32(0, a), orc.crc32(0, b), len(b)) == orc.crc32(0, a + b)
+    for ln in (0, 1, 65536, (1 << 32) + 17):
+        assert lib.mz_cuda_crc32_combine(0xDEADBEEF, 0x01020304, ln) == orc.crc32_combine(0xDEADBEEF, 0x01020304, ln)
+
+
+def test_mem64_support_stream(built):
+    import cuharness
+    tl = cuharness.TestLib()
+    sink = tl.sink()
+    buf = C.create_string_buffer(b"abcdef", 6)
+    assert tl.lib.mzt_write(sink, buf, 6) == 6 and tl.lib.mzt_tell(sink) == 6
+    assert tl.sink_bytes(sink) == b"abcdef"
+    tl.delete(sink)
