@@ -19,6 +19,7 @@ cpu_baseline the reference path (oracle/_ref: mz_strm_zlib.c + mz_crypt.c + zlib
 """
 import argparse
 import ctypes as C
+import faulthandler
 import json
 import os
 import subprocess
@@ -169,7 +170,8 @@ def host_text_sample(nbytes, seed=99):
             t = pkg.textgen(nbytes, seed=seed)
             torch.cuda.synchronize()
             buf = (C.c_uint8 * nbytes)()
-            C.memmove(buf, t.cpu().numpy().ctypes.data, nbytes)
+            arr = t.cpu().numpy()  # keep the array alive across the copy
+            C.memmove(buf, arr.ctypes.data, nbytes)
             return buf
     except Exception:
         pass
@@ -212,7 +214,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "ratio": round(comp / nbytes, 4),
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 # ---- our arm ---------------------------------------------------------------------------------------------------------
@@ -376,7 +378,9 @@ def run_ours(args, rank, world, local_rank):
         if refshim.ref_available():
             nb = min(args.cpu_sample_mib << 20, shard)
             sample = (C.c_uint8 * nb)()
-            C.memmove(sample, src[:nb].cpu().numpy().ctypes.data, nb)
+            arr = src[:nb].cpu().numpy()  # keep the array alive across the copy
+            C.memmove(sample, arr.ctypes.data, nb)
+            del arr
             v, thr, comp = cpu_reference_throughput(sample, args.level)
             cpu = {"value": round(v, 4), "unit": UNIT, "cores": thr, "kind": "reference",
                    "sample": "first %d MiB of the same buffer, mz_strm_zlib over zlib 1.3 level %d, one stream per <=32 MiB piece, all host threads; ratio %.4f" % (nb >> 20, args.level, comp / nb)}
@@ -392,10 +396,11 @@ def run_ours(args, rank, world, local_rank):
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clk, "e2e": e2e, "gpu_launches": launches,
         "ratio": round(comp_bytes / shard, 4), "crc32": "%08x" % crc_whole,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 def main():
+    faulthandler.enable()
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

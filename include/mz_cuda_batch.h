@@ -42,6 +42,7 @@ void mz_cuda_stream_destroy(void *stream);
 void *mz_cuda_event_create(void);
 void mz_cuda_event_destroy(void *event);
 int32_t mz_cuda_event_record(void *event, void *stream);
+int32_t mz_cuda_event_sync(void *event);
 float mz_cuda_event_elapsed_ms(void *start, void *stop); /* syncs on stop */
 
 /* ---- K1: CRC-32 ---------------------------------------------------------------------------------

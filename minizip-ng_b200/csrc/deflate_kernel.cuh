@@ -6,21 +6,27 @@
  *
  * Work decomposition (one CTA of 1024 threads per chunk; persistent grid-stride loop over chunks):
  *   chunk      <= 64 KiB of input, independent LZ77 history, resident in shared memory (TMA bulk load)
- *   sub-block  32 KiB = 1024 threads x 32-byte segments; one DEFLATE block per sub-block
+ *   sub-block  32 KiB = 1024 threads x 32-byte segments; normally one DEFLATE block per sub-block
  *   A parse    every thread runs a greedy hash-table parser over its own 32-byte segment; matches may
  *              overrun the segment (up to 258 B, clamped at the sub-block end); the hash table
- *              (shared memory, 16-bit chunk-relative positions, racy by design: every candidate is
- *              validated by comparing bytes, and any earlier position is a legal LZ77 source)
+ *              (shared memory, 16-bit chunk-relative positions) is racy by design: every candidate is
+ *              validated by comparing bytes, and any earlier position is a legal LZ77 source
  *   B cover    exclusive prefix-max over the threads' parse end positions: a thread drops / trims the
  *              tokens that an earlier thread's overrunning match already covers
- *   C hist     literal/length + distance histograms (shared-memory atomics)
- *   D codes    warp-parallel length-limited code construction (bisection on a global rounding offset
- *              of the ideal -log2 p lengths, then exact Kraft completion), canonical codes, block header
- *   E count    per-thread bit totals -> block exclusive scan -> bit offsets
- *   F emit     every thread packs its tokens at its bit offset into the staging buffer
- *   G flush    staging -> global in 16-byte units; partial tail carried into the next sub-block
- * Blocks that would not shrink are emitted as stored blocks.  A non-final chunk ends with an empty
- * stored block (00 00 FF FF after bit padding) so chunks join byte-wise; the final chunk carries BFINAL.
+ *   T tokens   every thread turns what it keeps into entries of ONE block-wide ordered token list
+ *              (16-bit: position | match flag), placed by a block exclusive scan of token counts
+ *   C hist     threads stride over the list: literal/length + distance histograms (shared-memory
+ *              atomics); match records are rewritten in place to their symbol form
+ *   D codes    block-parallel length-limited prefix codes: one thread per symbol, two 16-candidate
+ *              sweeps of a global rounding offset on the ideal -log2 p lengths (Kraft sums by warp
+ *              reduce + atomics), exact Kraft completion and canonical code ranks via per-warp
+ *              match_any counts; code-length code + header by one warp, overlapped with E
+ *   E count    every thread owns an equal, contiguous run of tokens: bit totals -> block scan
+ *   F emit     every thread packs its run at its bit offset into the staging buffer
+ *   G flush    staging -> global in 16-byte units; partial tail carried into the next block
+ * Blocks that would not shrink are emitted as stored blocks. If a sub-block has more tokens than the
+ * list holds it is coded as two blocks (thread halves). A non-final chunk ends with an empty stored
+ * block (00 00 FF FF after bit padding) so chunks join byte-wise; the final chunk carries BFINAL.
  */
 #ifndef MZ_DEFLATE_KERNEL_CUH
 #define MZ_DEFLATE_KERNEL_CUH
@@ -38,7 +44,9 @@ constexpr int DF_MINMATCH = 4;
 constexpr int DF_MAXREC = DF_SEG / DF_MINMATCH; /* 8 match records per thread per sub-block */
 constexpr int DF_HASH_ENTRIES = 16384;          /* u16 entries: 32 KiB */
 constexpr int DF_STAGE_WORDS = DF_SB / 4 + 64;
-constexpr int DF_HDR_WORDS = 96; /* dynamic header <= 17 + 57 + 316*7 bits = 2286 bits = 72 words */
+constexpr int DF_HDR_WORDS = 96;   /* dynamic header <= 17 + 57 + 316*7 bits = 2286 bits = 72 words */
+constexpr int DF_TOK_CAP = 24576;  /* token list entries (u16) */
+constexpr uint32_t DF_TOK_MATCH = 0x8000u;
 
 constexpr uint32_t DF_FLAG_FINAL = 1u; /* chunk ends the stream: BFINAL on its last block, no sync marker */
 
@@ -47,17 +55,19 @@ constexpr int DF_OFF_IN = 0;
 constexpr int DF_OFF_HASH = DF_OFF_IN + DF_CHUNK_MAX + 64;
 constexpr int DF_OFF_REC = DF_OFF_HASH + DF_HASH_ENTRIES * 2;
 constexpr int DF_OFF_STAGE = DF_OFF_REC + DF_MAXREC * DF_THREADS * 4;
-constexpr int DF_OFF_HDR = DF_OFF_STAGE + DF_STAGE_WORDS * 4;
-constexpr int DF_OFF_END = DF_OFF_HDR + DF_HDR_WORDS * 4;       /* u16[1024] parse end */
-constexpr int DF_OFF_BITOFF = DF_OFF_END + DF_THREADS * 2;      /* u32[1024] */
-constexpr int DF_OFF_HIST = DF_OFF_BITOFF + DF_THREADS * 4;     /* u32[288 + 32 + 32] */
+constexpr int DF_OFF_TOK = DF_OFF_STAGE + DF_STAGE_WORDS * 4;
+constexpr int DF_OFF_RECMASK = DF_OFF_TOK + DF_TOK_CAP * 2;
+constexpr int DF_OFF_HDR = DF_OFF_RECMASK + DF_THREADS * 4;
+constexpr int DF_OFF_HIST = DF_OFF_HDR + DF_HDR_WORDS * 4;      /* u32[288 + 32 + 32] */
 constexpr int DF_OFF_CODE = DF_OFF_HIST + (288 + 32 + 32) * 4;  /* u32[288 + 32 + 32] code | len<<16 */
 constexpr int DF_OFF_LENS = DF_OFF_CODE + (288 + 32 + 32) * 4;  /* u8[288 + 32 + 32] */
 constexpr int DF_OFF_SCAN = DF_OFF_LENS + (288 + 32 + 32);      /* u32[64] */
-constexpr int DF_OFF_MISC = DF_OFF_SCAN + 64 * 4;               /* u32[32] + mbarrier */
+constexpr int DF_OFF_BB = DF_OFF_SCAN + 64 * 4;                 /* u32[512] block code-builder scratch */
+constexpr int DF_OFF_MISC = DF_OFF_BB + 512 * 4;                /* u32[32] + mbarrier */
 constexpr int DF_SMEM_BYTES = DF_OFF_MISC + 32 * 4 + 16;
+static_assert(DF_SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
-enum { MISC_HDRBITS = 1, MISC_TOKBITS = 2, MISC_NLIT = 3, MISC_NDIST = 4, MISC_BLCNT = 8 /* 16 words */ };
+enum { MISC_HDRBITS = 1, MISC_E0 = 2, MISC_BLCNT = 8 /* 16 words */ };
 
 struct DeflateParams {
     const uint8_t *in;       /* device base of the uncompressed bytes */
@@ -75,20 +85,21 @@ struct DeflateParams {
 };
 
 __host__ __device__ inline uint64_t deflate_slot_bound(uint32_t chunk_size) {
-    return (((uint64_t)chunk_size + 5ull * ((chunk_size + DF_SB - 1) / DF_SB + 1) + 64 + 15) & ~15ull);
+    /* stored worst case: 5 bytes per block, up to 2 blocks per 32 KiB sub-block, + sync marker + slack */
+    return (((uint64_t)chunk_size + 12ull * ((chunk_size + DF_SB - 1) / DF_SB + 1) + 64 + 15) & ~15ull);
 }
 
 /* ---- symbol mapping (RFC1951 3.2.5) without tables ------------------------------------------- */
 __device__ __forceinline__ void length_symbol(uint32_t len, uint32_t &sym, uint32_t &ebits, uint32_t &eval) {
-    uint32_t l = len - 3;
+    uint32_t l = len - 3; /* sym is 0..28 (add 257 for the alphabet index) */
     if (l < 8) {
-        sym = 257 + l; ebits = 0; eval = 0;
+        sym = l; ebits = 0; eval = 0;
     } else if (len == 258) {
-        sym = 285; ebits = 0; eval = 0;
+        sym = 28; ebits = 0; eval = 0;
     } else {
         uint32_t msb = 31 - __clz((int)l); /* 3..7 */
         ebits = msb - 2;
-        sym = 257 + 4 * (ebits + 1) + ((l >> ebits) & 3);
+        sym = 4 * (ebits + 1) + ((l >> ebits) & 3);
         eval = l & ((1u << ebits) - 1);
     }
 }
@@ -103,6 +114,12 @@ __device__ __forceinline__ void dist_symbol(uint32_t dist, uint32_t &sym, uint32
         eval = d & ((1u << ebits) - 1);
     }
 }
+__device__ __forceinline__ uint32_t len_extra_bits(uint32_t lsym) { return (lsym < 8 || lsym == 28) ? 0u : (lsym >> 2) - 1; }
+__device__ __forceinline__ uint32_t dist_extra_bits(uint32_t dsym) { return dsym < 4 ? 0u : (dsym >> 1) - 1; }
+
+/* match record forms (32 bits each, 8 per thread, [r][tid] layout):
+ *   parsed : off(5) | (len-3)(8) << 5 | (dist-1)(15) << 13
+ *   symbol : lsym(5) | lextra(5) << 5 | dsym(5) << 10 | dextra(13) << 15     (after phase C) */
 
 /* OR `n` (<=32) bits of v into the staging bit string at bit position pos */
 __device__ __forceinline__ void stage_put(uint32_t *stage, uint32_t pos, uint32_t v, uint32_t n) {
@@ -113,67 +130,15 @@ __device__ __forceinline__ void stage_put(uint32_t *stage, uint32_t pos, uint32_
     if (s + n > 32) atomicOr(&stage[w + 1], v >> (32 - s));
 }
 
-/* ---- token walk --------------------------------------------------------------------------------
- * Thread t's parse tiles [seg_start, e_t) with literals and the recorded matches. `cover` is where
- * earlier threads' matches end; everything before it is dropped, a straddling match is trimmed. */
-template <typename V>
-__device__ __forceinline__ void walk_tokens(const uint8_t *s_in, const uint32_t *s_rec, uint32_t tid, uint32_t nrec,
-                                            uint32_t seg_start, uint32_t seg_end, uint32_t cover, V &vis) {
-    uint32_t pos = seg_start;
-    for (uint32_t r = 0; r < nrec; r++) {
-        uint32_t rec = s_rec[r * DF_THREADS + tid];
-        uint32_t rs = seg_start + (rec & 31);
-        uint32_t len = ((rec >> 5) & 255) + 3;
-        uint32_t dist = (rec >> 13) + 1;
-        for (uint32_t q = pos > cover ? pos : cover; q < rs; q++) vis.lit(s_in[q]);
-        uint32_t mend = rs + len;
-        if (mend > cover) {
-            uint32_t s = rs > cover ? rs : cover;
-            uint32_t rem = mend - s;
-            if (rem >= 3) {
-                vis.match(rem, dist);
-            } else {
-                for (uint32_t q = s; q < mend; q++) vis.lit(s_in[q]);
-            }
-        }
-        pos = mend;
-    }
-    for (uint32_t q = pos > cover ? pos : cover; q < seg_end; q++) vis.lit(s_in[q]);
-}
-
-struct HistVisitor {
-    uint32_t *hist_ll, *hist_d;
-    __device__ __forceinline__ void lit(uint32_t b) { atomicAdd(&hist_ll[b], 1u); }
-    __device__ __forceinline__ void match(uint32_t len, uint32_t dist) {
-        uint32_t s, eb, ev;
-        length_symbol(len, s, eb, ev);
-        atomicAdd(&hist_ll[s], 1u);
-        dist_symbol(dist, s, eb, ev);
-        atomicAdd(&hist_d[s], 1u);
-    }
-};
-
-struct CountVisitor {
-    const uint32_t *code_ll, *code_d;
-    uint32_t bits;
-    __device__ __forceinline__ void lit(uint32_t b) { bits += code_ll[b] >> 16; }
-    __device__ __forceinline__ void match(uint32_t len, uint32_t dist) {
-        uint32_t s, eb, ev;
-        length_symbol(len, s, eb, ev);
-        bits += (code_ll[s] >> 16) + eb;
-        dist_symbol(dist, s, eb, ev);
-        bits += (code_d[s] >> 16) + eb;
-    }
-};
-
-struct EmitVisitor {
-    const uint32_t *code_ll, *code_d;
+/* per-thread bit packer: first word of the range by atomicOr (shared with the previous thread), words it
+ * fills completely by plain store, the trailing partial word by atomicOr */
+struct BitWriter {
     uint32_t *stage;
     uint64_t acc;
     uint32_t nb, w;
     bool first;
-    __device__ __forceinline__ void init(uint32_t bitoff) {
-        w = bitoff >> 5; nb = bitoff & 31; acc = 0; first = true;
+    __device__ __forceinline__ void init(uint32_t *st, uint32_t bitoff) {
+        stage = st; w = bitoff >> 5; nb = bitoff & 31; acc = 0; first = true;
     }
     __device__ __forceinline__ void put(uint32_t v, uint32_t n) {
         acc |= (uint64_t)v << nb;
@@ -187,36 +152,20 @@ struct EmitVisitor {
     __device__ __forceinline__ void finish() {
         if (nb > 0) atomicOr(&stage[w], (uint32_t)acc);
     }
-    __device__ __forceinline__ void lit(uint32_t b) {
-        uint32_t c = code_ll[b];
-        put(c & 0xffff, c >> 16);
-    }
-    __device__ __forceinline__ void match(uint32_t len, uint32_t dist) {
-        uint32_t s, eb, ev;
-        length_symbol(len, s, eb, ev);
-        uint32_t c = code_ll[s];
-        uint32_t cl = c >> 16;
-        put((c & 0xffff) | (ev << cl), cl + eb); /* <= 15 + 5 */
-        dist_symbol(dist, s, eb, ev);
-        c = code_d[s];
-        cl = c >> 16;
-        put((c & 0xffff) | (ev << cl), cl + eb); /* <= 15 + 13 */
-    }
 };
 
-/* ---- warp-parallel code construction --------------------------------------------------------- */
-constexpr int DF_KSLOTS = 9; /* 9 * 32 = 288 symbols per warp pass */
-
-/* Length-limited prefix-code lengths for `n` (<=288) symbols, max `M` bits. One full warp.
+/* ---- warp-parallel code construction (used for the 19-symbol code-length code) ------------------ */
+/* Length-limited prefix-code lengths for `n` (<= 32*KS) symbols, max `M` bits. One full warp.
  * Output: complete code (Kraft sum exactly 1) with >= 2 coded symbols, as zlib's inflate requires
  * of dynamic blocks. lens[i] = 0 for unused symbols. */
+template <int KS>
 __device__ inline void warp_build_lengths(const uint32_t *hist, int n, int M, uint8_t *lens) {
     const unsigned lane = lane_id();
-    uint32_t c[DF_KSLOTS];
-    float ideal[DF_KSLOTS];
+    uint32_t c[KS];
+    float ideal[KS];
     uint32_t used = 0, total = 0, first_used = 0xffffffffu;
 #pragma unroll
-    for (int k = 0; k < DF_KSLOTS; k++) {
+    for (int k = 0; k < KS; k++) {
         int i = k * 32 + (int)lane;
         c[k] = (i < n) ? hist[i] : 0u;
         if (c[k]) {
@@ -233,11 +182,11 @@ __device__ inline void warp_build_lengths(const uint32_t *hist, int n, int M, ui
         if (lane == d1 && c[0] == 0) c[0] = 1;
     }
 #pragma unroll
-    for (int k = 0; k < DF_KSLOTS; k++) total += c[k];
+    for (int k = 0; k < KS; k++) total += c[k];
     total = __reduce_add_sync(MZ_FULL_MASK, total);
     const float lt = __log2f((float)total);
 #pragma unroll
-    for (int k = 0; k < DF_KSLOTS; k++) ideal[k] = c[k] ? lt - __log2f((float)c[k]) : 0.f;
+    for (int k = 0; k < KS; k++) ideal[k] = c[k] ? lt - __log2f((float)c[k]) : 0.f;
 
     const uint32_t one = 1u << M;
     float lo = -3.0f, hi = 1.0f;
@@ -245,7 +194,7 @@ __device__ inline void warp_build_lengths(const uint32_t *hist, int n, int M, ui
         float mid = 0.5f * (lo + hi);
         uint32_t kr = 0;
 #pragma unroll
-        for (int k = 0; k < DF_KSLOTS; k++)
+        for (int k = 0; k < KS; k++)
             if (c[k]) {
                 int l = (int)ceilf(ideal[k] - mid);
                 l = l < 1 ? 1 : (l > M ? M : l);
@@ -254,10 +203,10 @@ __device__ inline void warp_build_lengths(const uint32_t *hist, int n, int M, ui
         kr = __reduce_add_sync(MZ_FULL_MASK, kr);
         if (kr <= one) lo = mid; else hi = mid;
     }
-    int L[DF_KSLOTS];
+    int L[KS];
     uint32_t kr = 0;
 #pragma unroll
-    for (int k = 0; k < DF_KSLOTS; k++) {
+    for (int k = 0; k < KS; k++) {
         L[k] = 0;
         if (c[k]) {
             int l = (int)ceilf(ideal[k] - lo);
@@ -275,7 +224,7 @@ __device__ inline void warp_build_lengths(const uint32_t *hist, int n, int M, ui
             if (can == 0) continue;
             uint32_t base = 0;
 #pragma unroll
-            for (int k = 0; k < DF_KSLOTS; k++) {
+            for (int k = 0; k < KS; k++) {
                 unsigned b = __ballot_sync(MZ_FULL_MASK, L[k] == len);
                 uint32_t rank = base + (uint32_t)__popc(b & ((1u << lane) - 1));
                 if (L[k] == len && rank < can) L[k] = len - 1;
@@ -286,7 +235,7 @@ __device__ inline void warp_build_lengths(const uint32_t *hist, int n, int M, ui
         }
     }
 #pragma unroll
-    for (int k = 0; k < DF_KSLOTS; k++) {
+    for (int k = 0; k < KS; k++) {
         int i = k * 32 + (int)lane;
         if (i < n) lens[i] = (uint8_t)L[k];
     }
@@ -349,7 +298,7 @@ __device__ inline uint32_t warp_build_header(const uint8_t *lens_ll, const uint8
         atomicAdd(&hist_cl[v], 1u);
     }
     __syncwarp();
-    warp_build_lengths(hist_cl, 19, 7, lens_cl);
+    warp_build_lengths<1>(hist_cl, 19, 7, lens_cl);
     warp_assign_codes(lens_cl, 19, codes_cl, scratch);
     __syncwarp();
     uint32_t pos = 0;
@@ -361,9 +310,7 @@ __device__ inline uint32_t warp_build_header(const uint8_t *lens_ll, const uint8
     }
     pos = 17;
     if (lane < 19) {
-        /* order of code-length code lengths, RFC1951 3.2.7 */
-        const uint32_t ord_lo = 0x0A060908u, ord_mid = 0x030C040Bu; /* unused packing helpers */
-        (void)ord_lo; (void)ord_mid;
+        /* order in which code-length code lengths are sent, RFC1951 3.2.7 */
         uint32_t sym;
         switch (lane) {
             case 0: sym = 16; break; case 1: sym = 17; break; case 2: sym = 18; break; case 3: sym = 0; break;
@@ -428,18 +375,161 @@ __device__ inline uint32_t block_excl_max(uint32_t v, uint32_t identity, uint32_
     return res;
 }
 
-/* ---- the kernel ------------------------------------------------------------------------------- */
-struct MatchCfg {
-    int ways;  /* candidates per hash bucket: 1, 2 or 4 */
-    int lazy;  /* one-step lazy evaluation */
-};
-__host__ __device__ inline MatchCfg match_cfg_for_level(int level) {
-    MatchCfg m;
-    m.ways = level <= 1 ? 1 : (level <= 3 ? 2 : 4);
-    m.lazy = level >= 6;
-    return m;
+/* ---- D: block-parallel literal/length + distance codes ------------------------------------------------
+ * Thread i < 288 owns literal/length symbol i (286 used), thread 288 + j owns distance symbol j (30 used);
+ * both alphabets are warp aligned (warps 0-8 and warp 9). Every thread of the CTA must call.
+ * bb = 512 words of shared scratch. Outputs lens (u8) and codes (reversed code | len << 16). */
+enum { BB_STAT = 0 /* [2][4]: used,total,first */, BB_KRAFT = 8 /* [2 sweeps][2 alph][16] */, BB_K = 72 /* [2][16] */,
+       BB_NEXT = 104 /* [2][16] */, BB_SLACK = 136 /* [2] */, BB_CNTW = 144 /* [2 bufs][10 warps][16] */ };
+
+__device__ __forceinline__ void bb_count_lengths(uint32_t *cntw_row, uint32_t L, unsigned lane, unsigned &m) {
+    if (lane < 16) cntw_row[lane] = 0;
+    __syncwarp();
+    m = __match_any_sync(MZ_FULL_MASK, L);
+    if (L > 0 && lane == (unsigned)(__ffs((int)m) - 1)) cntw_row[L] = (uint32_t)__popc(m);
+    __syncwarp();
 }
 
+__device__ inline void block_build_codes(const uint32_t *hist_ll, const uint32_t *hist_d, uint8_t *lens_ll, uint8_t *lens_d,
+                                         uint32_t *code_ll, uint32_t *code_d, uint32_t *bb) {
+    const uint32_t tid = threadIdx.x;
+    const unsigned lane = lane_id(), w = warp_id();
+    const int a = tid < 288 ? 0 : (tid < 320 ? 1 : 2);
+    const uint32_t sym = a == 0 ? tid : tid - 288;
+    const uint32_t nsym = a == 0 ? 286u : 30u;
+    const int M = 15;
+    const uint32_t one = 1u << M;
+    const uint32_t w0 = a == 0 ? 0u : 9u; /* first warp of my alphabet */
+    uint32_t c = (a < 2 && sym < nsym) ? (a == 0 ? hist_ll[sym] : hist_d[sym]) : 0u;
+
+    if (tid < 144) bb[tid] = (tid == BB_STAT + 2 || tid == BB_STAT + 6) ? 0xffffffffu : 0u;
+    __syncthreads();
+    if (a < 2) {
+        uint32_t used_w = __reduce_add_sync(MZ_FULL_MASK, c ? 1u : 0u);
+        uint32_t tot_w = __reduce_add_sync(MZ_FULL_MASK, c);
+        uint32_t first_w = __reduce_min_sync(MZ_FULL_MASK, c ? sym : 0xffffffffu);
+        if (lane == 0) {
+            atomicAdd(&bb[BB_STAT + a * 4 + 0], used_w);
+            atomicAdd(&bb[BB_STAT + a * 4 + 1], tot_w);
+            atomicMin(&bb[BB_STAT + a * 4 + 2], first_w);
+        }
+    }
+    __syncthreads();
+    float ideal = 0.f;
+    if (a < 2) {
+        uint32_t used = bb[BB_STAT + a * 4 + 0], total = bb[BB_STAT + a * 4 + 1], fu = bb[BB_STAT + a * 4 + 2];
+        if (used < 2) { /* force two coded symbols (a complete code needs them; zlib's inflate insists) */
+            uint32_t d0 = used == 0 ? 0u : (fu == 0 ? 1u : 0u);
+            uint32_t d1 = used == 0 ? 1u : d0;
+            if ((sym == d0 || sym == d1) && c == 0) c = 1;
+            total += 2 - used;
+        }
+        if (c) ideal = __log2f((float)total) - __log2f((float)c);
+    }
+    /* two sweeps of 16 candidate rounding offsets: coarse step 1/4 over [-3, 1), then step 1/64 */
+    float lo = -3.0f, step = 0.25f;
+    uint32_t slack[2] = {0, 0};
+    for (int sweep = 0; sweep < 2; sweep++) {
+        if (a < 2) {
+#pragma unroll
+            for (int cnd = 0; cnd < 16; cnd++) {
+                uint32_t kr = 0;
+                if (c) {
+                    int l = (int)ceilf(ideal - (lo + step * (float)cnd));
+                    l = l < 1 ? 1 : (l > M ? M : l);
+                    kr = 1u << (M - l);
+                }
+                kr = __reduce_add_sync(MZ_FULL_MASK, kr);
+                if (lane == 0) atomicAdd(&bb[BB_KRAFT + sweep * 32 + a * 16 + cnd], kr);
+            }
+        }
+        __syncthreads();
+        /* everyone derives both alphabets' choices (uniform): the largest feasible candidate */
+        float lo_a = lo;
+        for (int aa = 0; aa < 2; aa++) {
+            int best = 0;
+            for (int cnd = 1; cnd < 16; cnd++)
+                if (bb[BB_KRAFT + sweep * 32 + aa * 16 + cnd] <= one) best = cnd;
+            slack[aa] = one - bb[BB_KRAFT + sweep * 32 + aa * 16 + best];
+            if (aa == a) lo_a = lo + step * (float)best;
+        }
+        /* lo is per alphabet from here on; the loop variable is private to the thread */
+        lo = lo_a;
+        step *= 0.0625f;
+    }
+    uint32_t L = 0;
+    if (c) {
+        int l = (int)ceilf(ideal - lo);
+        L = (uint32_t)(l < 1 ? 1 : (l > M ? M : l));
+    }
+    /* exact Kraft completion: shorten codes (short ones first) until the sum is exactly 1 */
+    unsigned m = 0;
+    int buf = 0;
+    for (int pass = 0; pass < 40; pass++) {
+        if (slack[0] == 0 && slack[1] == 0) break;
+        uint32_t *cntw = bb + BB_CNTW + buf * 160;
+        if (a < 2) bb_count_lengths(cntw + w * 16, L, lane, m);
+        __syncthreads();
+        if (tid == 0 || tid == 288) {
+            const int aa = tid == 0 ? 0 : 1;
+            const uint32_t wa = aa == 0 ? 0u : 9u, wb = aa == 0 ? 9u : 10u;
+            uint32_t sl = slack[aa];
+            for (int len = 2; len <= M; len++) {
+                uint32_t tot = 0;
+                for (uint32_t ww = wa; ww < wb; ww++) tot += cntw[ww * 16 + len];
+                uint32_t can = sl >> (M - len);
+                uint32_t k = tot < can ? tot : can;
+                bb[BB_K + aa * 16 + len] = k;
+                sl -= k << (M - len);
+            }
+            bb[BB_SLACK + aa] = sl;
+        }
+        __syncthreads();
+        if (a < 2 && L >= 2) {
+            uint32_t rank = (uint32_t)__popc(m & ((1u << lane) - 1));
+            for (uint32_t ww = w0; ww < w; ww++) rank += cntw[ww * 16 + L];
+            if (rank < bb[BB_K + a * 16 + L]) L -= 1;
+        }
+        slack[0] = bb[BB_SLACK + 0];
+        slack[1] = bb[BB_SLACK + 1];
+        buf ^= 1;
+    }
+    /* canonical codes: code = first code of its length + rank among equal lengths in symbol order */
+    uint32_t *cntw = bb + BB_CNTW + buf * 160;
+    if (a < 2) bb_count_lengths(cntw + w * 16, L, lane, m);
+    __syncthreads();
+    if (tid == 0 || tid == 288) {
+        const int aa = tid == 0 ? 0 : 1;
+        const uint32_t wa = aa == 0 ? 0u : 9u, wb = aa == 0 ? 9u : 10u;
+        uint32_t code = 0, prev = 0;
+        for (int len = 1; len <= M; len++) {
+            code = (code + prev) << 1;
+            bb[BB_NEXT + aa * 16 + len] = code;
+            prev = 0;
+            for (uint32_t ww = wa; ww < wb; ww++) prev += cntw[ww * 16 + len];
+        }
+    }
+    __syncthreads();
+    if (a < 2) {
+        uint32_t cw = 0;
+        if (L) {
+            uint32_t rank = (uint32_t)__popc(m & ((1u << lane) - 1));
+            for (uint32_t ww = w0; ww < w; ww++) rank += cntw[ww * 16 + L];
+            uint32_t code = bb[BB_NEXT + a * 16 + L] + rank;
+            cw = (__brev(code) >> (32 - L)) | (L << 16);
+        }
+        if (a == 0) {
+            lens_ll[sym] = (uint8_t)L; /* sym up to 287: entries 286, 287 get 0 */
+            code_ll[sym] = cw;
+        } else {
+            lens_d[sym] = (uint8_t)L;  /* sym up to 31 */
+            code_d[sym] = cw;
+        }
+    }
+    __syncthreads();
+}
+
+/* ---- A: match finding ---------------------------------------------------------------------------------- */
 /* longest match of in[p..] against in[cand..], both inside the chunk, at most maxlen bytes;
  * first 4 bytes already known equal */
 __device__ __forceinline__ uint32_t extend_match(const uint8_t *s_in, uint32_t cand, uint32_t p, uint32_t maxlen) {
@@ -459,14 +549,14 @@ __device__ __forceinline__ uint32_t extend_match(const uint8_t *s_in, uint32_t c
 __device__ __forceinline__ uint32_t hash4(uint32_t v, int bits) { return (v * 2654435761u) >> (32 - bits); }
 
 /* find the best match at p among the bucket's candidates and insert p; returns len (0 = none) */
-__device__ __forceinline__ uint32_t find_match(const uint8_t *s_in, uint16_t *s_hash, uint32_t p, uint32_t limit, int ways,
-                                               uint32_t &best_dist) {
+template <int WAYS>
+__device__ __forceinline__ uint32_t find_match(const uint8_t *s_in, uint16_t *s_hash, uint32_t p, uint32_t limit, uint32_t &best_dist) {
     uint32_t v = load32u(s_in, p);
     uint32_t maxlen = limit - p;
     if (maxlen > 258) maxlen = 258;
     uint32_t best = 0;
     best_dist = 0;
-    if (ways == 1) {
+    if (WAYS == 1) {
         uint32_t h = hash4(v, 14);
         uint32_t cand = s_hash[h];
         s_hash[h] = (uint16_t)p;
@@ -475,10 +565,11 @@ __device__ __forceinline__ uint32_t find_match(const uint8_t *s_in, uint16_t *s_
             best_dist = p - cand;
         }
     } else {
-        const int hb = ways == 2 ? 13 : 12;
-        uint32_t h = hash4(v, hb) * (uint32_t)ways;
+        constexpr int hb = WAYS == 2 ? 13 : 12;
+        uint32_t h = hash4(v, hb) * (uint32_t)WAYS;
         uint32_t prev_slot = p;
-        for (int wy = 0; wy < ways; wy++) {
+#pragma unroll
+        for (int wy = 0; wy < WAYS; wy++) {
             uint32_t cand = s_hash[h + wy];
             s_hash[h + wy] = (uint16_t)prev_slot; /* FIFO: newest first */
             prev_slot = cand;
@@ -491,12 +582,22 @@ __device__ __forceinline__ uint32_t find_match(const uint8_t *s_in, uint16_t *s_
     return best;
 }
 
+__device__ __forceinline__ uint32_t bit_range(uint32_t a, uint32_t b) { /* bits [a, b), 0 <= a, b <= 32 */
+    uint32_t hi = b >= 32 ? 0xffffffffu : (1u << b) - 1;
+    uint32_t lo = a >= 32 ? 0xffffffffu : (1u << a) - 1;
+    return hi & ~lo;
+}
+
+/* ---- the kernel ------------------------------------------------------------------------------- */
+template <int WAYS, bool LAZY>
 __global__ void __launch_bounds__(DF_THREADS, 1) deflate_chunks_kernel(DeflateParams P) {
     MZ_DYN_SMEM(smem);
     uint8_t *s_in = smem + DF_OFF_IN;
     uint16_t *s_hash = (uint16_t *)(smem + DF_OFF_HASH);
     uint32_t *s_rec = (uint32_t *)(smem + DF_OFF_REC);
     uint32_t *s_stage = (uint32_t *)(smem + DF_OFF_STAGE);
+    uint16_t *s_tok = (uint16_t *)(smem + DF_OFF_TOK);
+    uint32_t *s_recmask = (uint32_t *)(smem + DF_OFF_RECMASK);
     uint32_t *s_hdr = (uint32_t *)(smem + DF_OFF_HDR);
     uint32_t *s_hist_ll = (uint32_t *)(smem + DF_OFF_HIST);
     uint32_t *s_hist_d = s_hist_ll + 288;
@@ -508,6 +609,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deflate_chunks_kernel(DeflatePa
     uint8_t *s_lens_d = s_lens_ll + 288;
     uint8_t *s_lens_cl = s_lens_d + 32;
     uint32_t *s_scan = (uint32_t *)(smem + DF_OFF_SCAN);
+    uint32_t *s_bb = (uint32_t *)(smem + DF_OFF_BB);
     uint32_t *s_misc = (uint32_t *)(smem + DF_OFF_MISC);
 #ifndef MZ_EMU
     uint64_t *s_bar = (uint64_t *)(smem + DF_OFF_MISC + 32 * 4);
@@ -519,7 +621,6 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deflate_chunks_kernel(DeflatePa
     __syncthreads();
 #endif
     const uint32_t tid = threadIdx.x;
-    const MatchCfg mcfg = match_cfg_for_level(P.level);
 
     for (uint32_t chunk = blockIdx.x; chunk < P.nchunks; chunk += gridDim.x) {
         /* ---- locate the chunk -------------------------------------------------------------- */
@@ -582,22 +683,23 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deflate_chunks_kernel(DeflatePa
         for (uint32_t sb = 0; sb < nsb; sb++) {
             const uint32_t sb_start = sb * DF_SB;
             const uint32_t sb_end = (sb_start + DF_SB < len) ? sb_start + DF_SB : len;
-            const uint32_t sb_len = sb_end - sb_start;
-            const uint32_t bfinal = (sb == nsb - 1 && (flags & DF_FLAG_FINAL)) ? 1u : 0u;
             const uint32_t seg_start = sb_start + tid * DF_SEG < sb_end ? sb_start + tid * DF_SEG : sb_end;
             const uint32_t seg_end = seg_start + DF_SEG < sb_end ? seg_start + DF_SEG : sb_end;
-            bool stored = (P.level == 0);
-            uint32_t nrec = 0, cover = 0;
+            const bool last_sb = sb == nsb - 1;
+            uint32_t nhalf = 1, n_tok = 0, ntok_all = 0, tok_excl = 0, e0 = sb_end;
+            uint32_t litmask = 0, keptrec = 0, strad_cnt = 0, strad_pos = 0, strad_tok = 0;
+            bool strad_match = false;
 
-            if (!stored) {
+            if (P.level != 0) {
                 /* ---- A: parse ------------------------------------------------------------------ */
+                uint32_t nrec = 0;
                 uint32_t p = seg_start;
                 while (p < seg_end) {
                     uint32_t mlen = 0, mdist = 0;
                     if (p + DF_MINMATCH <= sb_end) {
-                        mlen = find_match(s_in, s_hash, p, sb_end, mcfg.ways, mdist);
-                        if (mcfg.lazy && mlen >= DF_MINMATCH && mlen < 32 && p + 1 < seg_end && p + 1 + DF_MINMATCH <= sb_end) {
-                            uint32_t d2, l2 = find_match(s_in, s_hash, p + 1, sb_end, mcfg.ways, d2);
+                        mlen = find_match<WAYS>(s_in, s_hash, p, sb_end, mdist);
+                        if (LAZY && mlen >= DF_MINMATCH && mlen < 32 && p + 1 < seg_end && p + 1 + DF_MINMATCH <= sb_end) {
+                            uint32_t d2, l2 = find_match<WAYS>(s_in, s_hash, p + 1, sb_end, d2);
                             if (l2 > mlen) { /* literal now, better match next */
                                 p += 1;
                                 mlen = l2;
@@ -614,100 +716,189 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deflate_chunks_kernel(DeflatePa
                     }
                 }
                 /* ---- B: cover = where earlier threads' matches end ------------------------------ */
-                cover = block_excl_max(p, sb_start, s_scan);
-                for (uint32_t i = tid; i < 288 + 32; i += DF_THREADS) s_hist_ll[i] = 0;
-                __syncthreads();
-                /* ---- C: histograms ---------------------------------------------------------------- */
-                {
-                    HistVisitor hv;
-                    hv.hist_ll = s_hist_ll;
-                    hv.hist_d = s_hist_d;
-                    if (cover < seg_end || nrec) walk_tokens(s_in, s_rec, tid, nrec, seg_start, seg_end, cover, hv);
-                    if (tid == 0) s_hist_ll[256] = 1;
-                }
-                __syncthreads();
-                /* ---- D: codes + header -------------------------------------------------------- */
-                if (warp_id() == 0) {
-                    warp_build_lengths(s_hist_ll, 286, 15, s_lens_ll);
-                    if (lane_id() < 2) s_lens_ll[286 + lane_id()] = 0;
-                    warp_assign_codes(s_lens_ll, 286, s_code_ll, s_misc + MISC_BLCNT);
-                } else if (warp_id() == 1) {
-                    warp_build_lengths(s_hist_d, 30, 15, s_lens_d);
-                    if (lane_id() < 2) s_lens_d[30 + lane_id()] = 0;
-                    warp_assign_codes(s_lens_d, 30, s_code_d, s_scan + 40); /* scan scratch idle here */
-                }
-                __syncthreads();
-                if (warp_id() == 0) {
-                    uint32_t hb = warp_build_header(s_lens_ll, s_lens_d, bfinal, s_hist_cl, s_lens_cl, s_code_cl,
-                                                    s_misc + MISC_BLCNT, s_hdr);
-                    if (lane_id() == 0) s_misc[MISC_HDRBITS] = hb;
-                }
-                /* ---- E: bit counts (other warps proceed; codes are final) ------------------------ */
-                CountVisitor cv;
-                cv.code_ll = s_code_ll;
-                cv.code_d = s_code_d;
-                cv.bits = 0;
-                if (cover < seg_end || nrec) walk_tokens(s_in, s_rec, tid, nrec, seg_start, seg_end, cover, cv);
-                uint32_t tokbits;
-                uint32_t myoff = block_excl_sum(cv.bits, s_scan, tokbits);
-                const uint32_t hdrbits = s_misc[MISC_HDRBITS];
-                const uint32_t eob = s_code_ll[256];
-                const uint32_t dyn_bits = hdrbits + tokbits + (eob >> 16);
-                const uint32_t stored_bits = (((bitpos + 3 + 7) & ~7u) - bitpos) + 32 + sb_len * 8;
-                if (dyn_bits >= stored_bits) {
-                    stored = true;
-                } else {
-                    /* ---- F: emit --------------------------------------------------------------- */
-                    const uint32_t base = bitpos + hdrbits;
-                    if (warp_id() == 0) {
-                        for (uint32_t j = lane_id(); j * 32 < hdrbits; j += 32) {
-                            uint32_t n = hdrbits - j * 32;
-                            stage_put(s_stage, bitpos + j * 32, s_hdr[j], n > 32 ? 32 : n);
+                const uint32_t cover = block_excl_max(p, sb_start, s_scan);
+                if (tid == DF_THREADS / 2) s_misc[MISC_E0] = cover; /* where the second thread half starts */
+                /* ---- T: classify what this thread keeps ------------------------------------------- */
+                const uint32_t c_rel = cover > seg_start ? cover - seg_start : 0u; /* may exceed 32 */
+                uint32_t recmask = 0, covmask = 0;
+                for (uint32_t r = 0; r < nrec; r++) {
+                    uint32_t rec = s_rec[r * DF_THREADS + tid];
+                    uint32_t roff = rec & 31, rlen = ((rec >> 5) & 255) + 3;
+                    uint32_t rend = roff + rlen;
+                    recmask |= 1u << roff;
+                    covmask |= bit_range(roff + 1, rend < 32 ? rend : 32);
+                    if (rend <= c_rel) continue; /* covered entirely by an earlier thread's match */
+                    if (roff >= c_rel) {
+                        keptrec |= 1u << roff;
+                    } else {
+                        uint32_t rem = rend - c_rel; /* straddles: trim the front */
+                        if (rem >= 3) {
+                            strad_match = true;
+                            strad_tok = DF_TOK_MATCH | (seg_start - sb_start + roff);
+                            s_rec[r * DF_THREADS + tid] = roff | ((rem - 3) << 5) | (rec & ~0x1fffu);
+                        } else {
+                            strad_cnt = rem; /* 1-2 bytes left: plain literals */
+                            strad_pos = seg_start + c_rel;
                         }
                     }
-                    if (cv.bits) {
-                        EmitVisitor ev;
-                        ev.code_ll = s_code_ll;
-                        ev.code_d = s_code_d;
-                        ev.stage = s_stage;
-                        ev.init(base + myoff);
-                        walk_tokens(s_in, s_rec, tid, nrec, seg_start, seg_end, cover, ev);
-                        ev.finish();
+                }
+                s_recmask[tid] = recmask;
+                const uint32_t valid = seg_end - seg_start;
+                litmask = ~covmask & ~recmask & ~bit_range(0, c_rel < 32 ? c_rel : 32) & bit_range(0, valid);
+                n_tok = (uint32_t)__popc(litmask) + (uint32_t)__popc(keptrec) + (strad_match ? 1u : 0u) + strad_cnt;
+                tok_excl = block_excl_sum(n_tok, s_scan, ntok_all);
+                e0 = s_misc[MISC_E0];
+                nhalf = ntok_all > (uint32_t)DF_TOK_CAP ? 2u : 1u;
+            }
+
+            for (uint32_t half = 0; half < nhalf; half++) {
+                /* byte range this block codes: the kept tokens of the participating threads tile it exactly */
+                const uint32_t blk_start = (nhalf == 2 && half == 1) ? e0 : sb_start;
+                const uint32_t blk_end = (nhalf == 2 && half == 0) ? e0 : sb_end;
+                const uint32_t blk_len = blk_end - blk_start;
+                const uint32_t bfinal = (last_sb && half == nhalf - 1 && (flags & DF_FLAG_FINAL)) ? 1u : 0u;
+                bool stored = (P.level == 0);
+
+                if (!stored) {
+                    uint32_t ntok = ntok_all, excl = tok_excl;
+                    const bool mine = nhalf == 1 || (tid >> 9) == half;
+                    if (nhalf == 2) excl = block_excl_sum(mine ? n_tok : 0u, s_scan, ntok);
+                    /* ---- T: write the ordered token list ------------------------------------------ */
+                    if (mine) {
+                        uint32_t o = excl;
+                        if (strad_match) s_tok[o++] = (uint16_t)strad_tok;
+                        for (uint32_t q = 0; q < strad_cnt; q++) s_tok[o++] = (uint16_t)(strad_pos + q - sb_start);
+                        uint32_t mm = litmask | keptrec;
+                        const uint32_t rel = seg_start - sb_start;
+                        while (mm) {
+                            uint32_t b = (uint32_t)__ffs((int)mm) - 1;
+                            mm &= mm - 1;
+                            s_tok[o++] = (uint16_t)((rel + b) | (((keptrec >> b) & 1u) << 15));
+                        }
                     }
-                    if (tid == DF_THREADS - 1) stage_put(s_stage, base + tokbits, eob & 0xffff, eob >> 16);
-                    bitpos += dyn_bits;
+                    for (uint32_t i = tid; i < 288 + 32; i += DF_THREADS) s_hist_ll[i] = 0;
+                    __syncthreads();
+                    /* ---- C: histograms; match records -> symbol form ------------------------------------ */
+                    for (uint32_t k = tid; k < ntok; k += DF_THREADS) {
+                        uint32_t e = s_tok[k];
+                        uint32_t rp = e & 0x7fffu;
+                        if (!(e & DF_TOK_MATCH)) {
+                            atomicAdd(&s_hist_ll[s_in[sb_start + rp]], 1u);
+                        } else {
+                            uint32_t owner = rp >> 5, roff = rp & 31;
+                            uint32_t r = (uint32_t)__popc(s_recmask[owner] & ((1u << roff) - 1));
+                            uint32_t rec = s_rec[r * DF_THREADS + owner];
+                            uint32_t ls, lb, lv, ds, db, dv;
+                            length_symbol(((rec >> 5) & 255) + 3, ls, lb, lv);
+                            dist_symbol((rec >> 13) + 1, ds, db, dv);
+                            s_rec[r * DF_THREADS + owner] = ls | (lv << 5) | (ds << 10) | (dv << 15);
+                            atomicAdd(&s_hist_ll[257 + ls], 1u);
+                            atomicAdd(&s_hist_d[ds], 1u);
+                        }
+                    }
+                    if (tid == 0) s_hist_ll[256] = 1;
+                    __syncthreads();
+                    /* ---- D: codes + header -------------------------------------------------------- */
+                    block_build_codes(s_hist_ll, s_hist_d, s_lens_ll, s_lens_d, s_code_ll, s_code_d, s_bb);
+                    if (warp_id() == 0) {
+                        uint32_t hb = warp_build_header(s_lens_ll, s_lens_d, bfinal, s_hist_cl, s_lens_cl, s_code_cl,
+                                                        s_misc + MISC_BLCNT, s_hdr);
+                        if (lane_id() == 0) s_misc[MISC_HDRBITS] = hb;
+                    }
+                    /* ---- E: bit counts over equal contiguous token runs (codes are final) ---------------- */
+                    const uint32_t run = ((ntok + DF_THREADS - 1) / DF_THREADS) | 1u; /* odd stride: no bank conflicts */
+                    const uint32_t k0 = tid * run < ntok ? tid * run : ntok;
+                    const uint32_t k1 = k0 + run < ntok ? k0 + run : ntok;
+                    uint32_t mybits = 0;
+                    for (uint32_t k = k0; k < k1; k++) {
+                        uint32_t e = s_tok[k];
+                        uint32_t rp = e & 0x7fffu;
+                        if (!(e & DF_TOK_MATCH)) {
+                            mybits += s_code_ll[s_in[sb_start + rp]] >> 16;
+                        } else {
+                            uint32_t owner = rp >> 5, roff = rp & 31;
+                            uint32_t r = (uint32_t)__popc(s_recmask[owner] & ((1u << roff) - 1));
+                            uint32_t rec = s_rec[r * DF_THREADS + owner];
+                            uint32_t ls = rec & 31, ds = (rec >> 10) & 31;
+                            mybits += (s_code_ll[257 + ls] >> 16) + len_extra_bits(ls) + (s_code_d[ds] >> 16) + dist_extra_bits(ds);
+                        }
+                    }
+                    uint32_t tokbits;
+                    uint32_t myoff = block_excl_sum(mybits, s_scan, tokbits);
+                    const uint32_t hdrbits = s_misc[MISC_HDRBITS];
+                    const uint32_t eob = s_code_ll[256];
+                    const uint32_t dyn_bits = hdrbits + tokbits + (eob >> 16);
+                    const uint32_t stored_bits = (((bitpos + 3 + 7) & ~7u) - bitpos) + 32 + blk_len * 8;
+                    if (dyn_bits >= stored_bits) {
+                        stored = true;
+                    } else {
+                        /* ---- F: emit --------------------------------------------------------------- */
+                        const uint32_t base = bitpos + hdrbits;
+                        if (warp_id() == 0) {
+                            for (uint32_t j = lane_id(); j * 32 < hdrbits; j += 32) {
+                                uint32_t n = hdrbits - j * 32;
+                                stage_put(s_stage, bitpos + j * 32, s_hdr[j], n > 32 ? 32 : n);
+                            }
+                        }
+                        if (mybits) {
+                            BitWriter bw;
+                            bw.init(s_stage, base + myoff);
+                            for (uint32_t k = k0; k < k1; k++) {
+                                uint32_t e = s_tok[k];
+                                uint32_t rp = e & 0x7fffu;
+                                if (!(e & DF_TOK_MATCH)) {
+                                    uint32_t cw = s_code_ll[s_in[sb_start + rp]];
+                                    bw.put(cw & 0xffff, cw >> 16);
+                                } else {
+                                    uint32_t owner = rp >> 5, roff = rp & 31;
+                                    uint32_t r = (uint32_t)__popc(s_recmask[owner] & ((1u << roff) - 1));
+                                    uint32_t rec = s_rec[r * DF_THREADS + owner];
+                                    uint32_t ls = rec & 31, ds = (rec >> 10) & 31;
+                                    uint32_t cw = s_code_ll[257 + ls];
+                                    uint32_t cl = cw >> 16;
+                                    bw.put((cw & 0xffff) | (((rec >> 5) & 31) << cl), cl + len_extra_bits(ls)); /* <= 15 + 5 */
+                                    cw = s_code_d[ds];
+                                    cl = cw >> 16;
+                                    bw.put((cw & 0xffff) | ((rec >> 15) << cl), cl + dist_extra_bits(ds)); /* <= 15 + 13 */
+                                }
+                            }
+                            bw.finish();
+                        }
+                        if (tid == DF_THREADS - 1) stage_put(s_stage, base + tokbits, eob & 0xffff, eob >> 16);
+                        bitpos += dyn_bits;
+                    }
                 }
-            }
-            if (stored) {
-                /* stored block: header, pad to byte, LEN, ~LEN, raw bytes */
-                const uint32_t p0 = (bitpos + 3 + 7) >> 3; /* byte index of LEN */
-                if (tid == 0) {
-                    stage_put(s_stage, bitpos, bfinal, 3);
-                    stage_put(s_stage, p0 * 8, sb_len, 16);
-                    stage_put(s_stage, p0 * 8 + 16, sb_len ^ 0xffffu, 16);
+                if (stored) {
+                    /* stored block: header, pad to byte, LEN, ~LEN, raw bytes */
+                    const uint32_t p0 = (bitpos + 3 + 7) >> 3; /* byte index of LEN */
+                    if (tid == 0) {
+                        stage_put(s_stage, bitpos, bfinal, 3);
+                        stage_put(s_stage, p0 * 8, blk_len, 16);
+                        stage_put(s_stage, p0 * 8 + 16, blk_len ^ 0xffffu, 16);
+                    }
+                    for (uint32_t i = tid * 4; i < blk_len; i += DF_THREADS * 4) {
+                        uint32_t v = load32u(s_in, blk_start + i);
+                        uint32_t n = blk_len - i;
+                        stage_put(s_stage, (p0 + 4 + i) * 8, v, n >= 4 ? 32 : n * 8);
+                    }
+                    bitpos = (p0 + 4 + blk_len) * 8;
                 }
-                for (uint32_t i = tid * 4; i < sb_len; i += DF_THREADS * 4) {
-                    uint32_t v = load32u(s_in, sb_start + i);
-                    uint32_t n = sb_len - i;
-                    stage_put(s_stage, (p0 + 4 + i) * 8, v, n >= 4 ? 32 : n * 8);
+                __syncthreads();
+                /* ---- G: flush whole 16-byte units, carry the tail ------------------------------------ */
+                {
+                    const uint32_t n16 = bitpos >> 7;
+                    const uint32_t used_words = (bitpos + 31) >> 5;
+                    for (uint32_t i = tid; i < n16; i += DF_THREADS) ((uint4 *)(gout + flushed))[i] = ((const uint4 *)s_stage)[i];
+                    uint32_t carry = 0;
+                    if (tid < 4 && n16 * 4 + tid < used_words) carry = s_stage[n16 * 4 + tid];
+                    __syncthreads();
+                    for (uint32_t i = tid; i < used_words; i += DF_THREADS) s_stage[i] = 0;
+                    __syncthreads();
+                    if (tid < 4) s_stage[tid] = carry;
+                    bitpos -= n16 * 128;
+                    flushed += n16 * 16;
+                    __syncthreads();
                 }
-                bitpos = (p0 + 4 + sb_len) * 8;
-            }
-            __syncthreads();
-            /* ---- G: flush whole 16-byte units, carry the tail ------------------------------------ */
-            {
-                const uint32_t n16 = bitpos >> 7;
-                const uint32_t used_words = (bitpos + 31) >> 5;
-                for (uint32_t i = tid; i < n16; i += DF_THREADS) ((uint4 *)(gout + flushed))[i] = ((const uint4 *)s_stage)[i];
-                uint32_t carry = 0;
-                if (tid < 4 && n16 * 4 + tid < used_words) carry = s_stage[n16 * 4 + tid];
-                __syncthreads();
-                for (uint32_t i = tid; i < used_words; i += DF_THREADS) s_stage[i] = 0;
-                __syncthreads();
-                if (tid < 4) s_stage[tid] = carry;
-                bitpos -= n16 * 128;
-                flushed += n16 * 16;
-                __syncthreads();
             }
         }
 
@@ -730,6 +921,10 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deflate_chunks_kernel(DeflatePa
         }
     }
 }
+
+/* level -> (bucket ways, lazy) */
+__host__ __device__ inline int deflate_ways_for_level(int level) { return level <= 1 ? 1 : (level <= 3 ? 2 : 4); }
+__host__ __device__ inline bool deflate_lazy_for_level(int level) { return level >= 6; }
 
 } // namespace mzc
 #endif

@@ -107,7 +107,10 @@ int32_t get_ctx(DeviceCtx **out) {
             CK(cudaMalloc(&c.d_word_off, off.size() * 4));
             CK(cudaMemcpy(c.d_words, words.data(), words.size(), cudaMemcpyHostToDevice));
             CK(cudaMemcpy(c.d_word_off, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
-            CK(cudaFuncSetAttribute(deflate_chunks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_SMEM_BYTES));
+            CK(cudaFuncSetAttribute(deflate_chunks_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_SMEM_BYTES));
+            CK(cudaFuncSetAttribute(deflate_chunks_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_SMEM_BYTES));
+            CK(cudaFuncSetAttribute(deflate_chunks_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_SMEM_BYTES));
+            CK(cudaFuncSetAttribute(deflate_chunks_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_SMEM_BYTES));
             CK(cudaFuncSetAttribute(crc32_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CRC_SMEM_BYTES));
             c.ready = true;
         }
@@ -220,6 +223,10 @@ void mz_cuda_event_destroy(void *e) {
 }
 int32_t mz_cuda_event_record(void *e, void *stream) {
     CK(cudaEventRecord((cudaEvent_t)e, (cudaStream_t)stream));
+    return MZ_OK;
+}
+int32_t mz_cuda_event_sync(void *e) {
+    CK(cudaEventSynchronize((cudaEvent_t)e));
     return MZ_OK;
 }
 float mz_cuda_event_elapsed_ms(void *a, void *b) {
@@ -346,7 +353,16 @@ int32_t mz_cuda_deflate_chunks(const void *d_in, uint64_t total_len, uint32_t ch
     P.slot_stride = slot_stride;
     P.out_len = d_out_len;
     uint32_t grid = nchunks < (uint32_t)c->sm_count ? nchunks : (uint32_t)c->sm_count;
-    MZ_LAUNCH(deflate_chunks_kernel, dim3(grid), dim3(DF_THREADS), DF_SMEM_BYTES, (cudaStream_t)stream, P);
+    const int ways = deflate_ways_for_level(level);
+    const bool lazy = deflate_lazy_for_level(level);
+    if (ways == 1)
+        MZ_LAUNCH((deflate_chunks_kernel<1, false>), dim3(grid), dim3(DF_THREADS), DF_SMEM_BYTES, (cudaStream_t)stream, P);
+    else if (ways == 2)
+        MZ_LAUNCH((deflate_chunks_kernel<2, false>), dim3(grid), dim3(DF_THREADS), DF_SMEM_BYTES, (cudaStream_t)stream, P);
+    else if (!lazy)
+        MZ_LAUNCH((deflate_chunks_kernel<4, false>), dim3(grid), dim3(DF_THREADS), DF_SMEM_BYTES, (cudaStream_t)stream, P);
+    else
+        MZ_LAUNCH((deflate_chunks_kernel<4, true>), dim3(grid), dim3(DF_THREADS), DF_SMEM_BYTES, (cudaStream_t)stream, P);
     CK(cudaGetLastError());
     return MZ_OK;
 }

@@ -28,15 +28,27 @@
 #define CU_CHUNK 65536u
 
 /* ---- workspaces: pinned + device buffers are expensive to create, so streams borrow them ---------- */
+#define CU_NSLOT 3 /* write pipeline depth: upload of batch k+1 overlaps compute of k and download of k-1 */
+
+typedef struct cu_slot_s {
+    void *stream;   /* cudaStream_t */
+    void *ev_h2d;   /* input upload finished: caller memory may be reused */
+    uint8_t *h_in;  /* pinned staging for pageable / small writes */
+    uint8_t *d_in, *d_slots, *d_out, *h_out;
+    uint32_t *d_out_len, *d_residue, *d_crc2;
+    uint64_t *d_offsets;
+    uint64_t *h_total; /* pinned: [0] joined bytes, [1] low word = crc32 of the batch */
+    size_t n;          /* input bytes of the batch in flight */
+    int busy;
+} cu_slot;
+
 typedef struct cu_ws_s {
     struct cu_ws_s *next;
     int kind; /* 1 write, 2 read */
     size_t batch;
     /* write */
-    uint8_t *h_in, *d_in, *d_slots, *d_out, *h_out;
-    uint32_t *d_out_len;
-    uint64_t *d_offsets;
-    uint64_t *h_total; /* pinned: offsets[nchunks] lands here */
+    cu_slot slot[CU_NSLOT];
+    int cur; /* slot being filled */
     uint32_t max_chunks;
     uint64_t slot_stride;
     /* read */
@@ -60,14 +72,21 @@ static size_t env_size(const char *name, size_t dflt, size_t unit) {
 static void ws_destroy(cu_ws *w) {
     if (!w)
         return;
-    mz_cuda_host_free(w->h_in);
-    mz_cuda_free(w->d_in);
-    mz_cuda_free(w->d_slots);
-    mz_cuda_free(w->d_out);
-    mz_cuda_host_free(w->h_out);
-    mz_cuda_free(w->d_out_len);
-    mz_cuda_free(w->d_offsets);
-    mz_cuda_host_free(w->h_total);
+    for (int i = 0; i < CU_NSLOT; i++) {
+        cu_slot *s = &w->slot[i];
+        mz_cuda_host_free(s->h_in);
+        mz_cuda_free(s->d_in);
+        mz_cuda_free(s->d_slots);
+        mz_cuda_free(s->d_out);
+        mz_cuda_host_free(s->h_out);
+        mz_cuda_free(s->d_out_len);
+        mz_cuda_free(s->d_residue);
+        mz_cuda_free(s->d_crc2);
+        mz_cuda_free(s->d_offsets);
+        mz_cuda_host_free(s->h_total);
+        mz_cuda_event_destroy(s->ev_h2d);
+        mz_cuda_stream_destroy(s->stream);
+    }
     mz_cuda_host_free(w->h_cin);
     mz_cuda_free(w->d_cin);
     mz_cuda_free(w->d_win);
@@ -102,17 +121,25 @@ static cu_ws *ws_acquire(int kind) {
         w->max_chunks = (uint32_t)(batch / CU_CHUNK);
         w->slot_stride = mz_cuda_deflate_slot_bound(CU_CHUNK);
         size_t slots = (size_t)w->max_chunks * w->slot_stride;
-        w->h_in = (uint8_t *)mz_cuda_host_alloc(batch);
-        w->d_in = (uint8_t *)mz_cuda_malloc(batch + 64);
-        w->d_slots = (uint8_t *)mz_cuda_malloc(slots);
-        w->d_out = (uint8_t *)mz_cuda_malloc(slots);
-        w->h_out = (uint8_t *)mz_cuda_host_alloc(slots);
-        w->d_out_len = (uint32_t *)mz_cuda_malloc((size_t)w->max_chunks * 4);
-        w->d_offsets = (uint64_t *)mz_cuda_malloc(((size_t)w->max_chunks + 1) * 8);
-        w->h_total = (uint64_t *)mz_cuda_host_alloc(8);
-        if (!w->h_in || !w->d_in || !w->d_slots || !w->d_out || !w->h_out || !w->d_out_len || !w->d_offsets || !w->h_total) {
-            ws_destroy(w);
-            return NULL;
+        for (int i = 0; i < CU_NSLOT; i++) {
+            cu_slot *s = &w->slot[i];
+            s->stream = mz_cuda_stream_create();
+            s->ev_h2d = mz_cuda_event_create();
+            s->h_in = (uint8_t *)mz_cuda_host_alloc(batch);
+            s->d_in = (uint8_t *)mz_cuda_malloc(batch + 64);
+            s->d_slots = (uint8_t *)mz_cuda_malloc(slots);
+            s->d_out = (uint8_t *)mz_cuda_malloc(slots);
+            s->h_out = (uint8_t *)mz_cuda_host_alloc(slots);
+            s->d_out_len = (uint32_t *)mz_cuda_malloc((size_t)w->max_chunks * 4);
+            s->d_residue = (uint32_t *)mz_cuda_malloc((size_t)w->max_chunks * 4);
+            s->d_crc2 = (uint32_t *)mz_cuda_malloc(8);
+            s->d_offsets = (uint64_t *)mz_cuda_malloc(((size_t)w->max_chunks + 1) * 8);
+            s->h_total = (uint64_t *)mz_cuda_host_alloc(16);
+            if (!s->stream || !s->ev_h2d || !s->h_in || !s->d_in || !s->d_slots || !s->d_out || !s->h_out || !s->d_out_len ||
+                !s->d_residue || !s->d_crc2 || !s->d_offsets || !s->h_total) {
+                ws_destroy(w);
+                return NULL;
+            }
         }
     } else {
         w->cin_cap = batch / 4 > (1u << 20) ? batch / 4 : (1u << 20);
@@ -136,6 +163,14 @@ static cu_ws *ws_acquire(int kind) {
 static void ws_release(cu_ws *w) {
     if (!w)
         return;
+    if (w->kind == 1) {
+        for (int i = 0; i < CU_NSLOT; i++) {
+            if (w->slot[i].busy)
+                mz_cuda_stream_sync(w->slot[i].stream);
+            w->slot[i].busy = 0;
+        }
+        w->cur = 0;
+    }
     pthread_mutex_lock(&g_pool_mu);
     w->next = g_pool;
     g_pool = w;
@@ -155,8 +190,9 @@ typedef struct mz_stream_cuda_s {
     int64_t max_total_in;
     cu_ws *ws;
     /* write */
-    size_t in_len;      /* bytes staged in ws->h_in */
+    size_t in_len;      /* bytes staged in the current slot's h_in */
     uint32_t crc;       /* running CRC-32 of the plaintext (gzip trailer) */
+    uint64_t crc_bytes; /* plaintext bytes folded into crc so far */
     uint32_t adler_a, adler_b;
     int8_t header_done;
     /* read */
@@ -220,6 +256,7 @@ int32_t mz_stream_cuda_open(void *stream, const char *path, int32_t mode) {
     }
     cu->in_len = 0;
     cu->crc = 0;
+    cu->crc_bytes = 0;
     cu->adler_a = 1;
     cu->adler_b = 0;
     cu->header_done = 0;
@@ -299,49 +336,78 @@ static void cu_adler_update(mz_stream_cuda *cu, const uint8_t *p, size_t n) {
     cu->adler_b = b;
 }
 
-/* compress the staged bytes as one batch of independent chunks and hand the joined stream to base */
-static int32_t cu_flush_batch(mz_stream_cuda *cu, int final) {
+/* Enqueue one batch on its slot's stream: upload, K2+K3, K4, K1 (gzip), and the 16 bytes of results.
+ * `src` is pinned host memory (the slot's staging buffer or the caller's own pinned buffer). */
+static int32_t cu_submit(mz_stream_cuda *cu, cu_slot *s, const uint8_t *src, size_t n, int final) {
     cu_ws *w = cu->ws;
-    size_t n = cu->in_len;
     int lvl = (int8_t)cu->level == -1 ? 6 : (int8_t)cu->level;
     uint32_t nchunks = n == 0 ? 1 : (uint32_t)((n + CU_CHUNK - 1) / CU_CHUNK);
+    int32_t err = MZ_OK;
+    if (n > 0)
+        err = mz_cuda_memcpy_h2d(s->d_in, src, n, s->stream);
+    if (err == MZ_OK)
+        err = mz_cuda_event_record(s->ev_h2d, s->stream);
+    if (err == MZ_OK)
+        err = mz_cuda_deflate_chunks(s->d_in, n, CU_CHUNK, NULL, NULL, NULL, nchunks, final ? MZ_CUDA_FLAG_FINAL : 0, lvl, s->d_slots,
+                                     w->slot_stride, s->d_out_len, s->stream);
+    if (err == MZ_OK)
+        err = mz_cuda_concat(s->d_slots, w->slot_stride, s->d_out_len, nchunks, s->d_offsets, s->d_out, s->stream);
+    if (err == MZ_OK && cu->wrap == 2 && n > 0) {
+        err = mz_cuda_crc32_segments(s->d_in, n, CU_CHUNK, NULL, NULL, nchunks, s->d_residue, NULL, s->stream);
+        if (err == MZ_OK)
+            err = mz_cuda_crc32_fold(s->d_residue, nchunks, CU_CHUNK, n, s->d_crc2, s->stream);
+        if (err == MZ_OK)
+            err = mz_cuda_memcpy_d2h(&s->h_total[1], &s->d_crc2[1], 4, s->stream);
+    }
+    if (err == MZ_OK)
+        err = mz_cuda_memcpy_d2h(&s->h_total[0], s->d_offsets + nchunks, 8, s->stream);
+    if (err != MZ_OK)
+        return err;
+    if (cu->wrap == 1 && n > 0)
+        cu_adler_update(cu, src, n); /* zlib framing is unused by minizip-ng callers; host Adler-32 */
+    s->n = n;
+    s->busy = 1;
+    return MZ_OK;
+}
+
+/* Wait for a batch, bring its joined stream to the host and hand it to base. In-order by construction. */
+static int32_t cu_retire(mz_stream_cuda *cu, cu_slot *s) {
     int32_t err;
-    if (n == 0 && !final)
+    if (!s->busy)
         return MZ_OK;
-    if (n > 0) {
-        err = mz_cuda_memcpy_h2d(w->d_in, w->h_in, n, NULL);
-        if (err)
-            return err;
-    }
-    err = mz_cuda_deflate_chunks(w->d_in, n, CU_CHUNK, NULL, NULL, NULL, nchunks, final ? MZ_CUDA_FLAG_FINAL : 0, lvl, w->d_slots,
-                                 w->slot_stride, w->d_out_len, NULL);
+    s->busy = 0;
+    err = mz_cuda_stream_sync(s->stream);
     if (err)
         return err;
-    err = mz_cuda_concat(w->d_slots, w->slot_stride, w->d_out_len, nchunks, w->d_offsets, w->d_out, NULL);
+    uint64_t total = s->h_total[0];
+    err = mz_cuda_memcpy_d2h(s->h_out, s->d_out, total, s->stream);
     if (err)
         return err;
-    if (cu->wrap == 2 && n > 0) {
-        err = mz_cuda_crc32_device(w->d_in, n, cu->crc, &cu->crc); /* chained running value */
-        if (err)
-            return err;
-    } else if (cu->wrap == 1 && n > 0) {
-        cu_adler_update(cu, w->h_in, n); /* zlib framing is unused by minizip-ng callers; host Adler-32 */
-    }
-    err = mz_cuda_memcpy_d2h(w->h_total, w->d_offsets + nchunks, 8, NULL);
+    err = mz_cuda_stream_sync(s->stream);
     if (err)
         return err;
-    err = mz_cuda_stream_sync(NULL);
-    if (err)
+    if (cu->wrap == 2 && s->n > 0) /* crc(A||B) from crc(A), crc(B), |B| */
+        cu->crc = cu->crc_bytes == 0 ? (uint32_t)s->h_total[1] : mz_cuda_crc32_combine(cu->crc, (uint32_t)s->h_total[1], s->n);
+    cu->crc_bytes += s->n;
+    return cu_emit(cu, s->h_out, total);
+}
+
+/* submit the slot being filled and advance the ring; the next slot is the oldest in flight */
+static int32_t cu_push(mz_stream_cuda *cu, const uint8_t *src, size_t n, int final) {
+    cu_ws *w = cu->ws;
+    int32_t err = cu_submit(cu, &w->slot[w->cur], src, n, final);
+    if (err != MZ_OK)
         return err;
-    uint64_t total = *w->h_total;
-    err = mz_cuda_memcpy_d2h(w->h_out, w->d_out, total, NULL);
-    if (err)
-        return err;
-    err = mz_cuda_stream_sync(NULL);
-    if (err)
-        return err;
-    cu->in_len = 0;
-    return cu_emit(cu, w->h_out, total);
+    w->cur = (w->cur + 1) % CU_NSLOT;
+    return cu_retire(cu, &w->slot[w->cur]);
+}
+
+static int32_t cu_drain(mz_stream_cuda *cu) {
+    cu_ws *w = cu->ws;
+    int32_t err = MZ_OK;
+    for (int k = 0; k < CU_NSLOT && err == MZ_OK; k++)
+        err = cu_retire(cu, &w->slot[(w->cur + k) % CU_NSLOT]); /* cur is the oldest after a push */
+    return err;
 }
 #endif
 
@@ -366,24 +432,51 @@ int32_t mz_stream_cuda_write(void *stream, const void *buf, int32_t size) {
     err = cu_write_header(cu);
     if (err != MZ_OK)
         return err;
+    /* zero-copy: whole batches straight out of a page-locked caller buffer (no staging memcpy) */
+    if (cu->in_len == 0 && (size_t)left >= cu->ws->batch && mz_cuda_host_is_pinned(p)) {
+        void *pending[CU_NSLOT];
+        int npend = 0;
+        while ((size_t)left >= cu->ws->batch) {
+            cu_slot *s = &cu->ws->slot[cu->ws->cur];
+            if (npend == CU_NSLOT) { /* ring wrapped: the oldest upload of this call is long done */
+                memmove(pending, pending + 1, sizeof(void *) * (CU_NSLOT - 1));
+                npend--;
+            }
+            pending[npend++] = s->ev_h2d;
+            err = cu_push(cu, p, cu->ws->batch, 0);
+            if (err != MZ_OK)
+                goto fail;
+            p += cu->ws->batch;
+            left -= (int32_t)cu->ws->batch;
+        }
+        /* the caller may reuse its buffer when we return: wait for the uploads (not for the compute) */
+        for (int i = 0; i < npend; i++)
+            if (mz_cuda_event_sync(pending[i]) != MZ_OK) {
+                err = MZ_INTERNAL_ERROR;
+                goto fail;
+            }
+    }
     while (left > 0) {
+        cu_slot *s = &cu->ws->slot[cu->ws->cur];
         size_t room = cu->ws->batch - cu->in_len;
         size_t k = (size_t)left < room ? (size_t)left : room;
-        memcpy(cu->ws->h_in + cu->in_len, p, k);
+        memcpy(s->h_in + cu->in_len, p, k);
         cu->in_len += k;
         p += k;
         left -= (int32_t)k;
         if (cu->in_len == cu->ws->batch) {
-            err = cu_flush_batch(cu, 0);
-            if (err != MZ_OK) {
-                if (err != MZ_WRITE_ERROR)
-                    cu->error = err;
-                return err == MZ_WRITE_ERROR ? err : MZ_DATA_ERROR;
-            }
+            err = cu_push(cu, s->h_in, cu->in_len, 0);
+            cu->in_len = 0;
+            if (err != MZ_OK)
+                goto fail;
         }
     }
     cu->total_in += size;
     return size;
+fail:
+    if (err != MZ_WRITE_ERROR)
+        cu->error = err;
+    return err == MZ_WRITE_ERROR ? err : MZ_DATA_ERROR;
 #endif
 }
 
@@ -664,8 +757,11 @@ int32_t mz_stream_cuda_close(void *stream) {
             cu->error = MZ_MEM_ERROR;
         } else if (cu->error == 0) {
             int32_t err = cu_write_header(cu);
+            if (err == MZ_OK) /* what is left (possibly nothing) is the final batch */
+                err = cu_push(cu, cu->ws->slot[cu->ws->cur].h_in, cu->in_len, 1);
+            cu->in_len = 0;
             if (err == MZ_OK)
-                err = cu_flush_batch(cu, 1);
+                err = cu_drain(cu);
             if (err == MZ_OK && cu->wrap == 2) {
                 uint32_t isz = (uint32_t)cu->total_in; /* ISIZE is mod 2^32 */
                 uint8_t t[8] = {(uint8_t)cu->crc, (uint8_t)(cu->crc >> 8), (uint8_t)(cu->crc >> 16), (uint8_t)(cu->crc >> 24),
