@@ -56,8 +56,7 @@ constexpr int DF_OFF_HASH = DF_OFF_IN + DF_CHUNK_MAX + 64;
 constexpr int DF_OFF_REC = DF_OFF_HASH + DF_HASH_ENTRIES * 2;
 constexpr int DF_OFF_STAGE = DF_OFF_REC + DF_MAXREC * DF_THREADS * 4;
 constexpr int DF_OFF_TOK = DF_OFF_STAGE + DF_STAGE_WORDS * 4;
-constexpr int DF_OFF_RECMASK = DF_OFF_TOK + DF_TOK_CAP * 2;
-constexpr int DF_OFF_HDR = DF_OFF_RECMASK + DF_THREADS * 4;
+constexpr int DF_OFF_HDR = DF_OFF_TOK + DF_TOK_CAP * 2;
 constexpr int DF_OFF_HIST = DF_OFF_HDR + DF_HDR_WORDS * 4;      /* u32[288 + 32 + 32] */
 constexpr int DF_OFF_CODE = DF_OFF_HIST + (288 + 32 + 32) * 4;  /* u32[288 + 32 + 32] code | len<<16 */
 constexpr int DF_OFF_LENS = DF_OFF_CODE + (288 + 32 + 32) * 4;  /* u8[288 + 32 + 32] */
@@ -377,8 +376,10 @@ __device__ inline uint32_t block_excl_max(uint32_t v, uint32_t identity, uint32_
 
 /* ---- D: block-parallel literal/length + distance codes ------------------------------------------------
  * Thread i < 288 owns literal/length symbol i (286 used), thread 288 + j owns distance symbol j (30 used);
- * both alphabets are warp aligned (warps 0-8 and warp 9). Every thread of the CTA must call.
+ * both alphabets are warp aligned (warps 0-8 and warp 9). Called by threads 0..319 ONLY; they synchronise
+ * among themselves on named barrier 1 so the other 22 warps are not dragged through a dozen barriers.
  * bb = 512 words of shared scratch. Outputs lens (u8) and codes (reversed code | len << 16). */
+constexpr int DF_BB_THREADS = 320;
 enum { BB_STAT = 0 /* [2][4]: used,total,first */, BB_KRAFT = 8 /* [2 sweeps][2 alph][16] */, BB_K = 72 /* [2][16] */,
        BB_NEXT = 104 /* [2][16] */, BB_SLACK = 136 /* [2] */, BB_CNTW = 144 /* [2 bufs][10 warps][16] */ };
 
@@ -403,7 +404,7 @@ __device__ inline void block_build_codes(const uint32_t *hist_ll, const uint32_t
     uint32_t c = (a < 2 && sym < nsym) ? (a == 0 ? hist_ll[sym] : hist_d[sym]) : 0u;
 
     if (tid < 144) bb[tid] = (tid == BB_STAT + 2 || tid == BB_STAT + 6) ? 0xffffffffu : 0u;
-    __syncthreads();
+    bar_sync(1, DF_BB_THREADS);
     if (a < 2) {
         uint32_t used_w = __reduce_add_sync(MZ_FULL_MASK, c ? 1u : 0u);
         uint32_t tot_w = __reduce_add_sync(MZ_FULL_MASK, c);
@@ -414,7 +415,7 @@ __device__ inline void block_build_codes(const uint32_t *hist_ll, const uint32_t
             atomicMin(&bb[BB_STAT + a * 4 + 2], first_w);
         }
     }
-    __syncthreads();
+    bar_sync(1, DF_BB_THREADS);
     float ideal = 0.f;
     if (a < 2) {
         uint32_t used = bb[BB_STAT + a * 4 + 0], total = bb[BB_STAT + a * 4 + 1], fu = bb[BB_STAT + a * 4 + 2];
@@ -443,7 +444,7 @@ __device__ inline void block_build_codes(const uint32_t *hist_ll, const uint32_t
                 if (lane == 0) atomicAdd(&bb[BB_KRAFT + sweep * 32 + a * 16 + cnd], kr);
             }
         }
-        __syncthreads();
+        bar_sync(1, DF_BB_THREADS);
         /* everyone derives both alphabets' choices (uniform): the largest feasible candidate */
         float lo_a = lo;
         for (int aa = 0; aa < 2; aa++) {
@@ -469,7 +470,7 @@ __device__ inline void block_build_codes(const uint32_t *hist_ll, const uint32_t
         if (slack[0] == 0 && slack[1] == 0) break;
         uint32_t *cntw = bb + BB_CNTW + buf * 160;
         if (a < 2) bb_count_lengths(cntw + w * 16, L, lane, m);
-        __syncthreads();
+        bar_sync(1, DF_BB_THREADS);
         if (tid == 0 || tid == 288) {
             const int aa = tid == 0 ? 0 : 1;
             const uint32_t wa = aa == 0 ? 0u : 9u, wb = aa == 0 ? 9u : 10u;
@@ -484,7 +485,7 @@ __device__ inline void block_build_codes(const uint32_t *hist_ll, const uint32_t
             }
             bb[BB_SLACK + aa] = sl;
         }
-        __syncthreads();
+        bar_sync(1, DF_BB_THREADS);
         if (a < 2 && L >= 2) {
             uint32_t rank = (uint32_t)__popc(m & ((1u << lane) - 1));
             for (uint32_t ww = w0; ww < w; ww++) rank += cntw[ww * 16 + L];
@@ -497,7 +498,7 @@ __device__ inline void block_build_codes(const uint32_t *hist_ll, const uint32_t
     /* canonical codes: code = first code of its length + rank among equal lengths in symbol order */
     uint32_t *cntw = bb + BB_CNTW + buf * 160;
     if (a < 2) bb_count_lengths(cntw + w * 16, L, lane, m);
-    __syncthreads();
+    bar_sync(1, DF_BB_THREADS);
     if (tid == 0 || tid == 288) {
         const int aa = tid == 0 ? 0 : 1;
         const uint32_t wa = aa == 0 ? 0u : 9u, wb = aa == 0 ? 9u : 10u;
@@ -509,7 +510,7 @@ __device__ inline void block_build_codes(const uint32_t *hist_ll, const uint32_t
             for (uint32_t ww = wa; ww < wb; ww++) prev += cntw[ww * 16 + len];
         }
     }
-    __syncthreads();
+    bar_sync(1, DF_BB_THREADS);
     if (a < 2) {
         uint32_t cw = 0;
         if (L) {
@@ -526,7 +527,22 @@ __device__ inline void block_build_codes(const uint32_t *hist_ll, const uint32_t
             code_d[sym] = cw;
         }
     }
-    __syncthreads();
+}
+
+/* Dynamic block header with a FIXED code-length code (all sixteen length values 0..15 coded in 4 bits:
+ * a complete prefix code, so zlib accepts it) and no run-length symbols: constant size, every field at a
+ * known bit position, written by 317 threads in parallel. Costs ~30-60 bytes per block against an optimal
+ * code-length code; buys the removal of a serial warp-level code construction from the critical path. */
+constexpr uint32_t DF_HDR_BITS = 17 + 19 * 3 + 4 * (286 + 30);
+__device__ __forceinline__ void emit_block_header(uint32_t *stage, uint32_t pos, uint32_t bfinal, const uint8_t *lens_ll,
+                                                  const uint8_t *lens_d, uint32_t tid) {
+    if (tid == 0) stage_put(stage, pos, bfinal | (2u << 1) | (29u << 3) | (29u << 8) | (15u << 13), 17);
+    /* code-length code lengths in the order 16,17,18,0,8,7,...: three zeros, then sixteen 4s */
+    if (tid >= 1 && tid <= 16) stage_put(stage, pos + 17 + 9 + 3 * (tid - 1), 4u, 3);
+    if (tid < 286 + 30) {
+        uint32_t v = tid < 286 ? lens_ll[tid] : lens_d[tid - 286];
+        stage_put(stage, pos + 17 + 57 + 4 * tid, __brev(v) >> 28, 4); /* canonical 4-bit code of value v, MSB first */
+    }
 }
 
 /* ---- A: match finding ---------------------------------------------------------------------------------- */
@@ -597,8 +613,6 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deflate_chunks_kernel(DeflatePa
     uint32_t *s_rec = (uint32_t *)(smem + DF_OFF_REC);
     uint32_t *s_stage = (uint32_t *)(smem + DF_OFF_STAGE);
     uint16_t *s_tok = (uint16_t *)(smem + DF_OFF_TOK);
-    uint32_t *s_recmask = (uint32_t *)(smem + DF_OFF_RECMASK);
-    uint32_t *s_hdr = (uint32_t *)(smem + DF_OFF_HDR);
     uint32_t *s_hist_ll = (uint32_t *)(smem + DF_OFF_HIST);
     uint32_t *s_hist_d = s_hist_ll + 288;
     uint32_t *s_hist_cl = s_hist_d + 32;
@@ -687,7 +701,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deflate_chunks_kernel(DeflatePa
             const uint32_t seg_end = seg_start + DF_SEG < sb_end ? seg_start + DF_SEG : sb_end;
             const bool last_sb = sb == nsb - 1;
             uint32_t nhalf = 1, n_tok = 0, ntok_all = 0, tok_excl = 0, e0 = sb_end;
-            uint32_t litmask = 0, keptrec = 0, strad_cnt = 0, strad_pos = 0, strad_tok = 0;
+            uint32_t litmask = 0, keptrec = 0, recmask = 0, strad_cnt = 0, strad_pos = 0, strad_tok = 0;
             bool strad_match = false;
 
             if (P.level != 0) {
@@ -720,7 +734,8 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deflate_chunks_kernel(DeflatePa
                 if (tid == DF_THREADS / 2) s_misc[MISC_E0] = cover; /* where the second thread half starts */
                 /* ---- T: classify what this thread keeps ------------------------------------------- */
                 const uint32_t c_rel = cover > seg_start ? cover - seg_start : 0u; /* may exceed 32 */
-                uint32_t recmask = 0, covmask = 0;
+                uint32_t covmask = 0;
+                recmask = 0;
                 for (uint32_t r = 0; r < nrec; r++) {
                     uint32_t rec = s_rec[r * DF_THREADS + tid];
                     uint32_t roff = rec & 31, rlen = ((rec >> 5) & 255) + 3;
@@ -734,7 +749,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deflate_chunks_kernel(DeflatePa
                         uint32_t rem = rend - c_rel; /* straddles: trim the front */
                         if (rem >= 3) {
                             strad_match = true;
-                            strad_tok = DF_TOK_MATCH | (seg_start - sb_start + roff);
+                            strad_tok = DF_TOK_MATCH | (r * DF_THREADS + tid);
                             s_rec[r * DF_THREADS + tid] = roff | ((rem - 3) << 5) | (rec & ~0x1fffu);
                         } else {
                             strad_cnt = rem; /* 1-2 bytes left: plain literals */
@@ -742,7 +757,6 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deflate_chunks_kernel(DeflatePa
                         }
                     }
                 }
-                s_recmask[tid] = recmask;
                 const uint32_t valid = seg_end - seg_start;
                 litmask = ~covmask & ~recmask & ~bit_range(0, c_rel < 32 ? c_rel : 32) & bit_range(0, valid);
                 n_tok = (uint32_t)__popc(litmask) + (uint32_t)__popc(keptrec) + (strad_match ? 1u : 0u) + strad_cnt;
@@ -764,47 +778,54 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deflate_chunks_kernel(DeflatePa
                     const bool mine = nhalf == 1 || (tid >> 9) == half;
                     if (nhalf == 2) excl = block_excl_sum(mine ? n_tok : 0u, s_scan, ntok);
                     /* ---- T: write the ordered token list ------------------------------------------ */
+                    for (uint32_t i = tid; i < 288 + 32; i += DF_THREADS) s_hist_ll[i] = 0;
+                    __syncthreads();
+                    /* literal entry = the byte itself; match entry = flag | record slot (r * 1024 + owner) */
                     if (mine) {
                         uint32_t o = excl;
                         if (strad_match) s_tok[o++] = (uint16_t)strad_tok;
-                        for (uint32_t q = 0; q < strad_cnt; q++) s_tok[o++] = (uint16_t)(strad_pos + q - sb_start);
+                        for (uint32_t q = 0; q < strad_cnt; q++) s_tok[o++] = s_in[strad_pos + q];
                         uint32_t mm = litmask | keptrec;
-                        const uint32_t rel = seg_start - sb_start;
                         while (mm) {
                             uint32_t b = (uint32_t)__ffs((int)mm) - 1;
                             mm &= mm - 1;
-                            s_tok[o++] = (uint16_t)((rel + b) | (((keptrec >> b) & 1u) << 15));
+                            uint32_t e = s_in[seg_start + b];
+                            if ((keptrec >> b) & 1u) e = DF_TOK_MATCH | ((uint32_t)__popc(recmask & ((1u << b) - 1)) * DF_THREADS + tid);
+                            s_tok[o++] = (uint16_t)e;
                         }
-                    }
-                    for (uint32_t i = tid; i < 288 + 32; i += DF_THREADS) s_hist_ll[i] = 0;
-                    __syncthreads();
-                    /* ---- C: histograms; match records -> symbol form ------------------------------------ */
-                    for (uint32_t k = tid; k < ntok; k += DF_THREADS) {
-                        uint32_t e = s_tok[k];
-                        uint32_t rp = e & 0x7fffu;
-                        if (!(e & DF_TOK_MATCH)) {
-                            atomicAdd(&s_hist_ll[s_in[sb_start + rp]], 1u);
-                        } else {
-                            uint32_t owner = rp >> 5, roff = rp & 31;
-                            uint32_t r = (uint32_t)__popc(s_recmask[owner] & ((1u << roff) - 1));
-                            uint32_t rec = s_rec[r * DF_THREADS + owner];
+                        /* ---- C (matches): this thread's kept records -> symbol form + histograms ------------- */
+                        uint32_t mk = keptrec;
+                        bool do_strad = strad_match;
+                        while (mk || do_strad) {
+                            uint32_t slot;
+                            if (do_strad) {
+                                slot = strad_tok & 0x1fffu;
+                                do_strad = false;
+                            } else {
+                                uint32_t b = (uint32_t)__ffs((int)mk) - 1;
+                                mk &= mk - 1;
+                                slot = (uint32_t)__popc(recmask & ((1u << b) - 1)) * DF_THREADS + tid;
+                            }
+                            uint32_t rec = s_rec[slot];
                             uint32_t ls, lb, lv, ds, db, dv;
                             length_symbol(((rec >> 5) & 255) + 3, ls, lb, lv);
                             dist_symbol((rec >> 13) + 1, ds, db, dv);
-                            s_rec[r * DF_THREADS + owner] = ls | (lv << 5) | (ds << 10) | (dv << 15);
+                            s_rec[slot] = ls | (lv << 5) | (ds << 10) | (dv << 15);
                             atomicAdd(&s_hist_ll[257 + ls], 1u);
                             atomicAdd(&s_hist_d[ds], 1u);
                         }
                     }
+                    __syncthreads();
+                    /* ---- C (literals): threads stride over the list ------------------------------------------ */
+                    for (uint32_t k = tid; k < ntok; k += DF_THREADS) {
+                        uint32_t e = s_tok[k];
+                        if (!(e & DF_TOK_MATCH)) atomicAdd(&s_hist_ll[e], 1u);
+                    }
                     if (tid == 0) s_hist_ll[256] = 1;
                     __syncthreads();
-                    /* ---- D: codes + header -------------------------------------------------------- */
-                    block_build_codes(s_hist_ll, s_hist_d, s_lens_ll, s_lens_d, s_code_ll, s_code_d, s_bb);
-                    if (warp_id() == 0) {
-                        uint32_t hb = warp_build_header(s_lens_ll, s_lens_d, bfinal, s_hist_cl, s_lens_cl, s_code_cl,
-                                                        s_misc + MISC_BLCNT, s_hdr);
-                        if (lane_id() == 0) s_misc[MISC_HDRBITS] = hb;
-                    }
+                    /* ---- D: codes (10 warps on a named barrier; the rest wait here) ------------------------- */
+                    if (tid < DF_BB_THREADS) block_build_codes(s_hist_ll, s_hist_d, s_lens_ll, s_lens_d, s_code_ll, s_code_d, s_bb);
+                    __syncthreads();
                     /* ---- E: bit counts over equal contiguous token runs (codes are final) ---------------- */
                     const uint32_t run = ((ntok + DF_THREADS - 1) / DF_THREADS) | 1u; /* odd stride: no bank conflicts */
                     const uint32_t k0 = tid * run < ntok ? tid * run : ntok;
@@ -812,20 +833,17 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deflate_chunks_kernel(DeflatePa
                     uint32_t mybits = 0;
                     for (uint32_t k = k0; k < k1; k++) {
                         uint32_t e = s_tok[k];
-                        uint32_t rp = e & 0x7fffu;
                         if (!(e & DF_TOK_MATCH)) {
-                            mybits += s_code_ll[s_in[sb_start + rp]] >> 16;
+                            mybits += s_code_ll[e] >> 16;
                         } else {
-                            uint32_t owner = rp >> 5, roff = rp & 31;
-                            uint32_t r = (uint32_t)__popc(s_recmask[owner] & ((1u << roff) - 1));
-                            uint32_t rec = s_rec[r * DF_THREADS + owner];
+                            uint32_t rec = s_rec[e & 0x1fffu];
                             uint32_t ls = rec & 31, ds = (rec >> 10) & 31;
                             mybits += (s_code_ll[257 + ls] >> 16) + len_extra_bits(ls) + (s_code_d[ds] >> 16) + dist_extra_bits(ds);
                         }
                     }
                     uint32_t tokbits;
                     uint32_t myoff = block_excl_sum(mybits, s_scan, tokbits);
-                    const uint32_t hdrbits = s_misc[MISC_HDRBITS];
+                    const uint32_t hdrbits = DF_HDR_BITS;
                     const uint32_t eob = s_code_ll[256];
                     const uint32_t dyn_bits = hdrbits + tokbits + (eob >> 16);
                     const uint32_t stored_bits = (((bitpos + 3 + 7) & ~7u) - bitpos) + 32 + blk_len * 8;
@@ -834,25 +852,17 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deflate_chunks_kernel(DeflatePa
                     } else {
                         /* ---- F: emit --------------------------------------------------------------- */
                         const uint32_t base = bitpos + hdrbits;
-                        if (warp_id() == 0) {
-                            for (uint32_t j = lane_id(); j * 32 < hdrbits; j += 32) {
-                                uint32_t n = hdrbits - j * 32;
-                                stage_put(s_stage, bitpos + j * 32, s_hdr[j], n > 32 ? 32 : n);
-                            }
-                        }
+                        emit_block_header(s_stage, bitpos, bfinal, s_lens_ll, s_lens_d, tid);
                         if (mybits) {
                             BitWriter bw;
                             bw.init(s_stage, base + myoff);
                             for (uint32_t k = k0; k < k1; k++) {
                                 uint32_t e = s_tok[k];
-                                uint32_t rp = e & 0x7fffu;
                                 if (!(e & DF_TOK_MATCH)) {
-                                    uint32_t cw = s_code_ll[s_in[sb_start + rp]];
+                                    uint32_t cw = s_code_ll[e];
                                     bw.put(cw & 0xffff, cw >> 16);
                                 } else {
-                                    uint32_t owner = rp >> 5, roff = rp & 31;
-                                    uint32_t r = (uint32_t)__popc(s_recmask[owner] & ((1u << roff) - 1));
-                                    uint32_t rec = s_rec[r * DF_THREADS + owner];
+                                    uint32_t rec = s_rec[e & 0x1fffu];
                                     uint32_t ls = rec & 31, ds = (rec >> 10) & 31;
                                     uint32_t cw = s_code_ll[257 + ls];
                                     uint32_t cl = cw >> 16;

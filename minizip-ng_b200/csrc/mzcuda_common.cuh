@@ -42,6 +42,15 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
 #endif
 }
 
+/* named barrier over the first `nthreads` threads' worth of warps (id 1..15; 0 is __syncthreads) */
+__device__ __forceinline__ void bar_sync(int id, int nthreads) {
+#ifdef MZ_EMU
+    emu_named_barrier(id, nthreads);
+#else
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+#endif
+}
+
 /* warp inclusive scan (sum) */
 __device__ __forceinline__ uint32_t warp_incl_sum(uint32_t v) {
 #pragma unroll

@@ -53,6 +53,19 @@ void emu_block_barrier(void) {
     while (g_bar_gen == gen) emu_yield();
 }
 
+static unsigned g_nb_count[16], g_nb_gen[16];
+void emu_named_barrier(int id, int nthreads) {
+    unsigned gen = g_nb_gen[id];
+    g_nb_count[id]++;
+    if (g_nb_count[id] >= (unsigned)nthreads) {
+        g_nb_count[id] = 0;
+        g_nb_gen[id]++;
+        g_progress++;
+        return;
+    }
+    while (g_nb_gen[id] == gen) emu_yield();
+}
+
 void emu_warp_barrier(unsigned mask) {
     emu_warp_state *w = emu_cur_warp();
     unsigned need = (unsigned)__builtin_popcount(mask & w->live_mask);
@@ -101,6 +114,7 @@ void emu_run_block(unsigned nthreads, void (*entry)(void *), void *arg, size_t d
     g_arg = arg;
     g_nthreads = g_live = nthreads;
     g_bar_count = 0;
+    for (int i = 0; i < 16; i++) g_nb_count[i] = 0;
     for (unsigned i = 0; i < nthreads; i++) {
         emu_fiber *f = &g_fibers[i];
         f->done = 0;

@@ -72,6 +72,7 @@ struct emu_warp_state {
 extern emu_warp_state *emu_cur_warp(void);
 extern int emu_lane(void);
 void emu_block_barrier(void);
+void emu_named_barrier(int id, int nthreads);
 void emu_warp_barrier(unsigned mask);
 
 static inline void __syncthreads() { emu_block_barrier(); }
