@@ -41,10 +41,7 @@ constexpr int DF_CHUNK_MAX = 65536;
 constexpr int DF_SEG = 32;
 constexpr int DF_SB = DF_THREADS * DF_SEG; /* 32768 */
 constexpr int DF_MINMATCH = 4;
-constexpr int DF_MAXREC = DF_SEG / DF_MINMATCH; /* 8 match records per thread span per sub-block */
-constexpr int DF_PSEG = 16;                      /* parse segment: the unit lanes take dynamically */
-constexpr int DF_NPSEG = DF_SB / DF_PSEG;        /* 2048 per sub-block, 64 per warp region */
-constexpr int DF_PMAXREC = DF_PSEG / DF_MINMATCH; /* 4 records per parse segment: rec[r][segment] */
+constexpr int DF_MAXREC = DF_SEG / DF_MINMATCH; /* 8 match records per thread per sub-block */
 constexpr int DF_HASH_ENTRIES = 16384;          /* u16 entries: 32 KiB */
 constexpr int DF_STAGE_WORDS = DF_SB / 4 + 64;
 constexpr int DF_HDR_WORDS = 96;   /* dynamic header <= 17 + 57 + 316*7 bits = 2286 bits = 72 words */
@@ -59,8 +56,8 @@ constexpr int DF_OFF_HASH = DF_OFF_IN + DF_CHUNK_MAX + 64;
 constexpr int DF_OFF_REC = DF_OFF_HASH + DF_HASH_ENTRIES * 2;
 constexpr int DF_OFF_STAGE = DF_OFF_REC + DF_MAXREC * DF_THREADS * 4;
 constexpr int DF_OFF_TOK = DF_OFF_STAGE + DF_STAGE_WORDS * 4;
-constexpr int DF_OFF_END = DF_OFF_TOK + DF_TOK_CAP * 2;        /* u32[2048]: parse end | nrec << 20 per parse segment */
-constexpr int DF_OFF_HIST = DF_OFF_END + DF_NPSEG * 4;         /* u32[288 + 32 + 32] */
+constexpr int DF_OFF_HDR = DF_OFF_TOK + DF_TOK_CAP * 2;
+constexpr int DF_OFF_HIST = DF_OFF_HDR + DF_HDR_WORDS * 4;      /* u32[288 + 32 + 32] */
 constexpr int DF_OFF_CODE = DF_OFF_HIST + (288 + 32 + 32) * 4;  /* u32[288 + 32 + 32] code | len<<16 */
 constexpr int DF_OFF_LENS = DF_OFF_CODE + (288 + 32 + 32) * 4;  /* u8[288 + 32 + 32] */
 constexpr int DF_OFF_SCAN = DF_OFF_LENS + (288 + 32 + 32);      /* u32[64] */
@@ -620,7 +617,6 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deflate_chunks_kernel(DeflatePa
     uint32_t *s_rec = (uint32_t *)(smem + DF_OFF_REC);
     uint32_t *s_stage = (uint32_t *)(smem + DF_OFF_STAGE);
     uint16_t *s_tok = (uint16_t *)(smem + DF_OFF_TOK);
-    uint32_t *s_end = (uint32_t *)(smem + DF_OFF_END);
     uint32_t *s_hist_ll = (uint32_t *)(smem + DF_OFF_HIST);
     uint32_t *s_hist_d = s_hist_ll + 288;
     uint32_t *s_hist_cl = s_hist_d + 32;
@@ -709,152 +705,65 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deflate_chunks_kernel(DeflatePa
             const uint32_t seg_end = seg_start + DF_SEG < sb_end ? seg_start + DF_SEG : sb_end;
             const bool last_sb = sb == nsb - 1;
             uint32_t nhalf = 1, n_tok = 0, ntok_all = 0, tok_excl = 0, e0 = sb_end;
-            uint32_t litmask = 0, keptrec = 0, recmask = 0, dropmask = 0;
-            uint32_t strad_cnt[2] = {0, 0}, strad_pos[2] = {0, 0}, strad_tok[2] = {0, 0};
+            uint32_t litmask = 0, keptrec = 0, recmask = 0, strad_cnt = 0, strad_pos = 0, strad_tok = 0;
+            bool strad_match = false;
 
             if (P.level != 0) {
-                /* ---- A: parse. A warp owns the 1 KiB region of its threads' spans, cut into 64 parse
-                 * segments of 16 bytes that its lanes take DYNAMICALLY (ballot-allocated): token counts per
-                 * segment vary a lot and a static lane<->segment map leaves most lanes idle most of the time. */
-                const unsigned lane = lane_id();
-                const uint32_t wseg0 = warp_id() * (2 * 32); /* first parse segment of my warp (sub-block relative) */
-                const uint32_t reg_base = sb_start + wseg0 * DF_PSEG;
-                const uint32_t nseg_reg = reg_base >= sb_end ? 0u : ((sb_end - reg_base + DF_PSEG - 1) / DF_PSEG < 64u ? (sb_end - reg_base + DF_PSEG - 1) / DF_PSEG : 64u);
-                /* parse end of segments that do not exist = sub-block end (neutral for the prefix max) */
-                s_end[2 * tid] = sb_end;
-                s_end[2 * tid + 1] = sb_end;
-                __syncwarp();
-                {
-                    uint32_t next = 32;
-                    int seg = lane < nseg_reg ? (int)lane : -1;
-                    uint32_t p = reg_base + lane * DF_PSEG, pend = p + DF_PSEG < sb_end ? p + DF_PSEG : sb_end, pstart = p;
-                    uint32_t nrec = 0, mlen = 0, mcand = 0, maxlen = 0;
-                    bool ext = false;
-                    for (;;) {
-                        if (seg >= 0 && !ext && p >= pend) { /* segment finished: publish where its parse ended */
-                            s_end[wseg0 + (uint32_t)seg] = p | (nrec << 20);
-                            seg = -1;
-                        }
-                        const unsigned idle = __ballot_sync(MZ_FULL_MASK, seg < 0);
-                        if (idle && next < nseg_reg) {
-                            if (seg < 0) {
-                                uint32_t my = next + (uint32_t)__popc(idle & ((1u << lane) - 1));
-                                if (my < nseg_reg) {
-                                    seg = (int)my;
-                                    p = pstart = reg_base + my * DF_PSEG;
-                                    pend = p + DF_PSEG < sb_end ? p + DF_PSEG : sb_end;
-                                    nrec = 0;
-                                }
-                            }
-                            next += (uint32_t)__popc(idle);
-                        }
-                        if (__ballot_sync(MZ_FULL_MASK, seg >= 0) == 0) break;
-                        if (seg < 0) continue;
-                        bool fin = false;
-                        uint32_t mdist = 0;
-                        if (WAYS == 1 && !LAZY) {
-                            /* state machine: one probe OR one 4-byte extension step per iteration, so a long
-                             * match in one lane does not stall the lanes that are probing */
-                            if (ext) {
-                                uint32_t x = load32u(s_in, p + mlen) ^ load32u(s_in, mcand + mlen);
-                                if (x) {
-                                    mlen += (uint32_t)(__ffs((int)x) - 1) >> 3;
-                                    fin = true;
-                                } else {
-                                    mlen += 4;
-                                    fin = mlen >= maxlen;
-                                }
-                                if (fin && mlen > maxlen) mlen = maxlen;
-                            } else if (p + DF_MINMATCH <= sb_end) {
-                                uint32_t v = load32u(s_in, p);
-                                uint32_t h = hash4(v, 14);
-                                uint32_t cand = s_hash[h];
-                                s_hash[h] = (uint16_t)p;
-                                if (cand < p && p - cand <= 32768u && load32u(s_in, cand) == v) {
-                                    mcand = cand;
-                                    mlen = 4;
-                                    maxlen = sb_end - p < 258u ? sb_end - p : 258u;
-                                    ext = maxlen > 4;
-                                    fin = !ext;
-                                } else {
-                                    p += 1;
-                                }
-                            } else {
+                /* ---- A: parse ------------------------------------------------------------------ */
+                uint32_t nrec = 0;
+                uint32_t p = seg_start;
+                while (p < seg_end) {
+                    uint32_t mlen = 0, mdist = 0;
+                    if (p + DF_MINMATCH <= sb_end) {
+                        mlen = find_match<WAYS>(s_in, s_hash, p, sb_end, mdist);
+                        if (LAZY && mlen >= DF_MINMATCH && mlen < 32 && p + 1 < seg_end && p + 1 + DF_MINMATCH <= sb_end) {
+                            uint32_t d2, l2 = find_match<WAYS>(s_in, s_hash, p + 1, sb_end, d2);
+                            if (l2 > mlen) { /* literal now, better match next */
                                 p += 1;
-                            }
-                            mdist = p - mcand;
-                        } else {
-                            if (p + DF_MINMATCH <= sb_end) {
-                                mlen = find_match<WAYS>(s_in, s_hash, p, sb_end, mdist);
-                                if (LAZY && mlen >= DF_MINMATCH && mlen < 32 && p + 1 < pend && p + 1 + DF_MINMATCH <= sb_end) {
-                                    uint32_t d2, l2 = find_match<WAYS>(s_in, s_hash, p + 1, sb_end, d2);
-                                    if (l2 > mlen) { /* literal now, better match next */
-                                        p += 1;
-                                        mlen = l2;
-                                        mdist = d2;
-                                    }
-                                }
-                                fin = mlen >= DF_MINMATCH;
-                                if (!fin) p += 1;
-                            } else {
-                                p += 1;
-                            }
-                        }
-                        if (fin) {
-                            ext = false;
-                            if (nrec < DF_PMAXREC) {
-                                s_rec[nrec * DF_NPSEG + wseg0 + (uint32_t)seg] = (p - pstart) | ((mlen - 3) << 5) | ((mdist - 1) << 13);
-                                nrec++;
-                                p += mlen;
-                            } else {
-                                p += 1; /* cannot happen with 16-byte segments and 4-byte matches; kept as a guard */
+                                mlen = l2;
+                                mdist = d2;
                             }
                         }
                     }
-                    __syncwarp();
+                    if (mlen >= DF_MINMATCH && nrec < DF_MAXREC) {
+                        s_rec[nrec * DF_THREADS + tid] = (p - seg_start) | ((mlen - 3) << 5) | ((mdist - 1) << 13);
+                        nrec++;
+                        p += mlen;
+                    } else {
+                        p += 1;
+                    }
                 }
-                /* ---- B: cover = where earlier segments' matches end ------------------------------ */
-                const uint32_t end0 = s_end[2 * tid], end1 = s_end[2 * tid + 1];
-                const uint32_t pe0 = end0 & 0xfffffu, pe1 = end1 & 0xfffffu;
-                const uint32_t cover0 = block_excl_max(pe0 > pe1 ? pe0 : pe1, sb_start, s_scan);
-                if (tid == DF_THREADS / 2) s_misc[MISC_E0] = cover0; /* where the second thread half starts */
-                /* ---- T: classify what this thread keeps (its span = parse segments 2t and 2t+1) ---------- */
+                /* ---- B: cover = where earlier threads' matches end ------------------------------ */
+                const uint32_t cover = block_excl_max(p, sb_start, s_scan);
+                if (tid == DF_THREADS / 2) s_misc[MISC_E0] = cover; /* where the second thread half starts */
+                /* ---- T: classify what this thread keeps ------------------------------------------- */
+                const uint32_t c_rel = cover > seg_start ? cover - seg_start : 0u; /* may exceed 32 */
                 uint32_t covmask = 0;
                 recmask = 0;
-                for (uint32_t j = 0; j < 2; j++) {
-                    const uint32_t cover = j == 0 ? cover0 : (cover0 > pe0 ? cover0 : pe0);
-                    const uint32_t c_rel = cover > seg_start ? cover - seg_start : 0u; /* relative to the span; may exceed 32 */
-                    const uint32_t nrec = (j == 0 ? end0 : end1) >> 20;
-                    const uint32_t pseg = 2 * tid + j;
-                    for (uint32_t r = 0; r < nrec; r++) {
-                        uint32_t rec = s_rec[r * DF_NPSEG + pseg];
-                        uint32_t roff = (rec & 31) + j * DF_PSEG, rlen = ((rec >> 5) & 255) + 3;
-                        uint32_t rend = roff + rlen;
-                        recmask |= 1u << roff;
-                        covmask |= bit_range(roff + 1, rend < 32 ? rend : 32);
-                        if (rend <= c_rel) continue; /* covered entirely by an earlier match */
-                        if (roff >= c_rel) {
-                            keptrec |= 1u << roff;
+                for (uint32_t r = 0; r < nrec; r++) {
+                    uint32_t rec = s_rec[r * DF_THREADS + tid];
+                    uint32_t roff = rec & 31, rlen = ((rec >> 5) & 255) + 3;
+                    uint32_t rend = roff + rlen;
+                    recmask |= 1u << roff;
+                    covmask |= bit_range(roff + 1, rend < 32 ? rend : 32);
+                    if (rend <= c_rel) continue; /* covered entirely by an earlier thread's match */
+                    if (roff >= c_rel) {
+                        keptrec |= 1u << roff;
+                    } else {
+                        uint32_t rem = rend - c_rel; /* straddles: trim the front */
+                        if (rem >= 3) {
+                            strad_match = true;
+                            strad_tok = DF_TOK_MATCH | (r * DF_THREADS + tid);
+                            s_rec[r * DF_THREADS + tid] = roff | ((rem - 3) << 5) | (rec & ~0x1fffu);
                         } else {
-                            uint32_t rem = rend - c_rel; /* straddles: trim the front */
-                            if (rem >= 3) {
-                                strad_tok[j] = DF_TOK_MATCH | (r * DF_NPSEG + pseg);
-                                s_rec[r * DF_NPSEG + pseg] = (rec & 31) | ((rem - 3) << 5) | (rec & ~0x1fffu);
-                            } else {
-                                strad_cnt[j] = rem; /* 1-2 bytes left: plain literals */
-                                strad_pos[j] = seg_start + c_rel;
-                            }
+                            strad_cnt = rem; /* 1-2 bytes left: plain literals */
+                            strad_pos = seg_start + c_rel;
                         }
                     }
-                    /* positions of this half-span in front of the cover are someone else's */
-                    uint32_t lo = j * DF_PSEG, hi = lo + DF_PSEG;
-                    uint32_t cr = c_rel < lo ? lo : (c_rel > hi ? hi : c_rel);
-                    dropmask |= bit_range(lo, cr);
                 }
                 const uint32_t valid = seg_end - seg_start;
-                litmask = ~covmask & ~recmask & ~dropmask & bit_range(0, valid);
-                n_tok = (uint32_t)__popc(litmask) + (uint32_t)__popc(keptrec) + (strad_tok[0] ? 1u : 0u) + (strad_tok[1] ? 1u : 0u) +
-                        strad_cnt[0] + strad_cnt[1];
+                litmask = ~covmask & ~recmask & ~bit_range(0, c_rel < 32 ? c_rel : 32) & bit_range(0, valid);
+                n_tok = (uint32_t)__popc(litmask) + (uint32_t)__popc(keptrec) + (strad_match ? 1u : 0u) + strad_cnt;
                 tok_excl = block_excl_sum(n_tok, s_scan, ntok_all);
                 e0 = s_misc[MISC_E0];
                 nhalf = ntok_all > (uint32_t)DF_TOK_CAP ? 2u : 1u;
@@ -878,34 +787,28 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deflate_chunks_kernel(DeflatePa
                     /* literal entry = the byte itself; match entry = flag | record slot (r * 1024 + owner) */
                     if (mine) {
                         uint32_t o = excl;
-                        for (uint32_t j = 0; j < 2; j++) {
-                            if (strad_tok[j]) s_tok[o++] = (uint16_t)strad_tok[j];
-                            for (uint32_t q = 0; q < strad_cnt[j]; q++) s_tok[o++] = s_in[strad_pos[j] + q];
-                            const uint32_t half_bits = j == 0 ? 0xffffu : 0xffff0000u;
-                            uint32_t mm = (litmask | keptrec) & half_bits;
-                            while (mm) {
-                                uint32_t b = (uint32_t)__ffs((int)mm) - 1;
-                                mm &= mm - 1;
-                                uint32_t e = s_in[seg_start + b];
-                                if ((keptrec >> b) & 1u) /* r = records of the same parse segment in front of b */
-                                    e = DF_TOK_MATCH | ((uint32_t)__popc(recmask & half_bits & ((1u << b) - 1)) * DF_NPSEG + 2 * tid + j);
-                                s_tok[o++] = (uint16_t)e;
-                            }
+                        if (strad_match) s_tok[o++] = (uint16_t)strad_tok;
+                        for (uint32_t q = 0; q < strad_cnt; q++) s_tok[o++] = s_in[strad_pos + q];
+                        uint32_t mm = litmask | keptrec;
+                        while (mm) {
+                            uint32_t b = (uint32_t)__ffs((int)mm) - 1;
+                            mm &= mm - 1;
+                            uint32_t e = s_in[seg_start + b];
+                            if ((keptrec >> b) & 1u) e = DF_TOK_MATCH | ((uint32_t)__popc(recmask & ((1u << b) - 1)) * DF_THREADS + tid);
+                            s_tok[o++] = (uint16_t)e;
                         }
                         /* ---- C (matches): this thread's kept records -> symbol form + histograms ------------- */
                         uint32_t mk = keptrec;
-                        uint32_t sq = (strad_tok[0] ? 1u : 0u) | (strad_tok[1] ? 2u : 0u);
-                        while (mk || sq) {
+                        bool do_strad = strad_match;
+                        while (mk || do_strad) {
                             uint32_t slot;
-                            if (sq) {
-                                uint32_t j = (sq & 1u) ? 0u : 1u;
-                                slot = strad_tok[j] & 0x1fffu;
-                                sq &= ~(1u << j);
+                            if (do_strad) {
+                                slot = strad_tok & 0x1fffu;
+                                do_strad = false;
                             } else {
                                 uint32_t b = (uint32_t)__ffs((int)mk) - 1;
                                 mk &= mk - 1;
-                                const uint32_t half_bits = b < 16 ? 0xffffu : 0xffff0000u;
-                                slot = (uint32_t)__popc(recmask & half_bits & ((1u << b) - 1)) * DF_NPSEG + 2 * tid + (b >> 4);
+                                slot = (uint32_t)__popc(recmask & ((1u << b) - 1)) * DF_THREADS + tid;
                             }
                             uint32_t rec = s_rec[slot];
                             uint32_t ls, lb, lv, ds, db, dv;
