@@ -46,7 +46,8 @@ constexpr int DF_HASH_ENTRIES = 16384;          /* u16 entries: 32 KiB */
 constexpr int DF_STAGE_WORDS = DF_SB / 4 + 64;
 constexpr int DF_HDR_WORDS = 96;   /* dynamic header <= 17 + 57 + 316*7 bits = 2286 bits = 72 words */
 constexpr int DF_TOK_CAP = 24576;  /* token list entries (u16) */
-constexpr uint32_t DF_TOK_MATCH = 0x8000u;
+constexpr uint32_t DF_TOK_MATCH = 0x8000u; /* entry is a code word of a match: bits 0-12 = record slot */
+constexpr uint32_t DF_TOK_DIST = 0x4000u;  /* ... its distance code word (else its length code word) */
 
 constexpr uint32_t DF_FLAG_FINAL = 1u; /* chunk ends the stream: BFINAL on its last block, no sync marker */
 
@@ -119,6 +120,22 @@ __device__ __forceinline__ uint32_t dist_extra_bits(uint32_t dsym) { return dsym
 /* match record forms (32 bits each, 8 per thread, [r][tid] layout):
  *   parsed : off(5) | (len-3)(8) << 5 | (dist-1)(15) << 13
  *   symbol : lsym(5) | lextra(5) << 5 | dsym(5) << 10 | dextra(13) << 15     (after phase C) */
+
+/* One token-list entry = one code word. Branch-free decode shared by the count and emit passes:
+ * idx = index into the concatenated code table (288 literal/length codes, then 32 distance codes),
+ * ev / eb = extra-bits value / count. Literal entries carry the byte; for them the record load reads an
+ * unrelated but valid word and the selects discard it. */
+__device__ __forceinline__ void token_code(uint32_t e, const uint32_t *s_rec, uint32_t &idx, uint32_t &ev, uint32_t &eb) {
+    const uint32_t rec = s_rec[e & 0x1fffu];
+    const bool isrec = (e & DF_TOK_MATCH) != 0, isdist = (e & DF_TOK_DIST) != 0;
+    const uint32_t ls = rec & 31, ds = (rec >> 10) & 31;
+    const uint32_t sym = isdist ? 288u + ds : 257u + ls;
+    const uint32_t xv = isdist ? rec >> 15 : (rec >> 5) & 31u;
+    const uint32_t xb = isdist ? dist_extra_bits(ds) : len_extra_bits(ls);
+    idx = isrec ? sym : e;
+    ev = isrec ? xv : 0u;
+    eb = isrec ? xb : 0u;
+}
 
 /* OR `n` (<=32) bits of v into the staging bit string at bit position pos */
 __device__ __forceinline__ void stage_put(uint32_t *stage, uint32_t pos, uint32_t v, uint32_t n) {
@@ -763,7 +780,7 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deflate_chunks_kernel(DeflatePa
                 }
                 const uint32_t valid = seg_end - seg_start;
                 litmask = ~covmask & ~recmask & ~bit_range(0, c_rel < 32 ? c_rel : 32) & bit_range(0, valid);
-                n_tok = (uint32_t)__popc(litmask) + (uint32_t)__popc(keptrec) + (strad_match ? 1u : 0u) + strad_cnt;
+                n_tok = (uint32_t)__popc(litmask) + 2u * ((uint32_t)__popc(keptrec) + (strad_match ? 1u : 0u)) + strad_cnt; /* a match = 2 code words */
                 tok_excl = block_excl_sum(n_tok, s_scan, ntok_all);
                 e0 = s_misc[MISC_E0];
                 nhalf = ntok_all > (uint32_t)DF_TOK_CAP ? 2u : 1u;
@@ -787,14 +804,21 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deflate_chunks_kernel(DeflatePa
                     /* literal entry = the byte itself; match entry = flag | record slot (r * 1024 + owner) */
                     if (mine) {
                         uint32_t o = excl;
-                        if (strad_match) s_tok[o++] = (uint16_t)strad_tok;
+                        if (strad_match) {
+                            s_tok[o++] = (uint16_t)strad_tok;
+                            s_tok[o++] = (uint16_t)(strad_tok | DF_TOK_DIST);
+                        }
                         for (uint32_t q = 0; q < strad_cnt; q++) s_tok[o++] = s_in[strad_pos + q];
                         uint32_t mm = litmask | keptrec;
                         while (mm) {
                             uint32_t b = (uint32_t)__ffs((int)mm) - 1;
                             mm &= mm - 1;
                             uint32_t e = s_in[seg_start + b];
-                            if ((keptrec >> b) & 1u) e = DF_TOK_MATCH | ((uint32_t)__popc(recmask & ((1u << b) - 1)) * DF_THREADS + tid);
+                            if ((keptrec >> b) & 1u) {
+                                e = DF_TOK_MATCH | ((uint32_t)__popc(recmask & ((1u << b) - 1)) * DF_THREADS + tid);
+                                s_tok[o++] = (uint16_t)e; /* length code word, then the distance code word */
+                                e |= DF_TOK_DIST;
+                            }
                             s_tok[o++] = (uint16_t)e;
                         }
                         /* ---- C (matches): this thread's kept records -> symbol form + histograms ------------- */
@@ -836,14 +860,9 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deflate_chunks_kernel(DeflatePa
                     const uint32_t k1 = k0 + run < ntok ? k0 + run : ntok;
                     uint32_t mybits = 0;
                     for (uint32_t k = k0; k < k1; k++) {
-                        uint32_t e = s_tok[k];
-                        if (!(e & DF_TOK_MATCH)) {
-                            mybits += s_code_ll[e] >> 16;
-                        } else {
-                            uint32_t rec = s_rec[e & 0x1fffu];
-                            uint32_t ls = rec & 31, ds = (rec >> 10) & 31;
-                            mybits += (s_code_ll[257 + ls] >> 16) + len_extra_bits(ls) + (s_code_d[ds] >> 16) + dist_extra_bits(ds);
-                        }
+                        uint32_t idx, ev, eb;
+                        token_code(s_tok[k], s_rec, idx, ev, eb);
+                        mybits += (s_code_ll[idx] >> 16) + eb;
                     }
                     uint32_t tokbits;
                     uint32_t myoff = block_excl_sum(mybits, s_scan, tokbits);
@@ -861,20 +880,11 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deflate_chunks_kernel(DeflatePa
                             BitWriter bw;
                             bw.init(s_stage, base + myoff);
                             for (uint32_t k = k0; k < k1; k++) {
-                                uint32_t e = s_tok[k];
-                                if (!(e & DF_TOK_MATCH)) {
-                                    uint32_t cw = s_code_ll[e];
-                                    bw.put(cw & 0xffff, cw >> 16);
-                                } else {
-                                    uint32_t rec = s_rec[e & 0x1fffu];
-                                    uint32_t ls = rec & 31, ds = (rec >> 10) & 31;
-                                    uint32_t cw = s_code_ll[257 + ls];
-                                    uint32_t cl = cw >> 16;
-                                    bw.put((cw & 0xffff) | (((rec >> 5) & 31) << cl), cl + len_extra_bits(ls)); /* <= 15 + 5 */
-                                    cw = s_code_d[ds];
-                                    cl = cw >> 16;
-                                    bw.put((cw & 0xffff) | ((rec >> 15) << cl), cl + dist_extra_bits(ds)); /* <= 15 + 13 */
-                                }
+                                uint32_t idx, ev, eb;
+                                token_code(s_tok[k], s_rec, idx, ev, eb);
+                                uint32_t cw = s_code_ll[idx]; /* distance codes follow the 288 literal/length codes */
+                                uint32_t cl = cw >> 16;
+                                bw.put((cw & 0xffff) | (ev << cl), cl + eb); /* <= 15 + 13 bits */
                             }
                             bw.finish();
                         }
