@@ -373,7 +373,7 @@ def run_ours(args, rank, world, local_rank):
                 "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": shard, "ms_per_launch": round(kms, 4)}
     cpu = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:  # reported baseline: rank 0 at N=1 only
         import refshim
         if refshim.ref_available():
             nb = min(args.cpu_sample_mib << 20, shard)

@@ -125,8 +125,8 @@ __device__ __forceinline__ uint32_t dist_extra_bits(uint32_t dsym) { return dsym
  * idx = index into the concatenated code table (288 literal/length codes, then 32 distance codes),
  * ev / eb = extra-bits value / count. Literal entries carry the byte; for them the record load reads an
  * unrelated but valid word and the selects discard it. */
-__device__ __forceinline__ void token_code(uint32_t e, const uint32_t *s_rec, uint32_t &idx, uint32_t &ev, uint32_t &eb) {
-    const uint32_t rec = s_rec[e & 0x1fffu];
+__device__ __forceinline__ void token_code(uint32_t e, const Smem &sm, uint32_t &idx, uint32_t &ev, uint32_t &eb) {
+    const uint32_t rec = sm.ld32(DF_OFF_REC + (e & 0x1fffu) * 4);
     const bool isrec = (e & DF_TOK_MATCH) != 0, isdist = (e & DF_TOK_DIST) != 0;
     const uint32_t ls = rec & 31, ds = (rec >> 10) & 31;
     const uint32_t sym = isdist ? 288u + ds : 257u + ls;
@@ -149,22 +149,22 @@ __device__ __forceinline__ void stage_put(uint32_t *stage, uint32_t pos, uint32_
 /* per-thread bit packer: first word of the range by atomicOr (shared with the previous thread), words it
  * fills completely by plain store, the trailing partial word by atomicOr */
 struct BitWriter {
-    uint32_t *stage;
+    Smem sm;
     uint64_t acc;
-    uint32_t nb, w;
-    __device__ __forceinline__ void init(uint32_t *st, uint32_t bitoff) {
-        stage = st; w = bitoff >> 5; nb = bitoff & 31; acc = 0;
+    uint32_t nb, wa; /* wa = byte offset of the current staging word */
+    __device__ __forceinline__ void init(const Smem &s, uint32_t bitoff) {
+        sm = s; wa = DF_OFF_STAGE + (bitoff >> 5) * 4; nb = bitoff & 31; acc = 0;
     }
     __device__ __forceinline__ void put(uint32_t v, uint32_t n) {
         acc |= (uint64_t)v << nb;
         nb += n;
         if (nb >= 32) { /* short body: predicated, no divergence */
-            atomicOr(&stage[w], (uint32_t)acc);
-            acc >>= 32; nb -= 32; w++;
+            sm.red_or32(wa, (uint32_t)acc);
+            acc >>= 32; nb -= 32; wa += 4;
         }
     }
     __device__ __forceinline__ void finish() {
-        if (nb > 0) atomicOr(&stage[w], (uint32_t)acc);
+        if (nb > 0) sm.red_or32(wa, (uint32_t)acc);
     }
 };
 
@@ -569,11 +569,10 @@ __device__ __forceinline__ void emit_block_header(uint32_t *stage, uint32_t pos,
 /* ---- A: match finding ---------------------------------------------------------------------------------- */
 /* longest match of in[p..] against in[cand..], both inside the chunk, at most maxlen bytes;
  * first 4 bytes already known equal */
-__device__ __forceinline__ uint32_t extend_match(const uint8_t *s_in, uint32_t cand, uint32_t p, uint32_t maxlen) {
+__device__ __forceinline__ uint32_t extend_match(const Smem &sm, uint32_t cand, uint32_t p, uint32_t maxlen) {
     uint32_t len = 4;
     while (len < maxlen) {
-        uint32_t a = load32u(s_in, p + len), b = load32u(s_in, cand + len);
-        uint32_t x = a ^ b;
+        uint32_t x = sm.ld32u(DF_OFF_IN, p + len) ^ sm.ld32u(DF_OFF_IN, cand + len);
         if (x) {
             len += (uint32_t)(__ffs((int)x) - 1) >> 3;
             break;
@@ -587,31 +586,31 @@ __device__ __forceinline__ uint32_t hash4(uint32_t v, int bits) { return (v * 26
 
 /* find the best match at p among the bucket's candidates and insert p; returns len (0 = none) */
 template <int WAYS>
-__device__ __forceinline__ uint32_t find_match(const uint8_t *s_in, uint16_t *s_hash, uint32_t p, uint32_t limit, uint32_t &best_dist) {
-    uint32_t v = load32u(s_in, p);
+__device__ __forceinline__ uint32_t find_match(const Smem &sm, uint32_t p, uint32_t limit, uint32_t &best_dist) {
+    uint32_t v = sm.ld32u(DF_OFF_IN, p);
     uint32_t maxlen = limit - p;
     if (maxlen > 258) maxlen = 258;
     uint32_t best = 0;
     best_dist = 0;
     if (WAYS == 1) {
-        uint32_t h = hash4(v, 14);
-        uint32_t cand = s_hash[h];
-        s_hash[h] = (uint16_t)p;
-        if (cand < p && p - cand <= 32768u && load32u(s_in, cand) == v) {
-            best = extend_match(s_in, cand, p, maxlen);
+        uint32_t ha = DF_OFF_HASH + hash4(v, 14) * 2;
+        uint32_t cand = sm.ld16(ha);
+        sm.st16(ha, p);
+        if (cand < p && p - cand <= 32768u && sm.ld32u(DF_OFF_IN, cand) == v) {
+            best = extend_match(sm, cand, p, maxlen);
             best_dist = p - cand;
         }
     } else {
         constexpr int hb = WAYS == 2 ? 13 : 12;
-        uint32_t h = hash4(v, hb) * (uint32_t)WAYS;
+        uint32_t ha = DF_OFF_HASH + hash4(v, hb) * (uint32_t)(WAYS * 2);
         uint32_t prev_slot = p;
 #pragma unroll
         for (int wy = 0; wy < WAYS; wy++) {
-            uint32_t cand = s_hash[h + wy];
-            s_hash[h + wy] = (uint16_t)prev_slot; /* FIFO: newest first */
+            uint32_t cand = sm.ld16(ha + 2 * wy);
+            sm.st16(ha + 2 * wy, prev_slot); /* FIFO: newest first */
             prev_slot = cand;
-            if (cand < p && p - cand <= 32768u && load32u(s_in, cand) == v) {
-                uint32_t l = extend_match(s_in, cand, p, maxlen);
+            if (cand < p && p - cand <= 32768u && sm.ld32u(DF_OFF_IN, cand) == v) {
+                uint32_t l = extend_match(sm, cand, p, maxlen);
                 if (l > best) { best = l; best_dist = p - cand; }
             }
         }
@@ -656,6 +655,8 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deflate_chunks_kernel(DeflatePa
     __syncthreads();
 #endif
     const uint32_t tid = threadIdx.x;
+    Smem sm;
+    sm.init(smem);
 
     for (uint32_t chunk = blockIdx.x; chunk < P.nchunks; chunk += gridDim.x) {
         /* ---- locate the chunk -------------------------------------------------------------- */
@@ -732,9 +733,9 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deflate_chunks_kernel(DeflatePa
                 while (p < seg_end) {
                     uint32_t mlen = 0, mdist = 0;
                     if (p + DF_MINMATCH <= sb_end) {
-                        mlen = find_match<WAYS>(s_in, s_hash, p, sb_end, mdist);
+                        mlen = find_match<WAYS>(sm, p, sb_end, mdist);
                         if (LAZY && mlen >= DF_MINMATCH && mlen < 32 && p + 1 < seg_end && p + 1 + DF_MINMATCH <= sb_end) {
-                            uint32_t d2, l2 = find_match<WAYS>(s_in, s_hash, p + 1, sb_end, d2);
+                            uint32_t d2, l2 = find_match<WAYS>(sm, p + 1, sb_end, d2);
                             if (l2 > mlen) { /* literal now, better match next */
                                 p += 1;
                                 mlen = l2;
@@ -742,13 +743,11 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deflate_chunks_kernel(DeflatePa
                             }
                         }
                     }
-                    if (mlen >= DF_MINMATCH && nrec < DF_MAXREC) {
-                        s_rec[nrec * DF_THREADS + tid] = (p - seg_start) | ((mlen - 3) << 5) | ((mdist - 1) << 13);
-                        nrec++;
-                        p += mlen;
-                    } else {
-                        p += 1;
-                    }
+                    /* at most 8 matches of >= 4 bytes start inside a 32-byte span, so nrec cannot overflow */
+                    const bool ism = mlen >= DF_MINMATCH;
+                    if (ism) sm.st32(DF_OFF_REC + (nrec * DF_THREADS + tid) * 4, (p - seg_start) | ((mlen - 3) << 5) | ((mdist - 1) << 13));
+                    nrec += ism ? 1u : 0u;
+                    p += ism ? mlen : 1u;
                 }
                 /* ---- B: cover = where earlier threads' matches end ------------------------------ */
                 const uint32_t cover = block_excl_max(p, sb_start, s_scan);
@@ -810,16 +809,19 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deflate_chunks_kernel(DeflatePa
                         }
                         for (uint32_t q = 0; q < strad_cnt; q++) s_tok[o++] = s_in[strad_pos + q];
                         uint32_t mm = litmask | keptrec;
+                        uint32_t oa = DF_OFF_TOK + o * 2;
                         while (mm) {
                             uint32_t b = (uint32_t)__ffs((int)mm) - 1;
                             mm &= mm - 1;
-                            uint32_t e = s_in[seg_start + b];
+                            uint32_t e = sm.ld8(DF_OFF_IN + seg_start + b);
                             if ((keptrec >> b) & 1u) {
                                 e = DF_TOK_MATCH | ((uint32_t)__popc(recmask & ((1u << b) - 1)) * DF_THREADS + tid);
-                                s_tok[o++] = (uint16_t)e; /* length code word, then the distance code word */
+                                sm.st16(oa, e); /* length code word, then the distance code word */
+                                oa += 2;
                                 e |= DF_TOK_DIST;
                             }
-                            s_tok[o++] = (uint16_t)e;
+                            sm.st16(oa, e);
+                            oa += 2;
                         }
                         /* ---- C (matches): this thread's kept records -> symbol form + histograms ------------- */
                         uint32_t mk = keptrec;
@@ -846,8 +848,8 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deflate_chunks_kernel(DeflatePa
                     __syncthreads();
                     /* ---- C (literals): threads stride over the list ------------------------------------------ */
                     for (uint32_t k = tid; k < ntok; k += DF_THREADS) {
-                        uint32_t e = s_tok[k];
-                        if (!(e & DF_TOK_MATCH)) atomicAdd(&s_hist_ll[e], 1u);
+                        uint32_t e = sm.ld16(DF_OFF_TOK + k * 2);
+                        if (!(e & DF_TOK_MATCH)) sm.red_add32(DF_OFF_HIST + e * 4, 1u);
                     }
                     if (tid == 0) s_hist_ll[256] = 1;
                     __syncthreads();
@@ -861,8 +863,8 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deflate_chunks_kernel(DeflatePa
                     uint32_t mybits = 0;
                     for (uint32_t k = k0; k < k1; k++) {
                         uint32_t idx, ev, eb;
-                        token_code(s_tok[k], s_rec, idx, ev, eb);
-                        mybits += (s_code_ll[idx] >> 16) + eb;
+                        token_code(sm.ld16(DF_OFF_TOK + k * 2), sm, idx, ev, eb);
+                        mybits += (sm.ld32(DF_OFF_CODE + idx * 4) >> 16) + eb;
                     }
                     uint32_t tokbits;
                     uint32_t myoff = block_excl_sum(mybits, s_scan, tokbits);
@@ -878,11 +880,11 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deflate_chunks_kernel(DeflatePa
                         emit_block_header(s_stage, bitpos, bfinal, s_lens_ll, s_lens_d, tid);
                         if (mybits) {
                             BitWriter bw;
-                            bw.init(s_stage, base + myoff);
+                            bw.init(sm, base + myoff);
                             for (uint32_t k = k0; k < k1; k++) {
                                 uint32_t idx, ev, eb;
-                                token_code(s_tok[k], s_rec, idx, ev, eb);
-                                uint32_t cw = s_code_ll[idx]; /* distance codes follow the 288 literal/length codes */
+                                token_code(sm.ld16(DF_OFF_TOK + k * 2), sm, idx, ev, eb);
+                                uint32_t cw = sm.ld32(DF_OFF_CODE + idx * 4); /* distance codes follow the 288 literal/length codes */
                                 uint32_t cl = cw >> 16;
                                 bw.put((cw & 0xffff) | (ev << cl), cl + eb); /* <= 15 + 13 bits */
                             }

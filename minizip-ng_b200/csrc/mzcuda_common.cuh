@@ -42,6 +42,52 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4 *p) {
 #endif
 }
 
+
+/* Explicit shared-state-space accessors for the hot loops. Going through generic pointers derived from
+ * `extern __shared__` makes nvcc re-derive the shared window base (S2R SR_CgaCtaId + LEA) at most uses;
+ * one 32-bit shared address kept in a register and ld.shared/st.shared on it avoids that. Under the CPU
+ * emulator the "address" is a byte offset into the emulated dynamic shared memory. */
+struct Smem {
+#ifdef MZ_EMU
+    uint8_t *b;
+    __device__ __forceinline__ void init(uint8_t *base) { b = base; }
+    __device__ __forceinline__ uint32_t ld32(uint32_t off) const { return *(const uint32_t *)(b + off); }
+    __device__ __forceinline__ uint32_t ld16(uint32_t off) const { return *(const uint16_t *)(b + off); }
+    __device__ __forceinline__ uint32_t ld8(uint32_t off) const { return b[off]; }
+    __device__ __forceinline__ void st32(uint32_t off, uint32_t v) const { *(uint32_t *)(b + off) = v; }
+    __device__ __forceinline__ void st16(uint32_t off, uint32_t v) const { *(uint16_t *)(b + off) = (uint16_t)v; }
+    __device__ __forceinline__ void red_or32(uint32_t off, uint32_t v) const { *(uint32_t *)(b + off) |= v; }
+    __device__ __forceinline__ void red_add32(uint32_t off, uint32_t v) const { *(uint32_t *)(b + off) += v; }
+#else
+    uint32_t b;
+    __device__ __forceinline__ void init(uint8_t *base) { b = (uint32_t)__cvta_generic_to_shared(base); }
+    __device__ __forceinline__ uint32_t ld32(uint32_t off) const {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(b + off));
+        return v;
+    }
+    __device__ __forceinline__ uint32_t ld16(uint32_t off) const {
+        uint32_t v;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(b + off));
+        return v;
+    }
+    __device__ __forceinline__ uint32_t ld8(uint32_t off) const {
+        uint32_t v;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(b + off));
+        return v;
+    }
+    __device__ __forceinline__ void st32(uint32_t off, uint32_t v) const { asm volatile("st.shared.u32 [%0], %1;" ::"r"(b + off), "r"(v) : "memory"); }
+    __device__ __forceinline__ void st16(uint32_t off, uint32_t v) const { asm volatile("st.shared.u16 [%0], %1;" ::"r"(b + off), "r"(v) : "memory"); }
+    __device__ __forceinline__ void red_or32(uint32_t off, uint32_t v) const { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(b + off), "r"(v) : "memory"); }
+    __device__ __forceinline__ void red_add32(uint32_t off, uint32_t v) const { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(b + off), "r"(v) : "memory"); }
+#endif
+    /* unaligned little-endian 32-bit load at byte offset `off + p` (region base `off` is 4-byte aligned) */
+    __device__ __forceinline__ uint32_t ld32u(uint32_t off, uint32_t p) const {
+        uint32_t a = off + (p & ~3u);
+        return __funnelshift_r(ld32(a), ld32(a + 4), (p & 3u) * 8u);
+    }
+};
+
 /* named barrier over the first `nthreads` threads' worth of warps (id 1..15; 0 is __syncthreads) */
 __device__ __forceinline__ void bar_sync(int id, int nthreads) {
 #ifdef MZ_EMU
