@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-sample-mib", type=int, default=2048)
+    ap.add_argument("--sub-batches", type=int, default=4, help="pieces per shard when N>1 (all-gather of piece j overlaps compression of j+1)")
     return ap.parse_args()
 
 
@@ -239,46 +240,57 @@ def run_ours(args, rank, world, local_rank):
         k = min(seg, shard - o)
         pkg.check(lib.mz_cuda_textgen(src.data_ptr() + o, k, 1000 + (c0 * 65536 + o) // seg, None), "textgen")
     torch.cuda.synchronize()
-    batch = pkg.DeflateBatch(shard)
-    is_last = rank == world - 1
+    # ---- sub-batches: with N>1 the shard is compressed in NB pieces so the all-gather of piece j overlaps the compression of j+1
+    NB = 1 if world == 1 else max(1, args.sub_batches)
+    nshard_chunks = c1 - c0
+    bounds = [nshard_chunks * j // NB for j in range(NB + 1)]
+    subs = [(bounds[j] * 65536, (bounds[j + 1] - bounds[j]) * 65536) for j in range(NB)]  # (byte offset in shard, bytes)
+    batches = [pkg.DeflateBatch(max(nb, 65536)) for _, nb in subs]
     stream = torch.cuda.current_stream()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * (args.steps + args.warmup) + 4)]
-    gathered = None
-    if world > 1:
-        cap = int(batch.stride) * batch.max_chunks
-        meta_local = torch.empty(2, dtype=torch.int64, device=dev)
-        meta_all = torch.empty(2 * world, dtype=torch.int64, device=dev)
+    comm_stream = torch.cuda.Stream() if world > 1 else None
+    ev_done = [torch.cuda.Event() for _ in range(NB)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    state = {"cap": None, "gathered": [None] * NB, "tbl_all": None}
 
-    def step(i, timed_kernel_events=None):
-        n = batch.nchunks(shard)
+    def compress_sub(j, kev=None):
+        off, nb = subs[j]
+        b = batches[j]
+        n = b.nchunks(nb)
         s = pkg._stream_ptr()
-        if timed_kernel_events is not None:
-            timed_kernel_events[0].record(stream)
-        pkg.check(lib.mz_cuda_deflate_chunks(src.data_ptr(), shard, 65536, None, None, None, n, pkg.FLAG_FINAL if is_last else 0, args.level,
-                                             batch.slots.data_ptr(), batch.stride, batch.out_len.data_ptr(), s), "deflate")
-        if timed_kernel_events is not None:
-            timed_kernel_events[1].record(stream)
-        pkg.check(lib.mz_cuda_crc32_segments(src.data_ptr(), shard, 65536, None, None, n, batch.residue.data_ptr(), batch.chunk_crc.data_ptr(), s), "crc")
-        pkg.check(lib.mz_cuda_crc32_fold(batch.residue.data_ptr(), n, 65536, shard, batch.crc_out.data_ptr(), s), "fold")
-        pkg.check(lib.mz_cuda_concat(batch.slots.data_ptr(), batch.stride, batch.out_len.data_ptr(), n, batch.offsets.data_ptr(),
-                                     batch.joined.data_ptr(), s), "concat")
-        launches = 5
-        if world > 1:
-            # one all-gather of the joined bitstreams (padded to the largest shard) + one of the per-chunk tables
-            nonlocal gathered
-            meta_local[0] = batch.offsets[n]
-            meta_local[1] = n
-            dist.all_gather_into_tensor(meta_all, meta_local)
-            mx = int(meta_all.view(world, 2)[:, 0].max().item())
-            mx = (mx + 255) // 256 * 256
-            if gathered is None or gathered.numel() < mx * world:
-                gathered = torch.empty(mx * world, dtype=torch.uint8, device=dev)
-            dist.all_gather_into_tensor(gathered[:mx * world], batch.joined[:mx])
-            tbl = torch.stack([batch.chunk_crc[:n].to(torch.int64), batch.out_len[:n].to(torch.int64)], 1)
-            tbl_all = torch.empty((world,) + tuple(tbl.shape), dtype=torch.int64, device=dev) if c1 - c0 == nchunks_total // world else None
-            if tbl_all is not None:
-                dist.all_gather_into_tensor(tbl_all, tbl)
-            launches += 3
+        final = pkg.FLAG_FINAL if (rank == world - 1 and j == NB - 1) else 0  # only the globally last chunk carries BFINAL
+        base = src.data_ptr() + off
+        if kev is not None:
+            kev[0].record(stream)
+        pkg.check(lib.mz_cuda_deflate_chunks(base, nb, 65536, None, None, None, n, final, args.level, b.slots.data_ptr(), b.stride,
+                                             b.out_len.data_ptr(), s), "deflate")
+        if kev is not None:
+            kev[1].record(stream)
+        pkg.check(lib.mz_cuda_crc32_segments(base, nb, 65536, None, None, n, b.residue.data_ptr(), b.chunk_crc.data_ptr(), s), "crc")
+        pkg.check(lib.mz_cuda_crc32_fold(b.residue.data_ptr(), n, 65536, nb, b.crc_out.data_ptr(), s), "fold")
+        pkg.check(lib.mz_cuda_concat(b.slots.data_ptr(), b.stride, b.out_len.data_ptr(), n, b.offsets.data_ptr(), b.joined.data_ptr(), s), "concat")
+        return 5
+
+    def step(kevs=None):
+        launches = 0
+        for j in range(NB):
+            launches += compress_sub(j, kevs[j] if kevs else None)
+            if world > 1 and state["cap"] is not None:
+                ev_done[j].record(stream)
+                with torch.cuda.stream(comm_stream):
+                    comm_stream.wait_event(ev_done[j])
+                    # THE collective of the path: every rank's joined bitstream of piece j (fixed capacity, sized in warm-up)
+                    dist.all_gather_into_tensor(state["gathered"][j], batches[j].joined[:state["cap"]])
+                launches += 1
+        if world > 1 and state["cap"] is not None:
+            with torch.cuda.stream(comm_stream):
+                comm_stream.wait_event(ev_done[NB - 1])
+                tbl = torch.cat([torch.stack([b.chunk_crc[:b.nchunks(nb)], b.out_len[:b.nchunks(nb)], b.offsets[:b.nchunks(nb)].to(torch.int32)], 1)
+                                 for b, (_, nb) in zip(batches, subs)]).contiguous()
+                if state["tbl_all"] is None:
+                    state["tbl_all"] = torch.empty((world * tbl.shape[0], 3), dtype=torch.int32, device=dev)
+                dist.all_gather_into_tensor(state["tbl_all"], tbl)  # per-chunk {crc32, out_len, offset} table
+            stream.wait_stream(comm_stream)
+            launches += 1
         return launches
 
     def barrier():
@@ -286,26 +298,47 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(args.warmup):
-        step(i)
+    def piece_totals():
+        return [int(b.offsets[b.nchunks(nb)].item()) for b, (_, nb) in zip(batches, subs)]
+
+    # warm-up: first pass sizes the gather slabs (max piece over all ranks + margin), the rest run the full pipeline
+    step()
     barrier()
-    # verify once (outside timing): the stream round-trips and the CRC matches an independent computation
-    n = batch.nchunks(shard)
-    comp_bytes = int(batch.offsets[n].item())
-    crc_whole = int(batch.crc_out[1].item()) & 0xFFFFFFFF
+    if world > 1:
+        mx = torch.tensor([max(piece_totals())], dtype=torch.int64, device=dev)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        state["cap"] = (int(mx.item()) * 51 // 50 + 4096 + 255) // 256 * 256
+        for j in range(NB):
+            state["gathered"][j] = torch.empty(state["cap"] * world, dtype=torch.uint8, device=dev)
+    for i in range(max(0, args.warmup - 1) + (1 if world > 1 else 0)):
+        step()
+    barrier()
+    totals = piece_totals()
+    comp_bytes = sum(totals)
+    # CRC of the shard = fold of the pieces' CRCs (host arithmetic); rank 0 reports its own shard's
+    crc_whole = 0
+    for j, (b, (_, nb)) in enumerate(zip(batches, subs)):
+        c = int(b.crc_out[1].item()) & 0xFFFFFFFF
+        crc_whole = c if j == 0 else lib.mz_cuda_crc32_combine(crc_whole, c, nb)
     clocks = ClockSampler(local_rank)
     clocks.start()
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(NB)] for _ in range(args.steps)]
     barrier()
     ev[0].record(stream)
     launches = 0
     for i in range(args.steps):
-        launches += step(i, kev[i])
+        launches += step(kev[i])
     ev[1].record(stream)
     barrier()
     ms = ev[0].elapsed_time(ev[1])
-    kms = sum(a.elapsed_time(b) for a, b in kev) / max(1, args.steps)
+    kms = sum(a.elapsed_time(b) for row in kev for a, b in row) / max(1, args.steps)
     clk = clocks.stop()
+    if world > 1:
+        assert max(piece_totals()) <= state["cap"], "gather slab too small"
+        # the gathered slabs really hold every rank's stream: spot-check piece 0 of the next rank against the table
+        nxt = (rank + 1) % world
+        rows = state["tbl_all"].view(world, -1, 3)[nxt]
+        assert int(rows[0, 2]) == 0 and int(rows[0, 1]) > 0
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -366,12 +399,13 @@ def run_ours(args, rank, world, local_rank):
     if os.path.exists(tp):
         try:
             traffic = json.load(open(tp)).get("dram_bytes_per_input_byte")
-            traffic = None if traffic is None else round(traffic * shard)
+            traffic = None if traffic is None else round(traffic * shard / NB)
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": "deflate_chunks_kernel", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": shard, "ms_per_launch": round(kms, 4)}
+                "algorithmic_bytes_per_launch": shard // NB, "ms_per_launch": round(kms / NB, 4), "launches_per_step": NB,
+                "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per input byte x bytes per launch (profiles/r1_deflate_kernel.json)"}
     cpu = None
     if not args.no_cpu and world == 1:  # reported baseline: rank 0 at N=1 only
         import refshim
@@ -392,7 +426,7 @@ def run_ours(args, rank, world, local_rank):
         "data": "synthetic",
         "config": {"workload": "C5: %.2f GiB enwik-style buffer, independent 64 KiB chunks, DEFLATE level %d + CRC-32 per chunk + fold + join" % (total / GiB, args.level),
                    "chunk_bytes": 65536, "level": args.level, "l2": "inputs (%.1f GiB per GPU) are far larger than L2; no flush needed" % (shard / GiB),
-                   "parallelism": "chunk-sharded x%d, one NCCL all-gather of bitstreams + per-chunk table" % world if world > 1 else "single GPU"},
+                   "parallelism": ("chunk-sharded x%d; per step one NCCL all-gather of the bitstreams (in %d pieces overlapped with compression) + one of the per-chunk {crc,len,offset} table" % (world, NB)) if world > 1 else "single GPU"},
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clk, "e2e": e2e, "gpu_launches": launches,
         "ratio": round(comp_bytes / shard, 4), "crc32": "%08x" % crc_whole,
     }
