@@ -67,7 +67,7 @@ constexpr int DF_OFF_MISC = DF_OFF_BB + 512 * 4;                /* u32[32] + mba
 constexpr int DF_SMEM_BYTES = DF_OFF_MISC + 32 * 4 + 16;
 static_assert(DF_SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
-enum { MISC_HDRBITS = 1, MISC_E0 = 2, MISC_BLCNT = 8 /* 16 words */ };
+enum { MISC_HDRBITS = 1, MISC_E0 = 2, MISC_CHUNK = 3, MISC_BLCNT = 8 /* 16 words */ };
 
 struct DeflateParams {
     const uint8_t *in;       /* device base of the uncompressed bytes */
@@ -82,6 +82,7 @@ struct DeflateParams {
     uint8_t *out;            /* slot i at out + i * slot_stride (16-byte aligned) */
     uint64_t slot_stride;
     uint32_t *out_len;       /* per-chunk compressed bytes */
+    uint32_t *work_counter;  /* zeroed before launch: CTAs take chunks dynamically (NULL = static striding) */
 };
 
 __host__ __device__ inline uint64_t deflate_slot_bound(uint32_t chunk_size) {
@@ -658,7 +659,16 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deflate_chunks_kernel(DeflatePa
     Smem sm;
     sm.init(smem);
 
-    for (uint32_t chunk = blockIdx.x; chunk < P.nchunks; chunk += gridDim.x) {
+    /* Chunks are handed out by an atomic counter: if another kernel (e.g. an NCCL all-gather overlapped with this
+     * one) holds some SMs, the resident CTAs simply take more chunks instead of leaving a tail to late CTAs. */
+    for (uint32_t chunk_static = blockIdx.x;; chunk_static += gridDim.x) {
+        uint32_t chunk = chunk_static;
+        if (P.work_counter) {
+            if (tid == 0) s_misc[MISC_CHUNK] = atomicAdd(P.work_counter, 1u);
+            __syncthreads();
+            chunk = s_misc[MISC_CHUNK];
+        }
+        if (chunk >= P.nchunks) break;
         /* ---- locate the chunk -------------------------------------------------------------- */
         uint64_t off;
         uint32_t len, flags;

@@ -21,6 +21,9 @@ namespace mzc {
 constexpr int INF_PB = 11;  /* primary lit/len table bits */
 constexpr int INF_DB = 9;   /* primary distance table bits */
 constexpr int INF_THREADS = 32;
+constexpr uint32_t INF_IN_RING = 4096;    /* compressed-input window in shared memory (bytes, power of two) */
+constexpr uint32_t INF_OUT_RING = 65536;  /* output ring in shared memory: 32 KiB of LZ77 history + unflushed output */
+constexpr uint32_t INF_FLUSH = 16384;     /* flush the ring to global memory when this much output is pending */
 
 enum { INF_ST_RUN = 0, INF_ST_END = 1, INF_ST_DATA_ERROR = -3, INF_ST_BUF_ERROR = -5 };
 enum { INF_PH_HEADER = 0, INF_PH_CODES = 1, INF_PH_STORED = 2 };
@@ -130,21 +133,23 @@ __device__ inline int inf_build(const uint8_t *lens, int n, uint16_t *count, uin
     return left;
 }
 
-struct InfBits { /* lane 0 only */
-    const uint8_t *in;
-    uint64_t pos;    /* next byte index (relative to in) to load */
-    uint64_t avail;  /* valid bytes */
+struct InfBits { /* lane 0 only; reads the compressed bytes from the shared-memory input ring */
+    const uint8_t *ring;
+    uint64_t pos;    /* next byte index (relative to job.in) to load into the bit buffer */
+    uint64_t avail;  /* valid bytes of the stream window (job.in_avail) */
     uint64_t bb;
     uint32_t bc;
-    __device__ __forceinline__ void init(const uint8_t *p, uint64_t avail_bytes, uint64_t rel_bitpos) {
-        in = p; avail = avail_bytes; pos = rel_bitpos >> 3; bb = 0; bc = 0;
+    __device__ __forceinline__ void init(const uint8_t *r, uint64_t avail_bytes, uint64_t rel_bitpos) {
+        ring = r; avail = avail_bytes; pos = rel_bitpos >> 3; bb = 0; bc = 0;
         refill();
         uint32_t skip = (uint32_t)(rel_bitpos & 7);
         bb >>= skip; bc -= skip;
     }
-    __device__ __forceinline__ void refill() { /* keep >= 32 bits; reads into the zero padding past avail */
+    __device__ __forceinline__ void refill() { /* keep >= 32 bits; the ring holds zero padding past avail */
         while (bc <= 32) {
-            uint32_t w = (uint32_t)in[pos] | ((uint32_t)in[pos + 1] << 8) | ((uint32_t)in[pos + 2] << 16) | ((uint32_t)in[pos + 3] << 24);
+            const uint32_t i = (uint32_t)pos;
+            uint32_t w = (uint32_t)ring[i & (INF_IN_RING - 1)] | ((uint32_t)ring[(i + 1) & (INF_IN_RING - 1)] << 8) |
+                         ((uint32_t)ring[(i + 2) & (INF_IN_RING - 1)] << 16) | ((uint32_t)ring[(i + 3) & (INF_IN_RING - 1)] << 24);
             bb |= (uint64_t)w << bc;
             pos += 4; bc += 32;
         }
@@ -156,6 +161,22 @@ struct InfBits { /* lane 0 only */
     __device__ __forceinline__ uint64_t bitpos() const { return pos * 8 - bc; }
     __device__ __forceinline__ int64_t bits_left() const { return (int64_t)(avail * 8) - (int64_t)bitpos(); }
 };
+
+/* Warp-cooperative: bring compressed bytes [loaded, ...) into the input ring, keeping everything from
+ * the byte the bit reader may still need (`keep_from`). Reads up to 16 bytes of the job's zero padding. */
+__device__ __forceinline__ uint64_t inf_fill_input(uint8_t *ring, const uint8_t *in, uint64_t keep_from, uint64_t loaded, uint64_t padded_total) {
+    uint64_t target = (keep_from & ~15ull) + INF_IN_RING;
+    if (target > padded_total) target = padded_total;
+    for (uint64_t a = loaded + lane_id(); a < target; a += 32) ring[(uint32_t)a & (INF_IN_RING - 1)] = in[a];
+    __syncwarp();
+    return target > loaded ? target : loaded;
+}
+
+/* Warp-cooperative: copy finished output [from, to) out of the shared ring into global memory (coalesced bytes) */
+__device__ __forceinline__ void inf_flush_output(const uint8_t *oring, uint8_t *out, uint64_t from, uint64_t to) {
+    for (uint64_t a = from + lane_id(); a < to; a += 32) out[a] = oring[(uint32_t)a & (INF_OUT_RING - 1)];
+    __syncwarp();
+}
 
 /* canonical bit-by-bit decode for codes longer than the primary table (lane 0) */
 __device__ inline int inf_slow_decode(InfBits &b, const uint16_t *count, const uint16_t *sorted) {
@@ -176,24 +197,30 @@ __device__ inline int inf_slow_decode(InfBits &b, const uint16_t *count, const u
     return -1;
 }
 
-/* warp-cooperative copy of a match; all source bytes of one round are already written */
-__device__ __forceinline__ void inf_copy_match(uint8_t *out, uint64_t dst, uint32_t len, uint32_t dist) {
+/* warp-cooperative copy of a match inside the shared output ring; all source bytes of one round are already written */
+__device__ __forceinline__ void inf_copy_match(uint8_t *oring, uint64_t dst, uint32_t len, uint32_t dist) {
     const unsigned lane = lane_id();
+    const uint32_t d0 = (uint32_t)dst, m = INF_OUT_RING - 1;
     if (dist < 32) {
-        for (uint32_t i = lane; i < len; i += 32) out[dst + i] = out[dst - dist + (i % dist)];
+        for (uint32_t i = lane; i < len; i += 32) oring[(d0 + i) & m] = oring[(d0 - dist + (i % dist)) & m];
     } else {
         uint32_t round = dist & ~31u;
         for (uint32_t done = 0; done < len; done += round) {
             uint32_t n = len - done < round ? len - done : round;
-            for (uint32_t i = lane; i < n; i += 32) out[dst + done + i] = out[dst + done + i - dist];
+            for (uint32_t i = lane; i < n; i += 32) oring[(d0 + done + i) & m] = oring[(d0 + done + i - dist) & m];
             __syncwarp();
         }
     }
     __syncwarp();
 }
 
+constexpr int INF_SMEM_BYTES = ((int)sizeof(InfTables) + 15) / 16 * 16 + (int)INF_IN_RING + (int)INF_OUT_RING;
+
 __global__ void __launch_bounds__(INF_THREADS) inflate_streams_kernel(const InflateJob *jobs, InflateState *states, uint32_t nstreams) {
-    __shared__ InfTables T;
+    MZ_DYN_SMEM(smem);
+    InfTables &T = *reinterpret_cast<InfTables *>(smem);
+    uint8_t *iring = smem + (sizeof(InfTables) + 15) / 16 * 16;
+    uint8_t *oring = iring + INF_IN_RING;
     const unsigned lane = lane_id();
     for (uint32_t sidx = blockIdx.x; sidx < nstreams; sidx += gridDim.x) {
         const InflateJob job = jobs[sidx];
@@ -206,7 +233,19 @@ __global__ void __launch_bounds__(INF_THREADS) inflate_streams_kernel(const Infl
         int status = INF_ST_RUN, why = INF_WHY_NONE;
         const uint64_t out_end = job.out_base + job.out_cap;
         uint8_t *out = job.out - job.out_base; /* index with absolute positions */
-        if (lane == 0) b.init(job.in, job.in_avail, st->in_bitpos - job.in_base * 8);
+        const uint64_t padded_total = job.in_avail + 16; /* the job guarantees 16 readable zero bytes past in_avail */
+        const uint64_t start_bit = st->in_bitpos - job.in_base * 8;
+        /* compressed-input window */
+        uint64_t loaded = (start_bit >> 3) & ~15ull;
+        loaded = inf_fill_input(iring, job.in, start_bit >> 3, loaded, padded_total);
+        /* output ring: bring back the LZ77 history (up to 32 KiB already in global memory) */
+        uint64_t flushed = out_pos;
+        {
+            uint64_t hist = out_pos - job.out_base < 32768 ? out_pos - job.out_base : 32768;
+            for (uint64_t a = out_pos - hist + lane; a < out_pos; a += 32) oring[(uint32_t)a & (INF_OUT_RING - 1)] = out[a];
+            __syncwarp();
+        }
+        if (lane == 0) b.init(iring, job.in_avail, start_bit);
         if (phase == INF_PH_CODES) { /* resume inside a Huffman block: rebuild the tables */
             for (int i = (int)lane; i < 320; i += 32) T.lens[i] = st->lens[i];
             __syncwarp();
@@ -216,6 +255,13 @@ __global__ void __launch_bounds__(INF_THREADS) inflate_streams_kernel(const Infl
         }
         while (status == INF_ST_RUN && why == INF_WHY_NONE) {
             if (phase == INF_PH_HEADER) {
+                /* the header is parsed by lane 0 alone: make sure the window holds it (<= ~600 bytes) */
+                {
+                    uint64_t bp = 0;
+                    if (lane == 0) bp = b.bitpos() >> 3;
+                    bp = __shfl_sync(MZ_FULL_MASK, bp, 0);
+                    if (loaded < padded_total && loaded - bp < 2048) loaded = inf_fill_input(iring, job.in, bp, loaded, padded_total);
+                }
                 /* a dynamic header is at most 14 + 57 + 320*(7+7) bits ~ 570 bytes: wait for it unless final */
                 int ok = 1, err = 0;
                 uint32_t type = 0;
@@ -346,7 +392,9 @@ __global__ void __launch_bounds__(INF_THREADS) inflate_streams_kernel(const Infl
                     break;
                 }
             } else if (phase == INF_PH_STORED) {
-                /* raw copy: bounded by the input and output windows */
+                /* raw copy, bounded by the input and output windows; the bytes go to global memory directly and
+                 * into the ring (they are history for later matches) */
+                inf_flush_output(oring, out, flushed, out_pos);
                 uint64_t ib = 0;
                 if (lane == 0) ib = b.bitpos() >> 3; /* byte aligned here */
                 ib = __shfl_sync(MZ_FULL_MASK, ib, 0);
@@ -355,11 +403,18 @@ __global__ void __launch_bounds__(INF_THREADS) inflate_streams_kernel(const Infl
                 uint32_t n = stored_rem;
                 if (n > in_left) n = (uint32_t)in_left;
                 if (n > out_left) n = (uint32_t)out_left;
-                for (uint32_t i = lane; i < n; i += 32) out[out_pos + i] = job.in[ib + i];
+                for (uint32_t i = lane; i < n; i += 32) {
+                    uint8_t v = job.in[ib + i];
+                    out[out_pos + i] = v;
+                    if (n - i <= 32768) oring[(uint32_t)(out_pos + i) & (INF_OUT_RING - 1)] = v; /* only the last 32 KiB can matter */
+                }
                 __syncwarp();
                 out_pos += n;
+                flushed = out_pos;
                 stored_rem -= n;
-                if (lane == 0) b.init(job.in, job.in_avail, (ib + n) * 8);
+                loaded = ((ib + n) & ~15ull);
+                loaded = inf_fill_input(iring, job.in, ib + n, loaded, padded_total);
+                if (lane == 0) b.init(iring, job.in_avail, (ib + n) * 8);
                 if (stored_rem == 0) {
                     phase = INF_PH_HEADER;
                     blocks++;
@@ -372,11 +427,14 @@ __global__ void __launch_bounds__(INF_THREADS) inflate_streams_kernel(const Infl
                     why = INF_WHY_INPUT;
                 }
             } else { /* INF_PH_CODES */
-                uint32_t ev = 0, mlen = 0, mdist = 0; /* ev: 1 match, 2 end of block, 3 need input, 4 need output, <0 error */
+                /* ev: 1 match, 2 end of block, 3 need input, 4 need output, 5 refill the input window, 6 flush the ring, <0 error */
+                uint32_t ev = 0, mlen = 0, mdist = 0;
                 if (lane == 0) {
                     for (;;) {
                         if (b.bits_left() < 0) { ev = (uint32_t)INF_ST_BUF_ERROR; break; } /* truncated */
                         if (!job.in_final && b.bits_left() < 64) { ev = 3; break; }
+                        if (b.pos + 16 > loaded && loaded < padded_total) { ev = 5; break; }
+                        if (out_pos - flushed >= INF_FLUSH) { ev = 6; break; }
                         /* near the end of the output window: remember the reader so a symbol that does
                          * not fit can be un-read */
                         const bool tight = out_pos + 258 > out_end;
@@ -393,7 +451,8 @@ __global__ void __launch_bounds__(INF_THREADS) inflate_streams_kernel(const Infl
                         }
                         if (sym < 256) {
                             if (tight && out_pos >= out_end) { b = saved; ev = 4; break; }
-                            out[out_pos++] = (uint8_t)sym;
+                            oring[(uint32_t)out_pos & (INF_OUT_RING - 1)] = (uint8_t)sym;
+                            out_pos++;
                             continue;
                         }
                         if (sym == 256) { ev = 2; break; }
@@ -423,11 +482,11 @@ __global__ void __launch_bounds__(INF_THREADS) inflate_streams_kernel(const Infl
                 }
                 ev = __shfl_sync(MZ_FULL_MASK, ev, 0);
                 out_pos = __shfl_sync(MZ_FULL_MASK, out_pos, 0);
+                __syncwarp();
                 if (ev == 1) {
                     mlen = __shfl_sync(MZ_FULL_MASK, mlen, 0);
                     mdist = __shfl_sync(MZ_FULL_MASK, mdist, 0);
-                    __syncwarp();
-                    inf_copy_match(out, out_pos, mlen, mdist);
+                    inf_copy_match(oring, out_pos, mlen, mdist);
                     out_pos += mlen;
                 } else if (ev == 2) {
                     phase = INF_PH_HEADER;
@@ -437,13 +496,22 @@ __global__ void __launch_bounds__(INF_THREADS) inflate_streams_kernel(const Infl
                     why = INF_WHY_INPUT;
                 } else if (ev == 4) {
                     why = INF_WHY_OUTPUT;
+                } else if (ev == 5) {
+                    uint64_t bp = 0;
+                    if (lane == 0) bp = b.bitpos() >> 3;
+                    bp = __shfl_sync(MZ_FULL_MASK, bp, 0);
+                    loaded = inf_fill_input(iring, job.in, bp, loaded, padded_total);
+                } else if (ev == 6) {
+                    inf_flush_output(oring, out, flushed, out_pos);
+                    flushed = out_pos;
                 } else {
                     status = (int)ev;
                 }
             }
         }
-        /* ---- save state ------------------------------------------------------------------------- */
+        /* ---- write back what is still in the ring, save state ----------------------------------------- */
         __syncwarp();
+        inf_flush_output(oring, out, flushed, out_pos);
         if (phase == INF_PH_CODES && status == INF_ST_RUN)
             for (int i = (int)lane; i < 320; i += 32) st->lens[i] = T.lens[i];
         if (lane == 0) {

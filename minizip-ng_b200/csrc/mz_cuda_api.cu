@@ -34,6 +34,8 @@ struct DeviceCtx {
     uint32_t *d_word_off = nullptr;
     uint32_t nwords = 0;
     uint32_t *d_crc_scratch = nullptr; /* residues for mz_cuda_crc32_device */
+    uint32_t *d_work = nullptr;        /* ring of work counters for dynamically scheduled launches */
+    unsigned work_next = 0;
     size_t crc_scratch_n = 0;
 };
 
@@ -112,6 +114,8 @@ int32_t get_ctx(DeviceCtx **out) {
             CK(cudaFuncSetAttribute(deflate_chunks_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_SMEM_BYTES));
             CK(cudaFuncSetAttribute(deflate_chunks_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_SMEM_BYTES));
             CK(cudaFuncSetAttribute(crc32_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CRC_SMEM_BYTES));
+            CK(cudaFuncSetAttribute(inflate_streams_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, INF_SMEM_BYTES));
+            CK(cudaMalloc(&c.d_work, 256 * sizeof(uint32_t)));
             c.ready = true;
         }
     }
@@ -352,6 +356,11 @@ int32_t mz_cuda_deflate_chunks(const void *d_in, uint64_t total_len, uint32_t ch
     P.out = (uint8_t *)d_slots;
     P.slot_stride = slot_stride;
     P.out_len = d_out_len;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        P.work_counter = c->d_work + (c->work_next++ & 255u);
+    }
+    CK(cudaMemsetAsync(P.work_counter, 0, sizeof(uint32_t), (cudaStream_t)stream));
     uint32_t grid = nchunks < (uint32_t)c->sm_count ? nchunks : (uint32_t)c->sm_count;
     const int ways = deflate_ways_for_level(level);
     const bool lazy = deflate_lazy_for_level(level);
@@ -387,9 +396,9 @@ int32_t mz_cuda_inflate_streams(const mz_cuda_inflate_job *d_jobs, mz_cuda_infla
     int32_t err = get_ctx(&c);
     if (err) return err;
     if (nstreams == 0) return MZ_OK;
-    uint32_t maxgrid = (uint32_t)c->sm_count * 32u;
+    uint32_t maxgrid = (uint32_t)c->sm_count * 3u; /* 3 single-warp CTAs of ~75 KB shared memory fit one SM */
     uint32_t grid = nstreams < maxgrid ? nstreams : maxgrid;
-    MZ_LAUNCH(inflate_streams_kernel, dim3(grid), dim3(INF_THREADS), 0, (cudaStream_t)stream, (const InflateJob *)d_jobs,
+    MZ_LAUNCH(inflate_streams_kernel, dim3(grid), dim3(INF_THREADS), INF_SMEM_BYTES, (cudaStream_t)stream, (const InflateJob *)d_jobs,
               (InflateState *)d_states, nstreams);
     CK(cudaGetLastError());
     return MZ_OK;

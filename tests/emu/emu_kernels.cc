@@ -46,6 +46,10 @@ int64_t emu_deflate(const uint8_t *in, uint64_t len, uint32_t chunk_size, int le
     P.out = sl;
     P.slot_stride = stride;
     P.out_len = out_len.data();
+    static uint32_t work_counter;
+    work_counter = 0;
+    P.work_counter = (grid & 0x80000000u) ? nullptr : &work_counter; /* high bit of grid selects static striding */
+    grid &= 0x7fffffffu;
     if (grid == 0 || grid > nchunks) grid = nchunks;
     const int ways = deflate_ways_for_level(level);
     if (ways == 1) MZ_LAUNCH((deflate_chunks_kernel<1, false>), dim3(grid), dim3(DF_THREADS), DF_SMEM_BYTES, 0, P);
@@ -114,7 +118,7 @@ int32_t emu_inflate(const uint8_t *in, uint64_t in_len, uint8_t *out, uint64_t o
         job.out_base = 0;
         job.out_cap = out_limit;
         job.in_final = fed == in_len;
-        MZ_LAUNCH(inflate_streams_kernel, dim3(1), dim3(INF_THREADS), 0, 0, (const InflateJob *)&job, &st, 1u);
+        MZ_LAUNCH(inflate_streams_kernel, dim3(1), dim3(INF_THREADS), INF_SMEM_BYTES, 0, (const InflateJob *)&job, &st, 1u);
         if (st.status != INF_ST_RUN) break;
         if (st.why == INF_WHY_INPUT) {
             if (fed == in_len) { st.status = -99; break; }

@@ -1,7 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+timeout 600 python tools/bench_inflate.py > gpurun_out/bench_inflate.log 2>&1; echo "inflate exit $?" >> gpurun_out/bench_inflate.log
 timeout 900 python bench.py > gpurun_out/bench_16g.log 2>&1; echo "bench exit $?" >> gpurun_out/bench_16g.log
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches.csv python bench.py --size-gib 1 --steps 2 --warmup 1 --no-e2e --no-cpu > gpurun_out/ncu_launches.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:deflate_chunks -s 1 -c 1 -o gpurun_out/prof_deflate python bench.py --size-gib 1 --steps 1 --warmup 1 --no-e2e --no-cpu > gpurun_out/ncu_deflate.log 2>&1
-tail -3 gpurun_out/pytest_gpu.log; tail -2 gpurun_out/bench_16g.log | cut -c1-1800
+tail -3 gpurun_out/pytest_gpu.log; cat gpurun_out/bench_inflate.log; tail -2 gpurun_out/bench_16g.log | cut -c1-900
