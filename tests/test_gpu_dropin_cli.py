@@ -1,0 +1,151 @@
+"""Drop-in proof: the REFERENCE's own `minigzip` / `minizip` programs and zip-container code, compiled where they lie
+with `mz_strm_zlib.c` left out of the link and its names aliased to `mz_stream_cuda_*` (oracle/Makefile targets
+`_ref/minigzip_cuda`, `_ref/minizip_cuda`; recipe = INTEGRATION.md 1b), must interoperate in both directions with the
+unmodified reference builds (`_ref/minigzip_ref`, `_ref/minizip_ref`) and with Python's gzip / zipfile.
+
+Call paths exercised: `minigzip.c:79-120` (create/set_prop/open/set_base/copy/close/delete, 16 KiB copy loop),
+`mz_zip.c:1771-1852` (entry open), `:2047-2064` (entry CRC via mz_crypt_crc32_update), `:2116-2160` (close + verify).
+"""
+import gzip
+import io
+import os
+import subprocess
+import zipfile
+import zlib
+
+import pytest
+
+import datagen
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REFDIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def _bin(name):
+    p = os.path.join(REFDIR, name)
+    if not os.path.exists(p):
+        pytest.skip(f"{name} not built (needs /root/reference at build time)")
+    return p
+
+
+def _run(args, cwd, ok=True):
+    r = subprocess.run(args, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+    if ok:
+        assert r.returncode == 0, (args, r.returncode, r.stdout[-600:], r.stderr[-600:])
+    return r
+
+
+def _corpus():
+    return {
+        "text.txt": datagen.text_like(3_000_000, seed=21),
+        "records.bin": datagen.binary_records(1_500_000, seed=22),
+        "random.bin": datagen.random_bytes(400_000, seed=23),
+        "mixed.dat": datagen.mixed(2_000_000, seed=24),
+        "tiny.txt": b"hello, hello, hello\n",
+        "one.bin": b"\x00",
+        "empty.bin": b"",
+    }
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("level", [1, 6, 9])
+def test_minigzip_cuda_writes_what_everyone_reads(built, tmp_path, level):
+    exe, ref = _bin("minigzip_cuda"), _bin("minigzip_ref")
+    data = datagen.text_like(5_000_000, seed=30 + level) + datagen.random_bytes(100_000, seed=3)
+    src = tmp_path / "doc.txt"
+    src.write_bytes(data)
+    r = _run([exe, f"-{level}", "doc.txt"], tmp_path)
+    assert b"Operation completed successfully" in r.stdout
+    gz = (tmp_path / "doc.txt.gz").read_bytes()
+    assert gz[:3] == b"\x1f\x8b\x08" and int.from_bytes(gz[-4:], "little") == len(data)
+    assert int.from_bytes(gz[-8:-4], "little") == zlib.crc32(data)
+    assert gzip.decompress(gz) == data
+    assert len(gz) < 0.62 * len(data)
+    out = tmp_path / "x"
+    _run([ref, "-x", "-d", "x", "doc.txt.gz"], tmp_path)
+    assert (out / "doc.txt").read_bytes() == data
+
+
+@pytest.mark.gpu
+def test_minigzip_cuda_reads_what_the_reference_and_gzip_write(built, tmp_path):
+    exe, ref = _bin("minigzip_cuda"), _bin("minigzip_ref")
+    data = datagen.mixed(6_000_000, seed=41)
+    (tmp_path / "a.bin").write_bytes(data)
+    _run([ref, "-6", "a.bin"], tmp_path)
+    _run([exe, "-x", "-d", "o1", "a.bin.gz"], tmp_path)
+    assert (tmp_path / "o1" / "a.bin").read_bytes() == data
+    buf = io.BytesIO()
+    with gzip.GzipFile(filename="named-member.bin", fileobj=buf, mode="wb", compresslevel=9, mtime=1) as f:  # FNAME header field
+        f.write(data)
+    (tmp_path / "b.bin.gz").write_bytes(buf.getvalue())
+    _run([exe, "-x", "-d", "o2", "b.bin.gz"], tmp_path)
+    assert (tmp_path / "o2" / "b.bin").read_bytes() == data
+    # corrupt one payload byte: the reference prints the stream error and exits non-zero
+    bad = bytearray(buf.getvalue())
+    bad[len(bad) // 2] ^= 0x10
+    (tmp_path / "c.bin.gz").write_bytes(bytes(bad))
+    r = _run([exe, "-x", "-d", "o3", "c.bin.gz"], tmp_path, ok=False)
+    assert r.returncode != 0 and b"Error" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("level", [1, 6])
+def test_minizip_cuda_archive_is_valid_everywhere(built, tmp_path, level):
+    exe, ref = _bin("minizip_cuda"), _bin("minizip_ref")
+    files = _corpus()
+    for name, blob in files.items():
+        (tmp_path / name).write_bytes(blob)
+    _run([exe, "-o", f"-{level}", "a.zip"] + sorted(files), tmp_path)
+    with zipfile.ZipFile(tmp_path / "a.zip") as z:
+        assert z.testzip() is None  # CRC of every member
+        assert sorted(z.namelist()) == sorted(files)
+        for name, blob in files.items():
+            info = z.getinfo(name)
+            assert z.read(name) == blob and info.CRC == zlib.crc32(blob) and info.file_size == len(blob)
+            if len(blob) > 100:
+                assert info.compress_type == zipfile.ZIP_DEFLATED
+        assert z.getinfo("text.txt").compress_size < 0.6 * len(files["text.txt"])
+    _run([ref, "-x", "-o", "-d", "out", "a.zip"], tmp_path)  # the unmodified reference extracts and CRC-checks
+    for name, blob in files.items():
+        assert (tmp_path / "out" / name).read_bytes() == blob
+
+
+@pytest.mark.gpu
+def test_minizip_cuda_extracts_foreign_archives(built, tmp_path):
+    exe, ref = _bin("minizip_cuda"), _bin("minizip_ref")
+    files = _corpus()
+    for name, blob in files.items():
+        (tmp_path / name).write_bytes(blob)
+    _run([ref, "-o", "-9", "r.zip"] + sorted(files), tmp_path)
+    _run([exe, "-x", "-o", "-d", "o1", "r.zip"], tmp_path)
+    with zipfile.ZipFile(tmp_path / "p.zip", "w", zipfile.ZIP_DEFLATED, compresslevel=6) as z:
+        for name, blob in files.items():
+            z.writestr(name, blob)
+    _run([exe, "-x", "-o", "-d", "o2", "p.zip"], tmp_path)
+    for name, blob in files.items():
+        assert (tmp_path / "o1" / name).read_bytes() == blob
+        assert (tmp_path / "o2" / name).read_bytes() == blob
+    # flip a bit inside a member's compressed data: extraction must report an error (data error or CRC mismatch)
+    raw = bytearray((tmp_path / "p.zip").read_bytes())
+    with zipfile.ZipFile(tmp_path / "p.zip") as z:
+        info = z.getinfo("text.txt")
+    raw[info.header_offset + 30 + len("text.txt") + info.compress_size // 2] ^= 0x04
+    (tmp_path / "bad.zip").write_bytes(bytes(raw))
+    r = _run([exe, "-x", "-o", "-d", "o3", "bad.zip"], tmp_path, ok=False)
+    assert r.returncode != 0 or b"Error" in r.stdout
+
+
+def test_dropin_binaries_refuse_to_run_without_a_gpu(built, tmp_path):
+    """No CPU fallback: on a box without a GPU the drop-in CLI must fail loudly rather than produce output."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("GPU present")
+    except ImportError:
+        pass
+    exe = _bin("minigzip_cuda")
+    (tmp_path / "f.txt").write_bytes(b"abc" * 1000)
+    r = _run([exe, "-6", "f.txt"], tmp_path, ok=False)
+    assert r.returncode != 0 and b"no CPU fallback" in r.stderr
+    assert not (tmp_path / "f.txt.gz").exists() or (tmp_path / "f.txt.gz").stat().st_size == 0
