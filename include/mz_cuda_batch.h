@@ -84,20 +84,44 @@ typedef struct mz_cuda_inflate_job {
     uint64_t out_base;
     uint64_t out_cap;
     uint32_t in_final;   /* no more input will follow */
-    uint32_t reserved;
+    uint32_t flags;      /* MZ_CUDA_INFLATE_STOP_AT_BLOCK: return (why = 3) after the next completed block */
 } mz_cuda_inflate_job;
+#define MZ_CUDA_INFLATE_STOP_AT_BLOCK 1u
 
 typedef struct mz_cuda_inflate_state {
     uint64_t in_bitpos;  /* consumed bits of the raw stream (TOTAL_IN = ceil(in_bitpos / 8) at END) */
     uint64_t out_pos;    /* produced bytes (TOTAL_OUT) */
     int32_t status;      /* 0 running, 1 end of stream, MZ_DATA_ERROR (-3), MZ_BUF_ERROR (-5) */
-    int32_t why;         /* when running: 1 needs input, 2 needs output space */
+    int32_t why;         /* when running: 1 needs input, 2 needs output space, 3 stopped at a block boundary */
     uint32_t phase, last_block, stored_remaining, nlit, ndist, blocks;
     uint8_t lens[320];
 } mz_cuda_inflate_state;
 
 int32_t mz_cuda_inflate_streams(const mz_cuda_inflate_job *d_jobs, mz_cuda_inflate_state *d_states, uint32_t nstreams,
                                 void *stream);
+
+/* ---- K6: one long foreign stream, segment-speculative (csrc/inflate_spec_kernel.cuh) ------------------------
+ * One ROUND decodes as much of the compressed window d_in[0..in_avail) as can be proven, starting at the block
+ * boundary `start_bit` (absolute bit; the serial decoder's state must be at a block header), into
+ * d_out[out_pos - out_base ...) up to absolute position out_end. 32 KiB of history before out_pos must be present
+ * in d_out (as for K5). The summary says how far the round got; the caller continues from there with another
+ * round or with mz_cuda_inflate_streams (which also owns every error / end-of-input decision: a round that
+ * meets anything unusual just stops early). d_in must be 4-byte aligned with 16 readable bytes past in_avail. */
+typedef struct mz_cuda_spec_summary {
+    uint64_t end_bit;    /* absolute bit position reached (a block boundary, or the end of the stream) */
+    uint64_t total_out;  /* bytes written from out_pos on */
+    uint32_t nchain;     /* segments proven and emitted; 0 = no progress, use the serial decoder */
+    int32_t status;      /* 0 running, 1 end of stream */
+    uint32_t blocks;
+    uint32_t flags;      /* != 0: internal cross-check failed, the round's output must be discarded */
+    uint32_t candidates;
+    uint32_t pad;
+} mz_cuda_spec_summary;
+uint64_t mz_cuda_inflate_spec_workspace_bytes(uint32_t max_segments);
+int32_t mz_cuda_inflate_spec_round(const void *d_in, uint64_t in_base, uint64_t in_avail, uint32_t in_final, uint64_t start_bit,
+                                   uint64_t seg_bytes, uint32_t nseg, void *d_out, uint64_t out_base, uint64_t out_pos,
+                                   uint64_t out_end, void *d_workspace, uint32_t max_segments, mz_cuda_spec_summary *d_summary,
+                                   void *stream);
 
 /* ---- bench/test support: synthetic enwik-style text on the device -------------------------- */
 int32_t mz_cuda_textgen(void *d_out, uint64_t nbytes, uint64_t seed, void *stream);

@@ -29,7 +29,7 @@ _lib = None
 
 class InflateJob(C.Structure):
     _fields_ = [("d_in", C.c_void_p), ("in_base", C.c_uint64), ("in_avail", C.c_uint64), ("d_out", C.c_void_p),
-                ("out_base", C.c_uint64), ("out_cap", C.c_uint64), ("in_final", C.c_uint32), ("reserved", C.c_uint32)]
+                ("out_base", C.c_uint64), ("out_cap", C.c_uint64), ("in_final", C.c_uint32), ("flags", C.c_uint32)]
 
 
 class InflateState(C.Structure):
@@ -51,6 +51,7 @@ EXPORTS = [
     "mz_cuda_event_create", "mz_cuda_event_destroy", "mz_cuda_event_record", "mz_cuda_event_sync", "mz_cuda_event_elapsed_ms",
     "mz_cuda_crc32_segments", "mz_cuda_crc32_fold", "mz_cuda_crc32_device", "mz_cuda_crc32_combine",
     "mz_cuda_deflate_slot_bound", "mz_cuda_deflate_chunks", "mz_cuda_concat", "mz_cuda_inflate_streams", "mz_cuda_textgen",
+    "mz_cuda_inflate_spec_workspace_bytes", "mz_cuda_inflate_spec_round",
 ]
 
 

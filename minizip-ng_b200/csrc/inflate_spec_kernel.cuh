@@ -1,0 +1,309 @@
+/* inflate_spec_kernel.cuh -- K6: one LONG foreign DEFLATE stream decoded by thousands of warps (sm_100a).
+ *
+ * What it accelerates: mz_stream_zlib_read over one big member (mz_strm_zlib.c:116-193, config C3: a 4 GiB
+ * .gz written by somebody else, no sync points). A DEFLATE stream has no index, so block starts are GUESSED and
+ * the guesses are proven afterwards; nothing unproven ever reaches the caller:
+ *
+ *   K6a find      the compressed window is cut into segments; warp k scans the bit offsets of segment k for the
+ *                 first position where a non-final dynamic block header parses into complete Huffman codes
+ *                 (RFC1951 3.2.7 + zlib's completeness rules -- the same inf_dynamic_header the decoder uses).
+ *                 Segment 0 starts at the known block boundary where the serial decoder stands.
+ *   K6b scan      warp k decodes from its start until the first block boundary at or after the next segment's
+ *                 start. The 32 KiB of history before its start are unknown, so the output is SYMBOLIC: a ring of
+ *                 16-bit symbols, < 256 = literal byte, 0x8000|i = "byte i of my unknown window" (copies of
+ *                 unknown bytes stay references). Nothing but the ring, the byte count and the end bit is kept.
+ *   K6c chain     one thread walks the segments from the anchored one: segment j joins the chain only if the
+ *                 previous chain member ended EXACTLY on j's guessed start (and the output still fits). A wrong
+ *                 guess, an error, missing input -- the chain simply ends there and the serial decoder carries on.
+ *   K6d resolve   one CTA turns each chain member's symbolic last-32-KiB into bytes, in chain order (member i's
+ *                 window = member i-1's resolved final window), 32768 symbols per step.
+ *   K6e emit      warp per chain member decodes its segment AGAIN, now with a resolved window and a known output
+ *                 offset, straight into the caller-visible output window; it must reproduce K6b's end bit and
+ *                 byte count or the whole round is discarded.
+ *
+ * Decoding twice costs instructions but needs no symbolic copy of the whole output and no per-segment output
+ * capacity guess (deflate can expand 1032:1). Traffic per output byte: K6b ~2 B ring (L2-resident), K6e 1 B
+ * written + the compressed bytes read twice.
+ */
+#ifndef MZ_INFLATE_SPEC_KERNEL_CUH
+#define MZ_INFLATE_SPEC_KERNEL_CUH
+
+#include "inflate_kernel.cuh"
+
+namespace mzc {
+
+constexpr uint64_t SPEC_NONE = ~0ull;
+constexpr uint32_t SPEC_RING = 65536;  /* symbols per segment ring */
+constexpr int SPEC_RESOLVE_THREADS = 1024;
+enum { SPEC_FLAG_MISMATCH = 1 };
+
+struct SpecSeg {
+    uint64_t start_bit; /* absolute bit of the (guessed) block start, SPEC_NONE if none was found */
+    uint64_t end_bit;   /* absolute bit where the scan stopped */
+    uint64_t out_count; /* bytes the segment produces */
+    uint64_t out_off;   /* chain: bytes produced by the chain members before this one */
+    int32_t status, why;
+    uint32_t blocks, pad;
+};
+
+struct SpecSummary {
+    uint64_t end_bit;    /* absolute bit position after the last chain member */
+    uint64_t total_out;  /* bytes emitted by the round */
+    uint32_t nchain;     /* segments accepted */
+    int32_t status;      /* INF_ST_RUN or INF_ST_END */
+    uint32_t blocks;
+    uint32_t flags;      /* SPEC_FLAG_* : the round must be discarded */
+    uint32_t candidates; /* segments in which a block start was found */
+    uint32_t pad;
+};
+
+struct SpecParams {
+    const uint8_t *in;   /* compressed window, 4-byte aligned, >= 16 readable bytes past in_avail */
+    uint64_t in_base;    /* absolute stream byte of in[0] */
+    uint64_t in_avail;
+    uint64_t start_bit;  /* absolute bit of the block boundary where the serial decoder stands */
+    uint64_t seg_bits;   /* segment length in bits */
+    uint8_t *out;        /* output window; out[0] is absolute output byte out_base */
+    uint64_t out_base;
+    uint64_t out_pos;    /* absolute output position where this round starts (history before it is in `out`) */
+    uint64_t out_end;    /* absolute end of the writable output window */
+    uint32_t in_final;
+    uint32_t nseg;
+    SpecSeg *seg;        /* [nseg] */
+    InflateState *states; /* [nseg] */
+    uint16_t *rings;     /* [nseg][SPEC_RING] */
+    uint8_t *wins;       /* [nseg][32768] */
+    uint32_t *chain;     /* [nseg] */
+    SpecSummary *summary;
+};
+
+/* ---- K6a ------------------------------------------------------------------------------------------------------ */
+/* cheap test of one bit offset: BFINAL=0, BTYPE=2, HLIT/HDIST in range and a COMPLETE code-length code */
+__device__ __forceinline__ bool spec_quick_test(const uint32_t *w, uint64_t relbit) {
+    const uint64_t i = relbit >> 5;
+    const uint32_t s = (uint32_t)relbit & 31u;
+    const uint32_t w0 = w[i], w1 = w[i + 1], w2 = w[i + 2], w3 = w[i + 3];
+    const uint32_t v0 = __funnelshift_r(w0, w1, s), v1 = __funnelshift_r(w1, w2, s), v2 = __funnelshift_r(w2, w3, s);
+    if ((v0 & 7u) != 4u) return false; /* bit 0 BFINAL = 0, bits 1..2 BTYPE = 2 */
+    if (((v0 >> 3) & 31u) > 29u || ((v0 >> 8) & 31u) > 29u) return false;
+    const uint32_t hc = ((v0 >> 13) & 15u) + 4u;
+    uint64_t x = ((((uint64_t)v1 << 32) | v0) >> 17) | ((uint64_t)v2 << 47);
+    uint32_t sum = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < 19; k++) {
+        const uint32_t l = (uint32_t)x & 7u;
+        x >>= 3;
+        if (k < hc && l) sum += 128u >> l;
+    }
+    return sum == 128u;
+}
+
+__global__ void __launch_bounds__(INF_THREADS) inflate_spec_find_kernel(SpecParams P) {
+    MZ_DYN_SMEM(smem);
+    InfTables &T = *reinterpret_cast<InfTables *>(smem);
+    const unsigned lane = lane_id();
+    for (uint32_t k = blockIdx.x; k < P.nseg; k += gridDim.x) {
+        uint64_t found = SPEC_NONE;
+        if (k == 0) {
+            found = P.start_bit;
+        } else {
+            const uint64_t base_abs = P.in_base * 8;
+            const uint64_t avail_bits = P.in_avail * 8;
+            uint64_t lo = P.start_bit + (uint64_t)k * P.seg_bits - base_abs; /* relative to in[0] */
+            uint64_t hi = lo + P.seg_bits;
+            const uint64_t limit = avail_bits > 160 ? avail_bits - 160 : 0; /* a header plus its first symbols must lie inside the window */
+            if (hi > limit) hi = limit;
+            const uint32_t *w = (const uint32_t *)P.in;
+            for (uint64_t p0 = lo; p0 < hi && found == SPEC_NONE; p0 += 32) {
+                const uint64_t p = p0 + lane;
+                const bool cand = p < hi && spec_quick_test(w, p);
+                unsigned m = __ballot_sync(MZ_FULL_MASK, cand);
+                while (m && found == SPEC_NONE) { /* full check, lowest offset first */
+                    const uint32_t l = (uint32_t)__ffs((int)m) - 1;
+                    m &= m - 1;
+                    InfBits b;
+                    if (lane == 0) b.init(P.in, P.in_avail, p0 + l + 3);
+                    uint32_t nlit, ndist;
+                    const int err = inf_dynamic_header(b, T, nlit, ndist);
+                    __syncwarp();
+                    if (!err) found = base_abs + p0 + l;
+                }
+            }
+        }
+        if (lane == 0) P.seg[k].start_bit = found;
+    }
+}
+
+/* ---- K6b ------------------------------------------------------------------------------------------------------ */
+__global__ void __launch_bounds__(INF_THREADS) inflate_spec_scan_kernel(SpecParams P) {
+    MZ_DYN_SMEM(smem);
+    InfTables &T = *reinterpret_cast<InfTables *>(smem);
+    const unsigned lane = lane_id();
+    for (uint32_t k = blockIdx.x; k < P.nseg; k += gridDim.x) {
+        SpecSeg *sg = &P.seg[k];
+        const uint64_t start = sg->start_bit;
+        if (start == SPEC_NONE) {
+            if (lane == 0) { sg->status = INF_ST_RUN; sg->why = INF_WHY_NONE; sg->out_count = 0; sg->end_bit = 0; sg->blocks = 0; }
+            continue;
+        }
+        /* stop at the first block boundary at or after the next guessed start */
+        uint64_t stop = SPEC_NONE;
+        for (uint32_t j0 = k + 1; j0 < P.nseg && stop == SPEC_NONE; j0 += 32) {
+            const uint32_t j = j0 + lane;
+            const uint64_t s = j < P.nseg ? P.seg[j].start_bit : SPEC_NONE;
+            const unsigned m = __ballot_sync(MZ_FULL_MASK, s != SPEC_NONE);
+            if (m) stop = __shfl_sync(MZ_FULL_MASK, s, __ffs((int)m) - 1);
+        }
+        /* the last guess of the window: go on to the first boundary past its own segment; what lies beyond is the
+         * next round's business */
+        if (stop == SPEC_NONE) stop = P.start_bit + (uint64_t)(k + 1) * P.seg_bits;
+        uint16_t *ring = P.rings + (size_t)k * SPEC_RING;
+        for (uint32_t i = lane; i < 32768; i += 32) ring[32768 + i] = (uint16_t)(0x8000u | i); /* positions -32768..-1 */
+        InflateState *st = &P.states[k];
+        if (lane == 0) {
+            st->in_bitpos = start;
+            st->out_pos = 0;
+            st->status = INF_ST_RUN;
+            st->why = INF_WHY_NONE;
+            st->phase = INF_PH_HEADER;
+            st->last_block = 0;
+            st->stored_remaining = 0;
+            st->nlit = st->ndist = 0;
+            st->blocks = 0;
+        }
+        __syncwarp();
+        InflateJob job;
+        job.in = P.in;
+        job.in_base = P.in_base;
+        job.in_avail = P.in_avail;
+        job.out = nullptr;
+        job.out_base = 0;
+        job.out_cap = 1ull << 62; /* the ring never fills */
+        job.in_final = P.in_final;
+        job.flags = 0;
+        OutSymRing o;
+        o.ring = ring;
+        inf_decode_window(job, st, T, o, stop);
+        if (lane == 0) {
+            sg->end_bit = st->in_bitpos;
+            sg->out_count = st->out_pos;
+            sg->status = st->status;
+            sg->why = st->why;
+            sg->blocks = st->blocks;
+        }
+        __syncwarp();
+    }
+}
+
+/* ---- K6c ------------------------------------------------------------------------------------------------------ */
+__global__ void inflate_spec_chain_kernel(SpecParams P) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    SpecSummary s;
+    s.end_bit = P.start_bit;
+    s.total_out = 0;
+    s.nchain = 0;
+    s.status = INF_ST_RUN;
+    s.blocks = 0;
+    s.flags = 0;
+    s.candidates = 0;
+    s.pad = 0;
+    for (uint32_t k = 0; k < P.nseg; k++) s.candidates += P.seg[k].start_bit != SPEC_NONE;
+    uint32_t cur = 0;
+    while (cur < P.nseg) {
+        SpecSeg *sg = &P.seg[cur];
+        const bool whole = (sg->status == INF_ST_RUN && sg->why == INF_WHY_BOUNDARY) || sg->status == INF_ST_END;
+        if (!whole) break;
+        if (P.out_pos + s.total_out + sg->out_count > P.out_end) break;
+        sg->out_off = s.total_out;
+        P.chain[s.nchain++] = cur;
+        s.total_out += sg->out_count;
+        s.blocks += sg->blocks;
+        s.end_bit = sg->end_bit;
+        if (sg->status == INF_ST_END) { s.status = INF_ST_END; break; }
+        uint32_t j = cur + 1;
+        while (j < P.nseg && P.seg[j].start_bit == SPEC_NONE) j++;
+        if (j >= P.nseg || P.seg[j].start_bit != sg->end_bit) break; /* the guess was not where the stream really continues */
+        cur = j;
+    }
+    *P.summary = s;
+}
+
+/* ---- K6d ------------------------------------------------------------------------------------------------------ */
+__global__ void __launch_bounds__(SPEC_RESOLVE_THREADS) inflate_spec_resolve_kernel(SpecParams P) {
+    MZ_DYN_SMEM(smem); /* two 32 KiB windows */
+    uint8_t *wa = smem, *wb = smem + 32768;
+    const uint32_t n = P.summary->nchain;
+    if (n == 0) return;
+    /* the window before the anchored member is real output (zeros where the stream has no history yet) */
+    for (uint32_t j = threadIdx.x; j < 32768; j += blockDim.x) {
+        const uint64_t back = 32768 - j;
+        const uint8_t v = back <= P.out_pos - P.out_base && back <= P.out_pos ? P.out[P.out_pos - back - P.out_base] : (uint8_t)0;
+        wa[j] = v;
+        P.wins[(size_t)P.chain[0] * 32768 + j] = v;
+    }
+    __syncthreads();
+    for (uint32_t i = 0; i + 1 < n; i++) {
+        const uint32_t k = P.chain[i], knext = P.chain[i + 1];
+        const uint16_t *ring = P.rings + (size_t)k * SPEC_RING;
+        const uint32_t tail = (uint32_t)P.seg[k].out_count - 32768u; /* ring index of window element 0 (mod 65536) */
+        uint8_t *dst = P.wins + (size_t)knext * 32768;
+        for (uint32_t j = threadIdx.x; j < 32768; j += blockDim.x) {
+            const uint32_t s = ring[(tail + j) & (SPEC_RING - 1)];
+            const uint8_t v = s & 0x8000u ? wa[s & 0x7fffu] : (uint8_t)s;
+            wb[j] = v;
+            dst[j] = v;
+        }
+        __syncthreads();
+        uint8_t *t = wa; wa = wb; wb = t;
+    }
+}
+
+/* ---- K6e ------------------------------------------------------------------------------------------------------ */
+__global__ void __launch_bounds__(INF_THREADS) inflate_spec_emit_kernel(SpecParams P) {
+    MZ_DYN_SMEM(smem);
+    InfTables &T = *reinterpret_cast<InfTables *>(smem);
+    const unsigned lane = lane_id();
+    const uint32_t n = P.summary->nchain;
+    for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+        const uint32_t k = P.chain[i];
+        const SpecSeg sg = P.seg[k];
+        const uint64_t first = P.out_pos + sg.out_off;
+        InflateState *st = &P.states[k];
+        __syncwarp();
+        if (lane == 0) {
+            st->in_bitpos = sg.start_bit;
+            st->out_pos = first;
+            st->status = INF_ST_RUN;
+            st->why = INF_WHY_NONE;
+            st->phase = INF_PH_HEADER;
+            st->last_block = 0;
+            st->stored_remaining = 0;
+            st->nlit = st->ndist = 0;
+            st->blocks = 0;
+        }
+        __syncwarp();
+        InflateJob job;
+        job.in = P.in;
+        job.in_base = P.in_base;
+        job.in_avail = P.in_avail;
+        job.out = P.out;
+        job.out_base = P.out_base;
+        job.out_cap = first + sg.out_count - P.out_base; /* exactly this member's bytes */
+        job.in_final = P.in_final;
+        job.flags = 0;
+        OutBytesWin o;
+        o.base = P.out - P.out_base;
+        o.win = P.wins + (size_t)k * 32768;
+        o.floor = first;
+        inf_decode_window(job, st, T, o, sg.end_bit);
+        if (lane == 0) {
+            const bool same = st->in_bitpos == sg.end_bit && st->out_pos == first + sg.out_count && st->status == sg.status &&
+                              (sg.status == INF_ST_END || st->why == INF_WHY_BOUNDARY);
+            if (!same) atomicOr(&P.summary->flags, (uint32_t)SPEC_FLAG_MISMATCH);
+        }
+        __syncwarp();
+    }
+}
+
+} // namespace mzc
+#endif

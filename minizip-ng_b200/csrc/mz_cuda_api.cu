@@ -12,6 +12,7 @@
 #include "crc32_kernel.cuh"
 #include "deflate_kernel.cuh"
 #include "inflate_kernel.cuh"
+#include "inflate_spec_kernel.cuh"
 
 #define MZ_OK 0
 #define MZ_MEM_ERROR (-4)
@@ -23,6 +24,7 @@ using namespace mzc;
 
 static_assert(sizeof(mz_cuda_inflate_job) == sizeof(InflateJob), "job layout");
 static_assert(sizeof(mz_cuda_inflate_state) == sizeof(InflateState), "state layout");
+static_assert(sizeof(mz_cuda_spec_summary) == sizeof(SpecSummary), "summary layout");
 
 namespace {
 
@@ -115,6 +117,7 @@ int32_t get_ctx(DeviceCtx **out) {
             CK(cudaFuncSetAttribute(deflate_chunks_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_SMEM_BYTES));
             CK(cudaFuncSetAttribute(crc32_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CRC_SMEM_BYTES));
             CK(cudaFuncSetAttribute(inflate_streams_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, INF_SMEM_BYTES));
+            CK(cudaFuncSetAttribute(inflate_spec_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
             CK(cudaMalloc(&c.d_work, 256 * sizeof(uint32_t)));
             c.ready = true;
         }
@@ -396,10 +399,57 @@ int32_t mz_cuda_inflate_streams(const mz_cuda_inflate_job *d_jobs, mz_cuda_infla
     int32_t err = get_ctx(&c);
     if (err) return err;
     if (nstreams == 0) return MZ_OK;
-    uint32_t maxgrid = (uint32_t)c->sm_count * 3u; /* 3 single-warp CTAs of ~75 KB shared memory fit one SM */
+    uint32_t maxgrid = (uint32_t)c->sm_count * 32u; /* 32 single-warp CTAs (6.4 KB of tables each) per SM */
     uint32_t grid = nstreams < maxgrid ? nstreams : maxgrid;
     MZ_LAUNCH(inflate_streams_kernel, dim3(grid), dim3(INF_THREADS), INF_SMEM_BYTES, (cudaStream_t)stream, (const InflateJob *)d_jobs,
               (InflateState *)d_states, nstreams);
+    CK(cudaGetLastError());
+    return MZ_OK;
+}
+
+/* workspace carving for K6 (all pieces 256-byte aligned) */
+static inline uint64_t al256(uint64_t v) { return (v + 255) & ~255ull; }
+uint64_t mz_cuda_inflate_spec_workspace_bytes(uint32_t max_segments) {
+    const uint64_t m = max_segments;
+    return al256(m * sizeof(SpecSeg)) + al256(m * sizeof(InflateState)) + al256(m * 4) + al256(m * SPEC_RING * 2) + al256(m * 32768) + 256;
+}
+
+int32_t mz_cuda_inflate_spec_round(const void *d_in, uint64_t in_base, uint64_t in_avail, uint32_t in_final, uint64_t start_bit,
+                                   uint64_t seg_bytes, uint32_t nseg, void *d_out, uint64_t out_base, uint64_t out_pos,
+                                   uint64_t out_end, void *d_workspace, uint32_t max_segments, mz_cuda_spec_summary *d_summary,
+                                   void *stream) {
+    DeviceCtx *c;
+    int32_t err = get_ctx(&c);
+    if (err) return err;
+    if (nseg == 0 || nseg > max_segments || seg_bytes < 64 || ((uintptr_t)d_in & 3) || !d_workspace || !d_summary) return MZ_PARAM_ERROR;
+    SpecParams P;
+    P.in = (const uint8_t *)d_in;
+    P.in_base = in_base;
+    P.in_avail = in_avail;
+    P.start_bit = start_bit;
+    P.seg_bits = seg_bytes * 8;
+    P.out = (uint8_t *)d_out;
+    P.out_base = out_base;
+    P.out_pos = out_pos;
+    P.out_end = out_end;
+    P.in_final = in_final;
+    P.nseg = nseg;
+    uint8_t *w = (uint8_t *)(((uintptr_t)d_workspace + 255) & ~(uintptr_t)255);
+    const uint64_t m = max_segments;
+    P.seg = (SpecSeg *)w;            w += al256(m * sizeof(SpecSeg));
+    P.states = (InflateState *)w;    w += al256(m * sizeof(InflateState));
+    P.chain = (uint32_t *)w;         w += al256(m * 4);
+    P.rings = (uint16_t *)w;         w += al256(m * SPEC_RING * 2);
+    P.wins = w;
+    P.summary = (SpecSummary *)d_summary;
+    cudaStream_t s = (cudaStream_t)stream;
+    const uint32_t maxgrid = (uint32_t)c->sm_count * 32u;
+    const uint32_t grid = nseg < maxgrid ? nseg : maxgrid;
+    MZ_LAUNCH(inflate_spec_find_kernel, dim3(grid), dim3(INF_THREADS), INF_SMEM_BYTES, s, P);
+    MZ_LAUNCH(inflate_spec_scan_kernel, dim3(grid), dim3(INF_THREADS), INF_SMEM_BYTES, s, P);
+    MZ_LAUNCH(inflate_spec_chain_kernel, dim3(1), dim3(32), 0, s, P);
+    MZ_LAUNCH(inflate_spec_resolve_kernel, dim3(1), dim3(SPEC_RESOLVE_THREADS), 65536, s, P);
+    MZ_LAUNCH(inflate_spec_emit_kernel, dim3(grid), dim3(INF_THREADS), INF_SMEM_BYTES, s, P);
     CK(cudaGetLastError());
     return MZ_OK;
 }

@@ -56,6 +56,12 @@ typedef struct cu_ws_s {
     size_t cin_cap, win_cap;
     mz_cuda_inflate_job *h_job, *d_job;
     mz_cuda_inflate_state *h_state, *d_state;
+    /* read, long streams: segment-speculative rounds (K6) */
+    int large;
+    void *d_spec;
+    uint32_t spec_max_seg;
+    size_t spec_seg_bytes;
+    mz_cuda_spec_summary *h_sum, *d_sum;
 } cu_ws;
 
 static pthread_mutex_t g_pool_mu = PTHREAD_MUTEX_INITIALIZER;
@@ -95,6 +101,9 @@ static void ws_destroy(cu_ws *w) {
     mz_cuda_free(w->d_job);
     mz_cuda_host_free(w->h_state);
     mz_cuda_free(w->d_state);
+    mz_cuda_free(w->d_spec);
+    mz_cuda_host_free(w->h_sum);
+    mz_cuda_free(w->d_sum);
     free(w);
 }
 
@@ -204,6 +213,10 @@ typedef struct mz_stream_cuda_s {
     uint64_t win_base;  /* output offset of ws->d_win[0] */
     size_t dec_pos, dec_len; /* decoded bytes waiting in ws->h_dec */
     uint64_t fed_in;    /* compressed bytes pulled from base (framing included) */
+    uint64_t deliv_pos; /* output bytes already copied out of ws->d_win */
+    uint64_t spec_resume_bit; /* no speculative round before the decoder has passed this stream bit */
+    double ratio_est;   /* output bytes per compressed byte seen so far (sizes the rounds) */
+    int8_t cin_dirty;   /* ws->h_cin changed since the last upload */
 } mz_stream_cuda;
 
 static mz_stream_vtbl mz_stream_cuda_vtbl = {
@@ -268,6 +281,10 @@ int32_t mz_stream_cuda_open(void *stream, const char *path, int32_t mode) {
     cu->win_base = 0;
     cu->dec_pos = cu->dec_len = 0;
     cu->fed_in = 0;
+    cu->deliv_pos = 0;
+    cu->spec_resume_bit = 0;
+    cu->ratio_est = 4.0;
+    cu->cin_dirty = 1;
     cu->initialized = 1;
     cu->mode = mode;
     return MZ_OK;
@@ -504,6 +521,7 @@ static int32_t cu_refill(mz_stream_cuda *cu) {
         }
         cu->cin_len += (size_t)got;
         cu->fed_in += (uint64_t)got;
+        cu->cin_dirty = 1;
     }
     return MZ_OK;
 }
@@ -557,7 +575,147 @@ static int32_t cu_parse_header(mz_stream_cuda *cu) {
     return mz_cuda_memcpy_h2d(w->d_state, w->h_state, sizeof(*w->h_state), NULL);
 }
 
-/* run the decoder once; afterwards ws->h_dec[0..dec_len) holds fresh output (possibly none) */
+/* A stream that fills the first (small) compressed window is a long one: switch the workspace to big windows and
+ * give it the scratch memory of the segment-speculative decoder (K6). Called before the first byte is decoded. */
+static void ws_read_upgrade(cu_ws *w, size_t cin_len) {
+    const char *off = getenv("MZ_CUDA_SPEC");
+    if (off && off[0] == '0')
+        return;
+    size_t cin_cap = env_size("MZ_CUDA_READ_WINDOW_KB", 32u << 10, 1024);
+    size_t seg = env_size("MZ_CUDA_SPEC_SEG_KB", 16, 1024);
+    if (cin_cap <= w->cin_cap || seg < 1024)
+        return;
+    size_t win_cap = 32768 + 4 * cin_cap;
+    uint32_t max_seg = (uint32_t)(cin_cap / seg) + 1;
+    uint8_t *h_cin = (uint8_t *)mz_cuda_host_alloc(cin_cap + 64);
+    uint8_t *d_cin = (uint8_t *)mz_cuda_malloc(cin_cap + 64);
+    uint8_t *d_win = (uint8_t *)mz_cuda_malloc(win_cap + 512);
+    void *d_spec = mz_cuda_malloc((size_t)mz_cuda_inflate_spec_workspace_bytes(max_seg));
+    mz_cuda_spec_summary *h_sum = (mz_cuda_spec_summary *)mz_cuda_host_alloc(sizeof(mz_cuda_spec_summary));
+    mz_cuda_spec_summary *d_sum = (mz_cuda_spec_summary *)mz_cuda_malloc(sizeof(mz_cuda_spec_summary));
+    if (!h_cin || !d_cin || !d_win || !d_spec || !h_sum || !d_sum) { /* stay small */
+        mz_cuda_host_free(h_cin);
+        mz_cuda_free(d_cin);
+        mz_cuda_free(d_win);
+        mz_cuda_free(d_spec);
+        mz_cuda_host_free(h_sum);
+        mz_cuda_free(d_sum);
+        return;
+    }
+    memcpy(h_cin, w->h_cin, cin_len);
+    mz_cuda_host_free(w->h_cin);
+    mz_cuda_free(w->d_cin);
+    mz_cuda_free(w->d_win);
+    w->h_cin = h_cin;
+    w->d_cin = d_cin;
+    w->d_win = d_win;
+    w->cin_cap = cin_cap;
+    w->win_cap = win_cap;
+    w->d_spec = d_spec;
+    w->spec_max_seg = max_seg;
+    w->spec_seg_bytes = seg;
+    w->h_sum = h_sum;
+    w->d_sum = d_sum;
+    w->large = 1;
+}
+
+/* end of the raw stream: account for consumed bytes, verify the trailer (gzip CRC-32 + ISIZE, zlib Adler-32) */
+static int32_t cu_finish_stream(mz_stream_cuda *cu) {
+    cu_ws *w = cu->ws;
+    mz_cuda_inflate_state *st = w->h_state;
+    uint64_t raw_bytes = (st->in_bitpos + 7) >> 3;
+    uint64_t tsize = cu->wrap == 2 ? 8 : (cu->wrap == 1 ? 4 : 0);
+    int32_t err;
+    cu->ended = 1;
+    cu->total_in = cu->hdr_size + (int64_t)raw_bytes + (int64_t)tsize;
+    if (tsize) {
+        size_t off = (size_t)(raw_bytes - cu->cin_base);
+        if (off + tsize > cu->cin_len) {
+            /* trailer not in the window yet: slide and pull */
+            memmove(w->h_cin, w->h_cin + off, cu->cin_len - off);
+            cu->cin_len -= off;
+            cu->cin_base += off;
+            cu->cin_dirty = 1;
+            off = 0;
+            err = cu_refill(cu);
+            if (err != MZ_OK)
+                return err;
+            if (tsize > cu->cin_len) {
+                cu->total_in = cu->hdr_size + (int64_t)raw_bytes + (int64_t)cu->cin_len;
+                return MZ_BUF_ERROR;
+            }
+        }
+        const uint8_t *t = w->h_cin + off;
+        if (cu->wrap == 2) {
+            uint32_t crc = t[0] | (t[1] << 8) | (t[2] << 16) | ((uint32_t)t[3] << 24);
+            uint32_t isz = t[4] | (t[5] << 8) | (t[6] << 16) | ((uint32_t)t[7] << 24);
+            if (crc != cu->crc || isz != (uint32_t)st->out_pos)
+                return MZ_DATA_ERROR;
+        } else {
+            uint32_t ad = ((uint32_t)t[0] << 24) | (t[1] << 16) | (t[2] << 8) | t[3];
+            if (ad != ((cu->adler_b << 16) | cu->adler_a))
+                return MZ_DATA_ERROR;
+        }
+    }
+    return MZ_OK;
+}
+
+/* One speculative round over the compressed window (K6). Returns 1 if the stream advanced, 0 if the serial decoder
+ * has to take the next step, < 0 on a CUDA failure. Stream errors are never decided here. */
+static int32_t cu_spec_round(mz_stream_cuda *cu) {
+    cu_ws *w = cu->ws;
+    mz_cuda_inflate_state *st = w->h_state;
+    const uint64_t pos_byte = st->in_bitpos >> 3;
+    const uint64_t bits_avail = (cu->cin_base + cu->cin_len) * 8 - st->in_bitpos;
+    const uint64_t seg_bits = (uint64_t)w->spec_seg_bytes * 8;
+    const uint64_t out_end = cu->win_base + w->win_cap;
+    const uint64_t room = out_end - st->out_pos;
+    int32_t err;
+    (void)pos_byte;
+    uint64_t nseg = (bits_avail + seg_bits - 1) / seg_bits;
+    /* do not scan far more input than the output window can take (the ratio estimate follows the stream) */
+    uint64_t fit = (uint64_t)((double)room / (cu->ratio_est * 1.25 * (double)w->spec_seg_bytes)) + 1;
+    if (nseg > fit)
+        nseg = fit;
+    if (nseg > w->spec_max_seg)
+        nseg = w->spec_max_seg;
+    if (nseg < 2)
+        return 0;
+    err = mz_cuda_inflate_spec_round(w->d_cin, cu->cin_base, cu->cin_len, cu->base_eof ? 1u : 0u, st->in_bitpos, w->spec_seg_bytes,
+                                     (uint32_t)nseg, w->d_win, cu->win_base, st->out_pos, out_end, w->d_spec, w->spec_max_seg, w->d_sum,
+                                     NULL);
+    if (err)
+        return err;
+    err = mz_cuda_memcpy_d2h(w->h_sum, w->d_sum, sizeof(*w->h_sum), NULL);
+    if (err)
+        return err;
+    err = mz_cuda_stream_sync(NULL);
+    if (err)
+        return err;
+    const mz_cuda_spec_summary *sm = w->h_sum;
+    if (sm->flags || sm->nchain == 0 || (sm->end_bit <= st->in_bitpos && sm->status != 1)) {
+        /* nothing proven: let the serial decoder move on; if the window holds no other block start at all
+         * (stored or fixed blocks, one giant block), do not try again before it has been consumed */
+        cu->spec_resume_bit = sm->candidates <= 1 ? st->in_bitpos + nseg * seg_bits : st->in_bitpos + 1;
+        return 0;
+    }
+    const uint64_t used_bytes = (sm->end_bit - st->in_bitpos + 7) >> 3;
+    if (used_bytes > 4096)
+        cu->ratio_est = (double)sm->total_out / (double)used_bytes < 1.0 ? 1.0 : (double)sm->total_out / (double)used_bytes;
+    st->in_bitpos = sm->end_bit;
+    st->out_pos += sm->total_out;
+    st->blocks += sm->blocks;
+    st->status = sm->status;
+    st->why = 0;
+    st->phase = 0;
+    err = mz_cuda_memcpy_h2d(w->d_state, st, sizeof(*st), NULL);
+    if (err)
+        return err;
+    return 1;
+}
+
+/* Make ws->h_dec[0..dec_len) hold fresh output, or finish the stream. Decoded bytes stay in the device window until
+ * they are delivered, at most one host buffer (`batch`) per call. */
 static int32_t cu_decode_more(mz_stream_cuda *cu) {
     cu_ws *w = cu->ws;
     mz_cuda_inflate_state *st = w->h_state;
@@ -569,24 +727,59 @@ static int32_t cu_decode_more(mz_stream_cuda *cu) {
         err = cu_parse_header(cu);
         if (err != MZ_OK)
             return err;
+        cu->cin_dirty = 1;
+        if (!w->large && cu->cin_len + (size_t)cu->hdr_size >= w->cin_cap && !cu->base_eof)
+            ws_read_upgrade(w, cu->cin_len);
     }
     for (;;) {
-        /* slide the compressed window: keep only bytes at or after the decoder's position */
-        uint64_t pos_byte = st->in_bitpos >> 3;
-        if (pos_byte > cu->cin_base) {
+        /* 1. deliver what is already decoded */
+        if (cu->deliv_pos < st->out_pos) {
+            uint64_t n = st->out_pos - cu->deliv_pos;
+            if (n > w->batch)
+                n = w->batch;
+            const uint8_t *src = w->d_win + (cu->deliv_pos - cu->win_base);
+            if (cu->wrap == 2) {
+                err = mz_cuda_crc32_device(src, n, cu->crc, &cu->crc);
+                if (err)
+                    return err;
+            }
+            err = mz_cuda_memcpy_d2h(w->h_dec, src, n, NULL);
+            if (err)
+                return err;
+            err = mz_cuda_stream_sync(NULL);
+            if (err)
+                return err;
+            if (cu->wrap == 1)
+                cu_adler_update(cu, w->h_dec, n);
+            cu->dec_pos = 0;
+            cu->dec_len = (size_t)n;
+            cu->deliv_pos += n;
+            return MZ_OK;
+        }
+        /* 2. everything delivered: terminal states */
+        if (st->status < 0)
+            return st->status; /* MZ_DATA_ERROR / MZ_BUF_ERROR, zlib-compatible */
+        if (st->status == 1)
+            return cu_finish_stream(cu);
+        /* 3. decode more. Slide the compressed window: keep only bytes at or after the decoder's position
+         * (4-byte aligned for the block-start scan) */
+        uint64_t pos_byte = (st->in_bitpos >> 3) & ~3ull;
+        if (pos_byte > cu->cin_base && (cu->cin_len == w->cin_cap || pos_byte - cu->cin_base >= cu->cin_len / 2 || !w->large)) {
             size_t drop = (size_t)(pos_byte - cu->cin_base);
             if (drop > cu->cin_len)
                 drop = cu->cin_len;
             memmove(w->h_cin, w->h_cin + drop, cu->cin_len - drop);
             cu->cin_len -= drop;
             cu->cin_base += drop;
+            cu->cin_dirty = 1;
         }
         err = cu_refill(cu);
         if (err != MZ_OK)
             return err;
-        /* slide the output window when it is full: keep 32 KiB of history at the front */
+        /* slide the output window when little room is left: keep 32 KiB of history at the front */
         uint64_t out_pos = st->out_pos;
-        if (out_pos - cu->win_base + 65536 > w->win_cap) {
+        uint64_t need = w->large ? w->win_cap / 2 : 65536;
+        if (out_pos - cu->win_base + need > w->win_cap) {
             uint64_t keep = out_pos - cu->win_base < 32768 ? out_pos - cu->win_base : 32768;
             /* ranges cannot overlap: the window is much larger than 64 KiB */
             err = mz_cuda_memcpy_d2d(w->d_win, w->d_win + (out_pos - cu->win_base - keep), keep, NULL);
@@ -594,10 +787,23 @@ static int32_t cu_decode_more(mz_stream_cuda *cu) {
                 return err;
             cu->win_base = out_pos - keep;
         }
-        memset(w->h_cin + cu->cin_len, 0, 64); /* the kernel may read a few bytes past the end */
-        err = mz_cuda_memcpy_h2d(w->d_cin, w->h_cin, cu->cin_len + 64, NULL);
-        if (err)
-            return err;
+        if (cu->cin_dirty) {
+            memset(w->h_cin + cu->cin_len, 0, 64); /* the kernels may read a few bytes past the end */
+            err = mz_cuda_memcpy_h2d(w->d_cin, w->h_cin, cu->cin_len + 64, NULL);
+            if (err)
+                return err;
+            cu->cin_dirty = 0;
+        }
+        if (w->large && st->phase == 0 && st->in_bitpos >= cu->spec_resume_bit &&
+            (cu->cin_base + cu->cin_len) * 8 > st->in_bitpos + 8 * 16 * (uint64_t)w->spec_seg_bytes) {
+            err = cu_spec_round(cu);
+            if (err < 0)
+                return err;
+            if (err == 1) {
+                cu->total_in = cu->hdr_size + (int64_t)(st->in_bitpos >> 3);
+                continue;
+            }
+        }
         w->h_job->d_in = w->d_cin;
         w->h_job->in_base = cu->cin_base;
         w->h_job->in_avail = cu->cin_len;
@@ -606,7 +812,7 @@ static int32_t cu_decode_more(mz_stream_cuda *cu) {
         /* at most one host buffer (`batch` bytes) of fresh output per launch */
         w->h_job->out_cap = (out_pos - cu->win_base) + w->batch < w->win_cap ? (out_pos - cu->win_base) + w->batch : w->win_cap;
         w->h_job->in_final = cu->base_eof ? 1u : 0u;
-        w->h_job->reserved = 0;
+        w->h_job->flags = w->large ? MZ_CUDA_INFLATE_STOP_AT_BLOCK : 0u; /* long streams: hand back at the next block so a round can start */
         err = mz_cuda_memcpy_h2d(w->d_job, w->h_job, sizeof(*w->h_job), NULL);
         if (err)
             return err;
@@ -619,68 +825,13 @@ static int32_t cu_decode_more(mz_stream_cuda *cu) {
         err = mz_cuda_stream_sync(NULL);
         if (err)
             return err;
-        uint64_t produced = st->out_pos - out_pos;
-        if (produced > 0) {
-            if (cu->wrap == 2) {
-                err = mz_cuda_crc32_device(w->d_win + (out_pos - cu->win_base), produced, cu->crc, &cu->crc);
-                if (err)
-                    return err;
-            }
-            err = mz_cuda_memcpy_d2h(w->h_dec, w->d_win + (out_pos - cu->win_base), produced, NULL);
-            if (err)
-                return err;
-            err = mz_cuda_stream_sync(NULL);
-            if (err)
-                return err;
-            if (cu->wrap == 1)
-                cu_adler_update(cu, w->h_dec, produced);
-            cu->dec_pos = 0;
-            cu->dec_len = (size_t)produced;
-        }
-        if (st->status < 0)
-            return st->status; /* MZ_DATA_ERROR / MZ_BUF_ERROR, zlib-compatible */
-        if (st->status == 1) {
-            /* end of the raw stream: account for consumed bytes, verify the trailer */
-            uint64_t raw_bytes = (st->in_bitpos + 7) >> 3;
-            uint64_t tsize = cu->wrap == 2 ? 8 : (cu->wrap == 1 ? 4 : 0);
-            cu->ended = 1;
-            cu->total_in = cu->hdr_size + (int64_t)raw_bytes + (int64_t)tsize;
-            if (tsize) {
-                size_t off = (size_t)(raw_bytes - cu->cin_base);
-                if (off + tsize > cu->cin_len) {
-                    /* trailer not in the window yet: slide and pull */
-                    memmove(w->h_cin, w->h_cin + off, cu->cin_len - off);
-                    cu->cin_len -= off;
-                    cu->cin_base += off;
-                    off = 0;
-                    err = cu_refill(cu);
-                    if (err != MZ_OK)
-                        return err;
-                    if (tsize > cu->cin_len) {
-                        cu->total_in = cu->hdr_size + (int64_t)raw_bytes + (int64_t)cu->cin_len;
-                        return MZ_BUF_ERROR;
-                    }
-                }
-                const uint8_t *t = w->h_cin + off;
-                if (cu->wrap == 2) {
-                    uint32_t crc = t[0] | (t[1] << 8) | (t[2] << 16) | ((uint32_t)t[3] << 24);
-                    uint32_t isz = t[4] | (t[5] << 8) | (t[6] << 16) | ((uint32_t)t[7] << 24);
-                    if (crc != cu->crc || isz != (uint32_t)st->out_pos)
-                        return MZ_DATA_ERROR;
-                } else {
-                    uint32_t ad = ((uint32_t)t[0] << 24) | (t[1] << 16) | (t[2] << 8) | t[3];
-                    if (ad != ((cu->adler_b << 16) | cu->adler_a))
-                        return MZ_DATA_ERROR;
-                }
-            }
-            return MZ_OK;
-        }
-        cu->total_in = cu->hdr_size + (int64_t)(st->in_bitpos >> 3);
-        if (produced > 0)
-            return MZ_OK;
+        if (st->status == 0)
+            cu->total_in = cu->hdr_size + (int64_t)(st->in_bitpos >> 3);
+        if (st->out_pos > out_pos || st->status != 0)
+            continue; /* deliver / finish at the top of the loop */
         if (st->why == 1 && cu->base_eof && w->h_job->in_final)
             return MZ_BUF_ERROR; /* decoder wants input that does not exist */
-        /* otherwise loop: more input was needed (refill) or the window had to slide */
+        /* otherwise loop: more input was needed (refill), the window had to slide, or an empty block ended */
     }
 }
 #endif

@@ -6,6 +6,7 @@
 #include "../../minizip-ng_b200/csrc/crc32_kernel.cuh"
 #include "../../minizip-ng_b200/csrc/deflate_kernel.cuh"
 #include "../../minizip-ng_b200/csrc/inflate_kernel.cuh"
+#include "../../minizip-ng_b200/csrc/inflate_spec_kernel.cuh"
 
 using namespace mzc;
 
@@ -134,6 +135,86 @@ int32_t emu_inflate(const uint8_t *in, uint64_t in_len, uint8_t *out, uint64_t o
     *consumed = (st.in_bitpos + 7) >> 3;
     *produced = st.out_pos;
     if (blocks) *blocks = st.blocks;
+    return st.status;
+}
+
+/* Decode one raw stream with the segment-speculative rounds (K6), falling back to one serially decoded block
+ * whenever a round makes no progress -- the same policy as the vtbl read path. stats: [0] rounds, [1] chain members,
+ * [2] serial launches, [3] candidates found, [4] rounds discarded by the cross-check. */
+int32_t emu_inflate_spec(const uint8_t *in, uint64_t in_len, uint8_t *out, uint64_t out_cap, uint64_t seg_bytes, uint32_t max_seg,
+                         uint64_t window, uint64_t *consumed, uint64_t *produced, uint32_t *stats) {
+    InflateState st;
+    memset(&st, 0, sizeof(st));
+    std::vector<SpecSeg> seg(max_seg);
+    std::vector<InflateState> states(max_seg);
+    std::vector<uint32_t> chain(max_seg);
+    std::vector<uint16_t> rings((size_t)max_seg * SPEC_RING);
+    std::vector<uint8_t> wins((size_t)max_seg * 32768);
+    std::vector<uint32_t> inbuf;
+    SpecSummary sum;
+    for (int i = 0; i < 5; i++) stats[i] = 0;
+    for (int iter = 0; iter < 1000000 && st.status == INF_ST_RUN; iter++) {
+        if (st.phase == INF_PH_HEADER) {
+            const uint64_t base = (st.in_bitpos >> 3) & ~3ull;
+            uint64_t avail = in_len - base;
+            if (window && avail > window) avail = window;
+            inbuf.assign((size_t)(avail + 64) / 4 + 1, 0);
+            memcpy(inbuf.data(), in + base, (size_t)avail);
+            SpecParams P;
+            memset(&P, 0, sizeof(P));
+            P.in = (const uint8_t *)inbuf.data();
+            P.in_base = base;
+            P.in_avail = avail;
+            P.start_bit = st.in_bitpos;
+            P.seg_bits = seg_bytes * 8;
+            P.out = out;
+            P.out_base = 0;
+            P.out_pos = st.out_pos;
+            P.out_end = out_cap;
+            P.in_final = base + avail == in_len;
+            uint64_t span = avail * 8 - (st.in_bitpos - base * 8);
+            uint64_t ns = (span + P.seg_bits - 1) / P.seg_bits;
+            P.nseg = (uint32_t)(ns > max_seg ? max_seg : (ns ? ns : 1));
+            P.seg = seg.data();
+            P.states = states.data();
+            P.rings = rings.data();
+            P.wins = wins.data();
+            P.chain = chain.data();
+            P.summary = &sum;
+            MZ_LAUNCH(inflate_spec_find_kernel, dim3(P.nseg), dim3(INF_THREADS), INF_SMEM_BYTES, 0, P);
+            MZ_LAUNCH(inflate_spec_scan_kernel, dim3(P.nseg), dim3(INF_THREADS), INF_SMEM_BYTES, 0, P);
+            MZ_LAUNCH(inflate_spec_chain_kernel, dim3(1), dim3(32), 0, 0, P);
+            MZ_LAUNCH(inflate_spec_resolve_kernel, dim3(1), dim3(SPEC_RESOLVE_THREADS), 65536, 0, P);
+            MZ_LAUNCH(inflate_spec_emit_kernel, dim3(P.nseg), dim3(INF_THREADS), INF_SMEM_BYTES, 0, P);
+            stats[0]++;
+            stats[3] += sum.candidates;
+            if (sum.flags) stats[4]++;
+            if (!sum.flags && sum.nchain > 0 && (sum.end_bit > st.in_bitpos || sum.status == INF_ST_END)) {
+                stats[1] += sum.nchain;
+                st.in_bitpos = sum.end_bit;
+                st.out_pos += sum.total_out;
+                st.blocks += sum.blocks;
+                st.status = sum.status;
+                continue;
+            }
+        }
+        /* serial: to the next block boundary */
+        std::vector<uint8_t> all((size_t)in_len + 64, 0);
+        memcpy(all.data(), in, (size_t)in_len);
+        InflateJob job;
+        memset(&job, 0, sizeof(job));
+        job.in = all.data();
+        job.in_avail = in_len;
+        job.out = out;
+        job.out_cap = out_cap;
+        job.in_final = 1;
+        job.flags = INF_JOB_STOP_AT_BOUNDARY;
+        MZ_LAUNCH(inflate_streams_kernel, dim3(1), dim3(INF_THREADS), INF_SMEM_BYTES, 0, (const InflateJob *)&job, &st, 1u);
+        stats[2]++;
+        if (st.status == INF_ST_RUN && st.why != INF_WHY_BOUNDARY) { st.status = st.why == INF_WHY_OUTPUT ? INF_ST_BUF_ERROR : -99; break; }
+    }
+    *consumed = (st.in_bitpos + 7) >> 3;
+    *produced = st.out_pos;
     return st.status;
 }
 

@@ -17,6 +17,8 @@ class EmuLib:
         L.emu_crc32_combine.argtypes = [u32, u32, u64]
         L.emu_inflate.restype = C.c_int32
         L.emu_inflate.argtypes = [vp, u64, vp, u64, u64, u64, C.POINTER(u64), C.POINTER(u64), C.POINTER(u32)]
+        L.emu_inflate_spec.restype = C.c_int32
+        L.emu_inflate_spec.argtypes = [vp, u64, vp, u64, u64, u32, u64, C.POINTER(u64), C.POINTER(u64), C.POINTER(u32)]
 
     def deflate(self, data, level=1, chunk=65536, final=True, grid=0):
         data = bytes(data)
@@ -42,3 +44,13 @@ class EmuLib:
         cons, prod, blocks = C.c_uint64(0), C.c_uint64(0), C.c_uint32(0)
         st = self.lib.emu_inflate(comp, len(comp), out, out_cap, in_window, out_window, C.byref(cons), C.byref(prod), C.byref(blocks))
         return st, out.raw[:prod.value], cons.value, blocks.value
+
+    def inflate_spec(self, comp, out_cap, seg_bytes=2048, max_seg=64, window=0):
+        """K6 rounds + serial fallback; returns (status, bytes, consumed, stats dict)"""
+        comp = bytes(comp)
+        out = C.create_string_buffer(max(out_cap, 1) + 300)
+        cons, prod = C.c_uint64(0), C.c_uint64(0)
+        stats = (C.c_uint32 * 5)()
+        st = self.lib.emu_inflate_spec(comp, len(comp), out, out_cap, seg_bytes, max_seg, window, C.byref(cons), C.byref(prod), stats)
+        names = ["rounds", "chain", "serial", "candidates", "discarded"]
+        return st, out.raw[:prod.value], cons.value, dict(zip(names, list(stats)))
