@@ -169,191 +169,6 @@ struct BitWriter {
     }
 };
 
-/* ---- warp-parallel code construction (used for the 19-symbol code-length code) ------------------ */
-/* Length-limited prefix-code lengths for `n` (<= 32*KS) symbols, max `M` bits. One full warp.
- * Output: complete code (Kraft sum exactly 1) with >= 2 coded symbols, as zlib's inflate requires
- * of dynamic blocks. lens[i] = 0 for unused symbols. */
-template <int KS>
-__device__ inline void warp_build_lengths(const uint32_t *hist, int n, int M, uint8_t *lens) {
-    const unsigned lane = lane_id();
-    uint32_t c[KS];
-    float ideal[KS];
-    uint32_t used = 0, total = 0, first_used = 0xffffffffu;
-#pragma unroll
-    for (int k = 0; k < KS; k++) {
-        int i = k * 32 + (int)lane;
-        c[k] = (i < n) ? hist[i] : 0u;
-        if (c[k]) {
-            used++;
-            if (first_used == 0xffffffffu) first_used = (uint32_t)i;
-        }
-    }
-    used = __reduce_add_sync(MZ_FULL_MASK, used);
-    first_used = __reduce_min_sync(MZ_FULL_MASK, first_used);
-    if (used < 2) { /* force two coded symbols */
-        uint32_t d0 = (used == 0) ? 0u : (first_used == 0 ? 1u : 0u);
-        uint32_t d1 = (used == 0) ? 1u : d0;
-        if (lane == d0 && c[0] == 0) c[0] = 1;
-        if (lane == d1 && c[0] == 0) c[0] = 1;
-    }
-#pragma unroll
-    for (int k = 0; k < KS; k++) total += c[k];
-    total = __reduce_add_sync(MZ_FULL_MASK, total);
-    const float lt = __log2f((float)total);
-#pragma unroll
-    for (int k = 0; k < KS; k++) ideal[k] = c[k] ? lt - __log2f((float)c[k]) : 0.f;
-
-    const uint32_t one = 1u << M;
-    float lo = -3.0f, hi = 1.0f;
-    for (int it = 0; it < 10; it++) {
-        float mid = 0.5f * (lo + hi);
-        uint32_t kr = 0;
-#pragma unroll
-        for (int k = 0; k < KS; k++)
-            if (c[k]) {
-                int l = (int)ceilf(ideal[k] - mid);
-                l = l < 1 ? 1 : (l > M ? M : l);
-                kr += 1u << (M - l);
-            }
-        kr = __reduce_add_sync(MZ_FULL_MASK, kr);
-        if (kr <= one) lo = mid; else hi = mid;
-    }
-    int L[KS];
-    uint32_t kr = 0;
-#pragma unroll
-    for (int k = 0; k < KS; k++) {
-        L[k] = 0;
-        if (c[k]) {
-            int l = (int)ceilf(ideal[k] - lo);
-            L[k] = l < 1 ? 1 : (l > M ? M : l);
-            kr += 1u << (M - L[k]);
-        }
-    }
-    kr = __reduce_add_sync(MZ_FULL_MASK, kr);
-    uint32_t slack = one - kr; /* kr <= one by construction (lo always feasible, -3 is) */
-    /* exact completion: shorten codes, short ones first, until the Kraft sum is exactly 1 */
-    for (int pass = 0; pass < 32 && slack > 0; pass++) {
-        for (int len = 2; len <= M && slack > 0; len++) {
-            uint32_t w = 1u << (M - len);
-            uint32_t can = slack >> (M - len); /* how many symbols of this length may be shortened */
-            if (can == 0) continue;
-            uint32_t base = 0;
-#pragma unroll
-            for (int k = 0; k < KS; k++) {
-                unsigned b = __ballot_sync(MZ_FULL_MASK, L[k] == len);
-                uint32_t rank = base + (uint32_t)__popc(b & ((1u << lane) - 1));
-                if (L[k] == len && rank < can) L[k] = len - 1;
-                base += (uint32_t)__popc(b);
-            }
-            uint32_t took = base < can ? base : can;
-            slack -= took * w;
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < KS; k++) {
-        int i = k * 32 + (int)lane;
-        if (i < n) lens[i] = (uint8_t)L[k];
-    }
-    __syncwarp();
-}
-
-/* Canonical codes (RFC1951 3.2.2), bit-reversed for LSB-first packing. One full warp.
- * codes[i] = reversed_code | len << 16.  `scratch` = 16 words of shared memory. */
-__device__ inline void warp_assign_codes(const uint8_t *lens, int n, uint32_t *codes, uint32_t *scratch) {
-    const unsigned lane = lane_id();
-    if (lane < 16) scratch[lane] = 0;
-    __syncwarp();
-    for (int i = (int)lane; i < n; i += 32)
-        if (lens[i]) atomicAdd(&scratch[lens[i]], 1u);
-    __syncwarp();
-    uint32_t next = 0;
-    if (lane >= 1 && lane < 16) {
-        for (unsigned b = 1; b <= lane; b++) next = (next + scratch[b - 1]) << 1; /* scratch[0] == 0 */
-    }
-    __syncwarp();
-    if (lane < 16) scratch[lane] = next;
-    __syncwarp();
-    for (int base = 0; base < n; base += 32) {
-        int i = base + (int)lane;
-        uint32_t l = (i < n) ? lens[i] : 0u;
-        unsigned m = __match_any_sync(MZ_FULL_MASK, l);
-        uint32_t rank = (uint32_t)__popc(m & ((1u << lane) - 1));
-        if (l) {
-            uint32_t code = scratch[l] + rank;
-            codes[i] = (__brev(code) >> (32 - l)) | (l << 16);
-        } else if (i < n) {
-            codes[i] = 0;
-        }
-        __syncwarp();
-        if (l && rank == 0) scratch[l] += (uint32_t)__popc(m);
-        __syncwarp();
-    }
-}
-
-/* Build the dynamic block header bit string into hdr[] (starting at bit 0); returns bit count.
- * One full warp. lens_ll[288], lens_d[32] final; hist_cl/codes_cl/lens_cl/scratch shared scratch. */
-__device__ inline uint32_t warp_build_header(const uint8_t *lens_ll, const uint8_t *lens_d, uint32_t bfinal, uint32_t *hist_cl,
-                                             uint8_t *lens_cl, uint32_t *codes_cl, uint32_t *scratch, uint32_t *hdr) {
-    const unsigned lane = lane_id();
-    /* HLIT / HDIST: trailing zero lengths are not sent */
-    uint32_t last_ll = 0, last_d = 0;
-    for (int i = (int)lane; i < 286; i += 32)
-        if (lens_ll[i]) last_ll = (uint32_t)i;
-    if (lane < 30 && lens_d[lane]) last_d = lane;
-    last_ll = __reduce_max_sync(MZ_FULL_MASK, last_ll);
-    last_d = __reduce_max_sync(MZ_FULL_MASK, last_d);
-    const uint32_t nlit = last_ll + 1 < 257 ? 257 : last_ll + 1;
-    const uint32_t ndist = last_d + 1;
-    const uint32_t nseq = nlit + ndist;
-    if (lane < 19) hist_cl[lane] = 0;
-    for (int j = (int)lane; j < DF_HDR_WORDS; j += 32) hdr[j] = 0;
-    __syncwarp();
-    for (uint32_t j = lane; j < nseq; j += 32) {
-        uint32_t v = j < nlit ? lens_ll[j] : lens_d[j - nlit];
-        atomicAdd(&hist_cl[v], 1u);
-    }
-    __syncwarp();
-    warp_build_lengths<1>(hist_cl, 19, 7, lens_cl);
-    warp_assign_codes(lens_cl, 19, codes_cl, scratch);
-    __syncwarp();
-    uint32_t pos = 0;
-    if (lane == 0) {
-        stage_put(hdr, 0, bfinal | (2u << 1), 3);
-        stage_put(hdr, 3, nlit - 257, 5);
-        stage_put(hdr, 8, ndist - 1, 5);
-        stage_put(hdr, 13, 19 - 4, 4);
-    }
-    pos = 17;
-    if (lane < 19) {
-        /* order in which code-length code lengths are sent, RFC1951 3.2.7 */
-        uint32_t sym;
-        switch (lane) {
-            case 0: sym = 16; break; case 1: sym = 17; break; case 2: sym = 18; break; case 3: sym = 0; break;
-            case 4: sym = 8; break; case 5: sym = 7; break; case 6: sym = 9; break; case 7: sym = 6; break;
-            case 8: sym = 10; break; case 9: sym = 5; break; case 10: sym = 11; break; case 11: sym = 4; break;
-            case 12: sym = 12; break; case 13: sym = 3; break; case 14: sym = 13; break; case 15: sym = 2; break;
-            case 16: sym = 14; break; case 17: sym = 1; break; default: sym = 15; break;
-        }
-        stage_put(hdr, pos + 3 * lane, lens_cl[sym], 3);
-    }
-    pos += 57;
-    __syncwarp();
-    for (uint32_t base = 0; base < nseq; base += 32) {
-        uint32_t j = base + lane;
-        uint32_t code = 0, nb = 0;
-        if (j < nseq) {
-            uint32_t v = j < nlit ? lens_ll[j] : lens_d[j - nlit];
-            code = codes_cl[v] & 0xffff;
-            nb = codes_cl[v] >> 16;
-        }
-        uint32_t incl = warp_incl_sum(nb);
-        stage_put(hdr, pos + incl - nb, code, nb);
-        pos += __shfl_sync(MZ_FULL_MASK, incl, 31);
-    }
-    __syncwarp();
-    return pos;
-}
-
 /* block-wide exclusive scans over one value per thread; `scan` = 64 words of shared scratch.
  * Contains __syncthreads: every thread of the CTA must call. */
 __device__ inline uint32_t block_excl_sum(uint32_t v, uint32_t *scan, uint32_t &total) {
@@ -636,13 +451,10 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deflate_chunks_kernel(DeflatePa
     uint16_t *s_tok = (uint16_t *)(smem + DF_OFF_TOK);
     uint32_t *s_hist_ll = (uint32_t *)(smem + DF_OFF_HIST);
     uint32_t *s_hist_d = s_hist_ll + 288;
-    uint32_t *s_hist_cl = s_hist_d + 32;
     uint32_t *s_code_ll = (uint32_t *)(smem + DF_OFF_CODE);
     uint32_t *s_code_d = s_code_ll + 288;
-    uint32_t *s_code_cl = s_code_d + 32;
     uint8_t *s_lens_ll = smem + DF_OFF_LENS;
     uint8_t *s_lens_d = s_lens_ll + 288;
-    uint8_t *s_lens_cl = s_lens_d + 32;
     uint32_t *s_scan = (uint32_t *)(smem + DF_OFF_SCAN);
     uint32_t *s_bb = (uint32_t *)(smem + DF_OFF_BB);
     uint32_t *s_misc = (uint32_t *)(smem + DF_OFF_MISC);

@@ -6,7 +6,8 @@
  *
  * Shape: block starts inside one foreign stream are only known by decoding, so ONE stream is walked serially by
  * one warp; parallelism comes from (a) many independent streams (zip entries) = many warps, (b) inside a warp:
- * table construction and match copies are warp-cooperative, lane 0 runs the symbol loop, and (c) for one long
+ * table construction and match copies are warp-cooperative, the symbol loop runs uniformly in all lanes (lane 0
+ * stores the literals), and (c) for one long
  * stream, the segment-speculative driver in inflate_spec_kernel.cuh, which runs this same decoder from guessed
  * block starts with a symbolic history. The decoder is RESUMABLE at symbol granularity through InflateState,
  * so the host can feed a long stream through a bounded device window (input refills, output drains) -- the
@@ -199,18 +200,15 @@ struct InfBits { /* lane 0 only: LSB-first bit reader over aligned 32-bit words,
     __device__ __forceinline__ int64_t bits_left() const { return (int64_t)avail_bits - (int64_t)bitpos(); }
 };
 
-/* canonical bit-by-bit decode for codes longer than the primary table (lane 0); consumes the code */
-__device__ __noinline__ int inf_slow_decode(InfBits &b, const uint16_t *count, const uint16_t *sorted) {
+/* canonical bit-by-bit decode for codes longer than the primary table: takes the next 15 stream bits, returns
+ * symbol | code length << 16, or -1. (Takes the bits by value so the bit reader never has to live in memory.) */
+__device__ __noinline__ int inf_slow_decode(uint32_t bits, const uint16_t *count, const uint16_t *sorted) {
     int code = 0, first = 0, index = 0;
 #pragma unroll 1
     for (int len = 1; len <= 15; len++) {
-        code |= (int)((b.bb >> (len - 1)) & 1);
+        code |= (int)((bits >> (len - 1)) & 1u);
         int c = count[len];
-        if (code - c < first) {
-            b.drop((uint32_t)len);
-            b.refill();
-            return sorted[index + (code - first)];
-        }
+        if (code - c < first) return (int)sorted[index + (code - first)] | (len << 16);
         index += c;
         first += c;
         first <<= 1;
@@ -220,69 +218,65 @@ __device__ __noinline__ int inf_slow_decode(InfBits &b, const uint16_t *count, c
 }
 
 /* Warp-cooperative: read a dynamic block header (the bits after BFINAL/BTYPE) and build both decode tables
- * (RFC1951 3.2.7; zlib's rules for incomplete sets). Lane 0 owns the bit reader. Returns 0 or an INF_ST_* error. */
+ * (RFC1951 3.2.7; zlib's rules for incomplete sets). EVERY lane runs the same bit reader over the same bits
+ * (uniform control flow, no broadcasts); shared memory is written by lane 0 or by lanes in parallel.
+ * Returns 0 or an INF_ST_* error (the same in all lanes). */
 __device__ __forceinline__ int inf_dynamic_header(InfBits &b, InfTables &T, uint32_t &nlit, uint32_t &ndist) {
     const unsigned lane = lane_id();
-    int err = 0;
-    /* code-length code, then the literal/length and distance lengths (lane 0 reads bits) */
-    uint32_t hl = 0, hd = 0, hc = 0;
-    if (lane == 0) {
-        hl = b.get(5) + 257; hd = b.get(5) + 1; hc = b.get(4) + 4;
-        if (hl > 286 || hd > 30) err = INF_ST_DATA_ERROR;
-    }
-    err = __shfl_sync(MZ_FULL_MASK, err, 0);
-    if (err) return err;
-    nlit = __shfl_sync(MZ_FULL_MASK, hl, 0);
-    ndist = __shfl_sync(MZ_FULL_MASK, hd, 0);
-    hc = __shfl_sync(MZ_FULL_MASK, hc, 0);
+    nlit = b.get(5) + 257;
+    ndist = b.get(5) + 1;
+    const uint32_t hc = b.get(4) + 4;
+    if (nlit > 286 || ndist > 30) return INF_ST_DATA_ERROR;
     if (lane < 19) T.lens[lane] = 0;
     __syncwarp();
-    if (lane == 0) {
-        for (uint32_t i = 0; i < hc; i++) {
-            uint32_t pos;
-            switch (i) {
-                case 0: pos = 16; break; case 1: pos = 17; break; case 2: pos = 18; break; case 3: pos = 0; break;
-                case 4: pos = 8; break; case 5: pos = 7; break; case 6: pos = 9; break; case 7: pos = 6; break;
-                case 8: pos = 10; break; case 9: pos = 5; break; case 10: pos = 11; break; case 11: pos = 4; break;
-                case 12: pos = 12; break; case 13: pos = 3; break; case 14: pos = 13; break; case 15: pos = 2; break;
-                case 16: pos = 14; break; case 17: pos = 1; break; default: pos = 15; break;
-            }
-            T.lens[pos] = (uint8_t)b.get(3);
+    for (uint32_t i = 0; i < hc; i++) {
+        uint32_t pos;
+        switch (i) {
+            case 0: pos = 16; break; case 1: pos = 17; break; case 2: pos = 18; break; case 3: pos = 0; break;
+            case 4: pos = 8; break; case 5: pos = 7; break; case 6: pos = 9; break; case 7: pos = 6; break;
+            case 8: pos = 10; break; case 9: pos = 5; break; case 10: pos = 11; break; case 11: pos = 4; break;
+            case 12: pos = 12; break; case 13: pos = 3; break; case 14: pos = 13; break; case 15: pos = 2; break;
+            case 16: pos = 14; break; case 17: pos = 1; break; default: pos = 15; break;
         }
+        const uint32_t v = b.get(3);
+        if (lane == 0) T.lens[pos] = (uint8_t)v;
     }
     __syncwarp();
     int left = inf_build(T.lens, 19, T.lcount, T.lsym, T.lit, 7, INF_ALPHA_PLAIN, T.scratch);
     __syncwarp();
     if (left != 0) return INF_ST_DATA_ERROR; /* code-length code must be complete */
-    if (lane == 0) {
-        uint32_t idx = 0, total = nlit + ndist;
+    {
+        uint32_t idx = 0, prev = 0;
+        const uint32_t total = nlit + ndist;
         uint8_t *lens = T.lens + 32; /* decoded lengths, staged after the 19 cl lengths */
-        while (idx < total && !err) {
-            uint32_t e = T.lit[b.peek(7)];
-            if (e == 0) { err = INF_ST_DATA_ERROR; break; }
+        while (idx < total) {
+            const uint32_t e = T.lit[b.peek(7)];
+            if (e == 0) return INF_ST_DATA_ERROR;
             b.drop(e & 15u);
             b.refill();
-            uint32_t sym = e >> 16;
+            const uint32_t sym = e >> 16;
             if (sym < 16) {
-                lens[idx++] = (uint8_t)sym;
+                if (lane == 0) lens[idx] = (uint8_t)sym;
+                idx++;
+                prev = sym;
             } else {
                 uint32_t rep, val = 0;
                 if (sym == 16) {
-                    if (idx == 0) { err = INF_ST_DATA_ERROR; break; }
-                    val = lens[idx - 1];
+                    if (idx == 0) return INF_ST_DATA_ERROR;
+                    val = prev;
                     rep = 3 + b.get(2);
                 } else if (sym == 17) rep = 3 + b.get(3);
                 else rep = 11 + b.get(7);
-                if (idx + rep > total) { err = INF_ST_DATA_ERROR; break; }
-                while (rep--) lens[idx++] = (uint8_t)val;
+                if (idx + rep > total) return INF_ST_DATA_ERROR;
+                for (uint32_t r = lane; r < rep; r += 32) lens[idx + r] = (uint8_t)val;
+                idx += rep;
+                prev = val;
             }
         }
-        if (!err && b.bits_left() < 0) err = INF_ST_BUF_ERROR;
-        if (!err && lens[256] == 0) err = INF_ST_DATA_ERROR; /* no end-of-block code */
+        if (b.bits_left() < 0) return INF_ST_BUF_ERROR;
+        __syncwarp();
+        if (lens[256] == 0) return INF_ST_DATA_ERROR; /* no end-of-block code */
     }
-    err = __shfl_sync(MZ_FULL_MASK, err, 0);
-    if (err) return err;
-    __syncwarp();
     /* move into place: lit/len lengths at T.lens[0..], distance lengths right after */
     uint8_t tmp[10];
     for (int k = 0; k < 10; k++) {
@@ -332,6 +326,7 @@ struct OutSymRing { /* 16-bit symbols in a 65536-entry ring: < 256 literal byte,
 template <class Out>
 __device__ __forceinline__ void inf_copy_match(const Out &o, uint64_t dst, uint32_t len, uint32_t dist) {
     const unsigned lane = lane_id();
+    __syncwarp(); /* lane 0's literal stores are history now */
     if (dist >= len) {
         for (uint32_t i = lane; i < len; i += 32) o.put(dst + i, o.get(dst + i - dist));
     } else if (dist >= 32) {
@@ -346,13 +341,15 @@ __device__ __forceinline__ void inf_copy_match(const Out &o, uint64_t dst, uint3
     __syncwarp();
 }
 
-/* events published by lane 0 (bits 28..31 of the packed word; bits 16..24 match length, bits 0..15 distance - 1) */
+/* what a run of tokens ended with (bits 28..31 of the packed word; bits 16..24 match length, bits 0..15 distance - 1) */
 enum { INF_EV_BUDGET = 0, INF_EV_MATCH = 1, INF_EV_EOB = 2, INF_EV_NEED_IN = 3, INF_EV_NEED_OUT = 4, INF_EV_DATA_ERR = 5, INF_EV_BUF_ERR = 6 };
 
-/* lane 0: decode tokens until something the warp must act on. CAREFUL: the output window may not hold the next
- * token -- decode exactly one and un-read it if it does not fit. */
+/* Decode tokens until something other than a literal happens. ALL lanes run this loop over the same bits: control
+ * flow stays uniform (no divergence, no broadcast of the result), only lane 0 stores the literals. CAREFUL: the
+ * output window may not hold the next token -- decode exactly one and un-read it if it does not fit. */
 template <class Out, bool CAREFUL>
 __device__ __forceinline__ uint32_t inf_run(const InfTables &T, InfBits &b, const Out &o, uint64_t &out_pos, uint64_t out_end, uint32_t &budget) {
+    const bool writer = lane_id() == 0;
     while (budget) {
         budget--;
         InfBits saved;
@@ -362,14 +359,16 @@ __device__ __forceinline__ uint32_t inf_run(const InfTables &T, InfBits &b, cons
             b.drop(e & 15u);
             b.refill();
         } else {
-            int sym = inf_slow_decode(b, T.lcount, T.lsym);
+            const int sym = inf_slow_decode((uint32_t)b.bb, T.lcount, T.lsym);
             if (sym < 0) return INF_EV_DATA_ERR << 28;
-            e = inf_entry(INF_ALPHA_LITLEN, (uint32_t)sym, 0);
+            b.drop((uint32_t)sym >> 16);
+            b.refill();
+            e = inf_entry(INF_ALPHA_LITLEN, (uint32_t)sym & 0xffffu, 0);
         }
         const uint32_t kind = (e >> 8) & 3u;
         if (kind == INF_K_LIT) {
             if (CAREFUL && out_pos >= out_end) { b = saved; return INF_EV_NEED_OUT << 28; }
-            o.put(out_pos, e >> 16);
+            if (writer) o.put(out_pos, e >> 16);
             out_pos++;
             continue;
         }
@@ -383,9 +382,11 @@ __device__ __forceinline__ uint32_t inf_run(const InfTables &T, InfBits &b, cons
             b.drop(de & 15u);
             b.refill();
         } else {
-            int ds = inf_slow_decode(b, T.dcount, T.dsym);
+            const int ds = inf_slow_decode((uint32_t)b.bb, T.dcount, T.dsym);
             if (ds < 0) return INF_EV_DATA_ERR << 28;
-            de = inf_entry(INF_ALPHA_DIST, (uint32_t)ds, 0);
+            b.drop((uint32_t)ds >> 16);
+            b.refill();
+            de = inf_entry(INF_ALPHA_DIST, (uint32_t)ds & 0xffffu, 0);
         }
         if (((de >> 8) & 3u) == INF_K_BAD) return INF_EV_DATA_ERR << 28;
         eb = (de >> 4) & 15u;
@@ -404,7 +405,7 @@ __device__ __forceinline__ uint32_t inf_run(const InfTables &T, InfBits &b, cons
 template <class Out>
 __device__ __forceinline__ void inf_decode_window(const InflateJob &job, InflateState *st, InfTables &T, const Out &o, uint64_t stop_bit) {
     const unsigned lane = lane_id();
-    InfBits b;
+    InfBits b; /* identical in every lane */
     uint64_t out_pos = st->out_pos;
     uint32_t phase = st->phase, last = st->last_block, stored_rem = st->stored_remaining;
     uint32_t nlit = st->nlit, ndist = st->ndist, blocks = st->blocks;
@@ -412,8 +413,8 @@ __device__ __forceinline__ void inf_decode_window(const InflateJob &job, Inflate
     const uint64_t out_end = job.out_base + job.out_cap;
     const uint64_t start_bit = st->in_bitpos - job.in_base * 8;
     const bool stop_each_block = (job.flags & INF_JOB_STOP_AT_BOUNDARY) != 0;
-    uint32_t budget = 0; /* lane 0: tokens that are known to fit the input and output windows */
-    if (lane == 0) b.init(job.in, job.in_avail, start_bit);
+    uint32_t budget = 0; /* tokens that are known to fit the input and output windows */
+    b.init(job.in, job.in_avail, start_bit);
     if (phase == INF_PH_CODES) { /* resume inside a Huffman block: rebuild the tables */
         for (int i = (int)lane; i < 320; i += 32) T.lens[i] = st->lens[i];
         __syncwarp();
@@ -424,39 +425,20 @@ __device__ __forceinline__ void inf_decode_window(const InflateJob &job, Inflate
     while (status == INF_ST_RUN && why == INF_WHY_NONE) {
         if (phase == INF_PH_HEADER) {
             /* a dynamic header is at most 14 + 57 + 320*(7+7) bits ~ 570 bytes: wait for it unless final */
-            int ok = 1, err = 0;
-            uint32_t type = 0;
-            if (lane == 0) {
-                if (!job.in_final && b.bits_left() < 8 * 1024) ok = 0;
-                else if (b.bits_left() < 3) err = INF_ST_BUF_ERROR;
-                else {
-                    last = b.get(1);
-                    type = b.get(2);
-                }
-            }
-            ok = __shfl_sync(MZ_FULL_MASK, ok, 0);
-            err = __shfl_sync(MZ_FULL_MASK, err, 0);
-            if (!ok) { why = INF_WHY_INPUT; break; }
-            if (err) { status = err; break; }
-            type = __shfl_sync(MZ_FULL_MASK, type, 0);
-            last = __shfl_sync(MZ_FULL_MASK, last, 0);
+            if (!job.in_final && b.bits_left() < 8 * 1024) { why = INF_WHY_INPUT; break; }
+            if (b.bits_left() < 3) { status = INF_ST_BUF_ERROR; break; }
+            last = b.get(1);
+            const uint32_t type = b.get(2);
             if (type == 0) {
-                uint32_t len = 0;
-                if (lane == 0) {
-                    b.drop(b.bc & 7); /* to byte boundary */
-                    b.refill();
-                    if (b.bits_left() < 32) err = INF_ST_BUF_ERROR;
-                    else {
-                        len = b.get(16);
-                        uint32_t nlen = b.get(16);
-                        if ((len ^ 0xffffu) != nlen) err = INF_ST_DATA_ERROR;
-                    }
-                }
-                err = __shfl_sync(MZ_FULL_MASK, err, 0);
-                if (err) { status = err; break; }
-                stored_rem = __shfl_sync(MZ_FULL_MASK, len, 0);
+                b.drop(b.bc & 7); /* to byte boundary */
+                b.refill();
+                if (b.bits_left() < 32) { status = INF_ST_BUF_ERROR; break; }
+                const uint32_t len = b.get(16), nlen = b.get(16);
+                if ((len ^ 0xffffu) != nlen) { status = INF_ST_DATA_ERROR; break; }
+                stored_rem = len;
                 phase = INF_PH_STORED;
             } else if (type == 1) {
+                __syncwarp();
                 for (int i = (int)lane; i < 288; i += 32) T.lens[i] = i < 144 ? 8 : (i < 256 ? 9 : (i < 280 ? 7 : 8));
                 if (lane < 30) T.lens[288 + lane] = 5;
                 nlit = 288; ndist = 30;
@@ -466,7 +448,8 @@ __device__ __forceinline__ void inf_decode_window(const InflateJob &job, Inflate
                 __syncwarp();
                 phase = INF_PH_CODES;
             } else if (type == 2) {
-                err = inf_dynamic_header(b, T, nlit, ndist);
+                __syncwarp();
+                const int err = inf_dynamic_header(b, T, nlit, ndist);
                 if (err) { status = err; break; }
                 phase = INF_PH_CODES;
             } else {
@@ -476,9 +459,7 @@ __device__ __forceinline__ void inf_decode_window(const InflateJob &job, Inflate
             budget = 0;
         } else if (phase == INF_PH_STORED) {
             /* raw copy, bounded by the input and output windows */
-            uint64_t ib = 0;
-            if (lane == 0) ib = b.bitpos() >> 3; /* byte aligned here */
-            ib = __shfl_sync(MZ_FULL_MASK, ib, 0);
+            const uint64_t ib = b.bitpos() >> 3; /* byte aligned here */
             uint64_t in_left = job.in_avail > ib ? job.in_avail - ib : 0;
             uint64_t out_left = out_end - out_pos;
             uint32_t n = stored_rem;
@@ -488,7 +469,7 @@ __device__ __forceinline__ void inf_decode_window(const InflateJob &job, Inflate
             __syncwarp();
             out_pos += n;
             stored_rem -= n;
-            if (lane == 0) b.init(job.in, job.in_avail, (ib + n) * 8);
+            b.init(job.in, job.in_avail, (ib + n) * 8);
             budget = 0;
             if (stored_rem == 0) {
                 phase = INF_PH_HEADER;
@@ -502,40 +483,35 @@ __device__ __forceinline__ void inf_decode_window(const InflateJob &job, Inflate
                 why = INF_WHY_INPUT;
             }
         } else { /* INF_PH_CODES */
-            uint32_t pk = 0, olo = 0;
-            if (lane == 0) {
-                bool careful = false;
-                if (budget == 0) {
-                    const int64_t left = b.bits_left();
-                    if (left < 0) pk = INF_EV_BUF_ERR << 28; /* ran past the end of the stream */
+            uint32_t pk = INF_EV_BUDGET << 28;
+            bool careful = false;
+            if (budget == 0) {
+                const int64_t left = b.bits_left();
+                if (left < 0) pk = INF_EV_BUF_ERR << 28; /* ran past the end of the stream */
+                else {
+                    /* a token reads at most 48 bits and writes at most 258 bytes */
+                    const uint64_t nin = job.in_final ? (uint64_t)(left >> 6) + 1u : (left < 192 ? 0u : (uint64_t)(left - 128) >> 6);
+                    const uint64_t room = out_end - out_pos;
+                    if (nin == 0) pk = INF_EV_NEED_IN << 28;
+                    else if (room < 512 || (job.in_final && left < 192)) { careful = true; budget = 1; } /* token by token near either end */
                     else {
-                        /* a token reads at most 48 bits and writes at most 258 bytes */
-                        const uint64_t nin = job.in_final ? (uint64_t)(left >> 6) + 1u : (left < 192 ? 0u : (uint64_t)(left - 128) >> 6);
-                        const uint64_t room = out_end - out_pos;
-                        if (nin == 0) pk = INF_EV_NEED_IN << 28;
-                        else if (room < 512 || (job.in_final && left < 192)) { careful = true; budget = 1; } /* token by token near either end */
-                        else {
-                            uint64_t n = room >> 9;
-                            if (n > nin) n = nin;
-                            budget = n > 65536u ? 65536u : (uint32_t)n;
-                        }
+                        uint64_t n = room >> 9;
+                        if (n > nin) n = nin;
+                        budget = n > 65536u ? 65536u : (uint32_t)n;
                     }
                 }
-                if (budget) {
-                    if (careful) {
-                        const uint64_t before = out_pos;
-                        pk = inf_run<Out, true>(T, b, o, out_pos, out_end, budget);
-                        budget = 0;
-                        if (b.bits_left() < 0) { out_pos = before; pk = INF_EV_BUF_ERR << 28; } /* the token lay past the end of the stream */
-                    } else {
-                        pk = inf_run<Out, false>(T, b, o, out_pos, out_end, budget);
-                    }
-                }
-                olo = (uint32_t)out_pos;
             }
-            pk = __shfl_sync(MZ_FULL_MASK, pk, 0);
-            olo = __shfl_sync(MZ_FULL_MASK, olo, 0);
-            out_pos += (uint32_t)(olo - (uint32_t)out_pos); /* lanes follow lane 0's literal count (a run advances < 2^32) */
+            if (budget) {
+                if (careful) {
+                    const uint64_t before = out_pos;
+                    pk = inf_run<Out, true>(T, b, o, out_pos, out_end, budget);
+                    budget = 0;
+                    if (b.bits_left() < 0) { out_pos = before; pk = INF_EV_BUF_ERR << 28; } /* the token lay past the end of the stream */
+                } else {
+                    pk = inf_run<Out, false>(T, b, o, out_pos, out_end, budget);
+                    if ((pk >> 28) == INF_EV_EOB && b.bits_left() < 0) pk = INF_EV_BUF_ERR << 28; /* the end-of-block code lay past the end */
+                }
+            }
             const uint32_t ev = pk >> 28;
             if (ev == INF_EV_MATCH) {
                 const uint32_t mlen = (pk >> 16) & 0x1ffu, mdist = (pk & 0xffffu) + 1u;
@@ -557,10 +533,7 @@ __device__ __forceinline__ void inf_decode_window(const InflateJob &job, Inflate
             }
         }
         if (phase == INF_PH_HEADER && status == INF_ST_RUN && why == INF_WHY_NONE) { /* at a block boundary */
-            uint64_t bp = 0;
-            if (lane == 0) bp = b.bitpos();
-            bp = __shfl_sync(MZ_FULL_MASK, bp, 0);
-            if (stop_each_block || job.in_base * 8 + bp >= stop_bit) why = INF_WHY_BOUNDARY;
+            if (stop_each_block || job.in_base * 8 + b.bitpos() >= stop_bit) why = INF_WHY_BOUNDARY;
         }
     }
     /* ---- save state ------------------------------------------------------------------------------- */

@@ -78,14 +78,18 @@ struct SpecParams {
 };
 
 /* ---- K6a ------------------------------------------------------------------------------------------------------ */
-/* cheap test of one bit offset: BFINAL=0, BTYPE=2, HLIT/HDIST in range and a COMPLETE code-length code */
-__device__ __forceinline__ bool spec_quick_test(const uint32_t *w, uint64_t relbit) {
+constexpr int SPEC_FIND_SMEM = INF_SMEM_BYTES + 256 * 2; /* decode tables + a queue of 256 surviving bit offsets */
+
+/* first 17 bits of a would-be header: BFINAL=0, BTYPE=2, HLIT <= 29, HDIST <= 29 */
+__device__ __forceinline__ bool spec_head_ok(uint32_t h) {
+    return (h & 7u) == 4u && ((h >> 3) & 31u) <= 29u && ((h >> 8) & 31u) <= 29u;
+}
+/* the code-length code announced at this offset must be COMPLETE (zlib rejects anything else, inftrees.c CODES) */
+__device__ __forceinline__ bool spec_kraft_ok(const uint32_t *w, uint64_t relbit) {
     const uint64_t i = relbit >> 5;
     const uint32_t s = (uint32_t)relbit & 31u;
     const uint32_t w0 = w[i], w1 = w[i + 1], w2 = w[i + 2], w3 = w[i + 3];
     const uint32_t v0 = __funnelshift_r(w0, w1, s), v1 = __funnelshift_r(w1, w2, s), v2 = __funnelshift_r(w2, w3, s);
-    if ((v0 & 7u) != 4u) return false; /* bit 0 BFINAL = 0, bits 1..2 BTYPE = 2 */
-    if (((v0 >> 3) & 31u) > 29u || ((v0 >> 8) & 31u) > 29u) return false;
     const uint32_t hc = ((v0 >> 13) & 15u) + 4u;
     uint64_t x = ((((uint64_t)v1 << 32) | v0) >> 17) | ((uint64_t)v2 << 47);
     uint32_t sum = 0;
@@ -101,6 +105,7 @@ __device__ __forceinline__ bool spec_quick_test(const uint32_t *w, uint64_t relb
 __global__ void __launch_bounds__(INF_THREADS) inflate_spec_find_kernel(SpecParams P) {
     MZ_DYN_SMEM(smem);
     InfTables &T = *reinterpret_cast<InfTables *>(smem);
+    uint16_t *queue = reinterpret_cast<uint16_t *>(smem + INF_SMEM_BYTES);
     const unsigned lane = lane_id();
     for (uint32_t k = blockIdx.x; k < P.nseg; k += gridDim.x) {
         uint64_t found = SPEC_NONE;
@@ -114,20 +119,41 @@ __global__ void __launch_bounds__(INF_THREADS) inflate_spec_find_kernel(SpecPara
             const uint64_t limit = avail_bits > 160 ? avail_bits - 160 : 0; /* a header plus its first symbols must lie inside the window */
             if (hi > limit) hi = limit;
             const uint32_t *w = (const uint32_t *)P.in;
-            for (uint64_t p0 = lo; p0 < hi && found == SPEC_NONE; p0 += 32) {
-                const uint64_t p = p0 + lane;
-                const bool cand = p < hi && spec_quick_test(w, p);
-                unsigned m = __ballot_sync(MZ_FULL_MASK, cand);
-                while (m && found == SPEC_NONE) { /* full check, lowest offset first */
-                    const uint32_t l = (uint32_t)__ffs((int)m) - 1;
-                    m &= m - 1;
-                    InfBits b;
-                    if (lane == 0) b.init(P.in, P.in_avail, p0 + l + 3);
-                    uint32_t nlit, ndist;
-                    const int err = inf_dynamic_header(b, T, nlit, ndist);
-                    __syncwarp();
-                    if (!err) found = base_abs + p0 + l;
+            /* 256 bit offsets per step: each lane screens 8 consecutive ones on their first 17 bits; the survivors
+             * (~11 %) are queued in offset order so that the 19-field Kraft test runs on full warps */
+            for (uint64_t p0 = lo; p0 < hi && found == SPEC_NONE; p0 += 256) {
+                const uint64_t q0 = p0 + lane * 8u;
+                uint32_t mask = 0;
+                if (q0 < hi) {
+                    const uint64_t i = q0 >> 5;
+                    const uint32_t v = __funnelshift_r(w[i], w[i + 1], (uint32_t)q0 & 31u);
+#pragma unroll
+                    for (uint32_t j = 0; j < 8; j++)
+                        if (spec_head_ok(v >> j) && q0 + j < hi) mask |= 1u << j;
                 }
+                const uint32_t cnt = (uint32_t)__popc(mask);
+                const uint32_t incl = warp_incl_sum(cnt);
+                const uint32_t total = __shfl_sync(MZ_FULL_MASK, incl, 31);
+                uint32_t at = incl - cnt;
+                for (uint32_t mm = mask; mm; mm &= mm - 1) queue[at++] = (uint16_t)(lane * 8u + (uint32_t)__ffs((int)mm) - 1u);
+                __syncwarp();
+                for (uint32_t r0 = 0; r0 < total && found == SPEC_NONE; r0 += 32) {
+                    const uint32_t qi = r0 + lane;
+                    const bool cand = qi < total && spec_kraft_ok(w, p0 + queue[qi]);
+                    unsigned m = __ballot_sync(MZ_FULL_MASK, cand);
+                    while (m && found == SPEC_NONE) { /* the real header parse, lowest offset first */
+                        const uint32_t l = (uint32_t)__ffs((int)m) - 1;
+                        m &= m - 1;
+                        const uint64_t p = p0 + queue[r0 + l];
+                        InfBits b;
+                        b.init(P.in, P.in_avail, p + 3);
+                        uint32_t nlit, ndist;
+                        const int err = inf_dynamic_header(b, T, nlit, ndist);
+                        __syncwarp();
+                        if (!err) found = base_abs + p;
+                    }
+                }
+                __syncwarp();
             }
         }
         if (lane == 0) P.seg[k].start_bit = found;

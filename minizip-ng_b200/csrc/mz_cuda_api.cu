@@ -445,7 +445,7 @@ int32_t mz_cuda_inflate_spec_round(const void *d_in, uint64_t in_base, uint64_t 
     cudaStream_t s = (cudaStream_t)stream;
     const uint32_t maxgrid = (uint32_t)c->sm_count * 32u;
     const uint32_t grid = nseg < maxgrid ? nseg : maxgrid;
-    MZ_LAUNCH(inflate_spec_find_kernel, dim3(grid), dim3(INF_THREADS), INF_SMEM_BYTES, s, P);
+    MZ_LAUNCH(inflate_spec_find_kernel, dim3(grid), dim3(INF_THREADS), SPEC_FIND_SMEM, s, P);
     MZ_LAUNCH(inflate_spec_scan_kernel, dim3(grid), dim3(INF_THREADS), INF_SMEM_BYTES, s, P);
     MZ_LAUNCH(inflate_spec_chain_kernel, dim3(1), dim3(32), 0, s, P);
     MZ_LAUNCH(inflate_spec_resolve_kernel, dim3(1), dim3(SPEC_RESOLVE_THREADS), 65536, s, P);

@@ -181,7 +181,7 @@ int32_t emu_inflate_spec(const uint8_t *in, uint64_t in_len, uint8_t *out, uint6
             P.wins = wins.data();
             P.chain = chain.data();
             P.summary = &sum;
-            MZ_LAUNCH(inflate_spec_find_kernel, dim3(P.nseg), dim3(INF_THREADS), INF_SMEM_BYTES, 0, P);
+            MZ_LAUNCH(inflate_spec_find_kernel, dim3(P.nseg), dim3(INF_THREADS), SPEC_FIND_SMEM, 0, P);
             MZ_LAUNCH(inflate_spec_scan_kernel, dim3(P.nseg), dim3(INF_THREADS), INF_SMEM_BYTES, 0, P);
             MZ_LAUNCH(inflate_spec_chain_kernel, dim3(1), dim3(32), 0, 0, P);
             MZ_LAUNCH(inflate_spec_resolve_kernel, dim3(1), dim3(SPEC_RESOLVE_THREADS), 65536, 0, P);

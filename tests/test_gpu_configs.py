@@ -153,3 +153,48 @@ def test_c5_chunked_level1_with_crc_fold(env, ref):
     # and by the reference's own stream reader on the first 64 MiB worth of compressed data boundaries
     out, rinfo = ref.decompress_with(ref.lib.mz_stream_zlib_create, parts[1], window_bits=-15, read_size=65536)
     assert rinfo["read_err"] == 0 and zlib.crc32(out) == zlib.crc32(host[half:])
+
+
+def test_c3_long_member_speculative_rounds_match_serial(env, ref, monkeypatch):
+    """the segment-speculative rounds (K6) and the serial decoder must deliver identical bytes and totals for the same
+    foreign member; zlib level 1/6/9 members, Z_FULL_FLUSH-riddled members and a member with a long stored run inside"""
+    p, lib, tl, torch = env
+    n = 48 * MiB
+    text = _host_bytes(p.textgen(n, seed=17))
+    noise = datagen.random_bytes(6 * MiB, seed=5)
+    cases = []
+    for level in (1, 6, 9):
+        co = zlib.compressobj(level, zlib.DEFLATED, 31)
+        cases.append((text, co.compress(text) + co.flush()))
+    mixed = text[:20 * MiB] + noise + text[20 * MiB:30 * MiB]  # stored blocks in the middle: the rounds must hand over and resume
+    co = zlib.compressobj(6, zlib.DEFLATED, 31)
+    cases.append((mixed, co.compress(mixed) + co.flush()))
+    co = zlib.compressobj(6, zlib.DEFLATED, 31)
+    parts = []
+    for o in range(0, 24 * MiB, 300_000):
+        parts.append(co.compress(text[o:o + 300_000]))
+        parts.append(co.flush(zlib.Z_FULL_FLUSH))
+    parts.append(co.flush())
+    cases.append((text[:(24 * MiB + 299_999) // 300_000 * 300_000][:24 * MiB + 300_000], b"".join(parts)))
+    for plain, comp in cases:
+        plain = zlib.decompress(comp, 31)  # ground truth straight from zlib
+        outs = []
+        for spec in ("1", "0"):
+            monkeypatch.setenv("MZ_CUDA_SPEC", spec)
+            out, info = tl.decompress(lib.mz_stream_cuda_create, comp, len(plain), window_bits=31, read_size=1 << 20)
+            assert info["read"] == len(plain) and info["total_in"] == len(comp) and info["total_out"] == len(plain) and info["close"] == 0, (spec, info)
+            outs.append(zlib.crc32(out))
+        assert outs[0] == outs[1] == zlib.crc32(plain)
+    # a corrupted long member: same error class either way, and no wrong bytes before it
+    plain, comp = cases[1]
+    bad = bytearray(comp)
+    for k in range(len(bad) // 2, len(bad) // 2 + 64):
+        bad[k] ^= 0xA5
+    res = []
+    for spec in ("1", "0"):
+        monkeypatch.setenv("MZ_CUDA_SPEC", spec)
+        out, info = tl.decompress(lib.mz_stream_cuda_create, bytes(bad), len(plain), window_bits=31, read_size=1 << 20)
+        res.append((info["read"], info["error"]))
+        good = out if out else b""
+        assert plain.startswith(good)
+    assert res[0][1] != 0 and res[1][1] != 0

@@ -113,8 +113,38 @@ def crc(n_mib):
     print(json.dumps({"what": "crc32_device", "mib": n_mib, "ms": round(ms, 4), "GBps": round(n / ms / 1e6, 1)}), flush=True)
 
 
+def vtbl_long(n_mib, read_size=1 << 20, spec=True):
+    """config C3 shape through the drop-in API: one foreign gzip member (zlib level 6) read with mz_stream_cuda_read from a
+    host memory stream; time includes host<->device copies. Beside it: zlib's own inflate on one host core."""
+    import time
+    import cuharness
+    tl = cuharness.TestLib()
+    n = n_mib * MiB
+    host = bytes(pkg.textgen(n, seed=9).cpu().numpy().tobytes())
+    co = zlib.compressobj(6, zlib.DEFLATED, 31)
+    comp = co.compress(host) + co.flush()
+    os.environ["MZ_CUDA_SPEC"] = "1" if spec else "0"
+    best = None
+    for _ in range(2):
+        t0 = time.perf_counter()
+        out, info = tl.decompress(lib.mz_stream_cuda_create, comp, n, window_bits=31, read_size=read_size)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    ok = info["read"] == n and zlib.crc32(out) == zlib.crc32(host) and info["total_in"] == len(comp)
+    t0 = time.perf_counter()
+    zlib.decompress(comp, 31)
+    cpu = time.perf_counter() - t0
+    print(json.dumps({"what": "vtbl_read_one_gzip_member", "out_mib": n_mib, "spec": spec, "s": round(best, 3), "out_GBps": round(n / best / 1e9, 3),
+                      "zlib_1core_GBps": round(n / cpu / 1e9, 3), "ratio": round(len(comp) / n, 4), "ok": bool(ok)}), flush=True)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "single":
+        single(int(sys.argv[2]))
+        sys.exit(0)
     crc(64)
     crc(4096)
-    single(64)
+    single(16)
     batch(8192)
+    vtbl_long(32, spec=False)
+    vtbl_long(256, spec=True)
