@@ -76,6 +76,8 @@ struct InfTables {
     uint8_t lens[384];
 };
 constexpr int INF_SMEM_BYTES = ((int)sizeof(InfTables) + 15) / 16 * 16;
+constexpr uint32_t INF_OFF_LIT = 0;                          /* byte offsets inside InfTables, for the explicit */
+constexpr uint32_t INF_OFF_DIST = (1u << INF_PB) * 4u;        /* shared-space loads of the symbol loop */
 
 __device__ __forceinline__ uint32_t inf_len_base(uint32_t s, uint32_t &eb) { /* s = sym - 257 in 0..28 */
     if (s < 8) { eb = 0; return 3 + s; }
@@ -161,42 +163,50 @@ __device__ inline int inf_build(const uint8_t *lens, int n, uint16_t *count, uin
     return left;
 }
 
-struct InfBits { /* lane 0 only: LSB-first bit reader over aligned 32-bit words, next word prefetched */
-    const uint32_t *w0;    /* aligned word holding in[0] */
-    const uint32_t *wp;    /* word held in `nxt` (not merged yet) */
-    const uint32_t *wend;  /* first word that must not be read */
-    uint64_t bb;
+struct InfBits { /* LSB-first bit reader over aligned 32-bit words, next word prefetched; all state in 32-bit registers */
+    const uint32_t *w0;  /* aligned word holding in[0] */
     uint64_t avail_bits;
-    uint32_t bc, nxt, skew;
-    __device__ __forceinline__ uint32_t load(const uint32_t *p) const { return p < wend ? *p : 0u; }
+    uint32_t lo, hi;     /* bit buffer: stream bits 0..31 in lo, 32..63 in hi; bits past `bc` are zero */
+    uint32_t bc;         /* valid bits in hi:lo */
+    uint32_t widx;       /* index (from w0) of the word held in `nxt` (not merged yet) */
+    uint32_t wend;       /* first word index that must not be read */
+    uint32_t nxt, skew;
+    __device__ __forceinline__ void load() {
+        nxt = 0;
+        if (widx < wend) nxt = w0[widx];
+    }
     __device__ __forceinline__ void init(const uint8_t *in, uint64_t avail_bytes, uint64_t rel_bitpos) {
         const uintptr_t a = (uintptr_t)in;
         w0 = (const uint32_t *)(a & ~(uintptr_t)3);
         skew = (uint32_t)(a & 3) * 8u;
-        wend = (const uint32_t *)((a + avail_bytes + 16) & ~(uintptr_t)3);
+        wend = (uint32_t)(((a & 3) + avail_bytes + 16) >> 2);
         avail_bits = avail_bytes * 8;
         const uint64_t abs = rel_bitpos + skew;
-        wp = w0 + (abs >> 5);
-        nxt = load(wp);
-        bb = 0; bc = 0;
+        widx = (uint32_t)(abs >> 5);
+        load();
+        lo = hi = 0; bc = 0;
         refill();
-        const uint32_t skip = (uint32_t)abs & 31u;
-        bb >>= skip; bc -= skip;
+        drop((uint32_t)abs & 31u);
         refill();
     }
-    __device__ __forceinline__ void refill() { /* keeps >= 32 valid bits */
+    __device__ __forceinline__ void refill() { /* keeps >= 32 valid bits; below 32 everything valid sits in lo and hi is 0 */
         if (bc < 32) {
-            bb |= (uint64_t)nxt << bc;
+            lo |= nxt << bc;
+            hi = __funnelshift_rc(nxt, 0u, 32u - bc);
             bc += 32;
-            wp++;
-            nxt = load(wp);
+            widx++;
+            load();
         }
     }
-    __device__ __forceinline__ uint32_t peek(uint32_t n) const { return (uint32_t)bb & ((1u << n) - 1u); }
-    __device__ __forceinline__ void drop(uint32_t n) { bb >>= n; bc -= n; }
+    __device__ __forceinline__ uint32_t peek(uint32_t n) const { return lo & ((1u << n) - 1u); }
+    __device__ __forceinline__ void drop(uint32_t n) { /* n <= 31 */
+        lo = __funnelshift_r(lo, hi, n);
+        hi >>= n;
+        bc -= n;
+    }
     __device__ __forceinline__ uint32_t get(uint32_t n) { uint32_t v = peek(n); drop(n); refill(); return v; } /* n <= 16 */
     /* bits consumed so far, relative to in[0] */
-    __device__ __forceinline__ uint64_t bitpos() const { return (uint64_t)(wp - w0) * 32u - bc - skew; }
+    __device__ __forceinline__ uint64_t bitpos() const { return (uint64_t)widx * 32u - bc - skew; }
     __device__ __forceinline__ int64_t bits_left() const { return (int64_t)avail_bits - (int64_t)bitpos(); }
 };
 
@@ -300,25 +310,55 @@ __device__ __forceinline__ int inf_dynamic_header(InfBits &b, InfTables &T, uint
     return 0;
 }
 
-/* ---- where decoded data goes (and where history is read back from) ------------------------------------------- */
+/* ---- where decoded data goes (and where history is read back from) -------------------------------------------
+ * put(p, v) stores one element at absolute position p; cursor(dst, dist) prepares a match copy: src(i) is the element
+ * at dst - dist + i, put(i, v) stores at dst + i (32-bit offsets, the 64-bit address arithmetic is done once). */
 struct OutBytes { /* final bytes in global memory, indexed by absolute output position */
     uint8_t *base;
+    struct Cursor {
+        uint8_t *d;
+        const uint8_t *s;
+        __device__ __forceinline__ uint32_t src(uint32_t i) const { return s[i]; }
+        __device__ __forceinline__ void put(uint32_t i, uint32_t v) const { d[i] = (uint8_t)v; }
+    };
     __device__ __forceinline__ void put(uint64_t p, uint32_t v) const { base[p] = (uint8_t)v; }
-    __device__ __forceinline__ uint32_t get(uint64_t p) const { return base[p]; }
+    __device__ __forceinline__ Cursor cursor(uint64_t dst, uint32_t dist) const { Cursor c; c.d = base + dst; c.s = c.d - dist; return c; }
     static constexpr uint32_t reach_before_start = 0; /* distances may not reach before absolute position 0 */
 };
 struct OutBytesWin { /* like OutBytes, but positions below `floor` are read from a resolved 32 KiB window */
     uint8_t *base;
     const uint8_t *win; /* win[32768 - k] = the byte k positions before `floor` */
     uint64_t floor;
+    struct Cursor {
+        uint8_t *d;
+        const uint8_t *s;  /* source in the output buffer */
+        const uint8_t *ws; /* source in the window for offsets below `nwin` */
+        uint32_t nwin;
+        __device__ __forceinline__ uint32_t src(uint32_t i) const { return i < nwin ? ws[i] : s[i]; }
+        __device__ __forceinline__ void put(uint32_t i, uint32_t v) const { d[i] = (uint8_t)v; }
+    };
     __device__ __forceinline__ void put(uint64_t p, uint32_t v) const { base[p] = (uint8_t)v; }
-    __device__ __forceinline__ uint32_t get(uint64_t p) const { return p < floor ? win[32768u - (uint32_t)(floor - p)] : base[p]; }
+    __device__ __forceinline__ Cursor cursor(uint64_t dst, uint32_t dist) const {
+        Cursor c;
+        c.d = base + dst;
+        c.s = c.d - dist;
+        const uint64_t first = dst - dist; /* may lie before the floor (never before floor - 32768) */
+        c.nwin = first < floor ? (uint32_t)(floor - first) : 0u;
+        c.ws = win + 32768 - c.nwin;
+        return c;
+    }
     static constexpr uint32_t reach_before_start = 0;
 };
 struct OutSymRing { /* 16-bit symbols in a 65536-entry ring: < 256 literal byte, 0x8000|i = byte i of the unknown 32 KiB window */
     uint16_t *ring;
+    struct Cursor {
+        uint16_t *ring;
+        uint32_t d0, s0;
+        __device__ __forceinline__ uint32_t src(uint32_t i) const { return ring[(s0 + i) & 65535u]; }
+        __device__ __forceinline__ void put(uint32_t i, uint32_t v) const { ring[(d0 + i) & 65535u] = (uint16_t)v; }
+    };
     __device__ __forceinline__ void put(uint64_t p, uint32_t v) const { ring[(uint32_t)p & 65535u] = (uint16_t)v; }
-    __device__ __forceinline__ uint32_t get(uint64_t p) const { return ring[(uint32_t)p & 65535u]; }
+    __device__ __forceinline__ Cursor cursor(uint64_t dst, uint32_t dist) const { Cursor c; c.ring = ring; c.d0 = (uint32_t)dst; c.s0 = c.d0 - dist; return c; }
     static constexpr uint32_t reach_before_start = 32768; /* relative positions: the window before 0 is legal history */
 };
 
@@ -326,17 +366,19 @@ struct OutSymRing { /* 16-bit symbols in a 65536-entry ring: < 256 literal byte,
 template <class Out>
 __device__ __forceinline__ void inf_copy_match(const Out &o, uint64_t dst, uint32_t len, uint32_t dist) {
     const unsigned lane = lane_id();
+    const typename Out::Cursor c = o.cursor(dst, dist);
     __syncwarp(); /* lane 0's literal stores are history now */
     if (dist >= len) {
-        for (uint32_t i = lane; i < len; i += 32) o.put(dst + i, o.get(dst + i - dist));
+        if (lane < len) c.put(lane, c.src(lane)); /* most matches are shorter than a warp */
+        for (uint32_t i = lane + 32; i < len; i += 32) c.put(i, c.src(i));
     } else if (dist >= 32) {
         for (uint32_t done = 0; done < len; done += 32) {
             const uint32_t i = done + lane;
-            if (i < len) o.put(dst + i, o.get(dst + i - dist));
+            if (i < len) c.put(i, c.src(i));
             __syncwarp();
         }
     } else { /* short period: every source lies before dst */
-        for (uint32_t i = lane; i < len; i += 32) o.put(dst + i, o.get(dst - dist + (i % dist)));
+        for (uint32_t i = lane; i < len; i += 32) c.put(i, c.src(i % dist));
     }
     __syncwarp();
 }
@@ -348,41 +390,42 @@ enum { INF_EV_BUDGET = 0, INF_EV_MATCH = 1, INF_EV_EOB = 2, INF_EV_NEED_IN = 3, 
  * flow stays uniform (no divergence, no broadcast of the result), only lane 0 stores the literals. CAREFUL: the
  * output window may not hold the next token -- decode exactly one and un-read it if it does not fit. */
 template <class Out, bool CAREFUL>
-__device__ __forceinline__ uint32_t inf_run(const InfTables &T, InfBits &b, const Out &o, uint64_t &out_pos, uint64_t out_end, uint32_t &budget) {
+__device__ __forceinline__ uint32_t inf_run(const Smem &sm, const InfTables &T, InfBits &b, const Out &o, uint64_t &out_pos, uint64_t out_end,
+                                            uint32_t &budget) {
     const bool writer = lane_id() == 0;
     while (budget) {
         budget--;
         InfBits saved;
         if (CAREFUL) saved = b;
-        uint32_t e = T.lit[(uint32_t)b.bb & ((1u << INF_PB) - 1u)];
+        uint32_t e = sm.ld32(INF_OFF_LIT + ((b.lo & ((1u << INF_PB) - 1u)) << 2));
         if (e) {
             b.drop(e & 15u);
             b.refill();
         } else {
-            const int sym = inf_slow_decode((uint32_t)b.bb, T.lcount, T.lsym);
+            const int sym = inf_slow_decode(b.lo, T.lcount, T.lsym);
             if (sym < 0) return INF_EV_DATA_ERR << 28;
             b.drop((uint32_t)sym >> 16);
             b.refill();
             e = inf_entry(INF_ALPHA_LITLEN, (uint32_t)sym & 0xffffu, 0);
         }
-        const uint32_t kind = (e >> 8) & 3u;
-        if (kind == INF_K_LIT) {
+        if ((e & 0x300u) == 0) { /* INF_K_LIT */
             if (CAREFUL && out_pos >= out_end) { b = saved; return INF_EV_NEED_OUT << 28; }
             if (writer) o.put(out_pos, e >> 16);
             out_pos++;
             continue;
         }
+        const uint32_t kind = (e >> 8) & 3u;
         if (kind == INF_K_EOB) return INF_EV_EOB << 28;
         if (kind == INF_K_BAD) return INF_EV_DATA_ERR << 28;
         uint32_t eb = (e >> 4) & 15u;
         const uint32_t mlen = (e >> 16) + b.peek(eb);
         b.drop(eb); /* >= 27 bits remain: enough for any distance code */
-        uint32_t de = T.dist[(uint32_t)b.bb & ((1u << INF_DB) - 1u)];
+        uint32_t de = sm.ld32(INF_OFF_DIST + ((b.lo & ((1u << INF_DB) - 1u)) << 2));
         if (de) {
             b.drop(de & 15u);
             b.refill();
         } else {
-            const int ds = inf_slow_decode((uint32_t)b.bb, T.dcount, T.dsym);
+            const int ds = inf_slow_decode(b.lo, T.dcount, T.dsym);
             if (ds < 0) return INF_EV_DATA_ERR << 28;
             b.drop((uint32_t)ds >> 16);
             b.refill();
@@ -400,12 +443,19 @@ __device__ __forceinline__ uint32_t inf_run(const InfTables &T, InfBits &b, cons
 }
 
 /* Decode one stream window with one warp. `o` receives the output; positions are the absolute out_pos of the
- * state. stop_bit: return with why = BOUNDARY at the first block boundary whose absolute bit position is >= stop_bit
- * (or after one block when the job asks for it). */
-template <class Out>
-__device__ __forceinline__ void inf_decode_window(const InflateJob &job, InflateState *st, InfTables &T, const Out &o, uint64_t stop_bit) {
+ * state. stop(pos): asked at every block boundary (absolute bit position); true = return with why = BOUNDARY
+ * (also after every block when the job asks for it). */
+struct StopAtBit { /* stop at the first block boundary at or after an absolute bit position */
+    uint64_t bit;
+    __device__ __forceinline__ bool operator()(uint64_t pos) const { return pos >= bit; }
+};
+
+template <class Out, class Stop>
+__device__ __forceinline__ void inf_decode_window(const InflateJob &job, InflateState *st, InfTables &T, const Out &o, const Stop &stop) {
     const unsigned lane = lane_id();
     InfBits b; /* identical in every lane */
+    Smem sm;
+    sm.init(reinterpret_cast<uint8_t *>(&T));
     uint64_t out_pos = st->out_pos;
     uint32_t phase = st->phase, last = st->last_block, stored_rem = st->stored_remaining;
     uint32_t nlit = st->nlit, ndist = st->ndist, blocks = st->blocks;
@@ -482,58 +532,62 @@ __device__ __forceinline__ void inf_decode_window(const InflateJob &job, Inflate
             } else {
                 why = INF_WHY_INPUT;
             }
-        } else { /* INF_PH_CODES */
-            uint32_t pk = INF_EV_BUDGET << 28;
-            bool careful = false;
-            if (budget == 0) {
-                const int64_t left = b.bits_left();
-                if (left < 0) pk = INF_EV_BUF_ERR << 28; /* ran past the end of the stream */
-                else {
-                    /* a token reads at most 48 bits and writes at most 258 bytes */
-                    const uint64_t nin = job.in_final ? (uint64_t)(left >> 6) + 1u : (left < 192 ? 0u : (uint64_t)(left - 128) >> 6);
-                    const uint64_t room = out_end - out_pos;
-                    if (nin == 0) pk = INF_EV_NEED_IN << 28;
-                    else if (room < 512 || (job.in_final && left < 192)) { careful = true; budget = 1; } /* token by token near either end */
+        } else { /* INF_PH_CODES: tokens until the block ends or a window limit is reached */
+            for (;;) {
+                uint32_t pk = INF_EV_BUDGET << 28;
+                if (budget == 0) {
+                    bool careful = false;
+                    const int64_t left = b.bits_left();
+                    if (left < 0) pk = INF_EV_BUF_ERR << 28; /* ran past the end of the stream */
                     else {
-                        uint64_t n = room >> 9;
-                        if (n > nin) n = nin;
-                        budget = n > 65536u ? 65536u : (uint32_t)n;
+                        /* a token reads at most 48 bits and writes at most 258 bytes */
+                        const uint64_t nin = job.in_final ? (uint64_t)(left >> 6) + 1u : (left < 192 ? 0u : (uint64_t)(left - 128) >> 6);
+                        const uint64_t room = out_end - out_pos;
+                        if (nin == 0) pk = INF_EV_NEED_IN << 28;
+                        else if (room < 512 || (job.in_final && left < 192)) careful = true; /* token by token near either end */
+                        else {
+                            uint64_t n = room >> 9;
+                            if (n > nin) n = nin;
+                            budget = n > 65536u ? 65536u : (uint32_t)n;
+                        }
+                    }
+                    if (careful) {
+                        const uint64_t before = out_pos;
+                        budget = 1;
+                        pk = inf_run<Out, true>(sm, T, b, o, out_pos, out_end, budget);
+                        budget = 0;
+                        if (b.bits_left() < 0) { out_pos = before; pk = INF_EV_BUF_ERR << 28; } /* the token lay past the end of the stream */
                     }
                 }
-            }
-            if (budget) {
-                if (careful) {
-                    const uint64_t before = out_pos;
-                    pk = inf_run<Out, true>(T, b, o, out_pos, out_end, budget);
-                    budget = 0;
-                    if (b.bits_left() < 0) { out_pos = before; pk = INF_EV_BUF_ERR << 28; } /* the token lay past the end of the stream */
-                } else {
-                    pk = inf_run<Out, false>(T, b, o, out_pos, out_end, budget);
-                    if ((pk >> 28) == INF_EV_EOB && b.bits_left() < 0) pk = INF_EV_BUF_ERR << 28; /* the end-of-block code lay past the end */
+                if (budget) pk = inf_run<Out, false>(sm, T, b, o, out_pos, out_end, budget);
+                const uint32_t ev = pk >> 28;
+                if (ev == INF_EV_MATCH) {
+                    const uint32_t mlen = (pk >> 16) & 0x1ffu, mdist = (pk & 0xffffu) + 1u;
+                    if (mdist > out_pos + Out::reach_before_start) { status = INF_ST_DATA_ERROR; break; } /* too far back */
+                    inf_copy_match(o, out_pos, mlen, mdist);
+                    out_pos += mlen;
+                    continue;
                 }
-            }
-            const uint32_t ev = pk >> 28;
-            if (ev == INF_EV_MATCH) {
-                const uint32_t mlen = (pk >> 16) & 0x1ffu, mdist = (pk & 0xffffu) + 1u;
-                if (mdist > out_pos + Out::reach_before_start) { status = INF_ST_DATA_ERROR; break; } /* too far back */
-                inf_copy_match(o, out_pos, mlen, mdist);
-                out_pos += mlen;
-            } else if (ev == INF_EV_EOB) {
-                phase = INF_PH_HEADER;
-                blocks++;
-                if (last) status = INF_ST_END;
-            } else if (ev == INF_EV_NEED_IN) {
-                why = INF_WHY_INPUT;
-            } else if (ev == INF_EV_NEED_OUT) {
-                why = INF_WHY_OUTPUT;
-            } else if (ev == INF_EV_DATA_ERR) {
-                status = INF_ST_DATA_ERROR;
-            } else if (ev == INF_EV_BUF_ERR) {
-                status = INF_ST_BUF_ERROR;
+                if (ev == INF_EV_BUDGET) continue;
+                if (ev == INF_EV_EOB) {
+                    if (b.bits_left() < 0) { status = INF_ST_BUF_ERROR; break; } /* the end-of-block code lay past the end */
+                    phase = INF_PH_HEADER;
+                    blocks++;
+                    if (last) status = INF_ST_END;
+                } else if (ev == INF_EV_NEED_IN) {
+                    why = INF_WHY_INPUT;
+                } else if (ev == INF_EV_NEED_OUT) {
+                    why = INF_WHY_OUTPUT;
+                } else if (ev == INF_EV_DATA_ERR) {
+                    status = INF_ST_DATA_ERROR;
+                } else {
+                    status = INF_ST_BUF_ERROR;
+                }
+                break;
             }
         }
         if (phase == INF_PH_HEADER && status == INF_ST_RUN && why == INF_WHY_NONE) { /* at a block boundary */
-            if (stop_each_block || job.in_base * 8 + b.bitpos() >= stop_bit) why = INF_WHY_BOUNDARY;
+            if (stop_each_block || stop(job.in_base * 8 + b.bitpos())) why = INF_WHY_BOUNDARY;
         }
     }
     /* ---- save state ------------------------------------------------------------------------------- */
@@ -566,7 +620,7 @@ __global__ void __launch_bounds__(INF_THREADS) inflate_streams_kernel(const Infl
         if (st->status != INF_ST_RUN) continue;
         OutBytes o;
         o.base = job.out - job.out_base; /* index with absolute positions */
-        inf_decode_window(job, st, T, o, ~0ull);
+        inf_decode_window(job, st, T, o, StopAtBit{~0ull});
     }
 }
 

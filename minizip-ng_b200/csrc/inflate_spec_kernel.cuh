@@ -161,6 +161,26 @@ __global__ void __launch_bounds__(INF_THREADS) inflate_spec_find_kernel(SpecPara
 }
 
 /* ---- K6b ------------------------------------------------------------------------------------------------------ */
+/* Where a scanning warp stops: at a block boundary that IS some later segment's guess (the chain can link there).
+ * A boundary that is nobody's guess (a segment whose only guess was a false positive, or one without any) is
+ * walked through: this warp simply decodes the next block as well. Past the last guess of the window it stops at
+ * the first boundary beyond its own segment; what lies further is the next round's business. */
+struct SpecStop {
+    const SpecSeg *seg;
+    uint64_t start0, seg_bits, first_later;
+    uint32_t nseg, k;
+    __device__ __forceinline__ bool operator()(uint64_t pos) const {
+        if (first_later != SPEC_NONE && pos < first_later) return false;
+        uint64_t j = (pos - start0) / seg_bits;
+        if (j <= k) j = k + 1;
+        for (; j < nseg; j++) {
+            const uint64_t g = seg[j].start_bit;
+            if (g != SPEC_NONE && g >= pos) return g == pos;
+        }
+        return pos >= start0 + (uint64_t)(k + 1) * seg_bits;
+    }
+};
+
 __global__ void __launch_bounds__(INF_THREADS) inflate_spec_scan_kernel(SpecParams P) {
     MZ_DYN_SMEM(smem);
     InfTables &T = *reinterpret_cast<InfTables *>(smem);
@@ -172,17 +192,21 @@ __global__ void __launch_bounds__(INF_THREADS) inflate_spec_scan_kernel(SpecPara
             if (lane == 0) { sg->status = INF_ST_RUN; sg->why = INF_WHY_NONE; sg->out_count = 0; sg->end_bit = 0; sg->blocks = 0; }
             continue;
         }
-        /* stop at the first block boundary at or after the next guessed start */
-        uint64_t stop = SPEC_NONE;
-        for (uint32_t j0 = k + 1; j0 < P.nseg && stop == SPEC_NONE; j0 += 32) {
+        /* the first guess after this segment: nothing can be linked before it */
+        uint64_t first_later = SPEC_NONE;
+        for (uint32_t j0 = k + 1; j0 < P.nseg && first_later == SPEC_NONE; j0 += 32) {
             const uint32_t j = j0 + lane;
             const uint64_t s = j < P.nseg ? P.seg[j].start_bit : SPEC_NONE;
             const unsigned m = __ballot_sync(MZ_FULL_MASK, s != SPEC_NONE);
-            if (m) stop = __shfl_sync(MZ_FULL_MASK, s, __ffs((int)m) - 1);
+            if (m) first_later = __shfl_sync(MZ_FULL_MASK, s, __ffs((int)m) - 1);
         }
-        /* the last guess of the window: go on to the first boundary past its own segment; what lies beyond is the
-         * next round's business */
-        if (stop == SPEC_NONE) stop = P.start_bit + (uint64_t)(k + 1) * P.seg_bits;
+        SpecStop stop;
+        stop.seg = P.seg;
+        stop.nseg = P.nseg;
+        stop.k = k;
+        stop.start0 = P.start_bit;
+        stop.seg_bits = P.seg_bits;
+        stop.first_later = first_later;
         uint16_t *ring = P.rings + (size_t)k * SPEC_RING;
         for (uint32_t i = lane; i < 32768; i += 32) ring[32768 + i] = (uint16_t)(0x8000u | i); /* positions -32768..-1 */
         InflateState *st = &P.states[k];
@@ -246,9 +270,9 @@ __global__ void inflate_spec_chain_kernel(SpecParams P) {
         s.blocks += sg->blocks;
         s.end_bit = sg->end_bit;
         if (sg->status == INF_ST_END) { s.status = INF_ST_END; break; }
-        uint32_t j = cur + 1;
-        while (j < P.nseg && P.seg[j].start_bit == SPEC_NONE) j++;
-        if (j >= P.nseg || P.seg[j].start_bit != sg->end_bit) break; /* the guess was not where the stream really continues */
+        uint32_t j = cur + 1; /* guesses the scan walked through (false positives) lie before its end bit */
+        while (j < P.nseg && (P.seg[j].start_bit == SPEC_NONE || P.seg[j].start_bit < sg->end_bit)) j++;
+        if (j >= P.nseg || P.seg[j].start_bit != sg->end_bit) break; /* nobody started where the stream really continues */
         cur = j;
     }
     *P.summary = s;
@@ -321,7 +345,7 @@ __global__ void __launch_bounds__(INF_THREADS) inflate_spec_emit_kernel(SpecPara
         o.base = P.out - P.out_base;
         o.win = P.wins + (size_t)k * 32768;
         o.floor = first;
-        inf_decode_window(job, st, T, o, sg.end_bit);
+        inf_decode_window(job, st, T, o, StopAtBit{sg.end_bit});
         if (lane == 0) {
             const bool same = st->in_bitpos == sg.end_bit && st->out_pos == first + sg.out_count && st->status == sg.status &&
                               (sg.status == INF_ST_END || st->why == INF_WHY_BOUNDARY);

@@ -11,6 +11,8 @@
 #include "concat_kernel.cuh"
 #include "crc32_kernel.cuh"
 #include "deflate_kernel.cuh"
+#include <cstdlib>
+#include <cstdio>
 #include "inflate_kernel.cuh"
 #include "inflate_spec_kernel.cuh"
 
@@ -445,12 +447,29 @@ int32_t mz_cuda_inflate_spec_round(const void *d_in, uint64_t in_base, uint64_t 
     cudaStream_t s = (cudaStream_t)stream;
     const uint32_t maxgrid = (uint32_t)c->sm_count * 32u;
     const uint32_t grid = nseg < maxgrid ? nseg : maxgrid;
+    const bool trace = getenv("MZ_CUDA_TRACE") != nullptr; /* per-kernel times of the round on stderr (debug aid, serialises) */
+    cudaEvent_t ev[6];
+    if (trace)
+        for (int i = 0; i < 6; i++) CK(cudaEventCreate(&ev[i]));
+    if (trace) CK(cudaEventRecord(ev[0], s));
     MZ_LAUNCH(inflate_spec_find_kernel, dim3(grid), dim3(INF_THREADS), SPEC_FIND_SMEM, s, P);
+    if (trace) CK(cudaEventRecord(ev[1], s));
     MZ_LAUNCH(inflate_spec_scan_kernel, dim3(grid), dim3(INF_THREADS), INF_SMEM_BYTES, s, P);
+    if (trace) CK(cudaEventRecord(ev[2], s));
     MZ_LAUNCH(inflate_spec_chain_kernel, dim3(1), dim3(32), 0, s, P);
+    if (trace) CK(cudaEventRecord(ev[3], s));
     MZ_LAUNCH(inflate_spec_resolve_kernel, dim3(1), dim3(SPEC_RESOLVE_THREADS), 65536, s, P);
+    if (trace) CK(cudaEventRecord(ev[4], s));
     MZ_LAUNCH(inflate_spec_emit_kernel, dim3(grid), dim3(INF_THREADS), INF_SMEM_BYTES, s, P);
+    if (trace) CK(cudaEventRecord(ev[5], s));
     CK(cudaGetLastError());
+    if (trace) {
+        CK(cudaEventSynchronize(ev[5]));
+        float t[5];
+        for (int i = 0; i < 5; i++) CK(cudaEventElapsedTime(&t[i], ev[i], ev[i + 1]));
+        fprintf(stderr, "mz_cuda: K6 kernels ms: find %.3f scan %.3f chain %.3f resolve %.3f emit %.3f (%u segments)\n", t[0], t[1], t[2], t[3], t[4], nseg);
+        for (int i = 0; i < 6; i++) cudaEventDestroy(ev[i]);
+    }
     return MZ_OK;
 }
 

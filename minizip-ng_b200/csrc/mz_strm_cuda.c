@@ -581,8 +581,8 @@ static void ws_read_upgrade(cu_ws *w, size_t cin_len) {
     const char *off = getenv("MZ_CUDA_SPEC");
     if (off && off[0] == '0')
         return;
-    size_t cin_cap = env_size("MZ_CUDA_READ_WINDOW_KB", 32u << 10, 1024);
-    size_t seg = env_size("MZ_CUDA_SPEC_SEG_KB", 16, 1024);
+    size_t cin_cap = env_size("MZ_CUDA_READ_WINDOW_KB", 32u << 20, 1024);
+    size_t seg = env_size("MZ_CUDA_SPEC_SEG_KB", 16u << 10, 1024);
     if (cin_cap <= w->cin_cap || seg < 1024)
         return;
     size_t win_cap = 32768 + 4 * cin_cap;
@@ -693,6 +693,10 @@ static int32_t cu_spec_round(mz_stream_cuda *cu) {
     if (err)
         return err;
     const mz_cuda_spec_summary *sm = w->h_sum;
+    if (getenv("MZ_CUDA_TRACE"))
+        fprintf(stderr, "mz_strm_cuda: K6 round at bit %llu: %llu segments, %u guesses, %u proven, %llu bytes out, end bit %llu, status %d, flags %u\n",
+                (unsigned long long)st->in_bitpos, (unsigned long long)nseg, sm->candidates, sm->nchain, (unsigned long long)sm->total_out,
+                (unsigned long long)sm->end_bit, sm->status, sm->flags);
     if (sm->flags || sm->nchain == 0 || (sm->end_bit <= st->in_bitpos && sm->status != 1)) {
         /* nothing proven: let the serial decoder move on; if the window holds no other block start at all
          * (stored or fixed blocks, one giant block), do not try again before it has been consumed */
@@ -819,6 +823,8 @@ static int32_t cu_decode_more(mz_stream_cuda *cu) {
         err = mz_cuda_inflate_streams(w->d_job, w->d_state, 1, NULL);
         if (err)
             return err;
+        if (getenv("MZ_CUDA_TRACE"))
+            fprintf(stderr, "mz_strm_cuda: K5 launch at bit %llu (window %zu bytes, large %d)\n", (unsigned long long)st->in_bitpos, cu->cin_len, w->large);
         err = mz_cuda_memcpy_d2h(st, w->d_state, sizeof(*st), NULL);
         if (err)
             return err;

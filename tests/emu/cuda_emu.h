@@ -219,6 +219,10 @@ static inline unsigned __funnelshift_r(unsigned lo, unsigned hi, unsigned shift)
     uint64_t v = ((uint64_t)hi << 32) | lo;
     return (unsigned)(v >> (shift & 31));
 }
+static inline unsigned __funnelshift_rc(unsigned lo, unsigned hi, unsigned shift) { /* clamped at 32 */
+    if (shift >= 32) return hi;
+    return shift ? (lo >> shift) | (hi << (32 - shift)) : lo;
+}
 static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned shift) {
     uint64_t v = ((uint64_t)hi << 32) | lo;
     return (unsigned)((v << (shift & 31)) >> 32);

@@ -142,6 +142,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "single":
         single(int(sys.argv[2]))
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "batch":
+        batch(int(sys.argv[2]))
+        sys.exit(0)
     crc(64)
     crc(4096)
     single(16)
