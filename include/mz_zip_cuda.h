@@ -1,0 +1,53 @@
+/* mz_zip_cuda.h -- batch zip-entry writer on the reference's RAW-entry seam.
+ *
+ * The reference compresses a zip entry by pushing its bytes through mz_stream_zlib, one entry at a time
+ * (mz_zip_entry_write_open -> mz_zip_entry_write -> mz_zip_entry_close, mz_zip.c:1915,2056,2269). This routine keeps
+ * the container code exactly where it is and only moves the codec work: all entries of a batch are DEFLATE-compressed
+ * and CRC'd on the GPU in ONE launch each (every entry its own raw stream: 64 KiB chunks joined by sync markers,
+ * BFINAL on the entry's last chunk), then handed to the reference through its raw seam
+ *     mz_zip_entry_write_open(handle, &file_info, level, raw = 1, NULL)     mz_zip.c:1915
+ *     mz_zip_entry_write(handle, compressed, size)                          mz_zip.c:2056
+ *     mz_zip_entry_close_raw(handle, uncompressed_size, crc32)              mz_zip.c:2272
+ * so local headers, zip64 decisions and the central directory stay the reference's own code.
+ *
+ * Linking: the three functions above (plus nothing else) are taken from the HOST program, which links the
+ * reference's mz_zip.c. They are declared weak here, so libmz_strm_cuda.so still loads in a process that has no
+ * zip container (the call then returns MZ_SUPPORT_ERROR).
+ */
+#ifndef MZ_ZIP_CUDA_H
+#define MZ_ZIP_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mz_cuda_zip_item {
+    const char *filename;    /* utf-8, null terminated (stored with MZ_ZIP_FLAG_UTF8) */
+    const void *data;        /* host memory, `size` bytes (may be NULL when size == 0) */
+    int64_t size;
+    int64_t modified_date;   /* unix time; 0 = now */
+    uint32_t external_fa;    /* 0 = regular file 0644 */
+    uint32_t reserved;
+} mz_cuda_zip_item;
+
+typedef struct mz_cuda_zip_stats {
+    uint64_t bytes_in, bytes_out;
+    uint32_t entries, rounds;
+    double pack_ms, gpu_ms, container_ms; /* host packing + upload, device work + download, reference container calls */
+} mz_cuda_zip_stats;
+
+/* Append `count` entries to the zip that `zip_handle` (an open mz_zip writer, mz_zip.c:1237 mz_zip_open) is writing.
+ * level: 0..9 or -1 (= 6), as mz_zip_entry_write_open takes it. Returns MZ_OK or the first error (MZ_* codes).
+ * stats may be NULL. */
+int32_t mz_zip_cuda_add_buffers(void *zip_handle, const mz_cuda_zip_item *items, uint32_t count, int16_t level,
+                                mz_cuda_zip_stats *stats);
+
+/* sizeof the mz_zip_file mirror this library was built with: the host asserts it equals sizeof(mz_zip_file) */
+uint32_t mz_zip_cuda_abi_file_info_size(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -73,7 +73,7 @@ struct SpecParams {
     InflateState *states; /* [nseg] */
     uint16_t *rings;     /* [nseg][SPEC_RING] */
     uint8_t *wins;       /* [nseg][32768] */
-    uint32_t *chain;     /* [nseg] */
+    uint32_t *chain;     /* [nseg] pairs {segment, bytes produced mod 2^32}, chain order */
     SpecSummary *summary;
 };
 
@@ -246,8 +246,46 @@ __global__ void __launch_bounds__(INF_THREADS) inflate_spec_scan_kernel(SpecPara
 }
 
 /* ---- K6c ------------------------------------------------------------------------------------------------------ */
-__global__ void inflate_spec_chain_kernel(SpecParams P) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+/* One CTA. Parallel part: every segment decides whether its scan ended on a block boundary and which later segment
+ * (if any) starts exactly there; the verdicts go to shared memory. Serial part: thread 0 follows the links from the
+ * anchored segment -- a walk over shared memory, a few nanoseconds per member -- adding up output offsets until a
+ * link is missing, the output window is full, or the stream ends. chain[] holds {segment, byte count mod 2^32} pairs. */
+constexpr int SPEC_CHAIN_THREADS = 1024;
+constexpr uint32_t SPEC_LINK_NONE = 0xffffffffu, SPEC_LINK_END = 0xfffffffeu, SPEC_LINK_BROKEN = 0xfffffffdu;
+constexpr uint32_t SPEC_MAX_SEGMENTS = 12288; /* 16 bytes of shared memory per segment in K6c */
+__global__ void __launch_bounds__(SPEC_CHAIN_THREADS) inflate_spec_chain_kernel(SpecParams P) {
+    MZ_DYN_SMEM(smem);
+    uint64_t *s_cnt = reinterpret_cast<uint64_t *>(smem);
+    uint32_t *s_link = reinterpret_cast<uint32_t *>(smem + (size_t)P.nseg * 8);
+    uint32_t *s_blocks = s_link + P.nseg;
+    __shared__ uint32_t s_cand;
+    if (threadIdx.x == 0) s_cand = 0;
+    __syncthreads();
+    uint32_t cand = 0;
+    for (uint32_t k = threadIdx.x; k < P.nseg; k += blockDim.x) {
+        const SpecSeg sg = P.seg[k];
+        cand += sg.start_bit != SPEC_NONE;
+        uint32_t link = SPEC_LINK_BROKEN;
+        if (sg.start_bit != SPEC_NONE) {
+            if (sg.status == INF_ST_END) link = SPEC_LINK_END;
+            else if (sg.status == INF_ST_RUN && sg.why == INF_WHY_BOUNDARY) {
+                link = SPEC_LINK_NONE; /* whole, but maybe nobody starts where it ends */
+                uint32_t j = k + 1;    /* guesses the scan walked through (false positives) lie before its end bit */
+                while (j < P.nseg) {
+                    const uint64_t g = P.seg[j].start_bit;
+                    if (g != SPEC_NONE && g >= sg.end_bit) break;
+                    j++;
+                }
+                if (j < P.nseg && P.seg[j].start_bit == sg.end_bit) link = j;
+            }
+        }
+        s_link[k] = link;
+        s_cnt[k] = sg.out_count;
+        s_blocks[k] = sg.blocks;
+    }
+    if (cand) atomicAdd(&s_cand, cand);
+    __syncthreads();
+    if (threadIdx.x != 0) return;
     SpecSummary s;
     s.end_bit = P.start_bit;
     s.total_out = 0;
@@ -255,56 +293,98 @@ __global__ void inflate_spec_chain_kernel(SpecParams P) {
     s.status = INF_ST_RUN;
     s.blocks = 0;
     s.flags = 0;
-    s.candidates = 0;
+    s.candidates = s_cand;
     s.pad = 0;
-    for (uint32_t k = 0; k < P.nseg; k++) s.candidates += P.seg[k].start_bit != SPEC_NONE;
-    uint32_t cur = 0;
+    uint32_t cur = 0, lastk = SPEC_LINK_NONE;
     while (cur < P.nseg) {
-        SpecSeg *sg = &P.seg[cur];
-        const bool whole = (sg->status == INF_ST_RUN && sg->why == INF_WHY_BOUNDARY) || sg->status == INF_ST_END;
-        if (!whole) break;
-        if (P.out_pos + s.total_out + sg->out_count > P.out_end) break;
-        sg->out_off = s.total_out;
-        P.chain[s.nchain++] = cur;
-        s.total_out += sg->out_count;
-        s.blocks += sg->blocks;
-        s.end_bit = sg->end_bit;
-        if (sg->status == INF_ST_END) { s.status = INF_ST_END; break; }
-        uint32_t j = cur + 1; /* guesses the scan walked through (false positives) lie before its end bit */
-        while (j < P.nseg && (P.seg[j].start_bit == SPEC_NONE || P.seg[j].start_bit < sg->end_bit)) j++;
-        if (j >= P.nseg || P.seg[j].start_bit != sg->end_bit) break; /* nobody started where the stream really continues */
-        cur = j;
+        const uint32_t link = s_link[cur];
+        if (link == SPEC_LINK_BROKEN) break;
+        const uint64_t cnt = s_cnt[cur];
+        if (P.out_pos + s.total_out + cnt > P.out_end) break;
+        P.seg[cur].out_off = s.total_out;
+        P.chain[2 * s.nchain] = cur;
+        P.chain[2 * s.nchain + 1] = (uint32_t)cnt;
+        s.nchain++;
+        s.total_out += cnt;
+        s.blocks += s_blocks[cur];
+        lastk = cur;
+        if (link == SPEC_LINK_END) { s.status = INF_ST_END; break; }
+        if (link == SPEC_LINK_NONE) break; /* nobody started where the stream really continues */
+        cur = link;
     }
+    if (lastk != SPEC_LINK_NONE) s.end_bit = P.seg[lastk].end_bit;
     *P.summary = s;
 }
 
 /* ---- K6d ------------------------------------------------------------------------------------------------------ */
+/* One CTA, serial over the chain (member i's window needs member i-1's), 32768 symbols per step:
+ *   1. the member's last 32768 ring symbols are staged into shared memory with aligned 16-byte loads (the slice
+ *      starts anywhere in the ring). The loads for step i+1 are issued BEFORE step i's lookups and land in
+ *      registers, so the global round trip hides behind the arithmetic of the current step,
+ *   2. each thread resolves 8 x 4 symbols against the previous window (shared) and writes the bytes to the next
+ *      window (shared, for the next step) and to global (for K6e). */
+constexpr int SPEC_RESOLVE_SMEM = 32768 * 2 + (32768 + 16) * 2;
+constexpr int SPEC_SLICE_VECS = 32768 / 8 + 1; /* 16-byte vectors per slice */
+__device__ __forceinline__ void spec_load_slice(const SpecParams &P, uint32_t k, uint32_t cnt, uint4 (&r)[5]) {
+    const uint16_t *ring = P.rings + (size_t)k * SPEC_RING;
+    const uint32_t tail8 = (cnt - 32768u) & ~7u;
+#pragma unroll
+    for (int t = 0; t < 5; t++) {
+        const uint32_t v = threadIdx.x + (uint32_t)t * SPEC_RESOLVE_THREADS;
+        if (v < SPEC_SLICE_VECS) r[t] = *reinterpret_cast<const uint4 *>(ring + ((tail8 + 8u * v) & (SPEC_RING - 1)));
+    }
+}
 __global__ void __launch_bounds__(SPEC_RESOLVE_THREADS) inflate_spec_resolve_kernel(SpecParams P) {
-    MZ_DYN_SMEM(smem); /* two 32 KiB windows */
+    MZ_DYN_SMEM(smem);
     uint8_t *wa = smem, *wb = smem + 32768;
+    uint16_t *slice = reinterpret_cast<uint16_t *>(smem + 65536); /* 32768 + 8 symbols, starts at an 8-aligned ring index */
     const uint32_t n = P.summary->nchain;
     if (n == 0) return;
+    uint32_t k = P.chain[0], cnt = P.chain[1];
+    uint32_t knext = n > 1 ? P.chain[2] : 0, cntnext = n > 1 ? P.chain[3] : 0;
+    uint4 r[5];
+    if (n > 1) spec_load_slice(P, k, cnt, r);
     /* the window before the anchored member is real output (zeros where the stream has no history yet) */
     for (uint32_t j = threadIdx.x; j < 32768; j += blockDim.x) {
         const uint64_t back = 32768 - j;
         const uint8_t v = back <= P.out_pos - P.out_base && back <= P.out_pos ? P.out[P.out_pos - back - P.out_base] : (uint8_t)0;
         wa[j] = v;
-        P.wins[(size_t)P.chain[0] * 32768 + j] = v;
+        P.wins[(size_t)k * 32768 + j] = v;
     }
-    __syncthreads();
     for (uint32_t i = 0; i + 1 < n; i++) {
-        const uint32_t k = P.chain[i], knext = P.chain[i + 1];
-        const uint16_t *ring = P.rings + (size_t)k * SPEC_RING;
-        const uint32_t tail = (uint32_t)P.seg[k].out_count - 32768u; /* ring index of window element 0 (mod 65536) */
-        uint8_t *dst = P.wins + (size_t)knext * 32768;
-        for (uint32_t j = threadIdx.x; j < 32768; j += blockDim.x) {
-            const uint32_t s = ring[(tail + j) & (SPEC_RING - 1)];
-            const uint8_t v = s & 0x8000u ? wa[s & 0x7fffu] : (uint8_t)s;
-            wb[j] = v;
-            dst[j] = v;
+        /* registers -> shared: member i's slice */
+#pragma unroll
+        for (int t = 0; t < 5; t++) {
+            const uint32_t v = threadIdx.x + (uint32_t)t * SPEC_RESOLVE_THREADS;
+            if (v < SPEC_SLICE_VECS) reinterpret_cast<uint4 *>(slice)[v] = r[t];
+        }
+        const uint32_t a = (cnt - 32768u) & 7u;
+        __syncthreads();
+        /* in flight during the lookups: member i+1's slice and the chain entry after it */
+        uint32_t k2 = 0, cnt2 = 0;
+        if (i + 2 < n) {
+            k2 = P.chain[2 * (i + 2)];
+            cnt2 = P.chain[2 * (i + 2) + 1];
+            spec_load_slice(P, knext, cntnext, r);
+        }
+        uint32_t *gd = reinterpret_cast<uint32_t *>(P.wins + (size_t)knext * 32768);
+        uint32_t *sd = reinterpret_cast<uint32_t *>(wb);
+#pragma unroll
+        for (int q = 0; q < 8; q++) { /* thread t owns symbols 4t..4t+3 of every 4096-symbol row: conflict-light shared accesses */
+            const uint32_t e0 = threadIdx.x * 4u + 4096u * q;
+            uint32_t acc = 0;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t s0 = slice[a + e0 + u];
+                acc |= (s0 & 0x8000u ? (uint32_t)wa[s0 & 0x7fffu] : (s0 & 0xffu)) << (8 * u);
+            }
+            gd[e0 >> 2] = acc;
+            sd[e0 >> 2] = acc;
         }
         __syncthreads();
         uint8_t *t = wa; wa = wb; wb = t;
+        k = knext; cnt = cntnext;
+        knext = k2; cntnext = cnt2;
     }
 }
 
@@ -315,7 +395,7 @@ __global__ void __launch_bounds__(INF_THREADS) inflate_spec_emit_kernel(SpecPara
     const unsigned lane = lane_id();
     const uint32_t n = P.summary->nchain;
     for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
-        const uint32_t k = P.chain[i];
+        const uint32_t k = P.chain[2 * i];
         const SpecSeg sg = P.seg[k];
         const uint64_t first = P.out_pos + sg.out_off;
         InflateState *st = &P.states[k];

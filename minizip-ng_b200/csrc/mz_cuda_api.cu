@@ -119,7 +119,8 @@ int32_t get_ctx(DeviceCtx **out) {
             CK(cudaFuncSetAttribute(deflate_chunks_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_SMEM_BYTES));
             CK(cudaFuncSetAttribute(crc32_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CRC_SMEM_BYTES));
             CK(cudaFuncSetAttribute(inflate_streams_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, INF_SMEM_BYTES));
-            CK(cudaFuncSetAttribute(inflate_spec_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+            CK(cudaFuncSetAttribute(inflate_spec_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SPEC_RESOLVE_SMEM));
+            CK(cudaFuncSetAttribute(inflate_spec_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SPEC_MAX_SEGMENTS * 16));
             CK(cudaMalloc(&c.d_work, 256 * sizeof(uint32_t)));
             c.ready = true;
         }
@@ -413,7 +414,7 @@ int32_t mz_cuda_inflate_streams(const mz_cuda_inflate_job *d_jobs, mz_cuda_infla
 static inline uint64_t al256(uint64_t v) { return (v + 255) & ~255ull; }
 uint64_t mz_cuda_inflate_spec_workspace_bytes(uint32_t max_segments) {
     const uint64_t m = max_segments;
-    return al256(m * sizeof(SpecSeg)) + al256(m * sizeof(InflateState)) + al256(m * 4) + al256(m * SPEC_RING * 2) + al256(m * 32768) + 256;
+    return al256(m * sizeof(SpecSeg)) + al256(m * sizeof(InflateState)) + al256(m * 8) + al256(m * SPEC_RING * 2) + al256(m * 32768) + 256;
 }
 
 int32_t mz_cuda_inflate_spec_round(const void *d_in, uint64_t in_base, uint64_t in_avail, uint32_t in_final, uint64_t start_bit,
@@ -423,7 +424,7 @@ int32_t mz_cuda_inflate_spec_round(const void *d_in, uint64_t in_base, uint64_t 
     DeviceCtx *c;
     int32_t err = get_ctx(&c);
     if (err) return err;
-    if (nseg == 0 || nseg > max_segments || seg_bytes < 64 || ((uintptr_t)d_in & 3) || !d_workspace || !d_summary) return MZ_PARAM_ERROR;
+    if (nseg == 0 || nseg > max_segments || max_segments > SPEC_MAX_SEGMENTS || seg_bytes < 64 || ((uintptr_t)d_in & 3) || !d_workspace || !d_summary) return MZ_PARAM_ERROR;
     SpecParams P;
     P.in = (const uint8_t *)d_in;
     P.in_base = in_base;
@@ -440,7 +441,7 @@ int32_t mz_cuda_inflate_spec_round(const void *d_in, uint64_t in_base, uint64_t 
     const uint64_t m = max_segments;
     P.seg = (SpecSeg *)w;            w += al256(m * sizeof(SpecSeg));
     P.states = (InflateState *)w;    w += al256(m * sizeof(InflateState));
-    P.chain = (uint32_t *)w;         w += al256(m * 4);
+    P.chain = (uint32_t *)w;         w += al256(m * 8);
     P.rings = (uint16_t *)w;         w += al256(m * SPEC_RING * 2);
     P.wins = w;
     P.summary = (SpecSummary *)d_summary;
@@ -456,9 +457,9 @@ int32_t mz_cuda_inflate_spec_round(const void *d_in, uint64_t in_base, uint64_t 
     if (trace) CK(cudaEventRecord(ev[1], s));
     MZ_LAUNCH(inflate_spec_scan_kernel, dim3(grid), dim3(INF_THREADS), INF_SMEM_BYTES, s, P);
     if (trace) CK(cudaEventRecord(ev[2], s));
-    MZ_LAUNCH(inflate_spec_chain_kernel, dim3(1), dim3(32), 0, s, P);
+    MZ_LAUNCH(inflate_spec_chain_kernel, dim3(1), dim3(SPEC_CHAIN_THREADS), (size_t)nseg * 16, s, P);
     if (trace) CK(cudaEventRecord(ev[3], s));
-    MZ_LAUNCH(inflate_spec_resolve_kernel, dim3(1), dim3(SPEC_RESOLVE_THREADS), 65536, s, P);
+    MZ_LAUNCH(inflate_spec_resolve_kernel, dim3(1), dim3(SPEC_RESOLVE_THREADS), SPEC_RESOLVE_SMEM, s, P);
     if (trace) CK(cudaEventRecord(ev[4], s));
     MZ_LAUNCH(inflate_spec_emit_kernel, dim3(grid), dim3(INF_THREADS), INF_SMEM_BYTES, s, P);
     if (trace) CK(cudaEventRecord(ev[5], s));

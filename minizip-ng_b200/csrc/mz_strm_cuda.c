@@ -581,12 +581,14 @@ static void ws_read_upgrade(cu_ws *w, size_t cin_len) {
     const char *off = getenv("MZ_CUDA_SPEC");
     if (off && off[0] == '0')
         return;
-    size_t cin_cap = env_size("MZ_CUDA_READ_WINDOW_KB", 32u << 20, 1024);
+    size_t cin_cap = env_size("MZ_CUDA_READ_WINDOW_KB", 128u << 20, 1024);
     size_t seg = env_size("MZ_CUDA_SPEC_SEG_KB", 16u << 10, 1024);
     if (cin_cap <= w->cin_cap || seg < 1024)
         return;
     size_t win_cap = 32768 + 4 * cin_cap;
     uint32_t max_seg = (uint32_t)(cin_cap / seg) + 1;
+    if (max_seg > 12288) /* K6c keeps 16 bytes of shared memory per segment */
+        max_seg = 12288;
     uint8_t *h_cin = (uint8_t *)mz_cuda_host_alloc(cin_cap + 64);
     uint8_t *d_cin = (uint8_t *)mz_cuda_malloc(cin_cap + 64);
     uint8_t *d_win = (uint8_t *)mz_cuda_malloc(win_cap + 512);

@@ -147,7 +147,7 @@ int32_t emu_inflate_spec(const uint8_t *in, uint64_t in_len, uint8_t *out, uint6
     memset(&st, 0, sizeof(st));
     std::vector<SpecSeg> seg(max_seg);
     std::vector<InflateState> states(max_seg);
-    std::vector<uint32_t> chain(max_seg);
+    std::vector<uint32_t> chain(2 * (size_t)max_seg);
     std::vector<uint16_t> rings((size_t)max_seg * SPEC_RING);
     std::vector<uint8_t> wins((size_t)max_seg * 32768);
     std::vector<uint32_t> inbuf;
@@ -183,8 +183,8 @@ int32_t emu_inflate_spec(const uint8_t *in, uint64_t in_len, uint8_t *out, uint6
             P.summary = &sum;
             MZ_LAUNCH(inflate_spec_find_kernel, dim3(P.nseg), dim3(INF_THREADS), SPEC_FIND_SMEM, 0, P);
             MZ_LAUNCH(inflate_spec_scan_kernel, dim3(P.nseg), dim3(INF_THREADS), INF_SMEM_BYTES, 0, P);
-            MZ_LAUNCH(inflate_spec_chain_kernel, dim3(1), dim3(32), 0, 0, P);
-            MZ_LAUNCH(inflate_spec_resolve_kernel, dim3(1), dim3(SPEC_RESOLVE_THREADS), 65536, 0, P);
+            MZ_LAUNCH(inflate_spec_chain_kernel, dim3(1), dim3(SPEC_CHAIN_THREADS), (size_t)P.nseg * 16, 0, P);
+            MZ_LAUNCH(inflate_spec_resolve_kernel, dim3(1), dim3(SPEC_RESOLVE_THREADS), SPEC_RESOLVE_SMEM, 0, P);
             MZ_LAUNCH(inflate_spec_emit_kernel, dim3(P.nseg), dim3(INF_THREADS), INF_SMEM_BYTES, 0, P);
             stats[0]++;
             stats[3] += sum.candidates;

@@ -15,14 +15,15 @@ def _pkg(built):
 def _declared(header):
     txt = open(header).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return sorted(set(re.findall(r"\b(mz_(?:stream_cuda|cuda|crypt)_[a-z0-9_]+)\s*\(", txt)))
+    return sorted(set(re.findall(r"\b(mz_(?:stream_cuda|cuda|crypt|zip_cuda)_[a-z0-9_]+)\s*\(", txt)))
 
 
 def test_library_exports_every_declared_symbol(built):
     p = _pkg(built)
     lib = C.CDLL(p.LIB_PATH)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    names = _declared(os.path.join(root, "include/mz_strm_cuda.h")) + _declared(os.path.join(root, "include/mz_cuda_batch.h"))
+    names = (_declared(os.path.join(root, "include/mz_strm_cuda.h")) + _declared(os.path.join(root, "include/mz_cuda_batch.h")) +
+             _declared(os.path.join(root, "include/mz_zip_cuda.h")))
     assert len(names) >= 40
     for n in names:
         assert hasattr(lib, n), "missing export " + n

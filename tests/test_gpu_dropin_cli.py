@@ -149,3 +149,37 @@ def test_dropin_binaries_refuse_to_run_without_a_gpu(built, tmp_path):
     r = _run([exe, "-6", "f.txt"], tmp_path, ok=False)
     assert r.returncode != 0 and b"no CPU fallback" in r.stderr
     assert not (tmp_path / "f.txt.gz").exists() or (tmp_path / "f.txt.gz").stat().st_size == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("level", [1, 6])
+def test_zip_batch_writer_on_the_raw_seam(built, tmp_path, level):
+    """config C4 shape: thousands of in-memory entries compressed + CRC'd in one GPU batch and written by
+    the REFERENCE's container code through mz_zip_entry_write_open(raw=1)/close_raw; the archive must be valid for
+    zipfile and for the unmodified reference extractor, and agree entry by entry (CRC, size) with the archive the
+    reference's own zlib path writes from the same buffers."""
+    exe, ref = _bin("zipbatch_cuda"), _bin("minizip_ref")
+    n, esz = 3000, 65536
+    (tmp_path / "dump").mkdir()
+    r = _run([exe, "c.zip", str(n), str(esz), str(level), "cuda", "dump", "37"], tmp_path)
+    import json
+    stats = json.loads(r.stdout.decode().strip().splitlines()[-1])
+    assert stats["err"] == 0 and stats["close_err"] == 0 and stats["entries"] == n and stats["rounds"] >= 1
+    _run([exe, "r.zip", str(n), str(esz), str(level), "ref"], tmp_path)
+    with zipfile.ZipFile(tmp_path / "c.zip") as zc, zipfile.ZipFile(tmp_path / "r.zip") as zr:
+        assert zc.testzip() is None
+        assert zc.namelist() == zr.namelist() == ["e/%06d" % i for i in range(n)]
+        tot_c = tot_r = 0
+        for i in range(n):
+            a, b = zc.getinfo("e/%06d" % i), zr.getinfo("e/%06d" % i)
+            assert a.CRC == b.CRC and a.file_size == b.file_size, i
+            assert a.compress_type == zipfile.ZIP_DEFLATED
+            tot_c += a.compress_size
+            tot_r += b.compress_size
+        assert zc.getinfo("e/000005").file_size == 0 and zc.getinfo("e/000006").file_size == 1
+        assert tot_c < 1.25 * tot_r  # compression ratio in the reference's neighbourhood
+        for i in range(0, n, 37):
+            assert zc.read("e/%06d" % i) == (tmp_path / "dump" / ("%06d" % i)).read_bytes()
+    _run([ref, "-x", "-o", "-d", "out", "c.zip"], tmp_path)  # the reference's extractor CRC-checks every entry
+    for i in range(0, n, 37):
+        assert (tmp_path / "out" / "e" / ("%06d" % i)).read_bytes() == (tmp_path / "dump" / ("%06d" % i)).read_bytes()

@@ -1,22 +1,14 @@
 #!/bin/bash
 mkdir -p gpurun_out
-MZ_CUDA_TRACE=1 timeout 600 python - > gpurun_out/trace.log 2>&1 <<'PY'
-import sys, os, zlib, time, json
-sys.path.insert(0, "tests"); sys.path.insert(0, ".")
-import cuharness
-p = cuharness.pkg(); lib = p.load(); lib.mz_cuda_init()
-tl = cuharness.TestLib()
-n = 256 << 20
-host = bytes(p.textgen(n, seed=9).cpu().numpy().tobytes())
-co = zlib.compressobj(6, zlib.DEFLATED, 31); comp = co.compress(host) + co.flush()
-for rep in range(2):
-    t0 = time.perf_counter()
-    out, info = tl.decompress(lib.mz_stream_cuda_create, comp, n, window_bits=31, read_size=1 << 20)
-    dt = time.perf_counter() - t0
-    print(json.dumps({"s": dt, "GBps": n / dt / 1e9, "ok": zlib.crc32(out) == zlib.crc32(host), "info": info}), flush=True)
-PY
-grep -c "K6 round" gpurun_out/trace.log; grep -c "K5 launch" gpurun_out/trace.log; grep "K6 round\|K6 kernels" gpurun_out/trace.log | head -12; grep GBps gpurun_out/trace.log
-timeout 300 python tools/bench_inflate.py single 16 > gpurun_out/single.log 2>&1; tail -1 gpurun_out/single.log
-timeout 300 python tools/bench_inflate.py batch 8192 > gpurun_out/batch.log 2>&1; tail -1 gpurun_out/batch.log
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:inflate_streams -s 1 -c 1 -o gpurun_out/prof_inflate_batch python tools/bench_inflate.py batch 8192 > gpurun_out/ncu_inflate_batch.log 2>&1
-tail -2 gpurun_out/ncu_inflate_batch.log
+MZ_CUDA_TRACE=1 timeout 600 python tools/bench_inflate.py long 1024 > gpurun_out/trace.log 2>&1
+grep "K6 round\|K6 kernels" gpurun_out/trace.log | head -6; grep GBps gpurun_out/trace.log
+timeout 900 python -m pytest tests -m gpu -x -q -k "c3 or c4 or inflate or read or dropin or decompress or zip_batch" > gpurun_out/pytest_gpu_inf.log 2>&1; tail -3 gpurun_out/pytest_gpu_inf.log
+cd /tmp && mkdir -p zb && cd zb
+timeout 600 /root/repo/oracle/_ref/zipbatch_cuda c4.zip 100000 65536 6 cuda > /root/repo/gpurun_out/zipbatch.log 2>&1
+timeout 600 /root/repo/oracle/_ref/zipbatch_cuda c4.zip 100000 65536 6 cuda >> /root/repo/gpurun_out/zipbatch.log 2>&1
+timeout 600 /root/repo/oracle/_ref/zipbatch_cuda c4l1.zip 100000 65536 1 cuda >> /root/repo/gpurun_out/zipbatch.log 2>&1
+timeout 600 /root/repo/oracle/_ref/zipbatch_cuda r.zip 4000 65536 6 ref >> /root/repo/gpurun_out/zipbatch.log 2>&1
+python -c "
+import zipfile,time
+t=time.time(); z=zipfile.ZipFile('c4.zip'); n=len(z.namelist()); bad=z.testzip(); print('zipfile check', n, bad, round(time.time()-t,1),'s')" >> /root/repo/gpurun_out/zipbatch.log 2>&1
+cat /root/repo/gpurun_out/zipbatch.log
