@@ -24,6 +24,7 @@ extern "C" {
 int32_t mz_cuda_init(void);                 /* idempotent, thread-safe; MZ_SUPPORT_ERROR without a usable GPU */
 int32_t mz_cuda_device_count(void);
 int32_t mz_cuda_set_device(int32_t ordinal);
+int32_t mz_cuda_get_device(void);           /* the calling thread's current device, -1 on failure */
 const char *mz_cuda_last_error(void);
 int32_t mz_cuda_sm_count(void);
 

@@ -45,7 +45,7 @@ EXPORTS = [
     "mz_stream_cuda_set_prop_int64", "mz_stream_cuda_create", "mz_stream_cuda_delete", "mz_stream_cuda_get_interface",
     "mz_crypt_crc32_update",
     # include/mz_cuda_batch.h
-    "mz_cuda_init", "mz_cuda_device_count", "mz_cuda_set_device", "mz_cuda_last_error", "mz_cuda_sm_count", "mz_cuda_malloc",
+    "mz_cuda_init", "mz_cuda_device_count", "mz_cuda_set_device", "mz_cuda_get_device", "mz_cuda_last_error", "mz_cuda_sm_count", "mz_cuda_malloc",
     "mz_cuda_free", "mz_cuda_host_alloc", "mz_cuda_host_free", "mz_cuda_memcpy_h2d", "mz_cuda_memcpy_d2h", "mz_cuda_memcpy_d2d",
     "mz_cuda_memset", "mz_cuda_host_is_pinned", "mz_cuda_stream_sync", "mz_cuda_stream_create", "mz_cuda_stream_destroy",
     "mz_cuda_event_create", "mz_cuda_event_destroy", "mz_cuda_event_record", "mz_cuda_event_sync", "mz_cuda_event_elapsed_ms",

@@ -15,8 +15,9 @@
  *   K6c chain     one thread walks the segments from the anchored one: segment j joins the chain only if the
  *                 previous chain member ended EXACTLY on j's guessed start (and the output still fits). A wrong
  *                 guess, an error, missing input -- the chain simply ends there and the serial decoder carries on.
- *   K6d resolve   one CTA turns each chain member's symbolic last-32-KiB into bytes, in chain order (member i's
- *                 window = member i-1's resolved final window), 32768 symbols per step.
+ *   K6d resolve   each chain member's symbolic last-32-KiB becomes bytes (member i's window = member i-1's resolved
+ *                 final window): windows are maps and maps compose, so the chain is folded group-wise in parallel,
+ *                 linked across groups serially (96 steps), then expanded group-wise in parallel.
  *   K6e emit      warp per chain member decodes its segment AGAIN, now with a resolved window and a known output
  *                 offset, straight into the caller-visible output window; it must reproduce K6b's end bit and
  *                 byte count or the whole round is discarded.
@@ -75,6 +76,8 @@ struct SpecParams {
     uint8_t *wins;       /* [nseg][32768] */
     uint32_t *chain;     /* [nseg] pairs {segment, bytes produced mod 2^32}, chain order */
     SpecSummary *summary;
+    uint16_t *gmaps;     /* [SPEC_GROUPS][32768] group maps (K6d compose) */
+    uint8_t *gwins;      /* [SPEC_GROUPS][32768] real window after each group (K6d link) */
 };
 
 /* ---- K6a ------------------------------------------------------------------------------------------------------ */
@@ -317,14 +320,29 @@ __global__ void __launch_bounds__(SPEC_CHAIN_THREADS) inflate_spec_chain_kernel(
 }
 
 /* ---- K6d ------------------------------------------------------------------------------------------------------ */
-/* One CTA, serial over the chain (member i's window needs member i-1's), 32768 symbols per step:
- *   1. the member's last 32768 ring symbols are staged into shared memory with aligned 16-byte loads (the slice
- *      starts anywhere in the ring). The loads for step i+1 are issued BEFORE step i's lookups and land in
- *      registers, so the global round trip hides behind the arithmetic of the current step,
- *   2. each thread resolves 8 x 4 symbols against the previous window (shared) and writes the bytes to the next
- *      window (shared, for the next step) and to global (for K6e). */
-constexpr int SPEC_RESOLVE_SMEM = 32768 * 2 + (32768 + 16) * 2;
+/* Turning symbolic windows into bytes is a chain: member i's window needs member i-1's. A window is a MAP over the
+ * window before it (each of its 32768 symbols is a literal or an index into the earlier window), and maps compose,
+ * so the chain is cut into SPEC_GROUPS groups and resolved in three short steps instead of one long serial one:
+ *   compose  (one CTA per group, parallel): fold the group's members into ONE map over the window before the group,
+ *   link     (one CTA): walk the groups -- SPEC_GROUPS steps -- turning each group map into the real bytes of the
+ *            window after that group,
+ *   resolve  (one CTA per group, parallel): walk the group's members again, now from real bytes, writing every
+ *            member's initial window for K6e.
+ * Per step: the member's last 32768 ring symbols are staged into shared memory with aligned 16-byte loads (the
+ * slice starts anywhere in the ring); the loads for step i+1 are issued BEFORE step i's lookups and land in
+ * registers, so the global round trip hides behind the arithmetic of the current step; each thread then handles
+ * 8 x 4 symbols against the previous window held in shared memory. */
+constexpr uint32_t SPEC_GROUPS = 96;
 constexpr int SPEC_SLICE_VECS = 32768 / 8 + 1; /* 16-byte vectors per slice */
+constexpr int SPEC_RESOLVE_SMEM = 32768 * 2 + (32768 + 16) * 2;   /* two byte windows + slice */
+constexpr int SPEC_COMPOSE_SMEM = 65536 * 2 + (32768 + 16) * 2;   /* two symbol windows + slice */
+
+__device__ __forceinline__ void spec_group_range(uint32_t n, uint32_t g, uint32_t &lo, uint32_t &hi) {
+    const uint32_t m = (n + SPEC_GROUPS - 1) / SPEC_GROUPS;
+    lo = g * m;
+    hi = lo + m < n ? lo + m : n;
+    if (lo > n) lo = n;
+}
 __device__ __forceinline__ void spec_load_slice(const SpecParams &P, uint32_t k, uint32_t cnt, uint4 (&r)[5]) {
     const uint16_t *ring = P.rings + (size_t)k * SPEC_RING;
     const uint32_t tail8 = (cnt - 32768u) & ~7u;
@@ -334,35 +352,122 @@ __device__ __forceinline__ void spec_load_slice(const SpecParams &P, uint32_t k,
         if (v < SPEC_SLICE_VECS) r[t] = *reinterpret_cast<const uint4 *>(ring + ((tail8 + 8u * v) & (SPEC_RING - 1)));
     }
 }
+__device__ __forceinline__ void spec_store_slice(uint16_t *slice, const uint4 (&r)[5]) {
+#pragma unroll
+    for (int t = 0; t < 5; t++) {
+        const uint32_t v = threadIdx.x + (uint32_t)t * SPEC_RESOLVE_THREADS;
+        if (v < SPEC_SLICE_VECS) reinterpret_cast<uint4 *>(slice)[v] = r[t];
+    }
+}
+/* the real window before absolute output position P.out_pos (zeros where the stream has no history yet) */
+__device__ __forceinline__ uint8_t spec_history_byte(const SpecParams &P, uint32_t j) {
+    const uint64_t back = 32768 - j;
+    return back <= P.out_pos - P.out_base && back <= P.out_pos ? P.out[P.out_pos - back - P.out_base] : (uint8_t)0;
+}
+
+/* compose: the group's members folded into one symbolic map (16-bit symbols over the window before the group) */
+__global__ void __launch_bounds__(SPEC_RESOLVE_THREADS) inflate_spec_compose_kernel(SpecParams P) {
+    MZ_DYN_SMEM(smem);
+    uint16_t *ca = reinterpret_cast<uint16_t *>(smem), *cb = ca + 32768;
+    uint16_t *slice = cb + 32768;
+    const uint32_t n = P.summary->nchain;
+    uint32_t lo, hi;
+    spec_group_range(n, blockIdx.x, lo, hi);
+    if (lo >= hi) return;
+    uint32_t k = P.chain[2 * lo], cnt = P.chain[2 * lo + 1];
+    uint4 r[5];
+    spec_load_slice(P, k, cnt, r);
+    for (uint32_t j = threadIdx.x; j < 32768; j += blockDim.x) ca[j] = (uint16_t)(0x8000u | j); /* identity */
+    for (uint32_t i = lo; i < hi; i++) {
+        spec_store_slice(slice, r);
+        const uint32_t a = (cnt - 32768u) & 7u;
+        __syncthreads();
+        if (i + 1 < hi) {
+            k = P.chain[2 * (i + 1)];
+            cnt = P.chain[2 * (i + 1) + 1];
+            spec_load_slice(P, k, cnt, r);
+        }
+        uint32_t *sd = reinterpret_cast<uint32_t *>(cb);
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const uint32_t e0 = threadIdx.x * 4u + 4096u * q;
+            uint32_t w01, w23;
+            {
+                const uint32_t s0 = slice[a + e0], s1 = slice[a + e0 + 1], s2 = slice[a + e0 + 2], s3 = slice[a + e0 + 3];
+                const uint32_t v0 = s0 & 0x8000u ? ca[s0 & 0x7fffu] : s0, v1 = s1 & 0x8000u ? ca[s1 & 0x7fffu] : s1;
+                const uint32_t v2 = s2 & 0x8000u ? ca[s2 & 0x7fffu] : s2, v3 = s3 & 0x8000u ? ca[s3 & 0x7fffu] : s3;
+                w01 = v0 | (v1 << 16);
+                w23 = v2 | (v3 << 16);
+            }
+            sd[e0 >> 1] = w01;
+            sd[(e0 >> 1) + 1] = w23;
+        }
+        __syncthreads();
+        uint16_t *t = ca; ca = cb; cb = t;
+    }
+    uint4 *dst = reinterpret_cast<uint4 *>(P.gmaps + (size_t)blockIdx.x * 32768);
+    for (uint32_t v = threadIdx.x; v < 32768 / 8; v += blockDim.x) dst[v] = reinterpret_cast<const uint4 *>(ca)[v];
+}
+
+/* link: real bytes of the window after every group, in group order */
+__global__ void __launch_bounds__(SPEC_RESOLVE_THREADS) inflate_spec_link_kernel(SpecParams P) {
+    MZ_DYN_SMEM(smem);
+    uint8_t *wa = smem, *wb = smem + 32768;
+    const uint32_t n = P.summary->nchain;
+    if (n == 0) return;
+    for (uint32_t j = threadIdx.x; j < 32768; j += blockDim.x) wa[j] = spec_history_byte(P, j);
+    __syncthreads();
+    for (uint32_t g = 0; g < SPEC_GROUPS; g++) {
+        uint32_t lo, hi;
+        spec_group_range(n, g, lo, hi);
+        if (lo >= hi) break;
+        const uint16_t *map = P.gmaps + (size_t)g * 32768;
+        uint32_t *gd = reinterpret_cast<uint32_t *>(P.gwins + (size_t)g * 32768);
+        uint32_t *sd = reinterpret_cast<uint32_t *>(wb);
+        uint2 m[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) m[q] = reinterpret_cast<const uint2 *>(map)[threadIdx.x + 1024u * q];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const uint32_t s0 = m[q].x & 0xffffu, s1 = m[q].x >> 16, s2 = m[q].y & 0xffffu, s3 = m[q].y >> 16;
+            const uint32_t v0 = s0 & 0x8000u ? wa[s0 & 0x7fffu] : s0 & 0xffu, v1 = s1 & 0x8000u ? wa[s1 & 0x7fffu] : s1 & 0xffu;
+            const uint32_t v2 = s2 & 0x8000u ? wa[s2 & 0x7fffu] : s2 & 0xffu, v3 = s3 & 0x8000u ? wa[s3 & 0x7fffu] : s3 & 0xffu;
+            const uint32_t acc = v0 | (v1 << 8) | (v2 << 16) | (v3 << 24);
+            gd[threadIdx.x + 1024u * q] = acc;
+            sd[threadIdx.x + 1024u * q] = acc;
+        }
+        __syncthreads();
+        uint8_t *t = wa; wa = wb; wb = t;
+    }
+}
+
+/* resolve: every member's initial window, group by group in parallel */
 __global__ void __launch_bounds__(SPEC_RESOLVE_THREADS) inflate_spec_resolve_kernel(SpecParams P) {
     MZ_DYN_SMEM(smem);
     uint8_t *wa = smem, *wb = smem + 32768;
     uint16_t *slice = reinterpret_cast<uint16_t *>(smem + 65536); /* 32768 + 8 symbols, starts at an 8-aligned ring index */
     const uint32_t n = P.summary->nchain;
-    if (n == 0) return;
-    uint32_t k = P.chain[0], cnt = P.chain[1];
-    uint32_t knext = n > 1 ? P.chain[2] : 0, cntnext = n > 1 ? P.chain[3] : 0;
+    uint32_t lo, hi;
+    spec_group_range(n, blockIdx.x, lo, hi);
+    if (lo >= hi) return;
+    uint32_t k = P.chain[2 * lo], cnt = P.chain[2 * lo + 1];
+    uint32_t knext = lo + 1 < hi ? P.chain[2 * (lo + 1)] : 0, cntnext = lo + 1 < hi ? P.chain[2 * (lo + 1) + 1] : 0;
     uint4 r[5];
-    if (n > 1) spec_load_slice(P, k, cnt, r);
-    /* the window before the anchored member is real output (zeros where the stream has no history yet) */
+    if (lo + 1 < hi) spec_load_slice(P, k, cnt, r);
+    /* the window before the group's first member: real history for group 0, the link step's result otherwise */
+    const uint8_t *init = blockIdx.x ? P.gwins + (size_t)(blockIdx.x - 1) * 32768 : nullptr;
     for (uint32_t j = threadIdx.x; j < 32768; j += blockDim.x) {
-        const uint64_t back = 32768 - j;
-        const uint8_t v = back <= P.out_pos - P.out_base && back <= P.out_pos ? P.out[P.out_pos - back - P.out_base] : (uint8_t)0;
+        const uint8_t v = init ? init[j] : spec_history_byte(P, j);
         wa[j] = v;
         P.wins[(size_t)k * 32768 + j] = v;
     }
-    for (uint32_t i = 0; i + 1 < n; i++) {
-        /* registers -> shared: member i's slice */
-#pragma unroll
-        for (int t = 0; t < 5; t++) {
-            const uint32_t v = threadIdx.x + (uint32_t)t * SPEC_RESOLVE_THREADS;
-            if (v < SPEC_SLICE_VECS) reinterpret_cast<uint4 *>(slice)[v] = r[t];
-        }
+    for (uint32_t i = lo; i + 1 < hi; i++) {
+        spec_store_slice(slice, r); /* member i's slice */
         const uint32_t a = (cnt - 32768u) & 7u;
         __syncthreads();
         /* in flight during the lookups: member i+1's slice and the chain entry after it */
         uint32_t k2 = 0, cnt2 = 0;
-        if (i + 2 < n) {
+        if (i + 2 < hi) {
             k2 = P.chain[2 * (i + 2)];
             cnt2 = P.chain[2 * (i + 2) + 1];
             spec_load_slice(P, knext, cntnext, r);

@@ -120,6 +120,8 @@ int32_t get_ctx(DeviceCtx **out) {
             CK(cudaFuncSetAttribute(crc32_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CRC_SMEM_BYTES));
             CK(cudaFuncSetAttribute(inflate_streams_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, INF_SMEM_BYTES));
             CK(cudaFuncSetAttribute(inflate_spec_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SPEC_RESOLVE_SMEM));
+            CK(cudaFuncSetAttribute(inflate_spec_compose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SPEC_COMPOSE_SMEM));
+            CK(cudaFuncSetAttribute(inflate_spec_link_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
             CK(cudaFuncSetAttribute(inflate_spec_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SPEC_MAX_SEGMENTS * 16));
             CK(cudaMalloc(&c.d_work, 256 * sizeof(uint32_t)));
             c.ready = true;
@@ -157,6 +159,12 @@ int32_t mz_cuda_device_count(void) {
 int32_t mz_cuda_set_device(int32_t ordinal) {
     CK(cudaSetDevice(ordinal));
     return MZ_OK;
+}
+
+int32_t mz_cuda_get_device(void) {
+    int d = -1;
+    if (cudaGetDevice(&d) != cudaSuccess) return -1;
+    return d;
 }
 
 int32_t mz_cuda_sm_count(void) {
@@ -414,7 +422,8 @@ int32_t mz_cuda_inflate_streams(const mz_cuda_inflate_job *d_jobs, mz_cuda_infla
 static inline uint64_t al256(uint64_t v) { return (v + 255) & ~255ull; }
 uint64_t mz_cuda_inflate_spec_workspace_bytes(uint32_t max_segments) {
     const uint64_t m = max_segments;
-    return al256(m * sizeof(SpecSeg)) + al256(m * sizeof(InflateState)) + al256(m * 8) + al256(m * SPEC_RING * 2) + al256(m * 32768) + 256;
+    return al256(m * sizeof(SpecSeg)) + al256(m * sizeof(InflateState)) + al256(m * 8) + al256(m * SPEC_RING * 2) + al256(m * 32768) + al256((uint64_t)SPEC_GROUPS * 65536) +
+           al256((uint64_t)SPEC_GROUPS * 32768) + 256;
 }
 
 int32_t mz_cuda_inflate_spec_round(const void *d_in, uint64_t in_base, uint64_t in_avail, uint32_t in_final, uint64_t start_bit,
@@ -443,7 +452,9 @@ int32_t mz_cuda_inflate_spec_round(const void *d_in, uint64_t in_base, uint64_t 
     P.states = (InflateState *)w;    w += al256(m * sizeof(InflateState));
     P.chain = (uint32_t *)w;         w += al256(m * 8);
     P.rings = (uint16_t *)w;         w += al256(m * SPEC_RING * 2);
-    P.wins = w;
+    P.wins = w;                      w += al256(m * 32768);
+    P.gmaps = (uint16_t *)w;         w += al256((uint64_t)SPEC_GROUPS * 65536);
+    P.gwins = w;
     P.summary = (SpecSummary *)d_summary;
     cudaStream_t s = (cudaStream_t)stream;
     const uint32_t maxgrid = (uint32_t)c->sm_count * 32u;
@@ -459,7 +470,9 @@ int32_t mz_cuda_inflate_spec_round(const void *d_in, uint64_t in_base, uint64_t 
     if (trace) CK(cudaEventRecord(ev[2], s));
     MZ_LAUNCH(inflate_spec_chain_kernel, dim3(1), dim3(SPEC_CHAIN_THREADS), (size_t)nseg * 16, s, P);
     if (trace) CK(cudaEventRecord(ev[3], s));
-    MZ_LAUNCH(inflate_spec_resolve_kernel, dim3(1), dim3(SPEC_RESOLVE_THREADS), SPEC_RESOLVE_SMEM, s, P);
+    MZ_LAUNCH(inflate_spec_compose_kernel, dim3(SPEC_GROUPS), dim3(SPEC_RESOLVE_THREADS), SPEC_COMPOSE_SMEM, s, P);
+    MZ_LAUNCH(inflate_spec_link_kernel, dim3(1), dim3(SPEC_RESOLVE_THREADS), 65536, s, P);
+    MZ_LAUNCH(inflate_spec_resolve_kernel, dim3(SPEC_GROUPS), dim3(SPEC_RESOLVE_THREADS), SPEC_RESOLVE_SMEM, s, P);
     if (trace) CK(cudaEventRecord(ev[4], s));
     MZ_LAUNCH(inflate_spec_emit_kernel, dim3(grid), dim3(INF_THREADS), INF_SMEM_BYTES, s, P);
     if (trace) CK(cudaEventRecord(ev[5], s));
@@ -468,7 +481,7 @@ int32_t mz_cuda_inflate_spec_round(const void *d_in, uint64_t in_base, uint64_t 
         CK(cudaEventSynchronize(ev[5]));
         float t[5];
         for (int i = 0; i < 5; i++) CK(cudaEventElapsedTime(&t[i], ev[i], ev[i + 1]));
-        fprintf(stderr, "mz_cuda: K6 kernels ms: find %.3f scan %.3f chain %.3f resolve %.3f emit %.3f (%u segments)\n", t[0], t[1], t[2], t[3], t[4], nseg);
+        fprintf(stderr, "mz_cuda: K6 kernels ms: find %.3f scan %.3f chain %.3f compose+link+resolve %.3f emit %.3f (%u segments)\n", t[0], t[1], t[2], t[3], t[4], nseg);
         for (int i = 0; i < 6; i++) cudaEventDestroy(ev[i]);
     }
     return MZ_OK;

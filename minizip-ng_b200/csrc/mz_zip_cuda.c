@@ -5,6 +5,7 @@
  * (mz_zip.c:2062-2064) and mz_zip_entry_close (mz_zip.c:2116-2160). Here the codec work of MANY entries is one
  * K2+K3 launch + one K1 launch + one K4 launch per round, and the container calls run with raw = 1.
  */
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -127,11 +128,71 @@ static uint32_t chunks_of(int64_t size) {
     return size <= 0 ? 1u : (uint32_t)(((uint64_t)size + ZC_CHUNK - 1) / ZC_CHUNK);
 }
 
-int32_t mz_zip_cuda_add_buffers(void *zip_handle, const mz_cuda_zip_item *items, uint32_t count, int16_t level, mz_cuda_zip_stats *stats) {
+/* one round = consecutive entries that fit the staging buffers; prepared (packed, compressed, downloaded) by a
+ * worker thread while the caller's thread hands the previous round to the container */
+typedef struct zc_round_s {
     zc_bufs b;
+    const mz_cuda_zip_item *items;
+    uint32_t count, first, last, nch;
+    int16_t level;
+    int32_t device, err;
+    double pack_ms, gpu_ms;
+} zc_round;
+
+static void *zc_prepare(void *arg) {
+    zc_round *r = (zc_round *)arg;
+    zc_bufs *b = &r->b;
+    int32_t err = mz_cuda_set_device(r->device);
+    double t0 = now_ms();
+    uint32_t last = r->first, nch = 0;
+    size_t pos = 0;
+    while (last < r->count) {
+        const size_t need = ((size_t)r->items[last].size + 15) & ~(size_t)15;
+        const uint32_t c = chunks_of(r->items[last].size);
+        if (last > r->first && (pos + need > b->round_bytes || nch + c > b->max_chunks))
+            break;
+        if (r->items[last].size > 0)
+            memcpy(b->h_in + pos, r->items[last].data, (size_t)r->items[last].size);
+        int64_t left = r->items[last].size;
+        for (uint32_t k = 0; k < c; k++) {
+            const uint32_t n = left > (int64_t)ZC_CHUNK ? ZC_CHUNK : (uint32_t)left;
+            b->h_off[nch] = pos + (uint64_t)k * ZC_CHUNK;
+            b->h_len[nch] = n;
+            b->h_flags[nch] = k + 1 == c ? 1u : 0u; /* BFINAL on the entry's last chunk */
+            left -= n;
+            nch++;
+        }
+        pos += need;
+        last++;
+    }
+    r->last = last;
+    r->nch = nch;
+    if (!err) err = mz_cuda_memcpy_h2d(b->d_in, b->h_in, pos + 16, NULL);
+    if (!err) err = mz_cuda_memcpy_h2d(b->d_off, b->h_off, (size_t)nch * 8, NULL);
+    if (!err) err = mz_cuda_memcpy_h2d(b->d_len, b->h_len, (size_t)nch * 4, NULL);
+    if (!err) err = mz_cuda_memcpy_h2d(b->d_flags, b->h_flags, nch, NULL);
+    double t1 = now_ms();
+    /* device: compress, checksum, join; download */
+    if (!err) err = mz_cuda_deflate_chunks(b->d_in, 0, 0, b->d_off, b->d_len, b->d_flags, nch, 0, r->level, b->d_slots, b->stride, b->d_out_len, NULL);
+    if (!err) err = mz_cuda_crc32_segments(b->d_in, 0, 0, b->d_off, b->d_len, nch, b->d_residue, b->d_crc, NULL);
+    if (!err) err = mz_cuda_concat(b->d_slots, b->stride, b->d_out_len, nch, b->d_joined_off, b->d_out, NULL);
+    if (!err) err = mz_cuda_memcpy_d2h(b->h_joined_off, b->d_joined_off, ((size_t)nch + 1) * 8, NULL);
+    if (!err) err = mz_cuda_memcpy_d2h(b->h_crc, b->d_crc, (size_t)nch * 4, NULL);
+    if (!err) err = mz_cuda_stream_sync(NULL);
+    if (!err) err = mz_cuda_memcpy_d2h(b->h_out, b->d_out, (size_t)b->h_joined_off[nch], NULL);
+    if (!err) err = mz_cuda_stream_sync(NULL);
+    r->pack_ms = t1 - t0;
+    r->gpu_ms = now_ms() - t1;
+    r->err = err;
+    return NULL;
+}
+
+int32_t mz_zip_cuda_add_buffers(void *zip_handle, const mz_cuda_zip_item *items, uint32_t count, int16_t level, mz_cuda_zip_stats *stats) {
+    zc_round rd[2];
     int32_t err = MZ_OK;
     mz_cuda_zip_stats st;
     memset(&st, 0, sizeof(st));
+    memset(rd, 0, sizeof(rd));
     if (!mz_zip_entry_write_open || !mz_zip_entry_write || !mz_zip_entry_close_raw)
         return MZ_SUPPORT_ERROR; /* no zip container in this process */
     if (!zip_handle || (!items && count))
@@ -147,6 +208,11 @@ int32_t mz_zip_cuda_add_buffers(void *zip_handle, const mz_cuda_zip_item *items,
     for (uint32_t i = 0; i < count; i++)
         if (!items[i].filename || items[i].size < 0 || (items[i].size > 0 && !items[i].data))
             return MZ_PARAM_ERROR;
+    if (count == 0) {
+        if (stats)
+            *stats = st;
+        return MZ_OK;
+    }
     size_t round_bytes = 256u << 20;
     {
         const char *v = getenv("MZ_CUDA_ZIP_ROUND_MB");
@@ -157,93 +223,73 @@ int32_t mz_zip_cuda_add_buffers(void *zip_handle, const mz_cuda_zip_item *items,
     for (uint32_t i = 0; i < count; i++)
         if ((size_t)items[i].size + 16 > round_bytes)
             round_bytes = ((size_t)items[i].size + 16 + 65535) & ~(size_t)65535;
-    /* chunks per round: full chunks by size, plus one (partial or empty) chunk per entry; entries are packed at
-     * 16-byte aligned offsets */
+    /* chunks per round: full chunks by size plus one (partial or empty) chunk per entry; size the tables for the
+     * densest window of the actual input (entries are packed at 16-byte aligned offsets) */
     uint32_t max_chunks = (uint32_t)(round_bytes / ZC_CHUNK) + 1;
     {
-        /* worst case number of entries in one round = as many small ones as fit (each takes >= 16 bytes) -- bounded
-         * by `count`; size the tables for the densest window of the actual input instead of the worst case */
-        uint32_t dens = 0, j = 0;
+        uint32_t j = 0, ch = 0, best = 0;
         size_t bytes = 0;
-        uint32_t ch = 0, best = 0;
-        for (uint32_t i = 0; i < count; i++) { /* sliding window over entries that fit a round */
-            size_t need = ((size_t)items[i].size + 15) & ~(size_t)15;
-            bytes += need;
+        for (uint32_t i = 0; i < count; i++) {
+            bytes += ((size_t)items[i].size + 15) & ~(size_t)15;
             ch += chunks_of(items[i].size);
-            dens++;
             while (bytes > round_bytes) {
                 bytes -= ((size_t)items[j].size + 15) & ~(size_t)15;
                 ch -= chunks_of(items[j].size);
                 j++;
-                dens--;
             }
             if (ch > best)
                 best = ch;
         }
-        (void)dens;
         if (best + 1 > max_chunks)
             max_chunks = best + 1;
     }
-    if (!zc_alloc(&b, round_bytes, max_chunks))
-        return MZ_MEM_ERROR;
-
-    uint32_t first = 0;
-    while (first < count && err == MZ_OK) {
-        /* ---- pack a round: entries first..last-1 ------------------------------------------------------------ */
-        double t0 = now_ms();
-        uint32_t last = first, nch = 0;
-        size_t pos = 0;
-        while (last < count) {
-            const size_t need = ((size_t)items[last].size + 15) & ~(size_t)15;
-            const uint32_t c = chunks_of(items[last].size);
-            if (last > first && (pos + need > round_bytes || nch + c > max_chunks))
-                break;
-            if (items[last].size > 0)
-                memcpy(b.h_in + pos, items[last].data, (size_t)items[last].size);
-            int64_t left = items[last].size;
-            for (uint32_t k = 0; k < c; k++) {
-                const uint32_t n = left > (int64_t)ZC_CHUNK ? ZC_CHUNK : (uint32_t)left;
-                b.h_off[nch] = pos + (uint64_t)k * ZC_CHUNK;
-                b.h_len[nch] = n;
-                b.h_flags[nch] = k + 1 == c ? 1u : 0u; /* BFINAL on the entry's last chunk */
-                left -= n;
-                nch++;
-            }
-            pos += need;
-            last++;
+    const int32_t device = mz_cuda_get_device();
+    for (int k = 0; k < 2; k++) {
+        if (!zc_alloc(&rd[k].b, round_bytes, max_chunks)) {
+            zc_free(&rd[0].b);
+            return MZ_MEM_ERROR;
         }
-        err = mz_cuda_memcpy_h2d(b.d_in, b.h_in, pos + 16, NULL);
-        if (!err) err = mz_cuda_memcpy_h2d(b.d_off, b.h_off, (size_t)nch * 8, NULL);
-        if (!err) err = mz_cuda_memcpy_h2d(b.d_len, b.h_len, (size_t)nch * 4, NULL);
-        if (!err) err = mz_cuda_memcpy_h2d(b.d_flags, b.h_flags, nch, NULL);
-        double t1 = now_ms();
-        /* ---- device: compress, checksum, join; download ------------------------------------------------------- */
-        if (!err) err = mz_cuda_deflate_chunks(b.d_in, 0, 0, b.d_off, b.d_len, b.d_flags, nch, 0, level, b.d_slots, b.stride, b.d_out_len, NULL);
-        if (!err) err = mz_cuda_crc32_segments(b.d_in, 0, 0, b.d_off, b.d_len, nch, b.d_residue, b.d_crc, NULL);
-        if (!err) err = mz_cuda_concat(b.d_slots, b.stride, b.d_out_len, nch, b.d_joined_off, b.d_out, NULL);
-        if (!err) err = mz_cuda_memcpy_d2h(b.h_joined_off, b.d_joined_off, ((size_t)nch + 1) * 8, NULL);
-        if (!err) err = mz_cuda_memcpy_d2h(b.h_crc, b.d_crc, (size_t)nch * 4, NULL);
-        if (!err) err = mz_cuda_stream_sync(NULL);
-        if (!err) err = mz_cuda_memcpy_d2h(b.h_out, b.d_out, (size_t)b.h_joined_off[nch], NULL);
-        if (!err) err = mz_cuda_stream_sync(NULL);
-        double t2 = now_ms();
+        rd[k].items = items;
+        rd[k].count = count;
+        rd[k].level = level;
+        rd[k].device = device < 0 ? 0 : device;
+    }
+    /* round r is prepared by a worker while this thread feeds round r-1 to the container */
+    int cur = 0;
+    pthread_t th;
+    rd[cur].first = 0;
+    zc_prepare(&rd[cur]);
+    while (err == MZ_OK) {
+        zc_round *r = &rd[cur];
+        err = r->err;
         if (err)
             break;
+        int have_next = r->last < count, started = 0;
+        if (have_next) {
+            rd[cur ^ 1].first = r->last;
+            started = pthread_create(&th, NULL, zc_prepare, &rd[cur ^ 1]) == 0;
+            if (!started)
+                zc_prepare(&rd[cur ^ 1]);
+        }
         /* ---- container: the reference writes headers and copies the finished streams --------------------------- */
+        double t2 = now_ms();
+        const zc_bufs *b = &r->b;
         uint32_t c0 = 0;
-        for (uint32_t i = first; i < last && err == MZ_OK; i++) {
+        for (uint32_t i = r->first; i < r->last && err == MZ_OK; i++) {
             const uint32_t c = chunks_of(items[i].size);
-            uint32_t crc = b.h_crc[c0];
+            uint32_t crc = b->h_crc[c0];
             for (uint32_t k = 1; k < c; k++)
-                crc = mz_cuda_crc32_combine(crc, b.h_crc[c0 + k], b.h_len[c0 + k]);
+                crc = mz_cuda_crc32_combine(crc, b->h_crc[c0 + k], b->h_len[c0 + k]);
             if (items[i].size == 0)
                 crc = 0;
-            const uint8_t *comp = b.h_out + b.h_joined_off[c0];
-            const uint64_t csize = b.h_joined_off[c0 + c] - b.h_joined_off[c0];
+            const uint8_t *comp = b->h_out + b->h_joined_off[c0];
+            const uint64_t csize = b->h_joined_off[c0 + c] - b->h_joined_off[c0];
             zc_file_info fi;
             memset(&fi, 0, sizeof(fi));
             fi.version_madeby = (3u << 8) | 45u; /* MZ_HOST_SYSTEM_UNIX (mz.h:104), zip 4.5 as MZ_VERSION_MADEBY without extra codecs (mz_os.h:27-42) */
-            fi.flag = 1u << 11;                  /* MZ_ZIP_FLAG_UTF8, mz.h:84 */
+            /* MZ_ZIP_FLAG_UTF8 (mz.h:84) | MZ_ZIP_FLAG_DATA_DESCRIPTOR (mz.h:83): like the reference's own compressed
+             * entries (mz_zip.c:1992) the sizes follow the data, so close_raw never seeks back to patch the header */
+            fi.flag = (1u << 11) | (1u << 3);
             fi.compression_method = 8;           /* MZ_COMPRESS_METHOD_DEFLATE, mz.h:64 */
             fi.modified_date = items[i].modified_date ? (time_t)items[i].modified_date : time(NULL);
             fi.crc = crc;
@@ -266,15 +312,19 @@ int32_t mz_zip_cuda_add_buffers(void *zip_handle, const mz_cuda_zip_item *items,
             st.bytes_out += csize;
             c0 += c;
         }
-        double t3 = now_ms();
-        st.pack_ms += t1 - t0;
-        st.gpu_ms += t2 - t1;
-        st.container_ms += t3 - t2;
-        st.entries += last - first;
+        st.container_ms += now_ms() - t2;
+        st.pack_ms += r->pack_ms;
+        st.gpu_ms += r->gpu_ms;
+        st.entries += r->last - r->first;
         st.rounds++;
-        first = last;
+        if (started)
+            pthread_join(th, NULL);
+        if (!have_next)
+            break;
+        cur ^= 1;
     }
-    zc_free(&b);
+    zc_free(&rd[0].b);
+    zc_free(&rd[1].b);
     if (stats)
         *stats = st;
     return err;

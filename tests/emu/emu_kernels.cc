@@ -150,6 +150,8 @@ int32_t emu_inflate_spec(const uint8_t *in, uint64_t in_len, uint8_t *out, uint6
     std::vector<uint32_t> chain(2 * (size_t)max_seg);
     std::vector<uint16_t> rings((size_t)max_seg * SPEC_RING);
     std::vector<uint8_t> wins((size_t)max_seg * 32768);
+    std::vector<uint16_t> gmaps((size_t)SPEC_GROUPS * 32768);
+    std::vector<uint8_t> gwins((size_t)SPEC_GROUPS * 32768);
     std::vector<uint32_t> inbuf;
     SpecSummary sum;
     for (int i = 0; i < 5; i++) stats[i] = 0;
@@ -179,12 +181,16 @@ int32_t emu_inflate_spec(const uint8_t *in, uint64_t in_len, uint8_t *out, uint6
             P.states = states.data();
             P.rings = rings.data();
             P.wins = wins.data();
+            P.gmaps = gmaps.data();
+            P.gwins = gwins.data();
             P.chain = chain.data();
             P.summary = &sum;
             MZ_LAUNCH(inflate_spec_find_kernel, dim3(P.nseg), dim3(INF_THREADS), SPEC_FIND_SMEM, 0, P);
             MZ_LAUNCH(inflate_spec_scan_kernel, dim3(P.nseg), dim3(INF_THREADS), INF_SMEM_BYTES, 0, P);
             MZ_LAUNCH(inflate_spec_chain_kernel, dim3(1), dim3(SPEC_CHAIN_THREADS), (size_t)P.nseg * 16, 0, P);
-            MZ_LAUNCH(inflate_spec_resolve_kernel, dim3(1), dim3(SPEC_RESOLVE_THREADS), SPEC_RESOLVE_SMEM, 0, P);
+            MZ_LAUNCH(inflate_spec_compose_kernel, dim3(SPEC_GROUPS), dim3(SPEC_RESOLVE_THREADS), SPEC_COMPOSE_SMEM, 0, P);
+            MZ_LAUNCH(inflate_spec_link_kernel, dim3(1), dim3(SPEC_RESOLVE_THREADS), 65536, 0, P);
+            MZ_LAUNCH(inflate_spec_resolve_kernel, dim3(SPEC_GROUPS), dim3(SPEC_RESOLVE_THREADS), SPEC_RESOLVE_SMEM, 0, P);
             MZ_LAUNCH(inflate_spec_emit_kernel, dim3(P.nseg), dim3(INF_THREADS), INF_SMEM_BYTES, 0, P);
             stats[0]++;
             stats[3] += sum.candidates;

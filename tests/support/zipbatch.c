@@ -17,6 +17,7 @@
 #include "mz.h"
 #include "mz_strm.h"
 #include "mz_os.h"
+#include "mz_strm_buf.h"
 #include "mz_strm_os.h"
 #include "mz_zip.h"
 
@@ -122,9 +123,12 @@ int main(int argc, char **argv) {
     }
     double t_gen = now_s() - t0;
 
-    void *stream = mz_stream_os_create();
+    /* file <- buffered stream <- zip, as the reference's own writer stacks them (mz_zip_rw.c:1205-1222) */
+    void *file_stream = mz_stream_os_create();
+    void *stream = mz_stream_buffered_create();
     void *zip = mz_zip_create();
-    int32_t err = mz_stream_os_open(stream, path, MZ_OPEN_MODE_CREATE | MZ_OPEN_MODE_WRITE);
+    mz_stream_set_base(stream, file_stream);
+    int32_t err = mz_stream_open(stream, path, MZ_OPEN_MODE_CREATE | MZ_OPEN_MODE_WRITE);
     if (err == MZ_OK) err = mz_zip_open(zip, stream, MZ_OPEN_MODE_WRITE);
     if (err != MZ_OK) { fprintf(stderr, "open failed %d\n", err); return 5; }
     mz_cuda_zip_stats st;
@@ -159,10 +163,11 @@ int main(int argc, char **argv) {
     double t_add = now_s() - t0;
     t0 = now_s();
     int32_t cerr = mz_zip_close(zip);
-    mz_stream_os_close(stream);
+    mz_stream_close(stream);
     double t_close = now_s() - t0;
     mz_zip_delete(&zip);
-    mz_stream_os_delete(&stream);
+    mz_stream_buffered_delete(&stream);
+    mz_stream_os_delete(&file_stream);
     printf("{\"mode\": \"%s\", \"entries\": %u, \"entry_bytes\": %zu, \"level\": %d, \"err\": %d, \"close_err\": %d, \"bytes_in\": %llu, "
            "\"bytes_out\": %llu, \"gen_s\": %.3f, \"add_s\": %.4f, \"close_s\": %.4f, \"entries_per_s\": %.0f, \"GiB_per_s\": %.3f, "
            "\"pack_ms\": %.1f, \"gpu_ms\": %.1f, \"container_ms\": %.1f, \"rounds\": %u}\n",

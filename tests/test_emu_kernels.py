@@ -116,3 +116,12 @@ def test_emu_inflate_speculative_hostile_inputs(emu):
         assert st == 1 and out == good
     else:
         assert st < 0, (st, stats)
+
+
+def test_emu_inflate_speculative_long_chain(emu):
+    """more chain members than K6d has groups: the compose / link / resolve steps really fold several members per group"""
+    data = datagen.text_like(700_000, seed=91)
+    comp = _raw(data, 6, flush_every=2500)  # ~280 dynamic blocks, each followed by an empty stored block
+    st, out, cons, stats = emu.inflate_spec(comp, len(data), seg_bytes=1024, max_seg=1024)
+    assert st == 1 and out == data and cons == len(comp), stats
+    assert stats["chain"] > 200 and stats["rounds"] <= 3 and stats["discarded"] == 0, stats
