@@ -355,11 +355,16 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
         sink_cap = shard // 2 + (64 << 20)
         hsink = torch.empty(sink_cap, dtype=torch.uint8, pin_memory=True)
-        times = []
+        times, times_discard = [], []
         out_bytes = 0
-        for i in range(args.e2e_steps + 1):
+        # the last pass repeats the measurement with a sink that drops the bytes: what is left is upload + kernels + download
+        # into the stream's pinned staging, i.e. the codec without the consumer's single-threaded memcpy
+        for i in range(args.e2e_steps + 2):
+            discard = i == args.e2e_steps + 1
             sink = tl.lib.mz_stream_mem64_create()
             tl.lib.mz_stream_mem64_set_sink(sink, hsink.data_ptr(), sink_cap)
+            if discard:
+                tl.lib.mz_stream_mem64_set_discard(sink, 1)
             s = lib.mz_stream_cuda_create()
             lib.mz_stream_cuda_set_prop_int64(s, pkg.MZ_STREAM_PROP_COMPRESS_LEVEL, args.level)
             tl.lib.mzt_set_base(s, sink)
@@ -375,13 +380,20 @@ def run_ours(args, rank, world, local_rank):
             ps = C.c_void_p(s)
             lib.mz_stream_cuda_delete(C.byref(ps))
             tl.delete(sink)
-            if i > 0:
+            if discard:
+                times_discard.append(dt)
+            elif i > 0:
                 times.append(dt)
-        tt = torch.tensor([sum(times) / len(times)], dtype=torch.float64, device=dev)
+            if not discard:
+                out_bytes_kept = out_bytes
+        out_bytes = out_bytes_kept
+        tt = torch.tensor([sum(times) / len(times), times_discard[0]], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": round((total / GiB) / float(tt.item()), 4), "unit": UNIT, "h2d_bytes_per_step": shard, "d2h_bytes_per_step": int(out_bytes),
-               "steps": len(times), "api": "mz_stream_cuda_open/write(1 GiB calls)/close over a 64-bit memory base stream, pinned host input"}
+        e2e = {"value": round((total / GiB) / float(tt[0].item()), 4), "unit": UNIT, "h2d_bytes_per_step": shard, "d2h_bytes_per_step": int(out_bytes),
+               "steps": len(times), "api": "mz_stream_cuda_open/write(1 GiB calls)/close over a 64-bit memory base stream, pinned host input",
+               "value_discarding_sink": round((total / GiB) / float(tt[1].item()), 4),
+               "note": "value: the base stream memcpy's every compressed byte (one host thread); value_discarding_sink: same calls, the base drops the bytes"}
         del hsrc, hsink
 
     if rank != 0:

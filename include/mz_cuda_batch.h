@@ -58,6 +58,8 @@ int32_t mz_cuda_crc32_fold(const uint32_t *d_residue, uint32_t nseg, uint64_t se
                            void *stream);
 /* whole device buffer, synchronous: *crc = mz_crypt_crc32_update(value, buffer, len) */
 int32_t mz_cuda_crc32_device(const void *d_in, uint64_t len, uint32_t value, uint32_t *crc);
+/* same, enqueued on `stream` and synchronised on it only (the scratch buffer is shared: one caller per device at a time) */
+int32_t mz_cuda_crc32_device_stream(const void *d_in, uint64_t len, uint32_t value, uint32_t *crc, void *stream);
 /* host arithmetic: crc(A||B) from crc(A), crc(B), |B|  (the "polynomial combine" of the north star) */
 uint32_t mz_cuda_crc32_combine(uint32_t crc_a, uint32_t crc_b, uint64_t len_b);
 

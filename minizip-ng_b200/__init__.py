@@ -49,7 +49,7 @@ EXPORTS = [
     "mz_cuda_free", "mz_cuda_host_alloc", "mz_cuda_host_free", "mz_cuda_memcpy_h2d", "mz_cuda_memcpy_d2h", "mz_cuda_memcpy_d2d",
     "mz_cuda_memset", "mz_cuda_host_is_pinned", "mz_cuda_stream_sync", "mz_cuda_stream_create", "mz_cuda_stream_destroy",
     "mz_cuda_event_create", "mz_cuda_event_destroy", "mz_cuda_event_record", "mz_cuda_event_sync", "mz_cuda_event_elapsed_ms",
-    "mz_cuda_crc32_segments", "mz_cuda_crc32_fold", "mz_cuda_crc32_device", "mz_cuda_crc32_combine",
+    "mz_cuda_crc32_segments", "mz_cuda_crc32_fold", "mz_cuda_crc32_device", "mz_cuda_crc32_device_stream", "mz_cuda_crc32_combine",
     "mz_cuda_deflate_slot_bound", "mz_cuda_deflate_chunks", "mz_cuda_concat", "mz_cuda_inflate_streams", "mz_cuda_textgen",
     "mz_cuda_inflate_spec_workspace_bytes", "mz_cuda_inflate_spec_round",
     # include/mz_zip_cuda.h

@@ -533,6 +533,10 @@ __device__ __forceinline__ void inf_decode_window(const InflateJob &job, Inflate
                 why = INF_WHY_INPUT;
             }
         } else { /* INF_PH_CODES: tokens until the block ends or a window limit is reached */
+            /* a short match's bytes are LOADED when it is decoded and STORED when the next match arrives (or the loop
+             * ends): the history read is an L2 round trip, and an in-order warp would otherwise sit on it */
+            typename Out::Cursor pend_c;
+            uint32_t pend_len = 0, pend_val = 0;
             for (;;) {
                 uint32_t pk = INF_EV_BUDGET << 28;
                 if (budget == 0) {
@@ -564,7 +568,18 @@ __device__ __forceinline__ void inf_decode_window(const InflateJob &job, Inflate
                 if (ev == INF_EV_MATCH) {
                     const uint32_t mlen = (pk >> 16) & 0x1ffu, mdist = (pk & 0xffffu) + 1u;
                     if (mdist > out_pos + Out::reach_before_start) { status = INF_ST_DATA_ERROR; break; } /* too far back */
-                    inf_copy_match(o, out_pos, mlen, mdist);
+                    if (pend_len) { /* the previous match's bytes become history before anything new is read */
+                        if (lane < pend_len) pend_c.put(lane, pend_val);
+                        pend_len = 0;
+                    }
+                    if (mlen <= 32 && mdist >= mlen) {
+                        pend_c = o.cursor(out_pos, mdist);
+                        __syncwarp(); /* lane 0's literals and the store above are visible to the loads below */
+                        pend_val = lane < mlen ? pend_c.src(lane) : 0u;
+                        pend_len = mlen;
+                    } else {
+                        inf_copy_match(o, out_pos, mlen, mdist);
+                    }
                     out_pos += mlen;
                     continue;
                 }
@@ -584,6 +599,10 @@ __device__ __forceinline__ void inf_decode_window(const InflateJob &job, Inflate
                     status = INF_ST_BUF_ERROR;
                 }
                 break;
+            }
+            if (pend_len) {
+                if (lane < pend_len) pend_c.put(lane, pend_val);
+                __syncwarp();
             }
         }
         if (phase == INF_PH_HEADER && status == INF_ST_RUN && why == INF_WHY_NONE) { /* at a block boundary */

@@ -290,6 +290,10 @@ int32_t mz_cuda_crc32_fold(const uint32_t *d_residue, uint32_t nseg, uint64_t se
 }
 
 int32_t mz_cuda_crc32_device(const void *d_in, uint64_t len, uint32_t value, uint32_t *crc) {
+    return mz_cuda_crc32_device_stream(d_in, len, value, crc, nullptr);
+}
+
+int32_t mz_cuda_crc32_device_stream(const void *d_in, uint64_t len, uint32_t value, uint32_t *crc, void *stream) {
     DeviceCtx *c;
     int32_t err = get_ctx(&c);
     if (err) return err;
@@ -315,12 +319,13 @@ int32_t mz_cuda_crc32_device(const void *d_in, uint64_t len, uint32_t value, uin
         }
     }
     uint32_t *d_res = c->d_crc_scratch, *d_out2 = c->d_crc_scratch + nseg;
-    err = mz_cuda_crc32_segments(d_in, len, seg, nullptr, nullptr, nseg, d_res, nullptr, nullptr);
+    err = mz_cuda_crc32_segments(d_in, len, seg, nullptr, nullptr, nseg, d_res, nullptr, stream);
     if (err) return err;
-    err = mz_cuda_crc32_fold(d_res, nseg, seg, len, d_out2, nullptr);
+    err = mz_cuda_crc32_fold(d_res, nseg, seg, len, d_out2, stream);
     if (err) return err;
     uint32_t h[2];
-    CK(cudaMemcpy(h, d_out2, 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpyAsync(h, d_out2, 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
     /* chain the running value: crc(v, D) = ~((~v) x^(8|D|) + R(D)) */
     *crc = ~(gf2_mulmod(~value, gf2_xpow(g_consts.x2n, 8ull * len)) ^ h[0]);
     return MZ_OK;

@@ -62,6 +62,11 @@ typedef struct cu_ws_s {
     uint32_t spec_max_seg;
     size_t spec_seg_bytes;
     mz_cuda_spec_summary *h_sum, *d_sum;
+    void *rstream;  /* decode stream: uploads, K5/K6 launches, state copies */
+    void *dstream;  /* delivery stream: CRC + download of finished output, overlaps a round in flight */
+    void *rev;      /* K6 round in flight finished (summary is in h_sum) */
+    int pending;    /* a K6 round is in flight */
+    uint64_t pend_nseg;
 } cu_ws;
 
 static pthread_mutex_t g_pool_mu = PTHREAD_MUTEX_INITIALIZER;
@@ -104,6 +109,9 @@ static void ws_destroy(cu_ws *w) {
     mz_cuda_free(w->d_spec);
     mz_cuda_host_free(w->h_sum);
     mz_cuda_free(w->d_sum);
+    mz_cuda_event_destroy(w->rev);
+    mz_cuda_stream_destroy(w->rstream);
+    mz_cuda_stream_destroy(w->dstream);
     free(w);
 }
 
@@ -161,7 +169,11 @@ static cu_ws *ws_acquire(int kind) {
         w->d_job = (mz_cuda_inflate_job *)mz_cuda_malloc(sizeof(mz_cuda_inflate_job));
         w->h_state = (mz_cuda_inflate_state *)mz_cuda_host_alloc(sizeof(mz_cuda_inflate_state));
         w->d_state = (mz_cuda_inflate_state *)mz_cuda_malloc(sizeof(mz_cuda_inflate_state));
-        if (!w->h_cin || !w->d_cin || !w->d_win || !w->h_dec || !w->h_job || !w->d_job || !w->h_state || !w->d_state) {
+        w->rstream = mz_cuda_stream_create();
+        w->dstream = mz_cuda_stream_create();
+        w->rev = mz_cuda_event_create();
+        if (!w->h_cin || !w->d_cin || !w->d_win || !w->h_dec || !w->h_job || !w->d_job || !w->h_state || !w->d_state || !w->rstream ||
+            !w->dstream || !w->rev) {
             ws_destroy(w);
             return NULL;
         }
@@ -172,6 +184,11 @@ static cu_ws *ws_acquire(int kind) {
 static void ws_release(cu_ws *w) {
     if (!w)
         return;
+    if (w->kind == 2) {
+        if (w->pending)
+            mz_cuda_stream_sync(w->rstream);
+        w->pending = 0;
+    }
     if (w->kind == 1) {
         for (int i = 0; i < CU_NSLOT; i++) {
             if (w->slot[i].busy)
@@ -572,7 +589,7 @@ static int32_t cu_parse_header(mz_stream_cuda *cu) {
     cu->cin_base = 0;
     cu->hdr_parsed = 1;
     memset(w->h_state, 0, sizeof(*w->h_state));
-    return mz_cuda_memcpy_h2d(w->d_state, w->h_state, sizeof(*w->h_state), NULL);
+    return mz_cuda_memcpy_h2d(w->d_state, w->h_state, sizeof(*w->h_state), w->rstream);
 }
 
 /* A stream that fills the first (small) compressed window is a long one: switch the workspace to big windows and
@@ -662,18 +679,53 @@ static int32_t cu_finish_stream(mz_stream_cuda *cu) {
     return MZ_OK;
 }
 
-/* One speculative round over the compressed window (K6). Returns 1 if the stream advanced, 0 if the serial decoder
- * has to take the next step, < 0 on a CUDA failure. Stream errors are never decided here. */
-static int32_t cu_spec_round(mz_stream_cuda *cu) {
+/* Slide the compressed window to the decoder's position, top it up from base, and make the device copy current.
+ * Only called while no round is in flight. */
+static int32_t cu_prepare_input(mz_stream_cuda *cu) {
     cu_ws *w = cu->ws;
     mz_cuda_inflate_state *st = w->h_state;
-    const uint64_t pos_byte = st->in_bitpos >> 3;
+    int32_t err;
+    /* keep only bytes at or after the decoder's position (4-byte aligned for the block-start scan) */
+    uint64_t pos_byte = (st->in_bitpos >> 3) & ~3ull;
+    if (pos_byte > cu->cin_base && (cu->cin_len == w->cin_cap || pos_byte - cu->cin_base >= cu->cin_len / 2 || !w->large)) {
+        size_t drop = (size_t)(pos_byte - cu->cin_base);
+        if (drop > cu->cin_len)
+            drop = cu->cin_len;
+        memmove(w->h_cin, w->h_cin + drop, cu->cin_len - drop);
+        cu->cin_len -= drop;
+        cu->cin_base += drop;
+        cu->cin_dirty = 1;
+    }
+    err = cu_refill(cu);
+    if (err != MZ_OK)
+        return err;
+    if (cu->cin_dirty) {
+        memset(w->h_cin + cu->cin_len, 0, 64); /* the kernels may read a few bytes past the end */
+        err = mz_cuda_memcpy_h2d(w->d_cin, w->h_cin, cu->cin_len + 64, w->rstream);
+        if (err)
+            return err;
+        cu->cin_dirty = 0;
+    }
+    return MZ_OK;
+}
+
+static int cu_spec_eligible(const mz_stream_cuda *cu) {
+    const cu_ws *w = cu->ws;
+    const mz_cuda_inflate_state *st = w->h_state;
+    return w->large && !w->pending && st->status == 0 && st->phase == 0 && st->in_bitpos >= cu->spec_resume_bit &&
+           (cu->cin_base + cu->cin_len) * 8 > st->in_bitpos + 8 * 16 * (uint64_t)w->spec_seg_bytes;
+}
+
+/* Start one speculative round (K6) over the compressed window, asynchronously on the decode stream. Returns 1 if a
+ * round is now in flight, 0 if none was started, < 0 on a CUDA failure. */
+static int32_t cu_spec_launch(mz_stream_cuda *cu) {
+    cu_ws *w = cu->ws;
+    mz_cuda_inflate_state *st = w->h_state;
     const uint64_t bits_avail = (cu->cin_base + cu->cin_len) * 8 - st->in_bitpos;
     const uint64_t seg_bits = (uint64_t)w->spec_seg_bytes * 8;
     const uint64_t out_end = cu->win_base + w->win_cap;
     const uint64_t room = out_end - st->out_pos;
     int32_t err;
-    (void)pos_byte;
     uint64_t nseg = (bits_avail + seg_bits - 1) / seg_bits;
     /* do not scan far more input than the output window can take (the ratio estimate follows the stream) */
     uint64_t fit = (uint64_t)((double)room / (cu->ratio_est * 1.25 * (double)w->spec_seg_bytes)) + 1;
@@ -685,24 +737,39 @@ static int32_t cu_spec_round(mz_stream_cuda *cu) {
         return 0;
     err = mz_cuda_inflate_spec_round(w->d_cin, cu->cin_base, cu->cin_len, cu->base_eof ? 1u : 0u, st->in_bitpos, w->spec_seg_bytes,
                                      (uint32_t)nseg, w->d_win, cu->win_base, st->out_pos, out_end, w->d_spec, w->spec_max_seg, w->d_sum,
-                                     NULL);
+                                     w->rstream);
     if (err)
         return err;
-    err = mz_cuda_memcpy_d2h(w->h_sum, w->d_sum, sizeof(*w->h_sum), NULL);
+    err = mz_cuda_memcpy_d2h(w->h_sum, w->d_sum, sizeof(*w->h_sum), w->rstream);
     if (err)
         return err;
-    err = mz_cuda_stream_sync(NULL);
+    err = mz_cuda_event_record(w->rev, w->rstream);
+    if (err)
+        return err;
+    w->pending = 1;
+    w->pend_nseg = nseg;
+    return 1;
+}
+
+/* Wait for the round in flight and take its result. Returns 1 if the stream advanced, 0 if the serial decoder has to
+ * take the next step, < 0 on a CUDA failure. Stream errors are never decided here. */
+static int32_t cu_spec_collect(mz_stream_cuda *cu) {
+    cu_ws *w = cu->ws;
+    mz_cuda_inflate_state *st = w->h_state;
+    const uint64_t seg_bits = (uint64_t)w->spec_seg_bytes * 8;
+    int32_t err = mz_cuda_event_sync(w->rev);
+    w->pending = 0;
     if (err)
         return err;
     const mz_cuda_spec_summary *sm = w->h_sum;
     if (getenv("MZ_CUDA_TRACE"))
         fprintf(stderr, "mz_strm_cuda: K6 round at bit %llu: %llu segments, %u guesses, %u proven, %llu bytes out, end bit %llu, status %d, flags %u\n",
-                (unsigned long long)st->in_bitpos, (unsigned long long)nseg, sm->candidates, sm->nchain, (unsigned long long)sm->total_out,
+                (unsigned long long)st->in_bitpos, (unsigned long long)w->pend_nseg, sm->candidates, sm->nchain, (unsigned long long)sm->total_out,
                 (unsigned long long)sm->end_bit, sm->status, sm->flags);
     if (sm->flags || sm->nchain == 0 || (sm->end_bit <= st->in_bitpos && sm->status != 1)) {
         /* nothing proven: let the serial decoder move on; if the window holds no other block start at all
          * (stored or fixed blocks, one giant block), do not try again before it has been consumed */
-        cu->spec_resume_bit = sm->candidates <= 1 ? st->in_bitpos + nseg * seg_bits : st->in_bitpos + 1;
+        cu->spec_resume_bit = sm->candidates <= 1 ? st->in_bitpos + w->pend_nseg * seg_bits : st->in_bitpos + 1;
         return 0;
     }
     const uint64_t used_bytes = (sm->end_bit - st->in_bitpos + 7) >> 3;
@@ -714,14 +781,17 @@ static int32_t cu_spec_round(mz_stream_cuda *cu) {
     st->status = sm->status;
     st->why = 0;
     st->phase = 0;
-    err = mz_cuda_memcpy_h2d(w->d_state, st, sizeof(*st), NULL);
+    err = mz_cuda_memcpy_h2d(w->d_state, st, sizeof(*st), w->rstream);
     if (err)
         return err;
+    if (st->status == 0)
+        cu->total_in = cu->hdr_size + (int64_t)(st->in_bitpos >> 3);
     return 1;
 }
 
 /* Make ws->h_dec[0..dec_len) hold fresh output, or finish the stream. Decoded bytes stay in the device window until
- * they are delivered, at most one host buffer (`batch`) per call. */
+ * they are delivered, at most one host buffer (`batch`) per call; while they are being delivered the next K6 round
+ * is already running on the decode stream. */
 static int32_t cu_decode_more(mz_stream_cuda *cu) {
     cu_ws *w = cu->ws;
     mz_cuda_inflate_state *st = w->h_state;
@@ -740,19 +810,32 @@ static int32_t cu_decode_more(mz_stream_cuda *cu) {
     for (;;) {
         /* 1. deliver what is already decoded */
         if (cu->deliv_pos < st->out_pos) {
+            /* keep the GPU busy meanwhile: if the decoder stands at a block boundary and the output window still has
+             * room behind the undelivered bytes, start the next round now */
+            if (w->large && !w->pending && st->status == 0 && st->phase == 0 &&
+                cu->win_base + w->win_cap - st->out_pos >= w->win_cap / 4) {
+                err = cu_prepare_input(cu);
+                if (err != MZ_OK)
+                    return err;
+                if (cu_spec_eligible(cu)) {
+                    err = cu_spec_launch(cu);
+                    if (err < 0)
+                        return err;
+                }
+            }
             uint64_t n = st->out_pos - cu->deliv_pos;
             if (n > w->batch)
                 n = w->batch;
             const uint8_t *src = w->d_win + (cu->deliv_pos - cu->win_base);
             if (cu->wrap == 2) {
-                err = mz_cuda_crc32_device(src, n, cu->crc, &cu->crc);
+                err = mz_cuda_crc32_device_stream(src, n, cu->crc, &cu->crc, w->dstream);
                 if (err)
                     return err;
             }
-            err = mz_cuda_memcpy_d2h(w->h_dec, src, n, NULL);
+            err = mz_cuda_memcpy_d2h(w->h_dec, src, n, w->dstream);
             if (err)
                 return err;
-            err = mz_cuda_stream_sync(NULL);
+            err = mz_cuda_stream_sync(w->dstream);
             if (err)
                 return err;
             if (cu->wrap == 1)
@@ -762,24 +845,21 @@ static int32_t cu_decode_more(mz_stream_cuda *cu) {
             cu->deliv_pos += n;
             return MZ_OK;
         }
-        /* 2. everything delivered: terminal states */
+        /* 2. a round in flight: its result decides what comes next */
+        if (w->pending) {
+            err = cu_spec_collect(cu);
+            if (err < 0)
+                return err;
+            if (err == 1)
+                continue;
+        }
+        /* 3. everything delivered: terminal states */
         if (st->status < 0)
             return st->status; /* MZ_DATA_ERROR / MZ_BUF_ERROR, zlib-compatible */
         if (st->status == 1)
             return cu_finish_stream(cu);
-        /* 3. decode more. Slide the compressed window: keep only bytes at or after the decoder's position
-         * (4-byte aligned for the block-start scan) */
-        uint64_t pos_byte = (st->in_bitpos >> 3) & ~3ull;
-        if (pos_byte > cu->cin_base && (cu->cin_len == w->cin_cap || pos_byte - cu->cin_base >= cu->cin_len / 2 || !w->large)) {
-            size_t drop = (size_t)(pos_byte - cu->cin_base);
-            if (drop > cu->cin_len)
-                drop = cu->cin_len;
-            memmove(w->h_cin, w->h_cin + drop, cu->cin_len - drop);
-            cu->cin_len -= drop;
-            cu->cin_base += drop;
-            cu->cin_dirty = 1;
-        }
-        err = cu_refill(cu);
+        /* 4. decode more */
+        err = cu_prepare_input(cu);
         if (err != MZ_OK)
             return err;
         /* slide the output window when little room is left: keep 32 KiB of history at the front */
@@ -788,27 +868,17 @@ static int32_t cu_decode_more(mz_stream_cuda *cu) {
         if (out_pos - cu->win_base + need > w->win_cap) {
             uint64_t keep = out_pos - cu->win_base < 32768 ? out_pos - cu->win_base : 32768;
             /* ranges cannot overlap: the window is much larger than 64 KiB */
-            err = mz_cuda_memcpy_d2d(w->d_win, w->d_win + (out_pos - cu->win_base - keep), keep, NULL);
+            err = mz_cuda_memcpy_d2d(w->d_win, w->d_win + (out_pos - cu->win_base - keep), keep, w->rstream);
             if (err)
                 return err;
             cu->win_base = out_pos - keep;
         }
-        if (cu->cin_dirty) {
-            memset(w->h_cin + cu->cin_len, 0, 64); /* the kernels may read a few bytes past the end */
-            err = mz_cuda_memcpy_h2d(w->d_cin, w->h_cin, cu->cin_len + 64, NULL);
-            if (err)
-                return err;
-            cu->cin_dirty = 0;
-        }
-        if (w->large && st->phase == 0 && st->in_bitpos >= cu->spec_resume_bit &&
-            (cu->cin_base + cu->cin_len) * 8 > st->in_bitpos + 8 * 16 * (uint64_t)w->spec_seg_bytes) {
-            err = cu_spec_round(cu);
+        if (cu_spec_eligible(cu)) {
+            err = cu_spec_launch(cu);
             if (err < 0)
                 return err;
-            if (err == 1) {
-                cu->total_in = cu->hdr_size + (int64_t)(st->in_bitpos >> 3);
-                continue;
-            }
+            if (err == 1)
+                continue; /* collected at step 2 */
         }
         w->h_job->d_in = w->d_cin;
         w->h_job->in_base = cu->cin_base;
@@ -819,18 +889,18 @@ static int32_t cu_decode_more(mz_stream_cuda *cu) {
         w->h_job->out_cap = (out_pos - cu->win_base) + w->batch < w->win_cap ? (out_pos - cu->win_base) + w->batch : w->win_cap;
         w->h_job->in_final = cu->base_eof ? 1u : 0u;
         w->h_job->flags = w->large ? MZ_CUDA_INFLATE_STOP_AT_BLOCK : 0u; /* long streams: hand back at the next block so a round can start */
-        err = mz_cuda_memcpy_h2d(w->d_job, w->h_job, sizeof(*w->h_job), NULL);
+        err = mz_cuda_memcpy_h2d(w->d_job, w->h_job, sizeof(*w->h_job), w->rstream);
         if (err)
             return err;
-        err = mz_cuda_inflate_streams(w->d_job, w->d_state, 1, NULL);
+        err = mz_cuda_inflate_streams(w->d_job, w->d_state, 1, w->rstream);
         if (err)
             return err;
         if (getenv("MZ_CUDA_TRACE"))
             fprintf(stderr, "mz_strm_cuda: K5 launch at bit %llu (window %zu bytes, large %d)\n", (unsigned long long)st->in_bitpos, cu->cin_len, w->large);
-        err = mz_cuda_memcpy_d2h(st, w->d_state, sizeof(*st), NULL);
+        err = mz_cuda_memcpy_d2h(st, w->d_state, sizeof(*st), w->rstream);
         if (err)
             return err;
-        err = mz_cuda_stream_sync(NULL);
+        err = mz_cuda_stream_sync(w->rstream);
         if (err)
             return err;
         if (st->status == 0)
