@@ -49,21 +49,65 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-sample-mib", type=int, default=2048)
-    ap.add_argument("--sub-batches", type=int, default=4, help="pieces per shard when N>1 (all-gather of piece j overlaps compression of j+1)")
+    ap.add_argument("--sub-batches", type=int, default=0, help="pieces per shard when N>1 (all-gather of piece j overlaps compression of j+1)")
     return ap.parse_args()
 
 
 # ---- clocks --------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region: NVML polled every few milliseconds from a thread
+    (a multi-GPU step is tens of milliseconds, too short for `nvidia-smi -lms`); falls back to nvidia-smi when the
+    NVML bindings are missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index):
         self.index = index
         self.proc = None
         self.path = None
+        self.thread = None
+        self.samples = []
+        self.mask = 0
+        self.max_mhz = None
+        self.stop_flag = False
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid)
+        except Exception:
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+
+    def _poll(self, nv, h):
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+            except Exception:
+                pass
+            time.sleep(0.004)
 
     def start(self):
+        try:
+            import threading
+            nv, h = self._nvml_handle()
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            self.thread = threading.Thread(target=self._poll, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
             self.path = f.name
@@ -73,6 +117,13 @@ class ClockSampler:
             self.proc = None
 
     def stop(self):
+        if self.thread:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            sm = sorted(self.samples)
+            reasons = sorted(name for bit, name in self.REASONS if self.mask & bit)
+            return {"sm_mhz": float(sm[len(sm) // 2]) if sm else None, "sm_max_mhz": float(self.max_mhz) if self.max_mhz else None, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -102,7 +153,8 @@ class ClockSampler:
             except Exception:
                 pass
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvidia-smi"}
 
 
 # ---- the reference's CPU path (oracle/_ref) -------------------------------------------------------------------------
@@ -241,7 +293,7 @@ def run_ours(args, rank, world, local_rank):
         pkg.check(lib.mz_cuda_textgen(src.data_ptr() + o, k, 1000 + (c0 * 65536 + o) // seg, None), "textgen")
     torch.cuda.synchronize()
     # ---- sub-batches: with N>1 the shard is compressed in NB pieces so the all-gather of piece j overlaps the compression of j+1
-    NB = 1 if world == 1 else max(1, args.sub_batches)
+    NB = 1 if world == 1 else (args.sub_batches if args.sub_batches > 0 else (8 if world >= 8 else 4))  # measured: 4 pieces best at N=2/4, 8 at N=8
     nshard_chunks = c1 - c0
     bounds = [nshard_chunks * j // NB for j in range(NB + 1)]
     subs = [(bounds[j] * 65536, (bounds[j + 1] - bounds[j]) * 65536) for j in range(NB)]  # (byte offset in shard, bytes)
@@ -359,10 +411,14 @@ def run_ours(args, rank, world, local_rank):
         out_bytes = 0
         # the last pass repeats the measurement with a sink that drops the bytes: what is left is upload + kernels + download
         # into the stream's pinned staging, i.e. the codec without the consumer's single-threaded memcpy
-        for i in range(args.e2e_steps + 2):
-            discard = i == args.e2e_steps + 1
+        SINK_THREADS = 8
+        times_single = []
+        for i in range(args.e2e_steps + 3):
+            single = i == args.e2e_steps + 1
+            discard = i == args.e2e_steps + 2
             sink = tl.lib.mz_stream_mem64_create()
             tl.lib.mz_stream_mem64_set_sink(sink, hsink.data_ptr(), sink_cap)
+            tl.lib.mz_stream_mem64_set_copy_threads(sink, 1 if single else SINK_THREADS)
             if discard:
                 tl.lib.mz_stream_mem64_set_discard(sink, 1)
             s = lib.mz_stream_cuda_create()
@@ -382,18 +438,23 @@ def run_ours(args, rank, world, local_rank):
             tl.delete(sink)
             if discard:
                 times_discard.append(dt)
+            elif single:
+                times_single.append(dt)
             elif i > 0:
                 times.append(dt)
             if not discard:
                 out_bytes_kept = out_bytes
         out_bytes = out_bytes_kept
-        tt = torch.tensor([sum(times) / len(times), times_discard[0]], dtype=torch.float64, device=dev)
+        tt = torch.tensor([sum(times) / len(times), times_discard[0], times_single[0]], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": round((total / GiB) / float(tt[0].item()), 4), "unit": UNIT, "h2d_bytes_per_step": shard, "d2h_bytes_per_step": int(out_bytes),
                "steps": len(times), "api": "mz_stream_cuda_open/write(1 GiB calls)/close over a 64-bit memory base stream, pinned host input",
+               "value_single_thread_sink": round((total / GiB) / float(tt[2].item()), 4),
                "value_discarding_sink": round((total / GiB) / float(tt[1].item()), 4),
-               "note": "value: the base stream memcpy's every compressed byte (one host thread); value_discarding_sink: same calls, the base drops the bytes"}
+               "sink": "host memory stream (tests/support/mem64.c) copying every compressed byte with %d threads" % SINK_THREADS,
+               "note": "value_single_thread_sink: the same sink with one memcpy thread (the consumer, not the codec, is then the limit); "
+                       "value_discarding_sink: the base stream drops the bytes (upload + kernels + download into pinned staging only)"}
         del hsrc, hsink
 
     if rank != 0:

@@ -60,7 +60,10 @@ struct Smem {
     __device__ __forceinline__ void red_add32(uint32_t off, uint32_t v) const { *(uint32_t *)(b + off) += v; }
 #else
     uint32_t b;
-    __device__ __forceinline__ void init(uint8_t *base) { b = (uint32_t)__cvta_generic_to_shared(base); }
+    __device__ __forceinline__ void init(uint8_t *base) {
+        b = (uint32_t)__cvta_generic_to_shared(base);
+        asm volatile("" : "+r"(b)); /* opaque: keep the address in a register instead of re-deriving it (S2R + LEA) at every use */
+    }
     __device__ __forceinline__ uint32_t ld32(uint32_t off) const {
         uint32_t v;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(b + off));

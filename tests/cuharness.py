@@ -33,6 +33,7 @@ class TestLib:
         L.mz_stream_mem64_set_buffer.argtypes = [vp, vp, i64]
         L.mz_stream_mem64_set_sink.argtypes = [vp, vp, i64]
         L.mz_stream_mem64_set_discard.argtypes = [vp, i32]
+        L.mz_stream_mem64_set_copy_threads.argtypes = [vp, i32]
         L.mz_stream_mem64_get_buffer.restype = i64
         L.mz_stream_mem64_get_buffer.argtypes = [vp, C.POINTER(vp)]
         for name, res, args in (("mzt_open", i32, [vp, C.c_char_p, i32]), ("mzt_is_open", i32, [vp]), ("mzt_read", i32, [vp, vp, i32]),

@@ -5,10 +5,77 @@
  * vtbl implementation the survey calls for: a growable sink / fixed source with 64-bit offsets,
  * speaking the same plug-in ABI (include/mz_abi.h).
  */
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include "../../include/mz_abi.h"
+
+/* ---- optional multi-threaded copy for large sink writes ------------------------------------------------------
+ * One host thread memcpy's ~10 GB/s; a consumer that absorbs the compressed stream at memory bandwidth (several
+ * copy engines / threads, what the reference arm of bench.py gets for free from its one-sink-per-thread layout) is
+ * modelled by mz_stream_mem64_set_copy_threads(sink, n). Default n = 1: a plain memcpy like mz_stream_mem. */
+#define PM_MAX 16
+static struct {
+    pthread_t th[PM_MAX];
+    pthread_mutex_t mu, op;
+    pthread_cond_t go, fin;
+    uint8_t *dst;
+    const uint8_t *src;
+    size_t n;
+    unsigned gen, done, nthreads, started;
+} pm = {.mu = PTHREAD_MUTEX_INITIALIZER, .op = PTHREAD_MUTEX_INITIALIZER, .go = PTHREAD_COND_INITIALIZER, .fin = PTHREAD_COND_INITIALIZER};
+
+static void *pm_worker(void *arg) {
+    const unsigned idx = (unsigned)(uintptr_t)arg;
+    unsigned seen = 0;
+    for (;;) {
+        pthread_mutex_lock(&pm.mu);
+        while (pm.gen == seen) pthread_cond_wait(&pm.go, &pm.mu);
+        seen = pm.gen;
+        uint8_t *dst = pm.dst;
+        const uint8_t *src = pm.src;
+        const size_t n = pm.n;
+        const unsigned nt = pm.nthreads;
+        pthread_mutex_unlock(&pm.mu);
+        if (idx < nt) {
+            const size_t per = (n / nt + 63) & ~(size_t)63, lo = (size_t)idx * per;
+            if (lo < n) memcpy(dst + lo, src + lo, lo + per > n ? n - lo : per);
+        }
+        pthread_mutex_lock(&pm.mu);
+        if (++pm.done == pm.started) pthread_cond_signal(&pm.fin);
+        pthread_mutex_unlock(&pm.mu);
+    }
+    return NULL;
+}
+
+static void par_memcpy(uint8_t *dst, const uint8_t *src, size_t n, unsigned nthreads) {
+    if (nthreads <= 1 || n < (4u << 20)) {
+        memcpy(dst, src, n);
+        return;
+    }
+    if (nthreads > PM_MAX) nthreads = PM_MAX;
+    pthread_mutex_lock(&pm.op); /* one parallel copy at a time */
+    pthread_mutex_lock(&pm.mu);
+    while (pm.started < nthreads) {
+        if (pthread_create(&pm.th[pm.started], NULL, pm_worker, (void *)(uintptr_t)pm.started) != 0) break;
+        pm.started++;
+    }
+    if (pm.started == 0) {
+        pthread_mutex_unlock(&pm.mu);
+        pthread_mutex_unlock(&pm.op);
+        memcpy(dst, src, n);
+        return;
+    }
+    pm.dst = dst; pm.src = src; pm.n = n;
+    pm.nthreads = nthreads < pm.started ? nthreads : pm.started;
+    pm.done = 0;
+    pm.gen++;
+    pthread_cond_broadcast(&pm.go);
+    while (pm.done < pm.started) pthread_cond_wait(&pm.fin, &pm.mu);
+    pthread_mutex_unlock(&pm.mu);
+    pthread_mutex_unlock(&pm.op);
+}
 
 typedef struct mem64_s {
     mz_stream stream;
@@ -19,6 +86,7 @@ typedef struct mem64_s {
     int32_t owns;
     int32_t open;
     int32_t discard;  /* sink that only counts */
+    int32_t copy_threads;
 } mem64;
 
 static int32_t m_open(void *s, const char *path, int32_t mode) { (void)path; (void)mode; ((mem64 *)s)->open = 1; return MZ_OK; }
@@ -44,7 +112,7 @@ static int32_t m_write(void *s, const void *buf, int32_t size) {
             if (!nb) return MZ_WRITE_ERROR;
             m->buf = nb; m->cap = ncap; m->owns = 1;
         }
-        memcpy(m->buf + m->pos, buf, (size_t)size);
+        par_memcpy(m->buf + m->pos, (const uint8_t *)buf, (size_t)size, (unsigned)m->copy_threads);
     }
     m->pos += size;
     if (m->pos > m->size) m->size = m->pos;
@@ -93,6 +161,7 @@ void mz_stream_mem64_set_sink(void *s, void *buf, int64_t cap) {
     m->buf = (uint8_t *)buf; m->cap = cap; m->size = 0; m->pos = 0; m->owns = 0;
 }
 void mz_stream_mem64_set_discard(void *s, int32_t on) { ((mem64 *)s)->discard = on; }
+void mz_stream_mem64_set_copy_threads(void *s, int32_t n) { ((mem64 *)s)->copy_threads = n; }
 int64_t mz_stream_mem64_get_buffer(void *s, const void **buf) {
     mem64 *m = (mem64 *)s;
     if (buf) *buf = m->buf;
