@@ -575,7 +575,7 @@ __device__ __forceinline__ void inf_decode_window(const InflateJob &job, Inflate
                     if (mlen <= 32 && mdist >= mlen) {
                         pend_c = o.cursor(out_pos, mdist);
                         __syncwarp(); /* lane 0's literals and the store above are visible to the loads below */
-                        pend_val = lane < mlen ? pend_c.src(lane) : 0u;
+                        if (lane < mlen) pend_val = pend_c.src(lane); /* predicated load straight into the carried register: no use of the value here */
                         pend_len = mlen;
                     } else {
                         inf_copy_match(o, out_pos, mlen, mdist);

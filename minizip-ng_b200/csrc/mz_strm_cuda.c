@@ -625,6 +625,9 @@ static void ws_read_upgrade(cu_ws *w, size_t cin_len) {
     mz_cuda_host_free(w->h_cin);
     mz_cuda_free(w->d_cin);
     mz_cuda_free(w->d_win);
+    mz_cuda_free(w->d_spec); /* the small-window K6 scratch, if a medium stream used this workspace before */
+    mz_cuda_host_free(w->h_sum);
+    mz_cuda_free(w->d_sum);
     w->h_cin = h_cin;
     w->d_cin = d_cin;
     w->d_win = d_win;
@@ -636,6 +639,37 @@ static void ws_read_upgrade(cu_ws *w, size_t cin_len) {
     w->h_sum = h_sum;
     w->d_sum = d_sum;
     w->large = 1;
+}
+
+/* K6 scratch for the current (small) windows: medium streams -- a zip entry of a few megabytes -- are decoded by
+ * speculative rounds too, without the big windows of a long stream. Allocated on first use, kept with the workspace. */
+static int ws_spec_ensure(cu_ws *w) {
+    if (w->d_spec)
+        return 1;
+    const char *off = getenv("MZ_CUDA_SPEC");
+    if (off && off[0] == '0')
+        return 0;
+    size_t seg = env_size("MZ_CUDA_SPEC_SEG_KB", 16u << 10, 1024);
+    if (seg < 1024)
+        return 0;
+    uint32_t max_seg = (uint32_t)(w->cin_cap / seg) + 1;
+    if (max_seg > 12288)
+        max_seg = 12288;
+    w->d_spec = mz_cuda_malloc((size_t)mz_cuda_inflate_spec_workspace_bytes(max_seg));
+    w->h_sum = (mz_cuda_spec_summary *)mz_cuda_host_alloc(sizeof(mz_cuda_spec_summary));
+    w->d_sum = (mz_cuda_spec_summary *)mz_cuda_malloc(sizeof(mz_cuda_spec_summary));
+    if (!w->d_spec || !w->h_sum || !w->d_sum) {
+        mz_cuda_free(w->d_spec);
+        mz_cuda_host_free(w->h_sum);
+        mz_cuda_free(w->d_sum);
+        w->d_spec = NULL;
+        w->h_sum = NULL;
+        w->d_sum = NULL;
+        return 0;
+    }
+    w->spec_max_seg = max_seg;
+    w->spec_seg_bytes = seg;
+    return 1;
 }
 
 /* end of the raw stream: account for consumed bytes, verify the trailer (gzip CRC-32 + ISIZE, zlib Adler-32) */
@@ -687,7 +721,7 @@ static int32_t cu_prepare_input(mz_stream_cuda *cu) {
     int32_t err;
     /* keep only bytes at or after the decoder's position (4-byte aligned for the block-start scan) */
     uint64_t pos_byte = (st->in_bitpos >> 3) & ~3ull;
-    if (pos_byte > cu->cin_base && (cu->cin_len == w->cin_cap || pos_byte - cu->cin_base >= cu->cin_len / 2 || !w->large)) {
+    if (pos_byte > cu->cin_base && (cu->cin_len == w->cin_cap || pos_byte - cu->cin_base >= cu->cin_len / 2)) {
         size_t drop = (size_t)(pos_byte - cu->cin_base);
         if (drop > cu->cin_len)
             drop = cu->cin_len;
@@ -709,11 +743,18 @@ static int32_t cu_prepare_input(mz_stream_cuda *cu) {
     return MZ_OK;
 }
 
-static int cu_spec_eligible(const mz_stream_cuda *cu) {
+/* enough compressed input ahead of the decoder for a speculative round to pay off (16 segments) */
+static int cu_spec_worthwhile(const mz_stream_cuda *cu) {
     const cu_ws *w = cu->ws;
+    const uint64_t seg = w->spec_seg_bytes ? w->spec_seg_bytes : 16384;
+    return (cu->cin_base + cu->cin_len) * 8 > w->h_state->in_bitpos + 8 * 16 * seg;
+}
+
+static int cu_spec_eligible(mz_stream_cuda *cu) {
+    cu_ws *w = cu->ws;
     const mz_cuda_inflate_state *st = w->h_state;
-    return w->large && !w->pending && st->status == 0 && st->phase == 0 && st->in_bitpos >= cu->spec_resume_bit &&
-           (cu->cin_base + cu->cin_len) * 8 > st->in_bitpos + 8 * 16 * (uint64_t)w->spec_seg_bytes;
+    return !w->pending && st->status == 0 && st->phase == 0 && st->in_bitpos >= cu->spec_resume_bit && cu_spec_worthwhile(cu) &&
+           ws_spec_ensure(w);
 }
 
 /* Start one speculative round (K6) over the compressed window, asynchronously on the decode stream. Returns 1 if a
@@ -812,7 +853,7 @@ static int32_t cu_decode_more(mz_stream_cuda *cu) {
         if (cu->deliv_pos < st->out_pos) {
             /* keep the GPU busy meanwhile: if the decoder stands at a block boundary and the output window still has
              * room behind the undelivered bytes, start the next round now */
-            if (w->large && !w->pending && st->status == 0 && st->phase == 0 &&
+            if (w->d_spec && !w->pending && st->status == 0 && st->phase == 0 &&
                 cu->win_base + w->win_cap - st->out_pos >= w->win_cap / 4) {
                 err = cu_prepare_input(cu);
                 if (err != MZ_OK)
@@ -864,7 +905,7 @@ static int32_t cu_decode_more(mz_stream_cuda *cu) {
             return err;
         /* slide the output window when little room is left: keep 32 KiB of history at the front */
         uint64_t out_pos = st->out_pos;
-        uint64_t need = w->large ? w->win_cap / 2 : 65536;
+        uint64_t need = w->d_spec ? w->win_cap / 2 : 65536;
         if (out_pos - cu->win_base + need > w->win_cap) {
             uint64_t keep = out_pos - cu->win_base < 32768 ? out_pos - cu->win_base : 32768;
             /* ranges cannot overlap: the window is much larger than 64 KiB */
@@ -888,7 +929,8 @@ static int32_t cu_decode_more(mz_stream_cuda *cu) {
         /* at most one host buffer (`batch` bytes) of fresh output per launch */
         w->h_job->out_cap = (out_pos - cu->win_base) + w->batch < w->win_cap ? (out_pos - cu->win_base) + w->batch : w->win_cap;
         w->h_job->in_final = cu->base_eof ? 1u : 0u;
-        w->h_job->flags = w->large ? MZ_CUDA_INFLATE_STOP_AT_BLOCK : 0u; /* long streams: hand back at the next block so a round can start */
+        /* streams that K6 can serve: hand back at the next block boundary so a round can start there */
+        w->h_job->flags = w->d_spec && cu_spec_worthwhile(cu) ? MZ_CUDA_INFLATE_STOP_AT_BLOCK : 0u;
         err = mz_cuda_memcpy_h2d(w->d_job, w->h_job, sizeof(*w->h_job), w->rstream);
         if (err)
             return err;

@@ -125,3 +125,40 @@ def test_emu_inflate_speculative_long_chain(emu):
     st, out, cons, stats = emu.inflate_spec(comp, len(data), seg_bytes=1024, max_seg=1024)
     assert st == 1 and out == data and cons == len(comp), stats
     assert stats["chain"] > 200 and stats["rounds"] <= 3 and stats["discarded"] == 0, stats
+
+
+def test_emu_inflate_speculative_never_lies_under_corruption(emu):
+    """seeded bit flips, byte runs and splices in a valid member: whatever the speculative rounds prove must be exactly
+    what zlib produces -- same bytes if zlib accepts the damaged stream, an error if zlib rejects it, and never more
+    clean output than zlib delivers before the error"""
+    import random
+    rng = random.Random(20260922)
+    data = datagen.text_like(260_000, seed=5) + datagen.binary_records(40_000, seed=6)
+    comp = _raw(data, 6, flush_every=0)
+    for trial in range(12):
+        bad = bytearray(comp)
+        kind = trial % 3
+        pos = rng.randrange(len(bad) // 8, len(bad) - 64)
+        if kind == 0:
+            bad[pos] ^= 1 << rng.randrange(8)
+        elif kind == 1:
+            for k in range(rng.randrange(2, 40)):
+                bad[pos + k] = rng.randrange(256)
+        else:  # splice: a piece of the stream copied over another place (valid-looking headers in the wrong spot)
+            src = rng.randrange(0, len(bad) - 4096)
+            bad[pos:pos + 2000] = comp[src:src + 2000]
+        ref = zlib.decompressobj(-15)
+        good = b""
+        try:
+            for o in range(0, len(bad), 4096):  # piecewise, so the bytes zlib delivered before an error are kept
+                good += ref.decompress(bytes(bad[o:o + 4096]))
+            ok = ref.eof
+        except zlib.error:
+            ok = False
+        st, out, cons, stats = emu.inflate_spec(bytes(bad), len(data) + 100_000, seg_bytes=2048, max_seg=256)
+        if ok:
+            assert st == 1 and out == good, (trial, kind, pos, st, stats)
+        else:
+            assert st < 0, (trial, kind, pos, st, stats)
+            n = min(len(out), len(good))
+            assert out[:n] == good[:n], (trial, kind, pos)

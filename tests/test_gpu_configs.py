@@ -166,6 +166,9 @@ def test_c3_long_member_speculative_rounds_match_serial(env, ref, monkeypatch):
     for level in (1, 6, 9):
         co = zlib.compressobj(level, zlib.DEFLATED, 31)
         cases.append((text, co.compress(text) + co.flush()))
+    for level, nbytes in ((6, 12 * MiB), (9, 3 * MiB), (1, 700_000)):  # medium members: K6 on the small windows (zip-entry sizes)
+        co = zlib.compressobj(level, zlib.DEFLATED, 31)
+        cases.append((text[:nbytes], co.compress(text[:nbytes]) + co.flush()))
     mixed = text[:20 * MiB] + noise + text[20 * MiB:30 * MiB]  # stored blocks in the middle: the rounds must hand over and resume
     co = zlib.compressobj(6, zlib.DEFLATED, 31)
     cases.append((mixed, co.compress(mixed) + co.flush()))

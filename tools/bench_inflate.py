@@ -167,5 +167,6 @@ if __name__ == "__main__":
     single(16)
     batch(8192)
     vtbl_long(32, spec=False)
+    vtbl_long(16, spec=True)
     vtbl_long(256, spec=True)
     vtbl_long(1024, spec=True)
