@@ -44,6 +44,20 @@ typedef struct mz_cuda_zip_stats {
 int32_t mz_zip_cuda_add_buffers(void *zip_handle, const mz_cuda_zip_item *items, uint32_t count, int16_t level,
                                 mz_cuda_zip_stats *stats);
 
+/* ---- batch extraction (scope row f2): the reverse direction ---------------------------------------------------
+ * The reference extracts entry by entry: mz_zip_entry_read_open(raw=0) creates a mz_stream_zlib, the caller's loop
+ * reads through it, mz_zip_entry_close compares the CRC (mz_zip_rw.c:818-909, mz_zip.c:2116-2128). Here the central
+ * directory is still walked by the reference's own reader (mz_zip_goto_first_entry / _next_entry /
+ * mz_zip_entry_get_info, mz_zip.c:2320-2400) and the compressed bytes are fetched through the raw seam
+ * (mz_zip_entry_read_open(raw=1) / mz_zip_entry_read, mz_zip.c:1874,2031), but all entries of a round are inflated by
+ * ONE K5 launch and checksummed by ONE K1 launch; the CRCs are compared with the headers on the host (MZ_CRC_ERROR on
+ * the first mismatch, MZ_DATA_ERROR if a stream does not decode to exactly its recorded size).
+ * `cb` is called once per entry in archive order with the plain bytes (valid during the call only); a non-zero return
+ * stops the extraction and is returned. Entries that are encrypted, use another method than STORE/DEFLATE, or exceed
+ * 1 GiB are not batched: the call returns MZ_SUPPORT_ERROR (use the per-entry stream path for such archives). */
+typedef int32_t (*mz_cuda_zip_entry_cb)(void *userdata, const char *filename, const void *data, int64_t size, uint32_t crc32);
+int32_t mz_zip_cuda_extract_all(void *zip_handle, mz_cuda_zip_entry_cb cb, void *userdata, mz_cuda_zip_stats *stats);
+
 /* sizeof the mz_zip_file mirror this library was built with: the host asserts it equals sizeof(mz_zip_file) */
 uint32_t mz_zip_cuda_abi_file_info_size(void);
 

@@ -53,7 +53,7 @@ EXPORTS = [
     "mz_cuda_deflate_slot_bound", "mz_cuda_deflate_chunks", "mz_cuda_concat", "mz_cuda_inflate_streams", "mz_cuda_textgen",
     "mz_cuda_inflate_spec_workspace_bytes", "mz_cuda_inflate_spec_round",
     # include/mz_zip_cuda.h
-    "mz_zip_cuda_add_buffers", "mz_zip_cuda_abi_file_info_size",
+    "mz_zip_cuda_add_buffers", "mz_zip_cuda_extract_all", "mz_zip_cuda_abi_file_info_size",
 ]
 
 

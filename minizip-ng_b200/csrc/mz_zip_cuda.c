@@ -51,6 +51,13 @@ extern int32_t mz_zip_entry_write_open(void *handle, const void *file_info, int1
     __attribute__((weak));
 extern int32_t mz_zip_entry_write(void *handle, const void *buf, int32_t len) __attribute__((weak));
 extern int32_t mz_zip_entry_close_raw(void *handle, int64_t uncompressed_size, uint32_t crc32) __attribute__((weak));
+/* reader side (mz_zip.h:115-172) */
+extern int32_t mz_zip_goto_first_entry(void *handle) __attribute__((weak));
+extern int32_t mz_zip_goto_next_entry(void *handle) __attribute__((weak));
+extern int32_t mz_zip_entry_get_info(void *handle, zc_file_info **file_info) __attribute__((weak));
+extern int32_t mz_zip_entry_read_open(void *handle, uint8_t raw, const char *password) __attribute__((weak));
+extern int32_t mz_zip_entry_read(void *handle, void *buf, int32_t len) __attribute__((weak));
+extern int32_t mz_zip_entry_close(void *handle) __attribute__((weak));
 
 uint32_t mz_zip_cuda_abi_file_info_size(void) {
     return (uint32_t)sizeof(zc_file_info);
@@ -325,6 +332,256 @@ int32_t mz_zip_cuda_add_buffers(void *zip_handle, const mz_cuda_zip_item *items,
     }
     zc_free(&rd[0].b);
     zc_free(&rd[1].b);
+    if (stats)
+        *stats = st;
+    return err;
+}
+
+/* ---- batch extraction ------------------------------------------------------------------------------------------ */
+typedef struct zx_entry_s {
+    uint64_t coff, csize, ooff, usize; /* offsets inside the round's compressed / plain buffers */
+    uint32_t crc, name_off;
+    uint16_t method;
+} zx_entry;
+
+typedef struct zx_bufs_s {
+    size_t comp_cap, out_cap;
+    uint32_t max_entries;
+    uint8_t *h_comp, *d_comp, *d_out, *h_out;
+    mz_cuda_inflate_job *h_job, *d_job;
+    mz_cuda_inflate_state *h_state, *d_state;
+    uint64_t *h_off, *d_off;
+    uint32_t *h_len, *d_len, *d_residue, *d_crc, *h_crc;
+    zx_entry *ent;
+    char *names;
+    size_t names_cap;
+} zx_bufs;
+
+static void zx_free(zx_bufs *b) {
+    mz_cuda_host_free(b->h_comp);
+    mz_cuda_free(b->d_comp);
+    mz_cuda_free(b->d_out);
+    mz_cuda_host_free(b->h_out);
+    mz_cuda_host_free(b->h_job);
+    mz_cuda_free(b->d_job);
+    mz_cuda_host_free(b->h_state);
+    mz_cuda_free(b->d_state);
+    mz_cuda_host_free(b->h_off);
+    mz_cuda_free(b->d_off);
+    mz_cuda_host_free(b->h_len);
+    mz_cuda_free(b->d_len);
+    mz_cuda_free(b->d_residue);
+    mz_cuda_free(b->d_crc);
+    mz_cuda_host_free(b->h_crc);
+    free(b->ent);
+    free(b->names);
+    memset(b, 0, sizeof(*b));
+}
+
+static int zx_alloc(zx_bufs *b, size_t comp_cap, size_t out_cap, uint32_t max_entries) {
+    memset(b, 0, sizeof(*b));
+    b->comp_cap = comp_cap;
+    b->out_cap = out_cap;
+    b->max_entries = max_entries;
+    b->names_cap = (size_t)max_entries * 64;
+    b->h_comp = (uint8_t *)mz_cuda_host_alloc(comp_cap + 64);
+    b->d_comp = (uint8_t *)mz_cuda_malloc(comp_cap + 64);
+    b->d_out = (uint8_t *)mz_cuda_malloc(out_cap + 512);
+    b->h_out = (uint8_t *)mz_cuda_host_alloc(out_cap + 512);
+    b->h_job = (mz_cuda_inflate_job *)mz_cuda_host_alloc((size_t)max_entries * sizeof(mz_cuda_inflate_job));
+    b->d_job = (mz_cuda_inflate_job *)mz_cuda_malloc((size_t)max_entries * sizeof(mz_cuda_inflate_job));
+    b->h_state = (mz_cuda_inflate_state *)mz_cuda_host_alloc((size_t)max_entries * sizeof(mz_cuda_inflate_state));
+    b->d_state = (mz_cuda_inflate_state *)mz_cuda_malloc((size_t)max_entries * sizeof(mz_cuda_inflate_state));
+    b->h_off = (uint64_t *)mz_cuda_host_alloc((size_t)max_entries * 8);
+    b->d_off = (uint64_t *)mz_cuda_malloc((size_t)max_entries * 8);
+    b->h_len = (uint32_t *)mz_cuda_host_alloc((size_t)max_entries * 4);
+    b->d_len = (uint32_t *)mz_cuda_malloc((size_t)max_entries * 4);
+    b->d_residue = (uint32_t *)mz_cuda_malloc((size_t)max_entries * 4);
+    b->d_crc = (uint32_t *)mz_cuda_malloc((size_t)max_entries * 4);
+    b->h_crc = (uint32_t *)mz_cuda_host_alloc((size_t)max_entries * 4);
+    b->ent = (zx_entry *)malloc((size_t)max_entries * sizeof(zx_entry));
+    b->names = (char *)malloc(b->names_cap);
+    if (!b->h_comp || !b->d_comp || !b->d_out || !b->h_out || !b->h_job || !b->d_job || !b->h_state || !b->d_state || !b->h_off || !b->d_off ||
+        !b->h_len || !b->d_len || !b->d_residue || !b->d_crc || !b->h_crc || !b->ent || !b->names) {
+        zx_free(b);
+        return 0;
+    }
+    return 1;
+}
+
+/* decode + checksum + deliver the entries collected in b->ent[0..n) */
+static int32_t zx_flush(zx_bufs *b, uint32_t n, size_t comp_used, size_t out_used, mz_cuda_zip_entry_cb cb, void *userdata, mz_cuda_zip_stats *st) {
+    int32_t err = MZ_OK;
+    uint32_t njobs = 0;
+    double t0 = now_ms();
+    if (n == 0)
+        return MZ_OK;
+    memset(b->h_state, 0, (size_t)n * sizeof(mz_cuda_inflate_state));
+    for (uint32_t i = 0; i < n; i++) {
+        const zx_entry *e = &b->ent[i];
+        b->h_off[i] = e->ooff;
+        b->h_len[i] = (uint32_t)e->usize;
+        if (e->method == 8) {
+            mz_cuda_inflate_job *j = &b->h_job[njobs];
+            j->d_in = b->d_comp + e->coff;
+            j->in_base = 0;
+            j->in_avail = e->csize;
+            j->d_out = b->d_out + e->ooff;
+            j->out_base = 0;
+            j->out_cap = e->usize;
+            j->in_final = 1;
+            j->flags = 0;
+            njobs++;
+        }
+    }
+    err = mz_cuda_memcpy_h2d(b->d_comp, b->h_comp, comp_used + 32, NULL);
+    /* stored entries: their bytes are the plain bytes */
+    for (uint32_t i = 0; i < n && !err; i++)
+        if (b->ent[i].method == 0 && b->ent[i].usize)
+            err = mz_cuda_memcpy_d2d(b->d_out + b->ent[i].ooff, b->d_comp + b->ent[i].coff, (size_t)b->ent[i].usize, NULL);
+    if (!err && njobs) {
+        err = mz_cuda_memcpy_h2d(b->d_job, b->h_job, (size_t)njobs * sizeof(mz_cuda_inflate_job), NULL);
+        if (!err) err = mz_cuda_memcpy_h2d(b->d_state, b->h_state, (size_t)njobs * sizeof(mz_cuda_inflate_state), NULL);
+        if (!err) err = mz_cuda_inflate_streams(b->d_job, b->d_state, njobs, NULL);
+        if (!err) err = mz_cuda_memcpy_d2h(b->h_state, b->d_state, (size_t)njobs * sizeof(mz_cuda_inflate_state), NULL);
+    }
+    if (!err) err = mz_cuda_memcpy_h2d(b->d_off, b->h_off, (size_t)n * 8, NULL);
+    if (!err) err = mz_cuda_memcpy_h2d(b->d_len, b->h_len, (size_t)n * 4, NULL);
+    if (!err) err = mz_cuda_crc32_segments(b->d_out, 0, 0, b->d_off, b->d_len, n, b->d_residue, b->d_crc, NULL);
+    if (!err) err = mz_cuda_memcpy_d2h(b->h_crc, b->d_crc, (size_t)n * 4, NULL);
+    if (!err) err = mz_cuda_memcpy_d2h(b->h_out, b->d_out, out_used, NULL);
+    if (!err) err = mz_cuda_stream_sync(NULL);
+    double t1 = now_ms();
+    if (err)
+        return err;
+    uint32_t jk = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const zx_entry *e = &b->ent[i];
+        if (e->method == 8) {
+            const mz_cuda_inflate_state *s = &b->h_state[jk++];
+            /* the stream must end, produce exactly the recorded size and use exactly the recorded bytes (mz_zip.c:2116-2128 checks
+             * the same three things through total_in / total_out / crc) */
+            if (s->status != 1 || s->out_pos != e->usize || ((s->in_bitpos + 7) >> 3) != e->csize)
+                return s->status < 0 ? s->status : MZ_DATA_ERROR;
+        }
+        const uint32_t crc = e->usize ? b->h_crc[i] : 0u;
+        if (crc != e->crc)
+            return MZ_CRC_ERROR;
+    }
+    double t2 = now_ms();
+    for (uint32_t i = 0; i < n; i++) {
+        const zx_entry *e = &b->ent[i];
+        if (cb) {
+            err = cb(userdata, b->names + e->name_off, b->h_out + e->ooff, (int64_t)e->usize, e->crc);
+            if (err)
+                return err;
+        }
+        st->bytes_in += e->csize;
+        st->bytes_out += e->usize;
+    }
+    st->gpu_ms += t1 - t0;
+    st->container_ms += now_ms() - t2;
+    st->entries += n;
+    st->rounds++;
+    return MZ_OK;
+}
+
+int32_t mz_zip_cuda_extract_all(void *zip_handle, mz_cuda_zip_entry_cb cb, void *userdata, mz_cuda_zip_stats *stats) {
+    zx_bufs b;
+    mz_cuda_zip_stats st;
+    int32_t err;
+    memset(&st, 0, sizeof(st));
+    if (!mz_zip_goto_first_entry || !mz_zip_goto_next_entry || !mz_zip_entry_get_info || !mz_zip_entry_read_open || !mz_zip_entry_read ||
+        !mz_zip_entry_close)
+        return MZ_SUPPORT_ERROR; /* no zip container in this process */
+    if (!zip_handle)
+        return MZ_PARAM_ERROR;
+    if (mz_cuda_init() != MZ_OK) {
+        fprintf(stderr, "mz_zip_cuda: no usable sm_100 GPU (%s); there is no CPU fallback\n", mz_cuda_last_error());
+        return MZ_SUPPORT_ERROR;
+    }
+    size_t comp_cap = 128u << 20, out_cap = 512u << 20;
+    {
+        const char *v = getenv("MZ_CUDA_ZIP_ROUND_MB");
+        if (v && atoll(v) > 0) {
+            comp_cap = (size_t)atoll(v) << 20;
+            out_cap = comp_cap * 4;
+        }
+    }
+    const uint32_t max_entries = 65536;
+    if (!zx_alloc(&b, comp_cap, out_cap, max_entries))
+        return MZ_MEM_ERROR;
+    uint32_t n = 0;
+    size_t comp_used = 0, out_used = 0, names_used = 0;
+    err = mz_zip_goto_first_entry(zip_handle);
+    while (err == MZ_OK) {
+        zc_file_info *fi = NULL;
+        double t0 = now_ms();
+        err = mz_zip_entry_get_info(zip_handle, &fi);
+        if (err != MZ_OK)
+            break;
+        if ((fi->flag & 1u) || (fi->compression_method != 0 && fi->compression_method != 8) || fi->compressed_size < 0 ||
+            fi->uncompressed_size < 0 || fi->uncompressed_size > (1ll << 30) || fi->compressed_size > (1ll << 30)) {
+            err = MZ_SUPPORT_ERROR; /* encrypted, another codec, or too large for the batch path */
+            break;
+        }
+        if (fi->compression_method == 0 && fi->compressed_size != fi->uncompressed_size) {
+            err = MZ_FORMAT_ERROR;
+            break;
+        }
+        const size_t csz = (size_t)fi->compressed_size, usz = (size_t)fi->uncompressed_size;
+        const size_t cneed = (csz + 32 + 15) & ~(size_t)15, oneed = (usz + 15) & ~(size_t)15; /* K5 reads up to 16 bytes past a stream */
+        const size_t nlen = strlen(fi->filename) + 1;
+        if (cneed > b.comp_cap || oneed > b.out_cap) { /* one entry larger than a round: not batched */
+            err = MZ_SUPPORT_ERROR;
+            break;
+        }
+        if (n == b.max_entries || comp_used + cneed > b.comp_cap || out_used + oneed > b.out_cap || names_used + nlen > b.names_cap) {
+            err = zx_flush(&b, n, comp_used, out_used, cb, userdata, &st);
+            if (err)
+                break;
+            n = 0;
+            comp_used = out_used = names_used = 0;
+        }
+        zx_entry *e = &b.ent[n];
+        e->coff = comp_used;
+        e->csize = csz;
+        e->ooff = out_used;
+        e->usize = usz;
+        e->crc = fi->crc;
+        e->method = fi->compression_method;
+        e->name_off = (uint32_t)names_used;
+        memcpy(b.names + names_used, fi->filename, nlen);
+        /* the compressed bytes, untouched, through the raw seam */
+        if (csz) {
+            err = mz_zip_entry_read_open(zip_handle, 1, NULL);
+            size_t got = 0;
+            while (err == MZ_OK && got < csz) {
+                const int32_t want = csz - got > (1u << 30) ? (int32_t)(1u << 30) : (int32_t)(csz - got);
+                const int32_t r = mz_zip_entry_read(zip_handle, b.h_comp + comp_used + got, want);
+                if (r <= 0) {
+                    err = r < 0 ? r : MZ_READ_ERROR;
+                    break;
+                }
+                got += (size_t)r;
+            }
+            const int32_t cerr = mz_zip_entry_close(zip_handle);
+            if (err == MZ_OK && cerr != MZ_OK)
+                err = cerr;
+            if (err != MZ_OK)
+                break;
+        }
+        memset(b.h_comp + comp_used + csz, 0, cneed - csz);
+        comp_used += cneed;
+        out_used += oneed;
+        names_used += nlen;
+        n++;
+        st.pack_ms += now_ms() - t0;
+        err = mz_zip_goto_next_entry(zip_handle);
+    }
+    if (err == MZ_END_OF_LIST)
+        err = zx_flush(&b, n, comp_used, out_used, cb, userdata, &st);
+    zx_free(&b);
     if (stats)
         *stats = st;
     return err;

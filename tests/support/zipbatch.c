@@ -5,6 +5,7 @@
  * container code in both modes is the reference's.
  *
  *   zipbatch_cuda <out.zip> <entries> <entry_bytes> <level> <cuda|ref> [dump_dir dump_every]
+ *   zipbatch_cuda <in.zip>  <entries> <entry_bytes> <level> <extract|extract_ref>   (batch extractor / the reference's loop)
  *
  * Entry i: i%10 < 7 text-like, < 9 binary records, else incompressible; name e/%06d.
  * With dump_dir, every dump_every-th entry's plain bytes are also written to dump_dir/%06d for comparison.
@@ -80,7 +81,90 @@ static double now_s(void) {
     return (double)ts.tv_sec + (double)ts.tv_nsec * 1e-9;
 }
 
+/* ---- extraction modes ------------------------------------------------------------------------------------------ */
+typedef struct xstate_s {
+    uint64_t entries, bytes, verified, mismatches;
+    size_t esz;
+    uint8_t *scratch;
+} xstate;
+
+static int32_t on_entry(void *ud, const char *name, const void *data, int64_t size, uint32_t crc) {
+    xstate *x = (xstate *)ud;
+    (void)crc;
+    x->entries++;
+    x->bytes += (uint64_t)size;
+    unsigned idx = 0;
+    if (sscanf(name, "e/%u", &idx) == 1 && idx % 101 == 0 && (size_t)size <= x->esz) { /* regenerate and compare a sample */
+        gen_entry(x->scratch, (size_t)size, idx);
+        x->verified++;
+        if (size && memcmp(x->scratch, data, (size_t)size) != 0) x->mismatches++;
+    }
+    return MZ_OK;
+}
+
+static int extract_main(const char *path, size_t esz, int use_cuda) {
+    void *file_stream = mz_stream_os_create();
+    void *stream = mz_stream_buffered_create();
+    void *zip = mz_zip_create();
+    mz_stream_set_base(stream, file_stream);
+    int32_t err = mz_stream_open(stream, path, MZ_OPEN_MODE_READ);
+    if (err == MZ_OK) err = mz_zip_open(zip, stream, MZ_OPEN_MODE_READ);
+    if (err != MZ_OK) { fprintf(stderr, "open failed %d\n", err); return 5; }
+    xstate x;
+    memset(&x, 0, sizeof(x));
+    x.esz = esz;
+    x.scratch = (uint8_t *)malloc(esz + 16);
+    make_vocab();
+    mz_cuda_zip_stats st;
+    memset(&st, 0, sizeof(st));
+    double t0 = now_s();
+    if (use_cuda) {
+        err = mz_zip_cuda_extract_all(zip, on_entry, &x, &st);
+    } else { /* the reference's own loop: one mz_stream_zlib per entry, CRC checked by mz_zip_entry_close (mz_zip_rw.c:818-909) */
+        uint8_t *buf = (uint8_t *)malloc(esz + 65536);
+        err = mz_zip_goto_first_entry(zip);
+        while (err == MZ_OK) {
+            mz_zip_file *fi = NULL;
+            err = mz_zip_entry_get_info(zip, &fi);
+            if (err != MZ_OK) break;
+            err = mz_zip_entry_read_open(zip, 0, NULL);
+            if (err != MZ_OK) break;
+            int64_t got = 0;
+            for (;;) {
+                int32_t r = mz_zip_entry_read(zip, buf + got, 65536);
+                if (r < 0) { err = r; break; }
+                if (r == 0) break;
+                got += r;
+                if ((size_t)got > esz) { err = MZ_BUF_ERROR; break; }
+            }
+            if (err == MZ_OK) on_entry(&x, fi->filename, buf, got, fi->crc);
+            int32_t cerr = mz_zip_entry_close(zip);
+            if (err == MZ_OK) err = cerr;
+            if (err != MZ_OK) break;
+            err = mz_zip_goto_next_entry(zip);
+        }
+        if (err == MZ_END_OF_LIST) err = MZ_OK;
+        free(buf);
+    }
+    double dt = now_s() - t0;
+    mz_zip_close(zip);
+    mz_stream_close(stream);
+    mz_zip_delete(&zip);
+    mz_stream_buffered_delete(&stream);
+    mz_stream_os_delete(&file_stream);
+    printf("{\"mode\": \"%s\", \"err\": %d, \"entries\": %llu, \"bytes_out\": %llu, \"verified\": %llu, \"mismatches\": %llu, \"s\": %.4f, "
+           "\"entries_per_s\": %.0f, \"GiB_per_s\": %.3f, \"read_ms\": %.1f, \"gpu_ms\": %.1f, \"deliver_ms\": %.1f, \"rounds\": %u}\n",
+           use_cuda ? "extract_cuda" : "extract_ref", err, (unsigned long long)x.entries, (unsigned long long)x.bytes, (unsigned long long)x.verified,
+           (unsigned long long)x.mismatches, dt, x.entries / dt, (double)x.bytes / (1ull << 30) / dt, st.pack_ms, st.gpu_ms, st.container_ms, st.rounds);
+    free(x.scratch);
+    return err == MZ_OK && x.mismatches == 0 ? 0 : 1;
+}
+
 int main(int argc, char **argv) {
+    if (argc >= 6 && (strcmp(argv[5], "extract") == 0 || strcmp(argv[5], "extract_ref") == 0)) {
+        if (sizeof(mz_zip_file) != mz_zip_cuda_abi_file_info_size()) return 3;
+        return extract_main(argv[1], (size_t)atoll(argv[3]), strcmp(argv[5], "extract") == 0);
+    }
     if (argc < 6) {
         fprintf(stderr, "usage: %s out.zip entries entry_bytes level cuda|ref [dump_dir dump_every]\n", argv[0]);
         return 2;

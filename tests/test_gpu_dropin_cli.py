@@ -183,3 +183,39 @@ def test_zip_batch_writer_on_the_raw_seam(built, tmp_path, level):
     _run([ref, "-x", "-o", "-d", "out", "c.zip"], tmp_path)  # the reference's extractor CRC-checks every entry
     for i in range(0, n, 37):
         assert (tmp_path / "out" / "e" / ("%06d" % i)).read_bytes() == (tmp_path / "dump" / ("%06d" % i)).read_bytes()
+
+
+@pytest.mark.gpu
+def test_zip_batch_extractor_reads_every_kind_of_archive(built, tmp_path):
+    """scope row f2: the central directory is walked by the reference's reader, the compressed bytes come through its raw
+    seam, all entries are inflated + CRC'd in one launch each. Archives written by the batch writer (data descriptors), by the
+    reference's zlib path, and by zipfile (stored + deflated entries) must all extract with matching content; a damaged
+    archive must be refused."""
+    import json
+    exe = _bin("zipbatch_cuda")
+    n, esz = 2500, 65536
+    _run([exe, "c.zip", str(n), str(esz), "6", "cuda"], tmp_path)
+    _run([exe, "r.zip", str(n), str(esz), "9", "ref"], tmp_path)
+    for name in ("c.zip", "r.zip"):
+        got = json.loads(_run([exe, name, str(n), str(esz), "0", "extract"], tmp_path).stdout.decode().strip().splitlines()[-1])
+        want = json.loads(_run([exe, name, str(n), str(esz), "0", "extract_ref"], tmp_path).stdout.decode().strip().splitlines()[-1])
+        assert got["err"] == 0 and got["entries"] == want["entries"] == n and got["bytes_out"] == want["bytes_out"], (name, got, want)
+        assert got["verified"] >= n // 101 and got["mismatches"] == 0 and got["rounds"] >= 1
+    # zipfile: stored and deflated members side by side, names that are not of the e/%06d form (no regeneration check)
+    with zipfile.ZipFile(tmp_path / "p.zip", "w") as z:
+        for i in range(300):
+            blob = datagen.mixed(1000 + 137 * i, seed=i) if i % 3 else datagen.random_bytes(500 + i, seed=i)
+            z.writestr("dir/f%04d.bin" % i, blob, zipfile.ZIP_DEFLATED if i % 3 else zipfile.ZIP_STORED, compresslevel=6)
+        z.writestr("dir/empty.bin", b"")
+        total = sum(zi.file_size for zi in z.infolist())
+    got = json.loads(_run([exe, "p.zip", "301", "200000", "0", "extract"], tmp_path).stdout.decode().strip().splitlines()[-1])
+    assert got["err"] == 0 and got["entries"] == 301 and got["bytes_out"] == total
+    # damage a deflated member: the batch must be refused with an error, like the reference's close() refuses it
+    raw = bytearray((tmp_path / "p.zip").read_bytes())
+    with zipfile.ZipFile(tmp_path / "p.zip") as z:
+        info = z.getinfo("dir/f0200.bin")
+    raw[info.header_offset + 30 + len(info.filename) + info.compress_size // 2] ^= 0x40
+    (tmp_path / "bad.zip").write_bytes(bytes(raw))
+    r = _run([exe, "bad.zip", "301", "200000", "0", "extract"], tmp_path, ok=False)
+    bad = json.loads(r.stdout.decode().strip().splitlines()[-1])
+    assert r.returncode != 0 and bad["err"] in (-3, -105)  # MZ_DATA_ERROR or MZ_CRC_ERROR
