@@ -201,3 +201,29 @@ def test_c3_long_member_speculative_rounds_match_serial(env, ref, monkeypatch):
         good = out if out else b""
         assert plain.startswith(good)
     assert res[0][1] != 0 and res[1][1] != 0
+
+
+def test_c3_abandoned_long_read_leaves_the_workspace_usable(env):
+    """a caller may stop reading in the middle of a long member (a speculative round is then still in flight): close must
+    return cleanly and the pooled workspace must serve the next streams -- a long one, then a tiny one -- correctly"""
+    p, lib, tl, torch = env
+    import cuharness
+    text = _host_bytes(p.textgen(40 * MiB, seed=23))
+    co = zlib.compressobj(6, zlib.DEFLATED, 31)
+    comp = co.compress(text) + co.flush()
+    src, keep = tl.source(comp)
+    s = lib.mz_stream_cuda_create()
+    assert tl.lib.mzt_set_prop(s, p.MZ_STREAM_PROP_COMPRESS_WINDOW, 31) == 0
+    tl.lib.mzt_set_base(s, src)
+    assert tl.lib.mzt_open(s, None, p.MZ_OPEN_MODE_READ) == 0
+    buf = C.create_string_buffer(1 << 20)
+    got = tl.lib.mzt_read(s, buf, 1 << 20)
+    assert got > 0 and text.startswith(buf.raw[:got])
+    assert tl.lib.mzt_close(s) == 0  # 39 MiB never read
+    tl.delete(s)
+    tl.delete(src)
+    out, info = tl.decompress(lib.mz_stream_cuda_create, comp, len(text), window_bits=31, read_size=300_000)
+    assert info["read"] == len(text) and zlib.crc32(out) == zlib.crc32(text) and info["total_in"] == len(comp)
+    small = zlib.compress(b"tiny stream after a big one " * 40, 9)
+    out, info = tl.decompress(lib.mz_stream_cuda_create, small, 2000, window_bits=15, read_size=100)
+    assert out == b"tiny stream after a big one " * 40 and info["total_in"] == len(small) and info["close"] == 0
