@@ -162,3 +162,18 @@ def test_emu_inflate_speculative_never_lies_under_corruption(emu):
             assert st < 0, (trial, kind, pos, st, stats)
             n = min(len(out), len(good))
             assert out[:n] == good[:n], (trial, kind, pos)
+
+
+def test_emu_kernels_under_sanitizers():
+    """the same kernel sources built with AddressSanitizer + UBSan: out-of-bounds global accesses, shifts by >= 32,
+    signed overflow ... in the deflate, CRC, inflate and K6 kernels abort the run"""
+    here = os.path.dirname(os.path.abspath(__file__))
+    emu_dir = os.path.join(here, "emu")
+    r = subprocess.run(["make", "-s", "-C", emu_dir, "libmzemu_san.so"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    asan = subprocess.run(["/usr/bin/gcc", "-print-file-name=libasan.so"], stdout=subprocess.PIPE).stdout.decode().strip()
+    if r.returncode != 0 or not os.path.isabs(asan) or not os.path.exists(asan):
+        pytest.skip("no sanitizer runtime in this toolchain")
+    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0:halt_on_error=1")
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(emu_dir, "san_run.py")], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=900)
+    assert r.returncode == 0 and b"sanitized run ok" in r.stdout, r.stdout[-3000:]
