@@ -46,6 +46,7 @@ struct DeviceCtx {
 constexpr int kMaxDev = 16;
 DeviceCtx g_dev[kMaxDev];
 std::mutex g_mu;
+std::mutex g_crc_mu;
 CrcConsts g_consts;
 bool g_consts_ready = false;
 thread_local char g_err[256] = "";
@@ -308,6 +309,8 @@ int32_t mz_cuda_crc32_device_stream(const void *d_in, uint64_t len, uint32_t val
         nseg64 = (len + seg - 1) / seg;
     }
     uint32_t nseg = (uint32_t)nseg64;
+    /* the residue scratch is per device: threads sharing a device take turns for the whole operation */
+    std::lock_guard<std::mutex> crc_turn(g_crc_mu);
     {
         std::lock_guard<std::mutex> lk(g_mu);
         if (c->crc_scratch_n < (size_t)nseg + 2) {

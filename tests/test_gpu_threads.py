@@ -1,0 +1,51 @@
+"""Several host threads, one device: the reference is single-threaded per stream object but distinct objects are
+independent (SURVEY 8b "Threading"); the CUDA backend shares a process-wide context, a workspace pool, work counters and
+CRC scratch, so concurrent streams must not disturb each other."""
+import ctypes as C
+import threading
+import zlib
+
+import pytest
+
+import datagen
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env(built):
+    import cuharness
+    p = cuharness.pkg()
+    lib = p.load()
+    assert lib.mz_cuda_init() == 0
+    return p, lib
+
+
+def test_concurrent_streams_and_crc_calls(env):
+    import cuharness
+    p, lib = env
+    errors = []
+
+    def worker(k):
+        try:
+            tl = cuharness.TestLib()  # own ctypes handle per thread
+            data = datagen.mixed(2_500_000 + 111_111 * k, seed=100 + k) + datagen.text_like(1_000_000, seed=k)
+            for rep in range(3):
+                level = (1, 6, 9)[(k + rep) % 3]
+                wbits = (31, -15, 15)[(k + rep) % 3]
+                comp, info = tl.compress(lib.mz_stream_cuda_create, data, level=level, window_bits=wbits, write_size=65536 + 17 * k)
+                assert info["close"] == 0 and info["total_in"] == len(data)
+                assert zlib.decompress(comp, wbits) == data
+                out, rinfo = tl.decompress(lib.mz_stream_cuda_create, comp, len(data), window_bits=wbits, read_size=50_000 + k)
+                assert rinfo["read"] == len(data) and out == data and rinfo["total_in"] == len(comp)
+                buf = C.create_string_buffer(data, len(data))
+                assert lib.mz_crypt_crc32_update(0, buf, len(data)) == zlib.crc32(data)  # > 1 MiB: device path, shared scratch
+        except Exception as e:  # noqa: BLE001 -- collected and re-raised in the main thread
+            errors.append((k, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(6)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
