@@ -7,4 +7,4 @@ tail -4 gpurun_out/memcheck_run.log; tail -6 gpurun_out/memcheck.log
 cd /tmp && mkdir -p zs && cd zs
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 --log-file /root/repo/gpurun_out/memcheck_zip.log /root/repo/oracle/_ref/zipbatch_cuda s.zip 300 65536 6 cuda > /root/repo/gpurun_out/memcheck_zip_run.log 2>&1
 timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 --log-file /root/repo/gpurun_out/memcheck_zipx.log /root/repo/oracle/_ref/zipbatch_cuda s.zip 300 65536 6 extract >> /root/repo/gpurun_out/memcheck_zip_run.log 2>&1
-cut -c1-200 /root/repo/gpurun_out/memcheck_zip_run.log; tail -3 /root/repo/gpurun_out/memcheck_zip.log /root/repo/gpurun_out/memcheck_zipx.log
+cut -c1-200 /root/repo/gpurun_out/memcheck_zip_run.log; tail -n 3 /root/repo/gpurun_out/memcheck_zip.log; tail -n 3 /root/repo/gpurun_out/memcheck_zipx.log
