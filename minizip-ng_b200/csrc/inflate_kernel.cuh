@@ -630,10 +630,21 @@ __device__ __forceinline__ void inf_decode_window(const InflateJob &job, Inflate
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(INF_THREADS) inflate_streams_kernel(const InflateJob *jobs, InflateState *states, uint32_t nstreams) {
+/* the next unit of work for this warp: streams differ a lot in length, so warps pull indices from a counter instead
+ * of striding (a second stride would leave most of the GPU waiting for the unlucky warps) */
+__device__ __forceinline__ uint32_t inf_next_work(uint32_t *counter) {
+    uint32_t k = 0;
+    if (lane_id() == 0) k = atomicAdd(counter, 1u);
+    return __shfl_sync(MZ_FULL_MASK, k, 0);
+}
+
+__global__ void __launch_bounds__(INF_THREADS) inflate_streams_kernel(const InflateJob *jobs, InflateState *states, uint32_t nstreams,
+                                                                      uint32_t *work_counter) {
     MZ_DYN_SMEM(smem);
     InfTables &T = *reinterpret_cast<InfTables *>(smem);
-    for (uint32_t sidx = blockIdx.x; sidx < nstreams; sidx += gridDim.x) {
+    for (;;) {
+        const uint32_t sidx = inf_next_work(work_counter);
+        if (sidx >= nstreams) break;
         const InflateJob job = jobs[sidx];
         InflateState *st = &states[sidx];
         if (st->status != INF_ST_RUN) continue;

@@ -78,6 +78,7 @@ struct SpecParams {
     SpecSummary *summary;
     uint16_t *gmaps;     /* [SPEC_GROUPS][32768] group maps (K6d compose) */
     uint8_t *gwins;      /* [SPEC_GROUPS][32768] real window after each group (K6d link) */
+    uint32_t *work;      /* [4] work counters (zeroed per round): [0] scan, [1] emit */
 };
 
 /* ---- K6a ------------------------------------------------------------------------------------------------------ */
@@ -188,7 +189,9 @@ __global__ void __launch_bounds__(INF_THREADS) inflate_spec_scan_kernel(SpecPara
     MZ_DYN_SMEM(smem);
     InfTables &T = *reinterpret_cast<InfTables *>(smem);
     const unsigned lane = lane_id();
-    for (uint32_t k = blockIdx.x; k < P.nseg; k += gridDim.x) {
+    for (;;) { /* segments differ a lot in cost: pull them from a counter */
+        const uint32_t k = inf_next_work(&P.work[0]);
+        if (k >= P.nseg) break;
         SpecSeg *sg = &P.seg[k];
         const uint64_t start = sg->start_bit;
         if (start == SPEC_NONE) {
@@ -499,7 +502,9 @@ __global__ void __launch_bounds__(INF_THREADS) inflate_spec_emit_kernel(SpecPara
     InfTables &T = *reinterpret_cast<InfTables *>(smem);
     const unsigned lane = lane_id();
     const uint32_t n = P.summary->nchain;
-    for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+    for (;;) {
+        const uint32_t i = inf_next_work(&P.work[1]);
+        if (i >= n) break;
         const uint32_t k = P.chain[2 * i];
         const SpecSeg sg = P.seg[k];
         const uint64_t first = P.out_pos + sg.out_off;

@@ -420,8 +420,14 @@ int32_t mz_cuda_inflate_streams(const mz_cuda_inflate_job *d_jobs, mz_cuda_infla
     if (nstreams == 0) return MZ_OK;
     uint32_t maxgrid = (uint32_t)c->sm_count * 32u; /* 32 single-warp CTAs (6.4 KB of tables each) per SM */
     uint32_t grid = nstreams < maxgrid ? nstreams : maxgrid;
+    uint32_t *counter;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        counter = c->d_work + (c->work_next++ & 255u);
+    }
+    CK(cudaMemsetAsync(counter, 0, sizeof(uint32_t), (cudaStream_t)stream));
     MZ_LAUNCH(inflate_streams_kernel, dim3(grid), dim3(INF_THREADS), INF_SMEM_BYTES, (cudaStream_t)stream, (const InflateJob *)d_jobs,
-              (InflateState *)d_states, nstreams);
+              (InflateState *)d_states, nstreams, counter);
     CK(cudaGetLastError());
     return MZ_OK;
 }
@@ -431,7 +437,7 @@ static inline uint64_t al256(uint64_t v) { return (v + 255) & ~255ull; }
 uint64_t mz_cuda_inflate_spec_workspace_bytes(uint32_t max_segments) {
     const uint64_t m = max_segments;
     return al256(m * sizeof(SpecSeg)) + al256(m * sizeof(InflateState)) + al256(m * 8) + al256(m * SPEC_RING * 2) + al256(m * 32768) + al256((uint64_t)SPEC_GROUPS * 65536) +
-           al256((uint64_t)SPEC_GROUPS * 32768) + 256;
+           al256((uint64_t)SPEC_GROUPS * 32768) + 256 + 256;
 }
 
 int32_t mz_cuda_inflate_spec_round(const void *d_in, uint64_t in_base, uint64_t in_avail, uint32_t in_final, uint64_t start_bit,
@@ -462,11 +468,13 @@ int32_t mz_cuda_inflate_spec_round(const void *d_in, uint64_t in_base, uint64_t 
     P.rings = (uint16_t *)w;         w += al256(m * SPEC_RING * 2);
     P.wins = w;                      w += al256(m * 32768);
     P.gmaps = (uint16_t *)w;         w += al256((uint64_t)SPEC_GROUPS * 65536);
-    P.gwins = w;
+    P.gwins = w;                     w += al256((uint64_t)SPEC_GROUPS * 32768);
+    P.work = (uint32_t *)w;
     P.summary = (SpecSummary *)d_summary;
     cudaStream_t s = (cudaStream_t)stream;
     const uint32_t maxgrid = (uint32_t)c->sm_count * 32u;
     const uint32_t grid = nseg < maxgrid ? nseg : maxgrid;
+    CK(cudaMemsetAsync(P.work, 0, 16, s));
     const bool trace = getenv("MZ_CUDA_TRACE") != nullptr; /* per-kernel times of the round on stderr (debug aid, serialises) */
     cudaEvent_t ev[6];
     if (trace)

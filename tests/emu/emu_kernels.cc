@@ -19,6 +19,8 @@ static void ensure() {
     }
 }
 
+static uint32_t emu_work_counter;
+
 extern "C" {
 
 uint64_t emu_deflate_slot_bound(uint32_t chunk) { return deflate_slot_bound(chunk); }
@@ -119,7 +121,8 @@ int32_t emu_inflate(const uint8_t *in, uint64_t in_len, uint8_t *out, uint64_t o
         job.out_base = 0;
         job.out_cap = out_limit;
         job.in_final = fed == in_len;
-        MZ_LAUNCH(inflate_streams_kernel, dim3(1), dim3(INF_THREADS), INF_SMEM_BYTES, 0, (const InflateJob *)&job, &st, 1u);
+        emu_work_counter = 0;
+        MZ_LAUNCH(inflate_streams_kernel, dim3(1), dim3(INF_THREADS), INF_SMEM_BYTES, 0, (const InflateJob *)&job, &st, 1u, &emu_work_counter);
         if (st.status != INF_ST_RUN) break;
         if (st.why == INF_WHY_INPUT) {
             if (fed == in_len) { st.status = -99; break; }
@@ -183,6 +186,8 @@ int32_t emu_inflate_spec(const uint8_t *in, uint64_t in_len, uint8_t *out, uint6
             P.wins = wins.data();
             P.gmaps = gmaps.data();
             P.gwins = gwins.data();
+            uint32_t work[4] = {0, 0, 0, 0};
+            P.work = work;
             P.chain = chain.data();
             P.summary = &sum;
             MZ_LAUNCH(inflate_spec_find_kernel, dim3(P.nseg), dim3(INF_THREADS), SPEC_FIND_SMEM, 0, P);
@@ -215,7 +220,8 @@ int32_t emu_inflate_spec(const uint8_t *in, uint64_t in_len, uint8_t *out, uint6
         job.out_cap = out_cap;
         job.in_final = 1;
         job.flags = INF_JOB_STOP_AT_BOUNDARY;
-        MZ_LAUNCH(inflate_streams_kernel, dim3(1), dim3(INF_THREADS), INF_SMEM_BYTES, 0, (const InflateJob *)&job, &st, 1u);
+        emu_work_counter = 0;
+        MZ_LAUNCH(inflate_streams_kernel, dim3(1), dim3(INF_THREADS), INF_SMEM_BYTES, 0, (const InflateJob *)&job, &st, 1u, &emu_work_counter);
         stats[2]++;
         if (st.status == INF_ST_RUN && st.why != INF_WHY_BOUNDARY) { st.status = st.why == INF_WHY_OUTPUT ? INF_ST_BUF_ERROR : -99; break; }
     }
