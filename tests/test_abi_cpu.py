@@ -115,3 +115,31 @@ def test_mem64_support_stream(built):
     assert tl.lib.mzt_write(sink, buf, 6) == 6 and tl.lib.mzt_tell(sink) == 6
     assert tl.sink_bytes(sink) == b"abcdef"
     tl.delete(sink)
+    # the multi-threaded copy of large writes lands the same bytes as the plain memcpy
+    import datagen
+    blob = datagen.random_bytes((9 << 20) + 12345, seed=9)
+    src = C.create_string_buffer(blob, len(blob))
+    for threads in (1, 8):
+        dst = C.create_string_buffer(len(blob) + 64)
+        sink = tl.sink()
+        tl.lib.mz_stream_mem64_set_sink(sink, dst, len(blob) + 64)
+        tl.lib.mz_stream_mem64_set_copy_threads(sink, threads)
+        assert tl.lib.mzt_write_all(sink, src, len(blob), len(blob)) == len(blob) and tl.lib.mzt_tell(sink) == len(blob)
+        assert dst.raw[:len(blob)] == blob
+        tl.delete(sink)
+
+
+def test_zip_batch_calls_need_the_reference_container(built):
+    """mz_zip_cuda_* take the container functions from the HOST program (weak references); in a process without
+    mz_zip.c they must say so instead of crashing, before touching any GPU state. The file-info mirror has the
+    layout of mz_zip_file on this ABI (mz_zip.h:25-51: 3 time_t, 2 int64, 4 pointers ...)."""
+    p = _pkg(built)
+    lib = C.CDLL(p.LIB_PATH)
+    lib.mz_zip_cuda_add_buffers.restype = C.c_int32
+    lib.mz_zip_cuda_add_buffers.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int16, C.c_void_p]
+    lib.mz_zip_cuda_extract_all.restype = C.c_int32
+    lib.mz_zip_cuda_extract_all.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    fake = C.create_string_buffer(64)
+    assert lib.mz_zip_cuda_add_buffers(fake, None, 0, 6, None) == p.MZ_SUPPORT_ERROR
+    assert lib.mz_zip_cuda_extract_all(fake, None, None, None) == p.MZ_SUPPORT_ERROR
+    assert lib.mz_zip_cuda_abi_file_info_size() == 128  # == sizeof(mz_zip_file); the C4 driver asserts the same against the reference header
