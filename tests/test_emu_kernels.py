@@ -164,6 +164,21 @@ def test_emu_inflate_speculative_never_lies_under_corruption(emu):
             assert out[:n] == good[:n], (trial, kind, pos)
 
 
+def test_emu_degenerate_inputs_both_directions(emu):
+    """SURVEY 8c's degenerate streams: all-'A' input gives zlib blocks of megabytes made of distance-1 self-overlapping
+    runs (the overlap-aware copy, huge output per compressed byte); a 256-byte cycle and a 2-byte period exercise the
+    short-period copy paths. Decode (serial and speculative) must match zlib; our encoder's output must decode."""
+    data = b"A" * 3_000_000 + bytes(range(256)) * 2000 + b"AB" * 400_000 + b"\x00" * 70_000
+    for level in (1, 6):
+        comp = _raw(data, level)
+        st, out, cons, _ = emu.inflate(comp, len(data))
+        assert st == 1 and out == data and cons == len(comp)
+        st, out, cons, stats = emu.inflate_spec(comp, len(data), seg_bytes=1024, max_seg=64)
+        assert st == 1 and out == data and cons == len(comp), stats
+        ours, _ = emu.deflate(data, level=level)
+        assert zlib.decompress(ours, -15) == data and len(ours) < len(data) // 20
+
+
 def test_emu_kernels_under_sanitizers():
     """the same kernel sources built with AddressSanitizer + UBSan: out-of-bounds global accesses, shifts by >= 32,
     signed overflow ... in the deflate, CRC, inflate and K6 kernels abort the run"""
