@@ -179,6 +179,20 @@ def test_emu_degenerate_inputs_both_directions(emu):
         assert zlib.decompress(ours, -15) == data and len(ours) < len(data) // 20
 
 
+def test_emu_deflate_literal_heavy_blocks_take_the_split_path(emu):
+    """low-entropy data without repeats: a 32 KiB sub-block is 32 768 literal tokens, more than the 24 576-entry token
+    list holds, so it is coded as two blocks; still smaller than stored, and decodable"""
+    import random
+    rng = random.Random(5)
+    nib = bytes(rng.randrange(16) for _ in range(200_000))
+    mixed = nib[:70_000] + b"x" * 50_000 + nib[70_000:140_000]
+    for data in (nib, mixed):
+        for level in (1, 6):
+            comp, _ = emu.deflate(data, level=level)
+            assert zlib.decompress(comp, -15) == data
+            assert len(comp) < 0.6 * len(data)
+
+
 def test_emu_kernels_under_sanitizers():
     """the same kernel sources built with AddressSanitizer + UBSan: out-of-bounds global accesses, shifts by >= 32,
     signed overflow ... in the deflate, CRC, inflate and K6 kernels abort the run"""
