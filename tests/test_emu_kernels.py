@@ -33,6 +33,27 @@ def test_emu_deflate_roundtrip(emu, orc, level):
         assert err == 0 and out == data and cons == len(comp)
 
 
+def test_emu_deflate_size_sweep(emu):
+    """every size around the places where the kernel changes behaviour: empty and tiny chunks, the 258-byte match limit, the
+    32 KiB sub-block boundary, the 64 KiB chunk limit, and ragged last chunks of a multi-chunk stream (sync markers between)"""
+    base = datagen.text_like(200_000, 17)
+    sizes = list(range(0, 41)) + list(range(254, 262)) + list(range(32760, 32776)) + list(range(65529, 65537))
+    for n in sizes:
+        data = base[1000:1000 + n]
+        comp, _ = emu.deflate(data, level=1)
+        assert zlib.decompress(comp, -15) == data, n
+    for n in (65537, 65536 + 32768, 131071, 131073, 196609):
+        for level in (1, 6):
+            data = base[:n]
+            comp, lens = emu.deflate(data, level=level)
+            assert zlib.decompress(comp, -15) == data, (n, level)
+            assert len(lens) == (n + 65535) // 65536
+    # long matches that straddle the sub-block and chunk boundaries
+    rep = (b"0123456789abcdefghijklmnopqrstuvwxyz" * 8000)[:150_000]
+    comp, _ = emu.deflate(rep, level=6)
+    assert zlib.decompress(comp, -15) == rep and len(comp) < 10_000
+
+
 def test_emu_deflate_ratio_sane(emu):
     data = datagen.text_like(1 << 18, 9)
     comp, _ = emu.deflate(data, level=1)
