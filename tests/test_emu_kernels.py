@@ -200,6 +200,21 @@ def test_emu_degenerate_inputs_both_directions(emu):
         assert zlib.decompress(ours, -15) == data and len(ours) < len(data) // 20
 
 
+def test_emu_inflate_resumes_through_tiny_windows(emu):
+    """the decoder is resumable at symbol granularity: input fed 33 bytes at a time, output space granted 258 / 300 bytes at a
+    time (a match may have to be un-read and retried), stored / fixed / dynamic blocks alike"""
+    data = datagen.mixed(30_000, 3) + b"Q" * 3000 + datagen.text_like(12_000, 4)
+    for level in (0, 6):
+        comp = _raw(data, level)
+        for iw, ow in ((33, 0), (0, 258), (13, 300)):
+            st, out, cons, _ = emu.inflate(comp, len(data), iw, ow)
+            assert st == 1 and out == data and cons == len(comp), (level, iw, ow, st)
+    tiny = _raw(b"abcabcabcabc", 6)  # one fixed-Huffman block
+    for iw, ow in ((1, 0), (0, 1), (2, 3)):
+        st, out, cons, _ = emu.inflate(tiny, 12, iw, ow)
+        assert st == 1 and out == b"abcabcabcabc" and cons == len(tiny)
+
+
 def test_emu_deflate_literal_heavy_blocks_take_the_split_path(emu):
     """low-entropy data without repeats: a 32 KiB sub-block is 32 768 literal tokens, more than the 24 576-entry token
     list holds, so it is coded as two blocks; still smaller than stored, and decodable"""
