@@ -65,7 +65,13 @@ def load():
     if not os.path.exists(LIB_PATH):
         raise RuntimeError("libmz_strm_cuda.so is missing: run __graft_entry__.build() (nvcc, sm_100a). "
                            "There is no CPU fallback.")
-    L = C.CDLL(LIB_PATH)
+    _lib = configure(C.CDLL(LIB_PATH))
+    return _lib
+
+
+def configure(L):
+    """ctypes prototypes of the C-ABI on an already loaded library (the product .so, or -- in the CPU test suite -- the same
+    sources built against the execution-model emulator, tests/emu/libmz_strm_emu.so)."""
     vp, i32, i64, u32, u64, sz = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_size_t
 
     def sig(name, res, args):
@@ -118,7 +124,6 @@ def load():
     sig("mz_cuda_concat", i32, [vp, u64, vp, u32, vp, vp, vp])
     sig("mz_cuda_inflate_streams", i32, [vp, vp, u32, vp])
     sig("mz_cuda_textgen", i32, [vp, u64, u64, vp])
-    _lib = L
     return L
 
 

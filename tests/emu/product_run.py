@@ -1,0 +1,133 @@
+"""Scenarios for tests/test_emu_product.py: the WHOLE product library (real host C + real API shim + kernel sources) built
+against the CPU execution-model emulator (tests/emu/libmz_strm_emu.so) and driven through the vtbl exactly like the GPU
+tests drive libmz_strm_cuda.so. One scenario per process (workspaces are pooled per process and read their environment
+knobs when created). TEST INFRASTRUCTURE ONLY."""
+import ctypes as C
+import os
+import sys
+import zlib
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import cuharness
+import datagen
+import refshim
+
+p = cuharness.pkg()
+lib = p.configure(C.CDLL(os.path.join(HERE, "libmz_strm_emu.so")))
+tl = cuharness.TestLib()
+CREATE = lib.mz_stream_cuda_create
+
+
+def gz(data, level=6, wbits=31, flush_every=0):
+    co = zlib.compressobj(level, zlib.DEFLATED, wbits)
+    if not flush_every:
+        return co.compress(data) + co.flush()
+    parts = []
+    for o in range(0, len(data), flush_every):
+        parts.append(co.compress(data[o:o + flush_every]))
+        parts.append(co.flush(zlib.Z_FULL_FLUSH))
+    parts.append(co.flush())
+    return b"".join(parts)
+
+
+def scenario_write():
+    """write path: multi-batch pipeline (tiny batches), every framing, odd write sizes; zlib and the reference read it back"""
+    ref = refshim.RefLib() if os.path.exists(os.path.join(os.path.dirname(os.path.dirname(HERE)), "oracle", "_ref", "libmzref.so")) else None
+    data = datagen.mixed(700_000, 5) + datagen.random_bytes(70_001, 1) + datagen.text_like(200_000, 2)
+    for level, wbits, wsize in ((1, -15, 16384), (6, 31, 65535), (9, 15, 1), (0, 31, 100_000), (-1, -15, 333_333)):
+        d = data if wsize > 1 else data[:5000]
+        comp, info = tl.compress(CREATE, d, level=level, window_bits=wbits, write_size=wsize)
+        assert info["close"] == 0 and info["total_in"] == len(d) and info["total_out"] == len(comp) == info["sink_tell"], info
+        assert zlib.decompress(comp, wbits) == d, (level, wbits)
+        if wbits == 31:
+            assert comp[:4] == b"\x1f\x8b\x08\x00" and comp[8] == (2 if level == 9 else 4 if level in (0, 1) else 0)
+            assert int.from_bytes(comp[-4:], "little") == len(d) and int.from_bytes(comp[-8:-4], "little") == zlib.crc32(d)
+        if ref is not None:
+            out, rinfo = ref.decompress_with(ref.lib.mz_stream_zlib_create, comp, window_bits=wbits, read_size=65536)
+            assert rinfo["read_err"] == 0 and out == d and rinfo["total_in"] == len(comp)
+    comp, info = tl.compress(CREATE, b"", level=6, window_bits=-15)
+    assert comp == b"\x03\x00" and info["total_out"] == 2  # byte-identical to zlib
+    comp, info = tl.compress(CREATE, b"", level=6, window_bits=31)
+    assert comp == bytes.fromhex("1f8b0800000000000003") + b"\x03\x00" + bytes(8)
+
+
+def scenario_read(spec):
+    """read path on the small windows: foreign members, tiny reads, trailing garbage, TOTAL_IN_MAX, errors"""
+    text = datagen.text_like(900_000, 7)
+    mixed = datagen.mixed(500_000, 8) + datagen.random_bytes(90_000, 3) + text[:200_000]
+    for plain, level, wbits, rsize, flush in ((text, 6, 31, 16384, 0), (mixed, 1, -15, 65535, 0), (mixed, 9, 15, 4096, 0), (text, 6, -15, 300_000, 30_000),
+                                              (text[:70_000], 0, 31, 1000, 0), (b"", 6, 31, 10, 0), (b"a", 6, -15, 1, 0)):
+        comp = gz(plain, level, wbits, flush)
+        out, info = tl.decompress(CREATE, comp + b"\xee" * 5000 if wbits == -15 else comp, len(plain), window_bits=wbits, read_size=rsize)
+        assert info["read"] == len(plain) and out == plain and info["read_again"] == 0, (level, wbits, info)
+        assert info["total_in"] == len(comp) and info["total_out"] == len(plain) and info["error"] == 0 and info["close"] == 0, info
+    comp = gz(text, 6, -15)
+    out, info = tl.decompress(CREATE, comp + b"\x55" * 999, len(text), window_bits=-15, read_size=16384, total_in_max=len(comp))
+    assert out == text and info["total_in"] == len(comp) and info["base_tell"] == len(comp)  # never reads past TOTAL_IN_MAX
+    # truncated: clean prefix, then MZ_BUF_ERROR, sticky, close -> MZ_CLOSE_ERROR
+    out, info = tl.decompress(CREATE, comp[:len(comp) // 2], len(text), window_bits=-15, read_size=16384)
+    assert info["error"] == p.MZ_BUF_ERROR and info["close"] == p.MZ_CLOSE_ERROR, info
+    # wrong gzip trailer
+    g = bytearray(gz(text, 6, 31))
+    g[-6] ^= 1
+    out, info = tl.decompress(CREATE, bytes(g), len(text), window_bits=31, read_size=16384)
+    assert info["error"] == p.MZ_DATA_ERROR and info["close"] == p.MZ_CLOSE_ERROR, info
+    # raw deflate fed to a gzip reader
+    out, info = tl.decompress(CREATE, comp, len(text), window_bits=31, read_size=16384)
+    assert info["error"] == p.MZ_DATA_ERROR
+    # corruption in the middle
+    bad = bytearray(gz(text, 6, 31))
+    for k in range(len(bad) // 2, len(bad) // 2 + 30):
+        bad[k] ^= 0x5A
+    out, info = tl.decompress(CREATE, bytes(bad), len(text), window_bits=31, read_size=16384)
+    assert info["error"] != 0
+
+
+def scenario_long():
+    """a member that overflows the first window: the workspace switches to the long-stream windows and runs K6 rounds with the
+    delivery / next-round overlap; output windows slide several times"""
+    text = datagen.text_like(2_400_000, 11) + datagen.random_bytes(200_000, 4) + datagen.text_like(900_000, 12)
+    for level, rsize in ((6, 65536), (1, 1 << 20)):
+        comp = gz(text, level, 31)
+        assert len(comp) > (1 << 20)
+        out, info = tl.decompress(CREATE, comp, len(text), window_bits=31, read_size=rsize)
+        assert info["read"] == len(text) and out == text and info["total_in"] == len(comp) and info["close"] == 0, info
+    # abandoned half way, then the pooled workspace serves another stream
+    src, keep = tl.source(comp)
+    s = CREATE()
+    tl.lib.mzt_set_prop(s, p.MZ_STREAM_PROP_COMPRESS_WINDOW, 31)
+    tl.lib.mzt_set_base(s, src)
+    assert tl.lib.mzt_open(s, None, p.MZ_OPEN_MODE_READ) == 0
+    buf = C.create_string_buffer(50_000)
+    assert tl.lib.mzt_read(s, buf, 50_000) > 0
+    assert tl.lib.mzt_close(s) == 0
+    tl.delete(s)
+    tl.delete(src)
+    out, info = tl.decompress(CREATE, comp, len(text), window_bits=31, read_size=100_000)
+    assert out == text and info["total_in"] == len(comp)
+
+
+def scenario_crc():
+    data = datagen.random_bytes(3_000_001, 9)
+    buf = C.create_string_buffer(data, len(data))
+    assert lib.mz_crypt_crc32_update(0, buf, len(data)) == zlib.crc32(data)  # above the host threshold: K1 + fold
+    half = len(data) // 2
+    v = lib.mz_crypt_crc32_update(0, buf, half)
+    v = lib.mz_crypt_crc32_update(v, C.byref(buf, half), len(data) - half)
+    assert v == zlib.crc32(data)
+
+
+if __name__ == "__main__":
+    name = sys.argv[1]
+    if name == "write":
+        scenario_write()
+    elif name == "read":
+        scenario_read(os.environ.get("MZ_CUDA_SPEC", "1"))
+    elif name == "long":
+        scenario_long()
+    elif name == "crc":
+        scenario_crc()
+    else:
+        raise SystemExit("unknown scenario " + name)
+    print("scenario %s ok" % name)

@@ -1,0 +1,50 @@
+"""The whole product on the CPU: tests/emu/libmz_strm_emu.so is the REAL host-side C (mz_strm_cuda.c, mz_crypt_cuda.c,
+mz_zip_cuda.c) and the REAL extern "C" shim (mz_cuda_api.cu, compiled as C++) linked against the execution-model emulator
+and a host implementation of the handful of CUDA runtime calls (tests/emu/shim/cuda_runtime.h). The vtbl streams are then
+driven exactly as the GPU tests drive them -- so the host logic (batching, framing, window sliding, K5/K6 hand-over, error
+taxonomy of mz_strm_zlib.c:116-305) is covered without a GPU. One scenario per process: workspaces are pooled per process.
+This is test infrastructure: nothing here is part of, or a fallback for, the product library."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU = os.path.join(HERE, "emu")
+
+
+@pytest.fixture(scope="module")
+def emulib(built):
+    r = subprocess.run(["make", "-s", "-C", EMU, "libmz_strm_emu.so"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert r.returncode == 0, r.stdout[-3000:]
+    return os.path.join(EMU, "libmz_strm_emu.so")
+
+
+def _scenario(name, **env):
+    e = dict(os.environ)
+    e.update({k: str(v) for k, v in env.items()})
+    r = subprocess.run([sys.executable, os.path.join(EMU, "product_run.py"), name], env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       timeout=1500)
+    assert r.returncode == 0 and ("scenario %s ok" % name).encode() in r.stdout, r.stdout[-4000:].decode(errors="replace")
+    return r.stdout.decode(errors="replace")
+
+
+def test_write_path_batches_framing_and_reference_readback(emulib):
+    _scenario("write", MZ_CUDA_BATCH_KB=256)
+
+
+@pytest.mark.parametrize("spec", [1, 0])
+def test_read_path_small_windows_with_and_without_k6(emulib, spec):
+    out = _scenario("read", MZ_CUDA_SPEC=spec, MZ_CUDA_SPEC_SEG_KB=4, MZ_CUDA_BATCH_KB=1024, MZ_CUDA_TRACE=1)
+    rounds = out.count("K6 round")
+    assert (rounds >= 4) if spec else (rounds == 0)
+
+
+def test_read_path_long_member_switches_windows_and_overlaps_rounds(emulib):
+    out = _scenario("long", MZ_CUDA_SPEC_SEG_KB=4, MZ_CUDA_BATCH_KB=1024, MZ_CUDA_READ_WINDOW_KB=2048, MZ_CUDA_TRACE=1)
+    assert out.count("K6 round") >= 3
+
+
+def test_crc_symbol_device_path(emulib):
+    _scenario("crc", MZ_CUDA_CRC_MIN_BYTES=65536)
