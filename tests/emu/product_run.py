@@ -14,7 +14,7 @@ import datagen
 import refshim
 
 p = cuharness.pkg()
-lib = p.configure(C.CDLL(os.path.join(HERE, "libmz_strm_emu.so")))
+lib = p.configure(C.CDLL(os.environ.get("MZ_EMU_LIB") or os.path.join(HERE, "libmz_strm_emu.so")))  # MZ_EMU_LIB: the sanitizer build
 tl = cuharness.TestLib()
 CREATE = lib.mz_stream_cuda_create
 

@@ -48,3 +48,17 @@ def test_read_path_long_member_switches_windows_and_overlaps_rounds(emulib):
 
 def test_crc_symbol_device_path(emulib):
     _scenario("crc", MZ_CUDA_CRC_MIN_BYTES=65536)
+
+
+def test_host_paths_under_sanitizers(emulib):
+    """the same scenarios with the whole library (host C included) built with AddressSanitizer + UBSan: window arithmetic that
+    runs off a staging buffer, a stale pointer after the workspace switches windows, a shift by 32 ... abort the run"""
+    r = subprocess.run(["make", "-s", "-C", EMU, "libmz_strm_emu_san.so"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    asan = subprocess.run(["/usr/bin/gcc", "-print-file-name=libasan.so"], stdout=subprocess.PIPE).stdout.decode().strip()
+    if r.returncode != 0 or not os.path.isabs(asan) or not os.path.exists(asan):
+        pytest.skip("no sanitizer runtime in this toolchain")
+    san = dict(MZ_EMU_LIB=os.path.join(EMU, "libmz_strm_emu_san.so"), LD_PRELOAD=asan,
+               ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0:halt_on_error=1")
+    _scenario("write", MZ_CUDA_BATCH_KB=256, **san)
+    _scenario("read", MZ_CUDA_SPEC=1, MZ_CUDA_SPEC_SEG_KB=4, MZ_CUDA_BATCH_KB=1024, **san)
+    _scenario("long", MZ_CUDA_SPEC_SEG_KB=4, MZ_CUDA_BATCH_KB=1024, MZ_CUDA_READ_WINDOW_KB=2048, **san)
