@@ -1,32 +1,36 @@
-/* deflate_kernel.cuh -- K2+K3: per-chunk LZ77 match + dynamic-Huffman RFC1951 encode (sm_100a).
+/* deflate_kernel.cuh -- K2+K3 (v3): per-chunk LZ77 match + dynamic-Huffman RFC1951 encode (sm_100a).
  *
  * Replaces, on the write path, what zlib's deflate() does behind mz_stream_zlib_write /
  * mz_stream_zlib_close (mz_strm_zlib.c:203-240, :243-264, :280-305).  The compressed bytes are NOT
  * zlib's; parity = the reference inflate (mz_stream_zlib_read) reproduces the input bit-exactly.
  *
- * Work decomposition (one CTA of 1024 threads per chunk; persistent grid-stride loop over chunks):
- *   chunk      <= 64 KiB of input, independent LZ77 history, resident in shared memory (TMA bulk load)
- *   sub-block  32 KiB = 1024 threads x 32-byte segments; normally one DEFLATE block per sub-block
- *   A parse    every thread runs a greedy hash-table parser over its own 32-byte segment; matches may
- *              overrun the segment (up to 258 B, clamped at the sub-block end); the hash table
- *              (shared memory, 16-bit chunk-relative positions) is racy by design: every candidate is
- *              validated by comparing bytes, and any earlier position is a legal LZ77 source
- *   B cover    exclusive prefix-max over the threads' parse end positions: a thread drops / trims the
- *              tokens that an earlier thread's overrunning match already covers
- *   T tokens   every thread turns what it keeps into entries of ONE block-wide ordered token list
- *              (16-bit: position | match flag), placed by a block exclusive scan of token counts
- *   C hist     threads stride over the list: literal/length + distance histograms (shared-memory
- *              atomics); match records are rewritten in place to their symbol form
- *   D codes    block-parallel length-limited prefix codes: one thread per symbol, two 16-candidate
- *              sweeps of a global rounding offset on the ideal -log2 p lengths (Kraft sums by warp
- *              reduce + atomics), exact Kraft completion and canonical code ranks via per-warp
- *              match_any counts; code-length code + header by one warp, overlapped with E
- *   E count    every thread owns an equal, contiguous run of tokens: bit totals -> block scan
- *   F emit     every thread packs its run at its bit offset into the staging buffer
+ * Work decomposition (one CTA of 512 threads per chunk, two CTAs resident per SM, chunks pulled from a
+ * work counter):
+ *   chunk      <= 64 KiB of input = one output slot, byte-aligned at both ends
+ *   unit       <= 32 KiB of a chunk: one LZ77 domain (matches never leave it) resident in shared memory
+ *              (TMA bulk load), normally coded as ONE DEFLATE block
+ *   batch      4096 consecutive positions of a unit = 512 threads x 8-byte spans
+ *   A match    LOCKSTEP, every position: hash of 4 bytes -> table of 8192 32-bit keys.  Per batch:
+ *              read the old key | barrier | red.min(key = (7-batch)<<16 | position) | barrier | read the new
+ *              key.  So the candidate of p is the first position of p's own batch with the same hash
+ *              if that lies before p, else the first such position of the latest earlier batch that
+ *              had one -- a function of the data alone: the output is bit-reproducible.  All 32 lanes
+ *              verify their candidate against the next 8 bytes in lockstep (length 4..8, 8 = "or more")
+ *   W walk     every thread walks its own 8 positions (static, predicated; one-step lazy rule; lengths
+ *              capped at 8 are extended byte-exact only when the match is actually taken); at most 2
+ *              matches start in a span; results parked in shared memory (2 words per span)
+ *   B cover    exclusive prefix-max of the spans' end positions in position order: a span drops / trims
+ *              what an earlier span's overrunning match already covers
+ *   T tokens   every span turns what it keeps into entries of ONE ordered token list (16-bit, one
+ *              entry per code word: literal byte | length symbol + extra | distance), placed by a block
+ *              scan; literal / length / distance histograms by shared-memory atomics on the way
+ *   D codes    block-parallel length-limited prefix codes (10 warps, named barrier)
+ *   E count    every thread owns an equal, contiguous run of entries: bit totals -> block scan
+ *   F emit     every thread packs its run at its bit offset into the staging buffer (aliases the hash table)
  *   G flush    staging -> global in 16-byte units; partial tail carried into the next block
- * Blocks that would not shrink are emitted as stored blocks. If a sub-block has more tokens than the
- * list holds it is coded as two blocks (thread halves). A non-final chunk ends with an empty stored
- * block (00 00 FF FF after bit padding) so chunks join byte-wise; the final chunk carries BFINAL.
+ * Blocks that would not shrink are emitted as stored blocks. A unit with more entries than the list
+ * holds is coded as two blocks (batch halves). A non-final chunk ends with an empty stored block
+ * (00 00 FF FF after bit padding) so chunks join byte-wise; the final chunk carries BFINAL.
  */
 #ifndef MZ_DEFLATE_KERNEL_CUH
 #define MZ_DEFLATE_KERNEL_CUH
@@ -35,39 +39,43 @@
 
 namespace mzc {
 
-constexpr int DF_THREADS = 1024;
+constexpr int DF_THREADS = 512;
 constexpr int DF_WARPS = DF_THREADS / 32;
 constexpr int DF_CHUNK_MAX = 65536;
-constexpr int DF_SEG = 32;
-constexpr int DF_SB = DF_THREADS * DF_SEG; /* 32768 */
+constexpr int DF_UNIT = 32768;                  /* LZ77 domain */
+constexpr int DF_SB = DF_UNIT;                  /* (name kept for the slot bound) */
+constexpr int DF_SPAN = 8;                      /* positions per thread per batch */
+constexpr int DF_BATCH = DF_THREADS * DF_SPAN;  /* 4096 */
+constexpr int DF_NBATCH = DF_UNIT / DF_BATCH;   /* 8 */
 constexpr int DF_MINMATCH = 4;
-constexpr int DF_MAXREC = DF_SEG / DF_MINMATCH; /* 8 match records per thread per sub-block */
-constexpr int DF_HASH_ENTRIES = 16384;          /* u16 entries: 32 KiB */
-constexpr int DF_STAGE_WORDS = DF_SB / 4 + 64;
-constexpr int DF_HDR_WORDS = 96;   /* dynamic header <= 17 + 57 + 316*7 bits = 2286 bits = 72 words */
-constexpr int DF_TOK_CAP = 24576;  /* token list entries (u16) */
-constexpr uint32_t DF_TOK_MATCH = 0x8000u; /* entry is a code word of a match: bits 0-12 = record slot */
-constexpr uint32_t DF_TOK_DIST = 0x4000u;  /* ... its distance code word (else its length code word) */
+constexpr int DF_LOCKLEN = 8;                   /* lockstep verification depth */
+constexpr int DF_HASH_BITS = 13;
+constexpr int DF_HASH_ENTRIES = 1 << DF_HASH_BITS; /* u32 keys: 32 KiB */
+constexpr int DF_STAGE_WORDS = DF_UNIT / 4 + 64;
+constexpr int DF_HDR_WORDS = 96;
 
 constexpr uint32_t DF_FLAG_FINAL = 1u; /* chunk ends the stream: BFINAL on its last block, no sync marker */
 
-/* shared-memory carve-up (bytes) */
+/* shared-memory carve-up (bytes); two CTAs per SM: <= 113 KiB each */
 constexpr int DF_OFF_IN = 0;
-constexpr int DF_OFF_HASH = DF_OFF_IN + DF_CHUNK_MAX + 64;
-constexpr int DF_OFF_REC = DF_OFF_HASH + DF_HASH_ENTRIES * 2;
-constexpr int DF_OFF_STAGE = DF_OFF_REC + DF_MAXREC * DF_THREADS * 4;
-constexpr int DF_OFF_TOK = DF_OFF_STAGE + DF_STAGE_WORDS * 4;
-constexpr int DF_OFF_HDR = DF_OFF_TOK + DF_TOK_CAP * 2;
-constexpr int DF_OFF_HIST = DF_OFF_HDR + DF_HDR_WORDS * 4;      /* u32[288 + 32 + 32] */
-constexpr int DF_OFF_CODE = DF_OFF_HIST + (288 + 32 + 32) * 4;  /* u32[288 + 32 + 32] code | len<<16 */
-constexpr int DF_OFF_LENS = DF_OFF_CODE + (288 + 32 + 32) * 4;  /* u8[288 + 32 + 32] */
-constexpr int DF_OFF_SCAN = DF_OFF_LENS + (288 + 32 + 32);      /* u32[64] */
-constexpr int DF_OFF_BB = DF_OFF_SCAN + 64 * 4;                 /* u32[512] block code-builder scratch */
-constexpr int DF_OFF_MISC = DF_OFF_BB + 512 * 4;                /* u32[32] + mbarrier */
+constexpr int DF_OFF_HASH = DF_OFF_IN + DF_UNIT + 64;
+constexpr int DF_OFF_STAGE = DF_OFF_HASH;       /* bit staging aliases the hash table (dead after the parse) */
+constexpr int DF_OFF_REC = DF_OFF_HASH + DF_STAGE_WORDS * 4; /* span records: 4096 x 2 words */
+constexpr int DF_OFF_SPN = DF_OFF_REC + DF_NBATCH * DF_THREADS * 8; /* u16 per span: match extent -> cover -> bits -> bit offset */
+constexpr int DF_SPAN_BYTES = DF_NBATCH * DF_THREADS * 10;
+constexpr int DF_OFF_HIST = DF_OFF_REC + DF_SPAN_BYTES;      /* u32[288 + 32] */
+constexpr int DF_OFF_HIST2 = DF_OFF_HIST + (288 + 32) * 4;   /* u32[256]: second copy of the literal counts (odd lanes) */
+constexpr int DF_OFF_CODE = DF_OFF_HIST2 + 256 * 4;          /* u32[288 + 32]: code | len << 16 | extra bits << 20 */
+constexpr int DF_OFF_LENS = DF_OFF_CODE + (288 + 32) * 4;    /* u8[288 + 32] code lengths (header) */
+constexpr int DF_OFF_BITS = DF_OFF_LENS + (288 + 32);        /* u8[288 + 32] code length + extra bits */
+constexpr int DF_OFF_SCAN = DF_OFF_BITS + (288 + 32);        /* u32[256]: [0,128) per (batch, warp) partials, [128,256) scanned */
+constexpr int DF_OFF_BB = DF_OFF_SCAN + 256 * 4;             /* u32[512] code-builder scratch */
+constexpr int DF_OFF_MISC = DF_OFF_BB + 512 * 4;             /* u32[32] + mbarrier */
 constexpr int DF_SMEM_BYTES = DF_OFF_MISC + 32 * 4 + 16;
-static_assert(DF_SMEM_BYTES <= 227 * 1024, "shared memory budget");
+static_assert(DF_HASH_ENTRIES * 4 <= DF_STAGE_WORDS * 4, "hash fits the staging region");
+static_assert(DF_SMEM_BYTES <= 113 * 1024, "shared memory budget for two CTAs per SM");
 
-enum { MISC_HDRBITS = 1, MISC_E0 = 2, MISC_CHUNK = 3, MISC_BLCNT = 8 /* 16 words */ };
+enum { MISC_CHUNK = 3, MISC_CARRY = 8 /* 4 words */ };
 
 struct DeflateParams {
     const uint8_t *in;       /* device base of the uncompressed bytes */
@@ -86,57 +94,33 @@ struct DeflateParams {
 };
 
 __host__ __device__ inline uint64_t deflate_slot_bound(uint32_t chunk_size) {
-    /* stored worst case: 5 bytes per block, up to 2 blocks per 32 KiB sub-block, + sync marker + slack */
+    /* stored worst case: 5 bytes per block, up to 2 blocks per 32 KiB unit, + sync marker + slack */
     return (((uint64_t)chunk_size + 12ull * ((chunk_size + DF_SB - 1) / DF_SB + 1) + 64 + 15) & ~15ull);
 }
 
 /* ---- symbol mapping (RFC1951 3.2.5) without tables ------------------------------------------- */
 __device__ __forceinline__ void length_symbol(uint32_t len, uint32_t &sym, uint32_t &ebits, uint32_t &eval) {
-    uint32_t l = len - 3; /* sym is 0..28 (add 257 for the alphabet index) */
-    if (l < 8) {
-        sym = l; ebits = 0; eval = 0;
-    } else if (len == 258) {
-        sym = 28; ebits = 0; eval = 0;
-    } else {
-        uint32_t msb = 31 - __clz((int)l); /* 3..7 */
-        ebits = msb - 2;
-        sym = 4 * (ebits + 1) + ((l >> ebits) & 3);
-        eval = l & ((1u << ebits) - 1);
-    }
+    /* sym is 0..28 (add 257 for the alphabet index). Branch-free: for l = len - 3 >= 8, e = floor(log2 l) - 2 extra bits and
+     * sym = 4 (e + 1) + the two bits below the leading one; l < 8 and len == 258 are patched in by selects. */
+    const uint32_t l = len - 3;
+    const uint32_t msb = 31u - (uint32_t)__clz((int)(l | 4u)); /* 2..7 */
+    uint32_t e = msb - 2;
+    uint32_t sy = 4 * (e + 1) + ((l >> e) & 3u);
+    uint32_t ev = l & ((1u << e) - 1u);
+    sy = l < 8 ? l : sy;           /* (for 4 <= l < 8 the formula already gives l; below 4 it does not) */
+    const bool top = len == 258;
+    sym = top ? 28u : sy;
+    ebits = top ? 0u : e;
+    eval = top ? 0u : ev;
 }
-__device__ __forceinline__ void dist_symbol(uint32_t dist, uint32_t &sym, uint32_t &ebits, uint32_t &eval) {
-    uint32_t d = dist - 1;
-    if (d < 4) {
-        sym = d; ebits = 0; eval = 0;
-    } else {
-        uint32_t msb = 31 - __clz((int)d); /* 2..14 */
-        ebits = msb - 1;
-        sym = 2 * msb + ((d >> ebits) & 1);
-        eval = d & ((1u << ebits) - 1);
-    }
+/* d = distance - 1 (0..32767); branch-free: m = floor(log2(d | 1)), eb = max(m - 1, 0), sym = 2m + bit */
+__device__ __forceinline__ void dist_symbol0(uint32_t d, uint32_t &sym, uint32_t &ebits) {
+    uint32_t m = 31u - (uint32_t)__clz((int)(d | 1u));
+    ebits = m > 0 ? m - 1 : 0u;
+    sym = 2 * m + ((d >> ebits) & 1u);
 }
-__device__ __forceinline__ uint32_t len_extra_bits(uint32_t lsym) { return (lsym < 8 || lsym == 28) ? 0u : (lsym >> 2) - 1; }
+__device__ __forceinline__ uint32_t len_extra_bits(uint32_t lsym) { return (lsym < 8 || lsym >= 28) ? 0u : (lsym >> 2) - 1; }
 __device__ __forceinline__ uint32_t dist_extra_bits(uint32_t dsym) { return dsym < 4 ? 0u : (dsym >> 1) - 1; }
-
-/* match record forms (32 bits each, 8 per thread, [r][tid] layout):
- *   parsed : off(5) | (len-3)(8) << 5 | (dist-1)(15) << 13
- *   symbol : lsym(5) | lextra(5) << 5 | dsym(5) << 10 | dextra(13) << 15     (after phase C) */
-
-/* One token-list entry = one code word. Branch-free decode shared by the count and emit passes:
- * idx = index into the concatenated code table (288 literal/length codes, then 32 distance codes),
- * ev / eb = extra-bits value / count. Literal entries carry the byte; for them the record load reads an
- * unrelated but valid word and the selects discard it. */
-__device__ __forceinline__ void token_code(uint32_t e, const Smem &sm, uint32_t &idx, uint32_t &ev, uint32_t &eb) {
-    const uint32_t rec = sm.ld32(DF_OFF_REC + (e & 0x1fffu) * 4);
-    const bool isrec = (e & DF_TOK_MATCH) != 0, isdist = (e & DF_TOK_DIST) != 0;
-    const uint32_t ls = rec & 31, ds = (rec >> 10) & 31;
-    const uint32_t sym = isdist ? 288u + ds : 257u + ls;
-    const uint32_t xv = isdist ? rec >> 15 : (rec >> 5) & 31u;
-    const uint32_t xb = isdist ? dist_extra_bits(ds) : len_extra_bits(ls);
-    idx = isrec ? sym : e;
-    ev = isrec ? xv : 0u;
-    eb = isrec ? xb : 0u;
-}
 
 /* OR `n` (<=32) bits of v into the staging bit string at bit position pos */
 __device__ __forceinline__ void stage_put(uint32_t *stage, uint32_t pos, uint32_t v, uint32_t n) {
@@ -147,8 +131,14 @@ __device__ __forceinline__ void stage_put(uint32_t *stage, uint32_t pos, uint32_
     if (s + n > 32) atomicOr(&stage[w + 1], v >> (32 - s));
 }
 
-/* per-thread bit packer: first word of the range by atomicOr (shared with the previous thread), words it
- * fills completely by plain store, the trailing partial word by atomicOr */
+/* OR n (<= 15) bits of v into the staging bit string at bit position pos (explicit shared-space form) */
+__device__ __forceinline__ void stage_or(const Smem &sm, uint32_t pos, uint32_t v, uint32_t n) {
+    const uint32_t sh = pos & 31u, wa = DF_OFF_STAGE + ((pos >> 5) << 2);
+    sm.red_or32(wa, v << sh);
+    if (sh + n > 32) sm.red_or32(wa + 4, v >> (32 - sh));
+}
+
+/* per-thread bit packer: every completed 32-bit word goes out by red.or (words at run borders are shared) */
 struct BitWriter {
     Smem sm;
     uint64_t acc;
@@ -164,19 +154,22 @@ struct BitWriter {
             acc >>= 32; nb -= 32; wa += 4;
         }
     }
-    __device__ __forceinline__ void finish() {
+    /* position of the next bit, relative to the start of the staging buffer */
+    __device__ __forceinline__ uint32_t bitpos() const { return ((wa - (uint32_t)DF_OFF_STAGE) << 3) + nb; }
+    __device__ __forceinline__ void finish() { /* nb may exceed 32 after a gap left for a match */
         if (nb > 0) sm.red_or32(wa, (uint32_t)acc);
+        if (nb > 32) sm.red_or32(wa + 4, (uint32_t)(acc >> 32));
     }
 };
 
-/* block-wide exclusive scans over one value per thread; `scan` = 64 words of shared scratch.
+/* block-wide exclusive sum over one value per thread; `scan` = 64 words of shared scratch.
  * Contains __syncthreads: every thread of the CTA must call. */
 __device__ inline uint32_t block_excl_sum(uint32_t v, uint32_t *scan, uint32_t &total) {
     uint32_t incl = warp_incl_sum(v);
     if (lane_id() == 31) scan[warp_id()] = incl;
     __syncthreads();
     if (warp_id() == 0) {
-        uint32_t w = scan[lane_id()];
+        uint32_t w = lane_id() < (unsigned)DF_WARPS ? scan[lane_id()] : 0u;
         uint32_t wi = warp_incl_sum(w);
         scan[32 + lane_id()] = wi - w;
         if (lane_id() == 31) scan[31] = wi; /* grand total parked in slot 31 after use */
@@ -187,29 +180,13 @@ __device__ inline uint32_t block_excl_sum(uint32_t v, uint32_t *scan, uint32_t &
     __syncthreads();
     return res;
 }
-__device__ inline uint32_t block_excl_max(uint32_t v, uint32_t identity, uint32_t *scan) {
-    uint32_t incl = warp_incl_max(v);
-    if (lane_id() == 31) scan[warp_id()] = incl;
-    __syncthreads();
-    if (warp_id() == 0) {
-        uint32_t w = scan[lane_id()];
-        uint32_t wi = warp_incl_max(w);
-        uint32_t ex = __shfl_up_sync(MZ_FULL_MASK, wi, 1);
-        scan[32 + lane_id()] = lane_id() == 0 ? identity : ex;
-    }
-    __syncthreads();
-    uint32_t prev = __shfl_up_sync(MZ_FULL_MASK, incl, 1);
-    uint32_t wbase = scan[32 + warp_id()];
-    uint32_t res = lane_id() == 0 ? wbase : (prev > wbase ? prev : wbase);
-    __syncthreads();
-    return res;
-}
 
 /* ---- D: block-parallel literal/length + distance codes ------------------------------------------------
  * Thread i < 288 owns literal/length symbol i (286 used), thread 288 + j owns distance symbol j (30 used);
  * both alphabets are warp aligned (warps 0-8 and warp 9). Called by threads 0..319 ONLY; they synchronise
- * among themselves on named barrier 1 so the other 22 warps are not dragged through a dozen barriers.
- * bb = 512 words of shared scratch. Outputs lens (u8) and codes (reversed code | len << 16). */
+ * among themselves on named barrier 1 so the other warps are not dragged through a dozen barriers.
+ * bb = 512 words of shared scratch. Outputs lens (u8), codes (reversed code | len << 16 | extra bits << 20)
+ * and bits (u8: code length + extra bits = what one entry of that symbol costs). */
 constexpr int DF_BB_THREADS = 320;
 enum { BB_STAT = 0 /* [2][4]: used,total,first */, BB_KRAFT = 8 /* [2 sweeps][2 alph][16] */, BB_K = 72 /* [2][16] */,
        BB_NEXT = 104 /* [2][16] */, BB_SLACK = 136 /* [2] */, BB_CNTW = 144 /* [2 bufs][10 warps][16] */ };
@@ -222,8 +199,8 @@ __device__ __forceinline__ void bb_count_lengths(uint32_t *cntw_row, uint32_t L,
     __syncwarp();
 }
 
-__device__ inline void block_build_codes(const uint32_t *hist_ll, const uint32_t *hist_d, uint8_t *lens_ll, uint8_t *lens_d,
-                                         uint32_t *code_ll, uint32_t *code_d, uint32_t *bb) {
+__device__ inline void block_build_codes(const uint32_t *hist_ll, const uint32_t *hist_lit2, const uint32_t *hist_d, uint8_t *lens_ll, uint8_t *lens_d,
+                                         uint32_t *code_ll, uint32_t *code_d, uint8_t *bits_ll, uint8_t *bits_d, uint32_t *bb) {
     const uint32_t tid = threadIdx.x;
     const unsigned lane = lane_id(), w = warp_id();
     const int a = tid < 288 ? 0 : (tid < 320 ? 1 : 2);
@@ -232,7 +209,7 @@ __device__ inline void block_build_codes(const uint32_t *hist_ll, const uint32_t
     const int M = 15;
     const uint32_t one = 1u << M;
     const uint32_t w0 = a == 0 ? 0u : 9u; /* first warp of my alphabet */
-    uint32_t c = (a < 2 && sym < nsym) ? (a == 0 ? hist_ll[sym] : hist_d[sym]) : 0u;
+    uint32_t c = (a < 2 && sym < nsym) ? (a == 0 ? hist_ll[sym] + (sym < 256 ? hist_lit2[sym] : 0u) : hist_d[sym]) : 0u;
 
     if (tid < 144) bb[tid] = (tid == BB_STAT + 2 || tid == BB_STAT + 6) ? 0xffffffffu : 0u;
     bar_sync(1, DF_BB_THREADS);
@@ -357,19 +334,21 @@ __device__ inline void block_build_codes(const uint32_t *hist_ll, const uint32_t
             cw = (__brev(code) >> (32 - L)) | (L << 16);
         }
         if (a == 0) {
+            const uint32_t eb = sym >= 257 ? len_extra_bits(sym - 257) : 0u;
             lens_ll[sym] = (uint8_t)L; /* sym up to 287: entries 286, 287 get 0 */
-            code_ll[sym] = cw;
+            code_ll[sym] = cw | (eb << 20);
+            bits_ll[sym] = (uint8_t)(L + eb);
         } else {
             lens_d[sym] = (uint8_t)L;  /* sym up to 31 */
-            code_d[sym] = cw;
+            code_d[sym] = cw;          /* distance extra bits come from the entry, not the table */
+            bits_d[sym] = (uint8_t)(L + dist_extra_bits(sym));
         }
     }
 }
 
 /* Dynamic block header with a FIXED code-length code (all sixteen length values 0..15 coded in 4 bits:
  * a complete prefix code, so zlib accepts it) and no run-length symbols: constant size, every field at a
- * known bit position, written by 317 threads in parallel. Costs ~30-60 bytes per block against an optimal
- * code-length code; buys the removal of a serial warp-level code construction from the critical path. */
+ * known bit position, written by 317 threads in parallel. */
 constexpr uint32_t DF_HDR_BITS = 17 + 19 * 3 + 4 * (286 + 30);
 __device__ __forceinline__ void emit_block_header(uint32_t *stage, uint32_t pos, uint32_t bfinal, const uint8_t *lens_ll,
                                                   const uint8_t *lens_d, uint32_t tid) {
@@ -382,13 +361,12 @@ __device__ __forceinline__ void emit_block_header(uint32_t *stage, uint32_t pos,
     }
 }
 
-/* ---- A: match finding ---------------------------------------------------------------------------------- */
-/* longest match of in[p..] against in[cand..], both inside the chunk, at most maxlen bytes;
- * first 4 bytes already known equal */
-__device__ __forceinline__ uint32_t extend_match(const Smem &sm, uint32_t cand, uint32_t p, uint32_t maxlen) {
-    uint32_t len = 4;
+/* ---- A: match helpers ----------------------------------------------------------------------------------- */
+/* in[q..] against in[c..] agree for 8 bytes already; extend to at most maxlen bytes (both inside the unit) */
+__device__ __noinline__ uint32_t extend_match8(Smem sm, uint32_t c, uint32_t q, uint32_t maxlen) {
+    uint32_t len = 8;
     while (len < maxlen) {
-        uint32_t x = sm.ld32u(DF_OFF_IN, p + len) ^ sm.ld32u(DF_OFF_IN, cand + len);
+        uint32_t x = sm.ld32u(DF_OFF_IN, q + len) ^ sm.ld32u(DF_OFF_IN, c + len);
         if (x) {
             len += (uint32_t)(__ffs((int)x) - 1) >> 3;
             break;
@@ -398,63 +376,101 @@ __device__ __forceinline__ uint32_t extend_match(const Smem &sm, uint32_t cand, 
     return len < maxlen ? len : maxlen;
 }
 
-__device__ __forceinline__ uint32_t hash4(uint32_t v, int bits) { return (v * 2654435761u) >> (32 - bits); }
-
-/* find the best match at p among the bucket's candidates and insert p; returns len (0 = none) */
-template <int WAYS>
-__device__ __forceinline__ uint32_t find_match(const Smem &sm, uint32_t p, uint32_t limit, uint32_t &best_dist) {
-    uint32_t v = sm.ld32u(DF_OFF_IN, p);
-    uint32_t maxlen = limit - p;
-    if (maxlen > 258) maxlen = 258;
-    uint32_t best = 0;
-    best_dist = 0;
-    if (WAYS == 1) {
-        uint32_t ha = DF_OFF_HASH + hash4(v, 14) * 2;
-        uint32_t cand = sm.ld16(ha);
-        sm.st16(ha, p);
-        if (cand < p && p - cand <= 32768u && sm.ld32u(DF_OFF_IN, cand) == v) {
-            best = extend_match(sm, cand, p, maxlen);
-            best_dist = p - cand;
-        }
-    } else {
-        constexpr int hb = WAYS == 2 ? 13 : 12;
-        uint32_t ha = DF_OFF_HASH + hash4(v, hb) * (uint32_t)(WAYS * 2);
-        uint32_t prev_slot = p;
-#pragma unroll
-        for (int wy = 0; wy < WAYS; wy++) {
-            uint32_t cand = sm.ld16(ha + 2 * wy);
-            sm.st16(ha + 2 * wy, prev_slot); /* FIFO: newest first */
-            prev_slot = cand;
-            if (cand < p && p - cand <= 32768u && sm.ld32u(DF_OFF_IN, cand) == v) {
-                uint32_t l = extend_match(sm, cand, p, maxlen);
-                if (l > best) { best = l; best_dist = p - cand; }
-            }
-        }
-    }
-    return best;
+__device__ __forceinline__ uint32_t hash_addr(uint32_t v) { /* byte offset of the key of 4-byte value v */
+    return DF_OFF_HASH + (((v * 2654435761u) >> (32 - DF_HASH_BITS)) << 2);
 }
 
-__device__ __forceinline__ uint32_t bit_range(uint32_t a, uint32_t b) { /* bits [a, b), 0 <= a, b <= 32 */
-    uint32_t hi = b >= 32 ? 0xffffffffu : (1u << b) - 1;
-    uint32_t lo = a >= 32 ? 0xffffffffu : (1u << a) - 1;
-    return hi & ~lo;
+/* span record (two words, parked in the token region during the parse):
+ *   A = j0 | (L0 - 3) << 3 | c0 << 11 | (lit & 63) << 26      first match: start offset, length, candidate position
+ *   B = j1 | (L1 - 3) << 3 | c1 << 11 | (lit >> 6) << 26      second match; (L - 3) == 0 means none
+ * lit = the span's positions coded as literals. */
+__device__ __forceinline__ uint32_t rec_len(uint32_t r) { uint32_t l = (r >> 3) & 255u; return l ? l + 3 : 0u; }
+
+/* What a span keeps once the cover is known, in final form (three words, computed once):
+ *   F  = lit (bits 0-7: positions kept as literals) | ex << 8 (0..2 bytes that a match trimmed below 3 bytes leaves behind;
+ *        they come first) | first such byte << 16 | second << 24
+ *   MA, MB = the up to two matches, each whole or trimmed at the front: bit 31 valid | P (bits 0-2: the in-span position
+ *        the match is ordered at: literals below it come first; 8 -> 0, then there are no literals) | (len - 3) << 4
+ *        | (dist - 1) << 12; match_symbols() turns them into symbol form */
+__device__ __forceinline__ uint32_t fin_len(uint32_t m) { return ((m >> 4) & 255u) + 3u; }
+__device__ __forceinline__ uint32_t fin_dist(uint32_t m) { return ((m >> 12) & 0x7fffu) + 1u; }
+__device__ __forceinline__ void span_classify(const Smem &sm, uint32_t A, uint32_t B, uint32_t q0, uint32_t cover, uint32_t &F, uint32_t &MA,
+                                              uint32_t &MB) {
+    const uint32_t lit = (A >> 26) | ((B >> 26) << 6);
+    const uint32_t crel = cover > q0 ? cover - q0 : 0u;
+    const uint32_t cr8 = crel < 8 ? crel : 8u;
+    uint32_t ex = 0;
+    uint32_t M[2];
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const uint32_t R = r == 0 ? A : B;
+        const uint32_t L = rec_len(R), j = R & 7u, end = j + L;
+        const bool kept = L != 0 && j >= crel;
+        const bool strad = L != 0 && j < crel && end > crel;
+        const uint32_t rem = end - crel;
+        const uint32_t Lf = kept ? L : ((strad && rem >= 3) ? rem : 0u);
+        const uint32_t d1 = q0 + j - ((R >> 11) & 0x7fffu) - 1u;
+        M[r] = Lf ? (0x80000000u | ((kept ? j : cr8) & 7u) | ((Lf - 3) << 4) | (d1 << 12)) : 0u;
+        ex = (strad && rem < 3) ? rem : ex;
+    }
+    F = ((lit >> cr8) << cr8) | (ex << 8);
+    if (ex) { /* rare: fetch the leftover bytes now, the write pass then needs nothing but F */
+        const uint32_t p = DF_OFF_IN + q0 + crel;
+        F |= sm.ld8(p) << 16;
+        if (ex == 2) F |= sm.ld8(p + 1) << 24;
+    }
+    MA = M[0];
+    MB = M[1];
+}
+
+/* final match record (P | len | dist form) -> symbol form, counting its two symbols on the way:
+ *   bit 31 valid | P << 28 (3 bits; 8 -> 0: then the span has no literals, so the order does not matter)
+ *   | distance extra value << 15 (13 bits) | distance symbol << 10 | length extra value << 5 | length symbol (0..28) */
+__device__ __forceinline__ uint32_t match_symbols(const Smem &sm, uint32_t M) {
+    uint32_t ls, lb, lv, ds, db;
+    length_symbol(fin_len(M), ls, lb, lv);
+    const uint32_t d = fin_dist(M) - 1;
+    dist_symbol0(d, ds, db);
+    sm.red_add32(DF_OFF_HIST + (257u + ls) * 4, 1u);
+    sm.red_add32(DF_OFF_HIST + (288u + ds) * 4, 1u);
+    return 0x80000000u | ((M & 7u) << 28) | ((d & ((1u << db) - 1u)) << 15) | (ds << 10) | (lv << 5) | ls;
+}
+/* bits a match costs (both code words with their extra bits); 0 for an empty record */
+__device__ __forceinline__ uint32_t match_bits(const Smem &sm, uint32_t M) {
+    const uint32_t n = sm.ld8(DF_OFF_BITS + 257u + (M & 31u)) + sm.ld8(DF_OFF_BITS + 288u + ((M >> 10) & 31u));
+    return M ? n : 0u;
+}
+/* OR the <= 48 bits of a match (symbol form) into the staging bit string at bit position pos */
+__device__ __forceinline__ void put_match_bits(const Smem &sm, uint32_t pos, uint32_t M) {
+    const uint32_t cwl = sm.ld32(DF_OFF_CODE + (257u + (M & 31u)) * 4);
+    const uint32_t cwd = sm.ld32(DF_OFF_CODE + (288u + ((M >> 10) & 31u)) * 4);
+    const uint32_t cl = (cwl >> 16) & 15u, cd = (cwd >> 16) & 15u;
+    const uint32_t v1 = (cwl & 0x7fffu) | (((M >> 5) & 31u) << cl);          /* <= 15 + 5 bits */
+    const uint32_t n1 = cl + ((cwl >> 20) & 15u);
+    const uint32_t v2 = (cwd & 0x7fffu) | (((M >> 15) & 0x1fffu) << cd);     /* <= 15 + 13 bits */
+    const uint64_t V = (uint64_t)v1 | ((uint64_t)v2 << n1);
+    const uint32_t lo = (uint32_t)V, hi = (uint32_t)(V >> 32), sh = pos & 31u;
+    const uint32_t wa = DF_OFF_STAGE + (pos >> 5) * 4;
+    const uint32_t w0 = lo << sh, w1 = __funnelshift_l(lo, hi, sh), w2 = __funnelshift_l(hi, 0u, sh);
+    sm.red_or32(wa, w0);
+    if (w1) sm.red_or32(wa + 4, w1);
+    if (w2) sm.red_or32(wa + 8, w2);
 }
 
 /* ---- the kernel ------------------------------------------------------------------------------- */
-template <int WAYS, bool LAZY>
-__global__ void __launch_bounds__(DF_THREADS, 1) deflate_chunks_kernel(DeflateParams P) {
+template <int STRIDE, bool LAZY>
+__global__ void __launch_bounds__(DF_THREADS, 2) deflate_chunks_kernel(DeflateParams P) {
     MZ_DYN_SMEM(smem);
     uint8_t *s_in = smem + DF_OFF_IN;
-    uint16_t *s_hash = (uint16_t *)(smem + DF_OFF_HASH);
-    uint32_t *s_rec = (uint32_t *)(smem + DF_OFF_REC);
     uint32_t *s_stage = (uint32_t *)(smem + DF_OFF_STAGE);
-    uint16_t *s_tok = (uint16_t *)(smem + DF_OFF_TOK);
     uint32_t *s_hist_ll = (uint32_t *)(smem + DF_OFF_HIST);
     uint32_t *s_hist_d = s_hist_ll + 288;
     uint32_t *s_code_ll = (uint32_t *)(smem + DF_OFF_CODE);
     uint32_t *s_code_d = s_code_ll + 288;
     uint8_t *s_lens_ll = smem + DF_OFF_LENS;
     uint8_t *s_lens_d = s_lens_ll + 288;
+    uint8_t *s_bits_ll = smem + DF_OFF_BITS;
+    uint8_t *s_bits_d = s_bits_ll + 288;
     uint32_t *s_scan = (uint32_t *)(smem + DF_OFF_SCAN);
     uint32_t *s_bb = (uint32_t *)(smem + DF_OFF_BB);
     uint32_t *s_misc = (uint32_t *)(smem + DF_OFF_MISC);
@@ -468,11 +484,12 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deflate_chunks_kernel(DeflatePa
     __syncthreads();
 #endif
     const uint32_t tid = threadIdx.x;
+    const unsigned lane = lane_id(), warp = warp_id();
     Smem sm;
     sm.init(smem);
 
-    /* Chunks are handed out by an atomic counter: if another kernel (e.g. an NCCL all-gather overlapped with this
-     * one) holds some SMs, the resident CTAs simply take more chunks instead of leaving a tail to late CTAs. */
+    /* Chunks are handed out by an atomic counter: if another kernel holds some SMs, the resident CTAs simply
+     * take more chunks instead of leaving a tail to late CTAs. */
     for (uint32_t chunk_static = blockIdx.x;; chunk_static += gridDim.x) {
         uint32_t chunk = chunk_static;
         if (P.work_counter) {
@@ -494,285 +511,438 @@ __global__ void __launch_bounds__(DF_THREADS, 1) deflate_chunks_kernel(DeflatePa
             len = rem < P.chunk_size ? (uint32_t)rem : P.chunk_size;
             flags = P.flags ? P.flags[chunk] : (chunk == P.nchunks - 1 ? P.last_flags : 0u);
         }
-        const uint8_t *gin = P.in + off;
         uint8_t *gout = P.out + (uint64_t)chunk * P.slot_stride;
 
-        /* ---- load input into shared memory, reset tables ---------------------------------------- */
-        const uint32_t len16 = len & ~15u;
-        bool bulk = false;
-#ifndef MZ_EMU
-        bulk = (((uintptr_t)gin) & 15) == 0 && len16 > 0;
-        if (bulk && tid == 0) {
-            fence_proxy_async(); /* earlier generic-proxy reads of s_in are done (trailing __syncthreads) */
-            mbar_expect_tx(s_bar, len16);
-            tma_load_1d(s_in, gin, len16, s_bar);
-        }
-#endif
-        if (!bulk) {
-            if ((((uintptr_t)gin) & 15) == 0) {
-                for (uint32_t i = tid * 16; i < len16; i += DF_THREADS * 16) *(uint4 *)(s_in + i) = ldg_stream((const uint4 *)(gin + i));
-            } else {
-                for (uint32_t i = tid; i < len16; i += DF_THREADS) s_in[i] = gin[i];
-            }
-        }
-        for (uint32_t i = len16 + tid; i < len; i += DF_THREADS) s_in[i] = gin[i];
-        for (uint32_t i = len + tid; i < ((len + 63) & ~15u) + 16 && i < DF_CHUNK_MAX + 64; i += DF_THREADS) s_in[i] = 0; /* zero pad */
-        for (uint32_t i = tid; i < DF_HASH_ENTRIES / 8; i += DF_THREADS) ((uint4 *)s_hash)[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
-        for (uint32_t i = tid; i < DF_STAGE_WORDS; i += DF_THREADS) s_stage[i] = 0;
-#ifndef MZ_EMU
-        if (bulk) {
-            mbar_wait(s_bar, bar_phase);
-            bar_phase ^= 1;
-        }
-#endif
-        __syncthreads();
-
         uint32_t flushed = 0; /* bytes of this chunk already in global memory (multiple of 16) */
-        uint32_t bitpos = 0;  /* valid bits in the staging buffer; uniform across the CTA */
-        const uint32_t nsb = (len + DF_SB - 1) / DF_SB;
+        uint32_t bitpos = 0;  /* valid bits in the staging buffer (incl. the carried tail); uniform across the CTA */
+        const uint32_t nunits = (len + DF_UNIT - 1) / DF_UNIT;
+        if (tid < 4) s_misc[MISC_CARRY + tid] = 0;
 
-        if (len == 0 && (flags & DF_FLAG_FINAL)) {
-            /* zlib's answer for an empty stream: one fixed-Huffman block holding only EOB = 03 00 */
-            if (tid == 0) stage_put(s_stage, 0, 1u | (1u << 1), 3);
-            bitpos = 10;
+        if (len == 0) {
+            /* no unit will run: staging is used directly */
+            for (uint32_t i = tid; i < 64; i += DF_THREADS) s_stage[i] = 0;
+            __syncthreads();
+            if (flags & DF_FLAG_FINAL) {
+                /* zlib's answer for an empty stream: one fixed-Huffman block holding only EOB = 03 00 */
+                if (tid == 0) stage_put(s_stage, 0, 1u | (1u << 1), 3);
+                bitpos = 10;
+            }
             __syncthreads();
         }
 
-        for (uint32_t sb = 0; sb < nsb; sb++) {
-            const uint32_t sb_start = sb * DF_SB;
-            const uint32_t sb_end = (sb_start + DF_SB < len) ? sb_start + DF_SB : len;
-            const uint32_t seg_start = sb_start + tid * DF_SEG < sb_end ? sb_start + tid * DF_SEG : sb_end;
-            const uint32_t seg_end = seg_start + DF_SEG < sb_end ? seg_start + DF_SEG : sb_end;
-            const bool last_sb = sb == nsb - 1;
-            uint32_t nhalf = 1, n_tok = 0, ntok_all = 0, tok_excl = 0, e0 = sb_end;
-            uint32_t litmask = 0, keptrec = 0, recmask = 0, strad_cnt = 0, strad_pos = 0, strad_tok = 0;
-            bool strad_match = false;
+        for (uint32_t u = 0; u < nunits; u++) {
+            const uint32_t ustart = u * DF_UNIT;
+            const uint32_t ulen = (ustart + DF_UNIT < len) ? (uint32_t)DF_UNIT : len - ustart;
+            const uint8_t *gin = P.in + off + ustart;
+            const bool last_unit = u == nunits - 1;
+            const uint32_t nb = (ulen + DF_BATCH - 1) / DF_BATCH;
+
+            /* ---- load the unit into shared memory, reset the hash table ------------------------------ */
+            const uint32_t len16 = ulen & ~15u;
+            bool bulk = false;
+#ifndef MZ_EMU
+            bulk = (((uintptr_t)gin) & 15) == 0 && len16 > 0;
+            if (bulk && tid == 0) {
+                fence_proxy_async(); /* earlier generic-proxy accesses of s_in are done (trailing __syncthreads) */
+                mbar_expect_tx(s_bar, len16);
+                tma_load_1d(s_in, gin, len16, s_bar);
+            }
+#endif
+            if (!bulk) {
+                if ((((uintptr_t)gin) & 15) == 0) {
+                    for (uint32_t i = tid * 16; i < len16; i += DF_THREADS * 16) *(uint4 *)(s_in + i) = ldg_stream((const uint4 *)(gin + i));
+                } else {
+                    for (uint32_t i = tid; i < len16; i += DF_THREADS) s_in[i] = gin[i];
+                }
+            }
+            for (uint32_t i = len16 + tid; i < ulen; i += DF_THREADS) s_in[i] = gin[i];
+            for (uint32_t i = ulen + tid; i < ((ulen + 63) & ~15u) + 16 && i < DF_UNIT + 64; i += DF_THREADS) s_in[i] = 0; /* zero pad */
+            if (P.level != 0)
+                for (uint32_t i = tid; i < DF_HASH_ENTRIES / 4; i += DF_THREADS) sm.st128(DF_OFF_HASH + i * 16, ~0u, ~0u, ~0u, ~0u);
+#ifndef MZ_EMU
+            if (bulk) {
+                mbar_wait(s_bar, bar_phase);
+                bar_phase ^= 1;
+            }
+#endif
+            __syncthreads();
+
+            uint32_t fF[DF_NBATCH], fA[DF_NBATCH], fB[DF_NBATCH];
+            bool stored = (P.level == 0);
+            const uint32_t bfinal = (last_unit && (flags & DF_FLAG_FINAL)) ? 1u : 0u;
+            uint32_t tokbits = 0;
 
             if (P.level != 0) {
-                /* ---- A: parse ------------------------------------------------------------------ */
-                uint32_t nrec = 0;
-                uint32_t p = seg_start;
-                while (p < seg_end) {
-                    uint32_t mlen = 0, mdist = 0;
-                    if (p + DF_MINMATCH <= sb_end) {
-                        mlen = find_match<WAYS>(sm, p, sb_end, mdist);
-                        if (LAZY && mlen >= DF_MINMATCH && mlen < 32 && p + 1 < seg_end && p + 1 + DF_MINMATCH <= sb_end) {
-                            uint32_t d2, l2 = find_match<WAYS>(sm, p + 1, sb_end, d2);
-                            if (l2 > mlen) { /* literal now, better match next */
-                                p += 1;
-                                mlen = l2;
-                                mdist = d2;
-                            }
+                /* ---- A + W: batches ------------------------------------------------------------------ */
+#pragma unroll 1
+                for (uint32_t b = 0; b < nb; b++) {
+                    const uint32_t q0 = b * DF_BATCH + tid * DF_SPAN;
+                    uint32_t v[12], ha[8], lc[8];
+                    {
+                        const uint2 x = sm.ld64(DF_OFF_IN + q0), y = sm.ld64(DF_OFF_IN + q0 + 8);
+                        v[0] = x.x; v[4] = x.y; v[8] = y.x;
+#pragma unroll
+                        for (int k = 1; k < 4; k++) {
+                            v[k] = __funnelshift_r(x.x, x.y, 8 * k);
+                            v[4 + k] = __funnelshift_r(x.y, y.x, 8 * k);
+                            v[8 + k] = __funnelshift_r(y.x, y.y, 8 * k);
                         }
                     }
-                    /* at most 8 matches of >= 4 bytes start inside a 32-byte span, so nrec cannot overflow */
-                    const bool ism = mlen >= DF_MINMATCH;
-                    if (ism) sm.st32(DF_OFF_REC + (nrec * DF_THREADS + tid) * 4, (p - seg_start) | ((mlen - 3) << 5) | ((mdist - 1) << 13));
-                    nrec += ism ? 1u : 0u;
-                    p += ism ? mlen : 1u;
-                }
-                /* ---- B: cover = where earlier threads' matches end ------------------------------ */
-                const uint32_t cover = block_excl_max(p, sb_start, s_scan);
-                if (tid == DF_THREADS / 2) s_misc[MISC_E0] = cover; /* where the second thread half starts */
-                /* ---- T: classify what this thread keeps ------------------------------------------- */
-                const uint32_t c_rel = cover > seg_start ? cover - seg_start : 0u; /* may exceed 32 */
-                uint32_t covmask = 0;
-                recmask = 0;
-                for (uint32_t r = 0; r < nrec; r++) {
-                    uint32_t rec = s_rec[r * DF_THREADS + tid];
-                    uint32_t roff = rec & 31, rlen = ((rec >> 5) & 255) + 3;
-                    uint32_t rend = roff + rlen;
-                    recmask |= 1u << roff;
-                    covmask |= bit_range(roff + 1, rend < 32 ? rend : 32);
-                    if (rend <= c_rel) continue; /* covered entirely by an earlier thread's match */
-                    if (roff >= c_rel) {
-                        keptrec |= 1u << roff;
-                    } else {
-                        uint32_t rem = rend - c_rel; /* straddles: trim the front */
-                        if (rem >= 3) {
-                            strad_match = true;
-                            strad_tok = DF_TOK_MATCH | (r * DF_THREADS + tid);
-                            s_rec[r * DF_THREADS + tid] = roff | ((rem - 3) << 5) | (rec & ~0x1fffu);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        ha[j] = hash_addr(v[j]);
+                        if (j % STRIDE == 0) lc[j] = sm.ld32(ha[j]); /* key of the latest earlier batch that holds this hash */
+                    }
+                    const uint32_t nvalid = ulen > q0 ? (ulen - q0 < 8 ? ulen - q0 : 8u) : 0u;
+                    __syncthreads();
+                    {
+                        const uint32_t key0 = ((uint32_t)(DF_NBATCH - 1 - b) << 16) | q0;
+#pragma unroll
+                        for (int j = 0; j < 8; j++) sm.red_min32(ha[j], (uint32_t)j < nvalid ? key0 + j : 0xffffffffu);
+                    }
+                    __syncthreads();
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        if (j % STRIDE != 0) {
+                            lc[j] = 0;
+                            continue;
+                        }
+                        const uint32_t cn = sm.ld32(ha[j]) & 0xffffu;
+                        const uint32_t c = cn < q0 + j ? cn : (lc[j] & 0xffffu);
+                        const uint32_t ca = DF_OFF_IN + (c & ~3u);
+                        const uint32_t w0 = sm.ld32(ca), w1 = sm.ld32(ca + 4), w2 = sm.ld32(ca + 8);
+                        const uint32_t s = c << 3;
+                        const uint32_t x0 = __funnelshift_r(w0, w1, s) ^ v[j];
+                        const uint32_t x1 = __funnelshift_r(w1, w2, s) ^ v[j + 4];
+                        const uint32_t l = (c < q0 + j && x0 == 0) ? 4u + ((uint32_t)__clz((int)__brev(x1)) >> 3) : 0u;
+                        lc[j] = l | (c << 4);
+                    }
+                    if (q0 + 16 > ulen) { /* unit tail: the zero padding must not be matched */
+#pragma unroll
+                        for (int j = 0; j < 8; j += STRIDE) {
+                            const uint32_t room = ulen > q0 + j ? ulen - (q0 + j) : 0u;
+                            uint32_t l = lc[j] & 15u;
+                            l = l < room ? l : room;
+                            lc[j] = (lc[j] & ~15u) | (l >= (uint32_t)DF_MINMATCH ? l : 0u);
+                        }
+                    }
+                    /* ---- W: walk the span: static and branch-free. A match whose lockstep length is the cap (8) reaches the end of
+                     * the span whatever its true length is, so it is always the span's last token: it is extended once, after
+                     * the walk ------------------------------------------------------------------------------------------------ */
+                    uint32_t nxt = 0, lit = 0, mA = 0, mB = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const bool take = nxt == (uint32_t)j;
+                        if (j % STRIDE == 0) {
+                            const uint32_t l = lc[j] & 15u;
+                            bool ism = take && l >= (uint32_t)DF_MINMATCH;
+                            if (LAZY && STRIDE == 1 && j < 7) ism = ism && !((lc[j + 1] & 15u) > l);
+                            const uint32_t rec = (uint32_t)j | ((l - 3) << 3) | ((lc[j] >> 4) << 11);
+                            const bool first = mA == 0;
+                            mA = (ism && first) ? rec : mA;
+                            mB = (ism && !first) ? rec : mB;
+                            lit |= (take && !ism) ? (1u << j) : 0u;
+                            nxt = ism ? (uint32_t)j + l : (take ? (uint32_t)j + 1u : nxt);
                         } else {
-                            strad_cnt = rem; /* 1-2 bytes left: plain literals */
-                            strad_pos = seg_start + c_rel;
+                            lit |= take ? (1u << j) : 0u;
+                            nxt = take ? (uint32_t)j + 1u : nxt;
                         }
+                    }
+                    lit &= (1u << nvalid) - 1u;
+                    {
+                        const uint32_t last = mB ? mB : mA;
+                        if (((last >> 3) & 255u) == (uint32_t)(DF_LOCKLEN - 3)) { /* capped: find the true length */
+                            const uint32_t j = last & 7u, c = (last >> 11) & 0x7fffu;
+                            uint32_t maxlen = ulen - (q0 + j);
+                            maxlen = maxlen < 258 ? maxlen : 258u;
+                            const uint32_t l = extend_match8(sm, c, q0 + j, maxlen);
+                            const uint32_t rec = (last & ~(255u << 3)) | ((l - 3) << 3);
+                            if (mB) mB = rec; else mA = rec;
+                            nxt = j + l;
+                        }
+                    }
+                    sm.st64(DF_OFF_REC + (b * DF_THREADS + tid) * 8, mA | ((lit & 63u) << 26), mB | ((lit >> 6) << 26));
+                    {
+                        const uint32_t last = mB ? mB : mA; /* start offset and end (relative to the span) of the span's last match */
+                        sm.st16(DF_OFF_SPN + (b * DF_THREADS + tid) * 2, last ? ((last & 7u) << 9) | ((last & 7u) + rec_len(last)) : 0u);
                     }
                 }
-                const uint32_t valid = seg_end - seg_start;
-                litmask = ~covmask & ~recmask & ~bit_range(0, c_rel < 32 ? c_rel : 32) & bit_range(0, valid);
-                n_tok = (uint32_t)__popc(litmask) + 2u * ((uint32_t)__popc(keptrec) + (strad_match ? 1u : 0u)) + strad_cnt; /* a match = 2 code words */
-                tok_excl = block_excl_sum(n_tok, s_scan, ntok_all);
-                e0 = s_misc[MISC_E0];
-                nhalf = ntok_all > (uint32_t)DF_TOK_CAP ? 2u : 1u;
-            }
+                __syncthreads(); /* S1: records visible; the hash table is dead */
 
-            for (uint32_t half = 0; half < nhalf; half++) {
-                /* byte range this block codes: the kept tokens of the participating threads tile it exactly */
-                const uint32_t blk_start = (nhalf == 2 && half == 1) ? e0 : sb_start;
-                const uint32_t blk_end = (nhalf == 2 && half == 0) ? e0 : sb_end;
-                const uint32_t blk_len = blk_end - blk_start;
-                const uint32_t bfinal = (last_sb && half == nhalf - 1 && (flags & DF_FLAG_FINAL)) ? 1u : 0u;
-                bool stored = (P.level == 0);
+                /* ---- staging := 0 (+ the carried tail), histograms := 0 ------------------------------ */
+                for (uint32_t i = tid; i < DF_STAGE_WORDS / 4; i += DF_THREADS) {
+                    if (i == 0) sm.st128(DF_OFF_STAGE, s_misc[MISC_CARRY], s_misc[MISC_CARRY + 1], s_misc[MISC_CARRY + 2], s_misc[MISC_CARRY + 3]);
+                    else sm.st128(DF_OFF_STAGE + i * 16, 0, 0, 0, 0);
+                }
+                for (uint32_t i = tid; i < 288 + 32 + 256; i += DF_THREADS) s_hist_ll[i] = 0; /* + the second literal copy */
 
-                if (!stored) {
-                    uint32_t ntok = ntok_all, excl = tok_excl;
-                    const bool mine = nhalf == 1 || (tid >> 9) == half;
-                    if (nhalf == 2) excl = block_excl_sum(mine ? n_tok : 0u, s_scan, ntok);
-                    /* ---- T: write the ordered token list ------------------------------------------ */
-                    for (uint32_t i = tid; i < 288 + 32; i += DF_THREADS) s_hist_ll[i] = 0;
-                    __syncthreads();
-                    /* literal entry = the byte itself; match entry = flag | record slot (r * 1024 + owner) */
-                    if (mine) {
-                        uint32_t o = excl;
-                        if (strad_match) {
-                            s_tok[o++] = (uint16_t)strad_tok;
-                            s_tok[o++] = (uint16_t)(strad_tok | DF_TOK_DIST);
-                        }
-                        for (uint32_t q = 0; q < strad_cnt; q++) s_tok[o++] = s_in[strad_pos + q];
-                        uint32_t mm = litmask | keptrec;
-                        uint32_t oa = DF_OFF_TOK + o * 2;
-                        while (mm) {
-                            uint32_t b = (uint32_t)__ffs((int)mm) - 1;
-                            mm &= mm - 1;
-                            uint32_t e = sm.ld8(DF_OFF_IN + seg_start + b);
-                            if ((keptrec >> b) & 1u) {
-                                e = DF_TOK_MATCH | ((uint32_t)__popc(recmask & ((1u << b) - 1)) * DF_THREADS + tid);
-                                sm.st16(oa, e); /* length code word, then the distance code word */
-                                oa += 2;
-                                e |= DF_TOK_DIST;
-                            }
-                            sm.st16(oa, e);
-                            oa += 2;
-                        }
-                        /* ---- C (matches): this thread's kept records -> symbol form + histograms ------------- */
-                        uint32_t mk = keptrec;
-                        bool do_strad = strad_match;
-                        while (mk || do_strad) {
-                            uint32_t slot;
-                            if (do_strad) {
-                                slot = strad_tok & 0x1fffu;
-                                do_strad = false;
-                            } else {
-                                uint32_t b = (uint32_t)__ffs((int)mk) - 1;
-                                mk &= mk - 1;
-                                slot = (uint32_t)__popc(recmask & ((1u << b) - 1)) * DF_THREADS + tid;
-                            }
-                            uint32_t rec = s_rec[slot];
-                            uint32_t ls, lb, lv, ds, db, dv;
-                            length_symbol(((rec >> 5) & 255) + 3, ls, lb, lv);
-                            dist_symbol((rec >> 13) + 1, ds, db, dv);
-                            s_rec[slot] = ls | (lv << 5) | (ds << 10) | (dv << 15);
-                            atomicAdd(&s_hist_ll[257 + ls], 1u);
-                            atomicAdd(&s_hist_d[ds], 1u);
-                        }
-                    }
-                    __syncthreads();
-                    /* ---- C (literals): threads stride over the list ------------------------------------------ */
-                    for (uint32_t k = tid; k < ntok; k += DF_THREADS) {
-                        uint32_t e = sm.ld16(DF_OFF_TOK + k * 2);
-                        if (!(e & DF_TOK_MATCH)) sm.red_add32(DF_OFF_HIST + e * 4, 1u);
-                    }
-                    if (tid == 0) s_hist_ll[256] = 1;
-                    __syncthreads();
-                    /* ---- D: codes (10 warps on a named barrier; the rest wait here) ------------------------- */
-                    if (tid < DF_BB_THREADS) block_build_codes(s_hist_ll, s_hist_d, s_lens_ll, s_lens_d, s_code_ll, s_code_d, s_bb);
-                    __syncthreads();
-                    /* ---- E: bit counts over equal contiguous token runs (codes are final) ---------------- */
-                    const uint32_t run = ((ntok + DF_THREADS - 1) / DF_THREADS) | 1u; /* odd stride: no bank conflicts */
-                    const uint32_t k0 = tid * run < ntok ? tid * run : ntok;
-                    const uint32_t k1 = k0 + run < ntok ? k0 + run : ntok;
-                    uint32_t mybits = 0;
-                    for (uint32_t k = k0; k < k1; k++) {
-                        uint32_t idx, ev, eb;
-                        token_code(sm.ld16(DF_OFF_TOK + k * 2), sm, idx, ev, eb);
-                        mybits += (sm.ld32(DF_OFF_CODE + idx * 4) >> 16) + eb;
-                    }
-                    uint32_t tokbits;
-                    uint32_t myoff = block_excl_sum(mybits, s_scan, tokbits);
-                    const uint32_t hdrbits = DF_HDR_BITS;
-                    const uint32_t eob = s_code_ll[256];
-                    const uint32_t dyn_bits = hdrbits + tokbits + (eob >> 16);
-                    const uint32_t stored_bits = (((bitpos + 3 + 7) & ~7u) - bitpos) + 32 + blk_len * 8;
-                    if (dyn_bits >= stored_bits) {
-                        stored = true;
+                /* ---- B: cover. For this pass (and the offset pass below) thread T owns the 8 CONSECUTIVE spans 8T..8T+7 (64
+                 * positions), so one block scan per pass is enough; everything else keeps the parse mapping (span b*512+t),
+                 * whose shared-memory accesses are conflict-free. cover(span) = the largest end of a match of an earlier
+                 * span. Runs: inside a long repeat every span holds a maximal match, and the plain rule would cut each of
+                 * them down to the 8 bytes it adds to the cover. A span that lies wholly under the cover and whose match
+                 * sticks out of it is PENDING; a later such span whose match starts at or before the pending one's cover
+                 * takes its place (and its cover), so a run is coded by the last match that can still start at the cover. */
+                {
+                    uint32_t se[8];
+                    if (tid * 8 < nb * DF_THREADS) {
+                        const uint4 q = *(const uint4 *)(smem + DF_OFF_SPN + tid * 16);
+                        se[0] = q.x & 0xffffu; se[1] = q.x >> 16; se[2] = q.y & 0xffffu; se[3] = q.y >> 16;
+                        se[4] = q.z & 0xffffu; se[5] = q.z >> 16; se[6] = q.w & 0xffffu; se[7] = q.w >> 16;
                     } else {
-                        /* ---- F: emit --------------------------------------------------------------- */
-                        const uint32_t base = bitpos + hdrbits;
-                        emit_block_header(s_stage, bitpos, bfinal, s_lens_ll, s_lens_d, tid);
-                        if (mybits) {
-                            BitWriter bw;
-                            bw.init(sm, base + myoff);
-                            for (uint32_t k = k0; k < k1; k++) {
-                                uint32_t idx, ev, eb;
-                                token_code(sm.ld16(DF_OFF_TOK + k * 2), sm, idx, ev, eb);
-                                uint32_t cw = sm.ld32(DF_OFF_CODE + idx * 4); /* distance codes follow the 288 literal/length codes */
-                                uint32_t cl = cw >> 16;
-                                bw.put((cw & 0xffff) | (ev << cl), cl + eb); /* <= 15 + 13 bits */
-                            }
-                            bw.finish();
+#pragma unroll
+                        for (int k = 0; k < 8; k++) se[k] = 0;
+                    }
+                    const uint32_t p0 = tid * 64;
+                    uint32_t tmax = 0;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const uint32_t e = se[k] ? p0 + 8 * k + (se[k] & 511u) : 0u;
+                        tmax = tmax > e ? tmax : e;
+                    }
+                    const uint32_t incl = warp_incl_max(tmax);
+                    uint32_t cin = __shfl_up_sync(MZ_FULL_MASK, incl, 1);
+                    if (lane == 0) cin = 0;
+                    if (lane == 31) s_scan[warp] = incl;
+                    __syncthreads(); /* S2 */
+                    {
+                        const uint32_t w = (lane < (unsigned)DF_WARPS && lane < warp) ? s_scan[lane] : 0u;
+                        const uint32_t base = __reduce_max_sync(MZ_FULL_MASK, w);
+                        cin = cin > base ? cin : base;
+                    }
+                    uint32_t run = cin, drop = 0, pcv = 0, pendk = 0;
+                    bool alive = false;
+                    uint32_t cv[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        const uint32_t q0 = p0 + 8 * k;
+                        const uint32_t ms = q0 + (se[k] >> 9), me = q0 + (se[k] & 511u);
+                        const bool fc = run >= q0 + 8;
+                        const bool strad = se[k] != 0 && ms < run && me > run;
+                        const bool takes = fc && strad && alive && ms <= pcv;
+                        drop |= takes ? 1u << pendk : 0u;
+                        cv[k] = takes ? pcv : run;
+                        pcv = (fc && strad && !takes) ? run : pcv;
+                        pendk = (fc && strad) ? (uint32_t)k : pendk;
+                        alive = fc && (strad || alive);
+                        run = (se[k] != 0 && me > run) ? me : run;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 8; k++) cv[k] = ((drop >> k) & 1u) ? 0xffffu : cv[k];
+                    *(uint4 *)(smem + DF_OFF_SPN + tid * 16) = make_uint4(cv[0] | (cv[1] << 16), cv[2] | (cv[3] << 16), cv[4] | (cv[5] << 16), cv[6] | (cv[7] << 16));
+                }
+                __syncthreads(); /* S3: covers visible */
+
+                /* ---- T: classify every span once -> final records in registers; symbol counts ---------------------- */
+                const uint32_t hist_lit = (lane & 1u) ? (uint32_t)DF_OFF_HIST2 : (uint32_t)DF_OFF_HIST; /* two copies halve the same-address traffic */
+#pragma unroll
+                for (int b = 0; b < DF_NBATCH; b++) {
+                    uint32_t F = 0, MA = 0, MB = 0;
+                    if ((uint32_t)b < nb) {
+                        const uint32_t sidx = (uint32_t)b * DF_THREADS + tid;
+                        const uint32_t q0 = sidx * DF_SPAN;
+                        const uint2 r = sm.ld64(DF_OFF_REC + sidx * 8);
+                        const uint32_t cover = sm.ld16(DF_OFF_SPN + sidx * 2);
+                        span_classify(sm, r.x, r.y, q0, cover, F, MA, MB);
+                        const uint32_t ex = (F >> 8) & 3u;
+                        if (ex) {
+                            sm.red_add32(hist_lit + ((F >> 16) & 0xffu) * 4, 1u);
+                            if (ex == 2) sm.red_add32(hist_lit + (F >> 24) * 4, 1u);
                         }
-                        if (tid == DF_THREADS - 1) stage_put(s_stage, base + tokbits, eob & 0xffff, eob >> 16);
-                        bitpos += dyn_bits;
+                        const uint2 x = sm.ld64(DF_OFF_IN + q0);
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            const uint32_t by4 = j == 0 ? (x.x << 2) & 0x3fcu
+                                               : j < 4 ? (x.x >> (8 * j - 2)) & 0x3fcu
+                                               : j == 4 ? (x.y << 2) & 0x3fcu
+                                                        : (x.y >> (8 * (j - 4) - 2)) & 0x3fcu; /* byte * 4 */
+                            sm.red_add32_if(((F >> j) & 1u) != 0, hist_lit + by4, 1u);
+                        }
+                        if (MA) MA = match_symbols(sm, MA);
+                        if (MB) MB = match_symbols(sm, MB);
+                    }
+                    fF[b] = F; fA[b] = MA; fB[b] = MB;
+                }
+                if (tid == 0) sm.red_add32(DF_OFF_HIST + 256 * 4, 1u); /* end of block */
+                __syncthreads(); /* S4 */
+                /* ---- D: codes (10 warps on a named barrier; the rest wait here) ------------------------- */
+                if (tid < DF_BB_THREADS)
+                    block_build_codes(s_hist_ll, (const uint32_t *)(smem + DF_OFF_HIST2), s_hist_d, s_lens_ll, s_lens_d, s_code_ll, s_code_d, s_bits_ll, s_bits_d, s_bb);
+                __syncthreads(); /* S5 */
+                /* ---- E: bits per span -> offsets ------------------------------------------------------------------- */
+#pragma unroll
+                for (int b = 0; b < DF_NBATCH; b++) {
+                    if ((uint32_t)b < nb) {
+                        const uint32_t sidx = (uint32_t)b * DF_THREADS + tid;
+                        const uint32_t F = fF[b];
+                        const uint2 x = sm.ld64(DF_OFF_IN + sidx * DF_SPAN);
+                        uint32_t nbits = match_bits(sm, fA[b]) + match_bits(sm, fB[b]);
+                        const uint32_t ex = (F >> 8) & 3u;
+                        nbits += ex >= 1 ? sm.ld8(DF_OFF_BITS + ((F >> 16) & 0xffu)) : 0u;
+                        nbits += ex == 2 ? sm.ld8(DF_OFF_BITS + (F >> 24)) : 0u;
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            const uint32_t by = ((j < 4 ? x.x : x.y) >> (8 * (j & 3))) & 0xffu;
+                            const uint32_t l = sm.ld8(DF_OFF_BITS + by);
+                            nbits += ((F >> j) & 1u) ? l : 0u;
+                        }
+                        sm.st16(DF_OFF_SPN + sidx * 2, nbits);
                     }
                 }
-                if (stored) {
-                    /* stored block: header, pad to byte, LEN, ~LEN, raw bytes */
-                    const uint32_t p0 = (bitpos + 3 + 7) >> 3; /* byte index of LEN */
-                    if (tid == 0) {
-                        stage_put(s_stage, bitpos, bfinal, 3);
-                        stage_put(s_stage, p0 * 8, blk_len, 16);
-                        stage_put(s_stage, p0 * 8 + 16, blk_len ^ 0xffffu, 16);
+                __syncthreads(); /* S6 */
+                {
+                    uint32_t c[8];
+                    if (tid * 8 < nb * DF_THREADS) {
+                        const uint4 q = *(const uint4 *)(smem + DF_OFF_SPN + tid * 16);
+                        c[0] = q.x & 0xffffu; c[1] = q.x >> 16; c[2] = q.y & 0xffffu; c[3] = q.y >> 16;
+                        c[4] = q.z & 0xffffu; c[5] = q.z >> 16; c[6] = q.w & 0xffffu; c[7] = q.w >> 16;
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 8; k++) c[k] = 0;
                     }
-                    for (uint32_t i = tid * 4; i < blk_len; i += DF_THREADS * 4) {
-                        uint32_t v = load32u(s_in, blk_start + i);
-                        uint32_t n = blk_len - i;
-                        stage_put(s_stage, (p0 + 4 + i) * 8, v, n >= 4 ? 32 : n * 8);
+                    uint32_t r[8], acc = 0;
+#pragma unroll
+                    for (int k = 0; k < 8; k++) { r[k] = acc; acc += c[k]; }
+                    const uint32_t mybase = block_excl_sum(acc, s_scan, tokbits); /* S7, S8 inside */
+                    *(uint4 *)(smem + DF_OFF_SPN + tid * 16) = make_uint4(r[0] | (r[1] << 16), r[2] | (r[3] << 16), r[4] | (r[5] << 16), r[6] | (r[7] << 16));
+                    s_bb[tid] = mybase;
+                }
+                __syncthreads(); /* S9: offsets visible */
+                const uint32_t hdrbits = DF_HDR_BITS;
+                const uint32_t eob = s_code_ll[256];
+                const uint32_t dyn_bits = hdrbits + tokbits + ((eob >> 16) & 15u);
+                const uint32_t stored_bits = (((bitpos + 3 + 7) & ~7u) - bitpos) + 32 + ulen * 8;
+                if (dyn_bits >= stored_bits) {
+                    stored = true;
+                } else {
+                    /* ---- F: emit. Literals of a span go through a bit accumulator in slot order; a match leaves a gap of
+                     * its size in that stream (its slot puts zeros) and is OR-ed in afterwards at the recorded position. ---- */
+                    const uint32_t base = bitpos + hdrbits;
+                    emit_block_header(s_stage, bitpos, bfinal, s_lens_ll, s_lens_d, tid);
+#pragma unroll
+                    for (int b = 0; b < DF_NBATCH; b++) {
+                        if ((uint32_t)b < nb) {
+                            const uint32_t sidx = (uint32_t)b * DF_THREADS + tid;
+                            const uint32_t F = fF[b], MA = fA[b], MB = fB[b];
+                            if ((F | MA | MB) == 0) continue;
+                            const uint2 x = sm.ld64(DF_OFF_IN + sidx * DF_SPAN);
+                            uint32_t pos = base + s_bb[sidx >> 3] + sm.ld16(DF_OFF_SPN + sidx * 2); /* bit position in the staging buffer */
+                            const uint32_t ex = (F >> 8) & 3u;
+                            if (ex) {
+                                const uint32_t c0 = sm.ld32(DF_OFF_CODE + ((F >> 16) & 0xffu) * 4);
+                                stage_or(sm, pos, c0 & 0x7fffu, (c0 >> 16) & 15u);
+                                pos += (c0 >> 16) & 15u;
+                                if (ex == 2) {
+                                    const uint32_t c1 = sm.ld32(DF_OFF_CODE + (F >> 24) * 4);
+                                    stage_or(sm, pos, c1 & 0x7fffu, (c1 >> 16) & 15u);
+                                    pos += (c1 >> 16) & 15u;
+                                }
+                            }
+                            const uint32_t nA = match_bits(sm, MA), nB = match_bits(sm, MB);
+                            const uint32_t slotA = MA ? (MA >> 28) & 7u : 8u, slotB = MB ? (MB >> 28) & 7u : 8u;
+                            uint32_t posA = 0, posB = 0;
+#pragma unroll
+                            for (int jj = 0; jj < 4; jj++) { /* two positions per step: two literals go out as one OR of <= 30 bits */
+                                const uint32_t xw = jj < 2 ? x.x : x.y;
+                                const uint32_t b0 = jj & 1 ? (xw >> 14) & 0x3fcu : (xw << 2) & 0x3fcu;   /* byte * 4 */
+                                const uint32_t b1 = jj & 1 ? (xw >> 22) & 0x3fcu : (xw >> 6) & 0x3fcu;
+                                const uint32_t cw0 = sm.ld32(DF_OFF_CODE + b0), cw1 = sm.ld32(DF_OFF_CODE + b1);
+                                const bool l0 = ((F >> (2 * jj)) & 1u) != 0, l1 = ((F >> (2 * jj + 1)) & 1u) != 0;
+                                const uint32_t n0 = l0 ? (cw0 >> 16) & 15u : 0u, n1 = l1 ? (cw1 >> 16) & 15u : 0u;
+                                const uint32_t g0 = slotA == 2u * jj ? nA : (slotB == 2u * jj ? nB : 0u);            /* a match ordered here leaves a gap */
+                                const uint32_t g1 = slotA == 2u * jj + 1 ? nA : (slotB == 2u * jj + 1 ? nB : 0u);
+                                posA = slotA == 2u * jj ? pos : (slotA == 2u * jj + 1 ? pos + n0 : posA);
+                                posB = slotB == 2u * jj ? pos : (slotB == 2u * jj + 1 ? pos + n0 : posB);
+                                /* at most the two literals are in-band, and then they are adjacent (a match start covers its neighbour) */
+                                const uint32_t v = (l0 ? cw0 & 0x7fffu : 0u) | ((l1 ? cw1 & 0x7fffu : 0u) << n0);
+                                const uint32_t sh = pos & 31u, wa = DF_OFF_STAGE + ((pos >> 5) << 2);
+                                if (l0 || l1) {
+                                    sm.red_or32(wa, v << sh);
+                                    if (sh + n0 + n1 > 32) sm.red_or32(wa + 4, v >> (32 - sh));
+                                }
+                                pos += n0 + n1 + g0 + g1;
+                            }
+                            if (MA) put_match_bits(sm, posA, MA);
+                            if (MB) put_match_bits(sm, posB, MB);
+                        }
                     }
-                    bitpos = (p0 + 4 + blk_len) * 8;
+                    if (tid == DF_THREADS - 1) stage_put(s_stage, base + tokbits, eob & 0x7fffu, (eob >> 16) & 15u);
+                    bitpos += dyn_bits;
+                }
+            } else {
+                /* level 0: staging was never a hash table, but it still has to be clean */
+                for (uint32_t i = tid; i < DF_STAGE_WORDS / 4; i += DF_THREADS) {
+                    if (i == 0) sm.st128(DF_OFF_STAGE, s_misc[MISC_CARRY], s_misc[MISC_CARRY + 1], s_misc[MISC_CARRY + 2], s_misc[MISC_CARRY + 3]);
+                    else sm.st128(DF_OFF_STAGE + i * 16, 0, 0, 0, 0);
                 }
                 __syncthreads();
-                /* ---- G: flush whole 16-byte units, carry the tail ------------------------------------ */
-                {
-                    const uint32_t n16 = bitpos >> 7;
-                    const uint32_t used_words = (bitpos + 31) >> 5;
-                    for (uint32_t i = tid; i < n16; i += DF_THREADS) ((uint4 *)(gout + flushed))[i] = ((const uint4 *)s_stage)[i];
-                    uint32_t carry = 0;
-                    if (tid < 4 && n16 * 4 + tid < used_words) carry = s_stage[n16 * 4 + tid];
-                    __syncthreads();
-                    for (uint32_t i = tid; i < used_words; i += DF_THREADS) s_stage[i] = 0;
-                    __syncthreads();
-                    if (tid < 4) s_stage[tid] = carry;
-                    bitpos -= n16 * 128;
-                    flushed += n16 * 16;
-                    __syncthreads();
+            }
+            if (stored) {
+                /* stored block: header, pad to byte, LEN, ~LEN, raw bytes */
+                const uint32_t p0 = (bitpos + 3 + 7) >> 3; /* byte index of LEN */
+                if (tid == 0) {
+                    stage_put(s_stage, bitpos, bfinal, 3);
+                    stage_put(s_stage, p0 * 8, ulen, 16);
+                    stage_put(s_stage, p0 * 8 + 16, ulen ^ 0xffffu, 16);
                 }
+                for (uint32_t i = tid * 4; i < ulen; i += DF_THREADS * 4) {
+                    uint32_t v = load32u(s_in, i);
+                    uint32_t n = ulen - i;
+                    stage_put(s_stage, (p0 + 4 + i) * 8, v, n >= 4 ? 32 : n * 8);
+                }
+                bitpos = (p0 + 4 + ulen) * 8;
+            }
+            __syncthreads();
+            /* ---- G: flush whole 16-byte units, carry the tail ------------------------------------ */
+            {
+                const uint32_t n16 = bitpos >> 7;
+                const uint32_t used_words = (bitpos + 31) >> 5;
+                for (uint32_t i = tid; i < n16; i += DF_THREADS) ((uint4 *)(gout + flushed))[i] = ((const uint4 *)s_stage)[i];
+                if (tid < 4) s_misc[MISC_CARRY + tid] = (n16 * 4 + tid < used_words) ? s_stage[n16 * 4 + tid] : 0u;
+                bitpos -= n16 * 128;
+                flushed += n16 * 16;
+                __syncthreads();
             }
         }
 
-        /* ---- chunk trailer ---------------------------------------------------------------------- */
+
+        /* ---- chunk trailer (the carried tail is in s_misc) -------------------------------------------- */
         {
+            uint32_t cw[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) cw[i] = s_misc[MISC_CARRY + i];
+            if (len == 0) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) cw[i] = s_stage[i];
+            }
             if (flags & DF_FLAG_FINAL) {
                 bitpos = (bitpos + 7) & ~7u;
             } else {
                 /* empty stored block: BFINAL=0 BTYPE=00, pad, LEN=0000 NLEN=FFFF (sync-flush marker) */
-                uint32_t p0 = (bitpos + 3 + 7) >> 3;
-                if (tid == 0) stage_put(s_stage, p0 * 8 + 16, 0xffffu, 16);
+                const uint32_t p0 = (bitpos + 3 + 7) >> 3; /* <= 16: the marker may spill into a second 16-byte unit */
                 bitpos = (p0 + 4) * 8;
+                if (tid == 0) {
+                    /* bytes p0+2, p0+3 = FF FF */
+                    uint32_t ext[8] = {cw[0], cw[1], cw[2], cw[3], 0, 0, 0, 0};
+                    for (uint32_t k = p0 + 2; k < p0 + 4; k++) ext[k >> 2] |= 0xffu << (8 * (k & 3));
+                    *(uint4 *)(gout + flushed) = make_uint4(ext[0], ext[1], ext[2], ext[3]);
+                    *(uint4 *)(gout + flushed + 16) = make_uint4(ext[4], ext[5], ext[6], ext[7]);
+                    P.out_len[chunk] = flushed + (bitpos >> 3);
+                }
             }
-            __syncthreads();
-            const uint32_t bytes = bitpos >> 3;
-            const uint32_t n16 = (bytes + 15) >> 4; /* slot has >= 16 bytes of slack */
-            for (uint32_t i = tid; i < n16; i += DF_THREADS) ((uint4 *)(gout + flushed))[i] = ((const uint4 *)s_stage)[i];
-            if (tid == 0) P.out_len[chunk] = flushed + bytes;
+            if ((flags & DF_FLAG_FINAL) && tid == 0) {
+                *(uint4 *)(gout + flushed) = make_uint4(cw[0], cw[1], cw[2], cw[3]);
+                P.out_len[chunk] = flushed + (bitpos >> 3);
+            }
             __syncthreads();
         }
     }
 }
 
-/* level -> (bucket ways, lazy) */
-__host__ __device__ inline int deflate_ways_for_level(int level) { return level <= 1 ? 1 : (level <= 3 ? 2 : 4); }
-__host__ __device__ inline bool deflate_lazy_for_level(int level) { return level >= 6; }
+/* level -> match-finder configuration: 1 = candidates looked up at even positions only (every position is still
+ * inserted), 2..3 = every position, 4..9 = every position + one-step lazy evaluation */
+__host__ __device__ inline int deflate_stride_for_level(int level) { return level <= 1 ? 2 : 1; }
+__host__ __device__ inline bool deflate_lazy_for_level(int level) { return level >= 4; }
 
 } // namespace mzc
 #endif

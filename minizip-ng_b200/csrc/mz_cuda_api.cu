@@ -114,10 +114,9 @@ int32_t get_ctx(DeviceCtx **out) {
             CK(cudaMalloc(&c.d_word_off, off.size() * 4));
             CK(cudaMemcpy(c.d_words, words.data(), words.size(), cudaMemcpyHostToDevice));
             CK(cudaMemcpy(c.d_word_off, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
-            CK(cudaFuncSetAttribute(deflate_chunks_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_SMEM_BYTES));
             CK(cudaFuncSetAttribute(deflate_chunks_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_SMEM_BYTES));
-            CK(cudaFuncSetAttribute(deflate_chunks_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_SMEM_BYTES));
-            CK(cudaFuncSetAttribute(deflate_chunks_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_SMEM_BYTES));
+            CK(cudaFuncSetAttribute(deflate_chunks_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_SMEM_BYTES));
+            CK(cudaFuncSetAttribute(deflate_chunks_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_SMEM_BYTES));
             CK(cudaFuncSetAttribute(crc32_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CRC_SMEM_BYTES));
             CK(cudaFuncSetAttribute(inflate_streams_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, INF_SMEM_BYTES));
             CK(cudaFuncSetAttribute(inflate_spec_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SPEC_RESOLVE_SMEM));
@@ -383,17 +382,14 @@ int32_t mz_cuda_deflate_chunks(const void *d_in, uint64_t total_len, uint32_t ch
         P.work_counter = c->d_work + (c->work_next++ & 255u);
     }
     CK(cudaMemsetAsync(P.work_counter, 0, sizeof(uint32_t), (cudaStream_t)stream));
-    uint32_t grid = nchunks < (uint32_t)c->sm_count ? nchunks : (uint32_t)c->sm_count;
-    const int ways = deflate_ways_for_level(level);
-    const bool lazy = deflate_lazy_for_level(level);
-    if (ways == 1)
-        MZ_LAUNCH((deflate_chunks_kernel<1, false>), dim3(grid), dim3(DF_THREADS), DF_SMEM_BYTES, (cudaStream_t)stream, P);
-    else if (ways == 2)
+    const uint32_t resident = (uint32_t)c->sm_count * 2u; /* two 512-thread CTAs of 111 KB shared memory per SM */
+    uint32_t grid = nchunks < resident ? nchunks : resident;
+    if (deflate_stride_for_level(level) == 2)
         MZ_LAUNCH((deflate_chunks_kernel<2, false>), dim3(grid), dim3(DF_THREADS), DF_SMEM_BYTES, (cudaStream_t)stream, P);
-    else if (!lazy)
-        MZ_LAUNCH((deflate_chunks_kernel<4, false>), dim3(grid), dim3(DF_THREADS), DF_SMEM_BYTES, (cudaStream_t)stream, P);
+    else if (!deflate_lazy_for_level(level))
+        MZ_LAUNCH((deflate_chunks_kernel<1, false>), dim3(grid), dim3(DF_THREADS), DF_SMEM_BYTES, (cudaStream_t)stream, P);
     else
-        MZ_LAUNCH((deflate_chunks_kernel<4, true>), dim3(grid), dim3(DF_THREADS), DF_SMEM_BYTES, (cudaStream_t)stream, P);
+        MZ_LAUNCH((deflate_chunks_kernel<1, true>), dim3(grid), dim3(DF_THREADS), DF_SMEM_BYTES, (cudaStream_t)stream, P);
     CK(cudaGetLastError());
     return MZ_OK;
 }

@@ -58,6 +58,13 @@ struct Smem {
     __device__ __forceinline__ void st16(uint32_t off, uint32_t v) const { *(uint16_t *)(b + off) = (uint16_t)v; }
     __device__ __forceinline__ void red_or32(uint32_t off, uint32_t v) const { *(uint32_t *)(b + off) |= v; }
     __device__ __forceinline__ void red_add32(uint32_t off, uint32_t v) const { *(uint32_t *)(b + off) += v; }
+    __device__ __forceinline__ void red_min32(uint32_t off, uint32_t v) const { uint32_t *p = (uint32_t *)(b + off); if (v < *p) *p = v; }
+    __device__ __forceinline__ void st16_if(bool p, uint32_t off, uint32_t v) const { if (p) st16(off, v); }
+    __device__ __forceinline__ void red_add32_if(bool p, uint32_t off, uint32_t v) const { if (p) red_add32(off, v); }
+    __device__ __forceinline__ void red_or32_if(bool p, uint32_t off, uint32_t v) const { if (p) red_or32(off, v); }
+    __device__ __forceinline__ uint2 ld64(uint32_t off) const { return *(const uint2 *)(b + off); }
+    __device__ __forceinline__ void st64(uint32_t off, uint32_t x, uint32_t y) const { *(uint2 *)(b + off) = make_uint2(x, y); }
+    __device__ __forceinline__ void st128(uint32_t off, uint32_t x, uint32_t y, uint32_t z, uint32_t w) const { *(uint4 *)(b + off) = make_uint4(x, y, z, w); }
 #else
     uint32_t b;
     __device__ __forceinline__ void init(uint8_t *base) {
@@ -83,6 +90,26 @@ struct Smem {
     __device__ __forceinline__ void st16(uint32_t off, uint32_t v) const { asm volatile("st.shared.u16 [%0], %1;" ::"r"(b + off), "r"(v) : "memory"); }
     __device__ __forceinline__ void red_or32(uint32_t off, uint32_t v) const { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(b + off), "r"(v) : "memory"); }
     __device__ __forceinline__ void red_add32(uint32_t off, uint32_t v) const { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(b + off), "r"(v) : "memory"); }
+    __device__ __forceinline__ void red_min32(uint32_t off, uint32_t v) const { asm volatile("red.shared.min.u32 [%0], %1;" ::"r"(b + off), "r"(v) : "memory"); }
+    /* predicated forms: one instruction under a predicate instead of a branch around an asm statement */
+    __device__ __forceinline__ void st16_if(bool p, uint32_t off, uint32_t v) const {
+        asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q st.shared.u16 [%0], %1;\n}" ::"r"(b + off), "r"(v), "r"((uint32_t)p) : "memory");
+    }
+    __device__ __forceinline__ void red_add32_if(bool p, uint32_t off, uint32_t v) const {
+        asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q red.shared.add.u32 [%0], %1;\n}" ::"r"(b + off), "r"(v), "r"((uint32_t)p) : "memory");
+    }
+    __device__ __forceinline__ void red_or32_if(bool p, uint32_t off, uint32_t v) const {
+        asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q red.shared.or.b32 [%0], %1;\n}" ::"r"(b + off), "r"(v), "r"((uint32_t)p) : "memory");
+    }
+    __device__ __forceinline__ uint2 ld64(uint32_t off) const {
+        uint2 v;
+        asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(b + off));
+        return v;
+    }
+    __device__ __forceinline__ void st64(uint32_t off, uint32_t x, uint32_t y) const { asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(b + off), "r"(x), "r"(y) : "memory"); }
+    __device__ __forceinline__ void st128(uint32_t off, uint32_t x, uint32_t y, uint32_t z, uint32_t w) const {
+        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(b + off), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+    }
 #endif
     /* unaligned little-endian 32-bit load at byte offset `off + p` (region base `off` is 4-byte aligned) */
     __device__ __forceinline__ uint32_t ld32u(uint32_t off, uint32_t p) const {

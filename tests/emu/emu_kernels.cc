@@ -54,11 +54,9 @@ int64_t emu_deflate(const uint8_t *in, uint64_t len, uint32_t chunk_size, int le
     P.work_counter = (grid & 0x80000000u) ? nullptr : &work_counter; /* high bit of grid selects static striding */
     grid &= 0x7fffffffu;
     if (grid == 0 || grid > nchunks) grid = nchunks;
-    const int ways = deflate_ways_for_level(level);
-    if (ways == 1) MZ_LAUNCH((deflate_chunks_kernel<1, false>), dim3(grid), dim3(DF_THREADS), DF_SMEM_BYTES, 0, P);
-    else if (ways == 2) MZ_LAUNCH((deflate_chunks_kernel<2, false>), dim3(grid), dim3(DF_THREADS), DF_SMEM_BYTES, 0, P);
-    else if (!deflate_lazy_for_level(level)) MZ_LAUNCH((deflate_chunks_kernel<4, false>), dim3(grid), dim3(DF_THREADS), DF_SMEM_BYTES, 0, P);
-    else MZ_LAUNCH((deflate_chunks_kernel<4, true>), dim3(grid), dim3(DF_THREADS), DF_SMEM_BYTES, 0, P);
+    if (deflate_stride_for_level(level) == 2) MZ_LAUNCH((deflate_chunks_kernel<2, false>), dim3(grid), dim3(DF_THREADS), DF_SMEM_BYTES, 0, P);
+    else if (!deflate_lazy_for_level(level)) MZ_LAUNCH((deflate_chunks_kernel<1, false>), dim3(grid), dim3(DF_THREADS), DF_SMEM_BYTES, 0, P);
+    else MZ_LAUNCH((deflate_chunks_kernel<1, true>), dim3(grid), dim3(DF_THREADS), DF_SMEM_BYTES, 0, P);
     MZ_LAUNCH(scan_lengths_kernel, dim3(1), dim3(SCAN_THREADS), 0, 0, (const uint32_t *)out_len.data(), nchunks, (uint64_t)0, offs.data());
     if (offs[nchunks] > dst_cap) return -5;
     MZ_LAUNCH(gather_slots_kernel, dim3(nchunks < 8 ? nchunks : 8), dim3(GATHER_THREADS), 0, 0, (const uint8_t *)sl, stride,
