@@ -126,9 +126,6 @@ int32_t mz_cuda_inflate_spec_round(const void *d_in, uint64_t in_base, uint64_t 
                                    uint64_t out_end, void *d_workspace, uint32_t max_segments, mz_cuda_spec_summary *d_summary,
                                    void *stream);
 
-/* ---- bench/test support: synthetic enwik-style text on the device -------------------------- */
-int32_t mz_cuda_textgen(void *d_out, uint64_t nbytes, uint64_t seed, void *stream);
-
 #ifdef __cplusplus
 }
 #endif

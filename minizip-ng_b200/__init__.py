@@ -50,7 +50,7 @@ EXPORTS = [
     "mz_cuda_memset", "mz_cuda_host_is_pinned", "mz_cuda_stream_sync", "mz_cuda_stream_create", "mz_cuda_stream_destroy",
     "mz_cuda_event_create", "mz_cuda_event_destroy", "mz_cuda_event_record", "mz_cuda_event_sync", "mz_cuda_event_elapsed_ms",
     "mz_cuda_crc32_segments", "mz_cuda_crc32_fold", "mz_cuda_crc32_device", "mz_cuda_crc32_device_stream", "mz_cuda_crc32_combine",
-    "mz_cuda_deflate_slot_bound", "mz_cuda_deflate_chunks", "mz_cuda_concat", "mz_cuda_inflate_streams", "mz_cuda_textgen",
+    "mz_cuda_deflate_slot_bound", "mz_cuda_deflate_chunks", "mz_cuda_concat", "mz_cuda_inflate_streams",
     "mz_cuda_inflate_spec_workspace_bytes", "mz_cuda_inflate_spec_round",
     # include/mz_zip_cuda.h
     "mz_zip_cuda_add_buffers", "mz_zip_cuda_extract_all", "mz_zip_cuda_abi_file_info_size",
@@ -123,7 +123,6 @@ def configure(L):
     sig("mz_cuda_deflate_chunks", i32, [vp, u64, u32, vp, vp, vp, u32, u32, i32, vp, u64, vp, vp])
     sig("mz_cuda_concat", i32, [vp, u64, vp, u32, vp, vp, vp])
     sig("mz_cuda_inflate_streams", i32, [vp, vp, u32, vp])
-    sig("mz_cuda_textgen", i32, [vp, u64, u64, vp])
     return L
 
 
@@ -197,16 +196,6 @@ def crc32_device(tensor, nbytes=None, value=0):
     n = tensor.numel() * tensor.element_size() if nbytes is None else nbytes
     check(lib.mz_cuda_crc32_device(tensor.data_ptr(), n, value, C.byref(out)), "crc32_device")
     return out.value
-
-
-def textgen(nbytes, seed=1, out=None):
-    """Synthetic enwik-style text generated on the current CUDA device (bench/test input)."""
-    import torch
-    lib = load()
-    if out is None:
-        out = torch.empty(nbytes, dtype=torch.uint8, device=torch.device("cuda", torch.cuda.current_device()))
-    check(lib.mz_cuda_textgen(out.data_ptr(), nbytes, seed, _stream_ptr()), "textgen")
-    return out
 
 
 def inflate_device(comp, out_cap):

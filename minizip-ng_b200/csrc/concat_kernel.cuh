@@ -69,47 +69,5 @@ __global__ void __launch_bounds__(GATHER_THREADS) gather_slots_kernel(const uint
     }
 }
 
-/* ---- synthetic "enwik-style" text generator (bench / test support) ----
- * Zipf(1)-like draws from a fixed vocabulary joined by spaces, ~2% markup/newline/digit tokens.
- * One thread fills one 256-byte piece, seeded by (seed, piece index): deterministic and position-independent. */
-constexpr int TEXT_PIECE = 256;
-__device__ __forceinline__ uint32_t tg_next(uint64_t &s) { /* splitmix-style */
-    s += 0x9E3779B97F4A7C15ull;
-    uint64_t z = s;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return (uint32_t)((z ^ (z >> 31)) >> 32);
-}
-__global__ void __launch_bounds__(256) textgen_kernel(uint8_t *out, uint64_t nbytes, uint64_t seed, const uint8_t *words,
-                                                      const uint32_t *word_off, uint32_t nwords) {
-    const float lnw = __log2f((float)nwords);
-    const uint64_t npieces = (nbytes + TEXT_PIECE - 1) / TEXT_PIECE;
-    for (uint64_t piece = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; piece < npieces; piece += (uint64_t)gridDim.x * blockDim.x) {
-        uint64_t s = seed * 0xD1342543DE82EF95ull + piece * 0x2545F4914F6CDD1Dull + 1;
-        uint8_t *p = out + piece * TEXT_PIECE;
-        uint32_t room = (uint32_t)(nbytes - piece * TEXT_PIECE < TEXT_PIECE ? nbytes - piece * TEXT_PIECE : TEXT_PIECE);
-        uint32_t pos = 0;
-        while (pos < room) {
-            uint32_t r = tg_next(s);
-            float u = (float)(r >> 8) * (1.0f / 16777216.0f);
-            uint32_t rank = (uint32_t)exp2f(u * lnw);
-            if (rank >= nwords) rank = nwords - 1;
-            uint32_t a = word_off[rank], b = word_off[rank + 1];
-            for (uint32_t i = a; i < b && pos < room; i++) p[pos++] = words[i];
-            uint32_t m = r & 255;
-            if (m < 3 && pos < room) p[pos++] = '.';
-            if (m == 0 && pos < room) p[pos++] = '\n';
-            else if (m == 1) {
-                uint32_t d = tg_next(s);
-                if (pos < room) p[pos++] = ' ';
-                if (pos < room) p[pos++] = '<';
-                for (int k = 0; k < 4 && pos < room; k++) { p[pos++] = (uint8_t)('0' + d % 10); d /= 10; }
-                if (pos < room) p[pos++] = '>';
-            }
-            if (pos < room) p[pos++] = ' ';
-        }
-    }
-}
-
 } // namespace mzc
 #endif

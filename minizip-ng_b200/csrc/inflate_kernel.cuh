@@ -644,7 +644,15 @@ __global__ void __launch_bounds__(INF_THREADS) inflate_streams_kernel(const Infl
     InfTables &T = *reinterpret_cast<InfTables *>(smem);
     for (;;) {
         const uint32_t sidx = inf_next_work(work_counter);
-        if (sidx >= nstreams) break;
+        if (sidx >= nstreams) {
+            /* the last warp out puts the counter pair back to zero: the launch needs no memset, and the slot is clean for its
+             * next user (work_counter[1] counts the warps that have left; every CTA is one warp) */
+            if (lane_id() == 0 && atomicAdd(work_counter + 1, 1u) == gridDim.x - 1) {
+                work_counter[0] = 0;
+                work_counter[1] = 0;
+            }
+            break;
+        }
         const InflateJob job = jobs[sidx];
         InflateState *st = &states[sidx];
         if (st->status != INF_ST_RUN) continue;

@@ -1,15 +1,22 @@
 /* mz_crypt_cuda.c -- replacement for mz_crypt_crc32_update (mz_crypt.c:35-92).
  *
  * Same contract: `value` is the running CRC-32 (starts at 0, chains), inversion happens inside
- * (mz_crypt.c:81,90); size 0 returns value unchanged (mz_os.c:340 relies on it).
+ * (mz_crypt.c:81,90); size 0 returns value unchanged (mz_os.c:340 relies on it). Like the reference
+ * function it is re-entrant: any number of threads may call it at once with different buffers.
  *
- * Large buffers go to the K1 kernel (include/mz_cuda_batch.h). Tiny ones do not: the reference calls
- * this once per byte from the PKWARE key schedule (mz_strm_pkcrypt.c:79,86) and once per <=64 KiB from
- * the zip entry loop (mz_zip.c:2049,2064); a PCIe round trip per call would be absurd, so calls below
- * MZ_CUDA_CRC_MIN_BYTES (default 1 MiB) are answered by the same ten-line table loop the reference
- * keeps for builds without zlib (mz_crypt.c:81-90). That loop is the only host arithmetic in the
+ * Large buffers go to the K1 kernel (include/mz_cuda_batch.h) in 8 MiB pieces: the copy of piece k+1 into
+ * pinned staging overlaps the upload and the kernels of piece k, the pieces' CRCs are folded on the host
+ * (mz_cuda_crc32_combine). The staging (two pinned + two device buffers, a stream, two events, per DEVICE)
+ * is used by one caller at a time (mutex held over the whole call).
+ *
+ * Tiny buffers do not go to the GPU: the reference calls this once per byte from the PKWARE key schedule
+ * (mz_strm_pkcrypt.c:79,86) and once per <=64 KiB from the zip entry loop (mz_zip.c:2049,2064); a PCIe
+ * round trip per call would be absurd, so calls below MZ_CUDA_CRC_MIN_BYTES (default 1 MiB) are answered
+ * on the host by a slice-by-16 table loop (the table-driven form of mz_crypt.c:81-90, 16 bytes per step so
+ * that the zip path is not slower than with zlib's crc32). That loop is the only host arithmetic in the
  * product and it is stated here, in DESIGN.md and in include/mz_strm_cuda.h.
  */
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -18,79 +25,143 @@
 #include "mz_cuda_batch.h"
 #include "mz_strm_cuda.h"
 
-static uint32_t g_tab[256];
-static int g_tab_ready;
+/* ---- host path: slice-by-16 ------------------------------------------------------------------------------ */
+static uint32_t g_tab[16][256];
+static pthread_once_t g_tab_once = PTHREAD_ONCE_INIT;
 
 static void tab_init(void) {
     for (uint32_t n = 0; n < 256; n++) {
         uint32_t c = n;
         for (int k = 0; k < 8; k++)
             c = (c & 1) ? (0xEDB88320u ^ (c >> 1)) : (c >> 1);
-        g_tab[n] = c;
+        g_tab[0][n] = c;
     }
-    g_tab_ready = 1;
+    for (uint32_t n = 0; n < 256; n++)
+        for (int k = 1; k < 16; k++)
+            g_tab[k][n] = (g_tab[k - 1][n] >> 8) ^ g_tab[0][g_tab[k - 1][n] & 0xFF];
 }
 
-static uint32_t crc_small(uint32_t value, const uint8_t *buf, int32_t size) {
-    if (!g_tab_ready)
-        tab_init();
-    value = ~value;
+static inline uint32_t ld32le(const uint8_t *p) {
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+
+static uint32_t crc_small(uint32_t value, const uint8_t *buf, size_t size) {
+    pthread_once(&g_tab_once, tab_init);
+    uint32_t c = ~value;
+    while (size >= 16) {
+        const uint32_t a = ld32le(buf) ^ c, b = ld32le(buf + 4), d = ld32le(buf + 8), e = ld32le(buf + 12);
+        c = g_tab[15][a & 0xFF] ^ g_tab[14][(a >> 8) & 0xFF] ^ g_tab[13][(a >> 16) & 0xFF] ^ g_tab[12][a >> 24] ^
+            g_tab[11][b & 0xFF] ^ g_tab[10][(b >> 8) & 0xFF] ^ g_tab[9][(b >> 16) & 0xFF] ^ g_tab[8][b >> 24] ^
+            g_tab[7][d & 0xFF] ^ g_tab[6][(d >> 8) & 0xFF] ^ g_tab[5][(d >> 16) & 0xFF] ^ g_tab[4][d >> 24] ^
+            g_tab[3][e & 0xFF] ^ g_tab[2][(e >> 8) & 0xFF] ^ g_tab[1][(e >> 16) & 0xFF] ^ g_tab[0][e >> 24];
+        buf += 16;
+        size -= 16;
+    }
     while (size > 0) {
-        value = (value >> 8) ^ g_tab[(value ^ *buf) & 0xFF];
+        c = (c >> 8) ^ g_tab[0][(c ^ *buf) & 0xFF];
         buf += 1;
         size -= 1;
     }
-    return ~value;
+    return ~c;
 }
 
+/* ---- device path: per-device staging, one caller at a time ---------------------------------------------------- */
+#define CRC_PIECE ((size_t)8 << 20)
+#define CRC_SEG ((uint64_t)16384)
+#define CRC_MAX_DEV 16
+#define CRC_MAX_PIECES 256 /* 2 GiB / 8 MiB */
+
+typedef struct crc_dev {
+    pthread_mutex_t mu;
+    int ready;
+    void *stream;
+    void *ev[2];
+    uint8_t *dev[2];
+    uint8_t *pin[2];
+    uint32_t *d_res[2]; /* per slot: residues of the piece's segments + 2 words of fold output */
+    uint32_t *h_out;    /* pinned: 2 words per piece */
+} crc_dev;
+
+static crc_dev g_devs[CRC_MAX_DEV];
+static pthread_once_t g_dev_once = PTHREAD_ONCE_INIT;
 static int64_t g_min_bytes = -1;
-static uint8_t *g_dev;    /* device staging, grown on demand */
-static uint8_t *g_pinned; /* pinned bounce buffer for pageable callers */
-static size_t g_cap;
-#define CRC_PIECE ((size_t)64 << 20)
+
+static void dev_init_all(void) {
+    for (int i = 0; i < CRC_MAX_DEV; i++)
+        pthread_mutex_init(&g_devs[i].mu, NULL);
+    const char *v = getenv("MZ_CUDA_CRC_MIN_BYTES");
+    int64_t m = (v && *v) ? atoll(v) : (1 << 20);
+    g_min_bytes = m < 0 ? (1 << 20) : m;
+}
+
+static void die(const char *what) {
+    fprintf(stderr, "mz_crypt_crc32_update: %s: %s\n", what, mz_cuda_last_error());
+    abort(); /* there is no error return in this contract, and a wrong CRC would be worse than a loud stop */
+}
+
+static void dev_prepare(crc_dev *d) { /* called with d->mu held */
+    if (d->ready)
+        return;
+    const size_t nres = (size_t)(CRC_PIECE / CRC_SEG) + 8;
+    d->stream = mz_cuda_stream_create();
+    for (int s = 0; s < 2; s++) {
+        d->ev[s] = mz_cuda_event_create();
+        d->dev[s] = (uint8_t *)mz_cuda_malloc(CRC_PIECE + 64);
+        d->pin[s] = (uint8_t *)mz_cuda_host_alloc(CRC_PIECE);
+        d->d_res[s] = (uint32_t *)mz_cuda_malloc(nres * 4);
+    }
+    d->h_out = (uint32_t *)mz_cuda_host_alloc(CRC_MAX_PIECES * 8);
+    if (!d->stream || !d->ev[0] || !d->ev[1] || !d->dev[0] || !d->dev[1] || !d->pin[0] || !d->pin[1] || !d->d_res[0] || !d->d_res[1] || !d->h_out)
+        die("cannot allocate the staging buffers");
+    d->ready = 1;
+}
 
 uint32_t mz_crypt_crc32_update(uint32_t value, const uint8_t *buf, int32_t size) {
     if (size <= 0 || !buf)
         return value;
-    if (g_min_bytes < 0) {
-        const char *v = getenv("MZ_CUDA_CRC_MIN_BYTES");
-        g_min_bytes = (v && *v) ? atoll(v) : (1 << 20);
-        if (g_min_bytes < 0)
-            g_min_bytes = 1 << 20;
-    }
+    pthread_once(&g_dev_once, dev_init_all);
     if ((int64_t)size < g_min_bytes)
-        return crc_small(value, buf, size);
+        return crc_small(value, buf, (size_t)size);
     if (mz_cuda_init() != MZ_OK) {
         fprintf(stderr, "mz_crypt_crc32_update: no usable sm_100 GPU (%s); refusing to fall back on the CPU for %d bytes\n",
                 mz_cuda_last_error(), size);
         abort();
     }
-    size_t need = (size_t)size < CRC_PIECE ? (size_t)size : CRC_PIECE;
-    if (g_cap < need) {
-        mz_cuda_free(g_dev);
-        mz_cuda_host_free(g_pinned);
-        g_dev = (uint8_t *)mz_cuda_malloc(need + 64);
-        g_pinned = (uint8_t *)mz_cuda_host_alloc(need);
-        g_cap = (g_dev && g_pinned) ? need : 0;
-        if (!g_cap) {
-            fprintf(stderr, "mz_crypt_crc32_update: cannot allocate %zu bytes of staging\n", need);
-            abort();
-        }
-    }
-    int pinned = mz_cuda_host_is_pinned(buf);
-    size_t pos = 0;
-    while (pos < (size_t)size) {
-        size_t n = (size_t)size - pos < g_cap ? (size_t)size - pos : g_cap;
-        const uint8_t *src = buf + pos;
+    const int ord = mz_cuda_get_device();
+    if (ord < 0 || ord >= CRC_MAX_DEV)
+        die("unexpected device ordinal");
+    crc_dev *d = &g_devs[ord];
+    pthread_mutex_lock(&d->mu);
+    dev_prepare(d);
+    const int pinned = mz_cuda_host_is_pinned(buf);
+    const size_t total = (size_t)size;
+    const uint32_t npieces = (uint32_t)((total + CRC_PIECE - 1) / CRC_PIECE);
+    for (uint32_t i = 0; i < npieces; i++) {
+        const int s = (int)(i & 1);
+        const size_t off = (size_t)i * CRC_PIECE;
+        const size_t n = total - off < CRC_PIECE ? total - off : CRC_PIECE;
+        const uint32_t nseg = (uint32_t)((n + CRC_SEG - 1) / CRC_SEG);
+        const uint8_t *src = buf + off;
+        if (i >= 2 && mz_cuda_event_sync(d->ev[s]) != MZ_OK) /* the slot's previous piece has left the staging */
+            die("event sync");
         if (!pinned) {
-            memcpy(g_pinned, src, n);
-            src = g_pinned;
+            memcpy(d->pin[s], src, n);
+            src = d->pin[s];
         }
-        if (mz_cuda_memcpy_h2d(g_dev, src, n, NULL) != MZ_OK || mz_cuda_crc32_device(g_dev, n, value, &value) != MZ_OK) {
-            fprintf(stderr, "mz_crypt_crc32_update: CUDA failure: %s\n", mz_cuda_last_error());
-            abort();
-        }
-        pos += n;
+        if (mz_cuda_memcpy_h2d(d->dev[s], src, n, d->stream) != MZ_OK ||
+            mz_cuda_crc32_segments(d->dev[s], n, CRC_SEG, NULL, NULL, nseg, d->d_res[s], NULL, d->stream) != MZ_OK ||
+            mz_cuda_crc32_fold(d->d_res[s], nseg, CRC_SEG, n, d->d_res[s] + nseg, d->stream) != MZ_OK ||
+            mz_cuda_memcpy_d2h(d->h_out + 2 * i, d->d_res[s] + nseg, 8, d->stream) != MZ_OK ||
+            mz_cuda_event_record(d->ev[s], d->stream) != MZ_OK)
+            die("CUDA failure");
     }
+    if (mz_cuda_stream_sync(d->stream) != MZ_OK)
+        die("stream sync");
+    for (uint32_t i = 0; i < npieces; i++) {
+        const size_t off = (size_t)i * CRC_PIECE;
+        const size_t n = total - off < CRC_PIECE ? total - off : CRC_PIECE;
+        value = mz_cuda_crc32_combine(value, d->h_out[2 * i + 1], n); /* crc(v, A) (+) crc(0, B) -> crc(v, A || B) */
+    }
+    pthread_mutex_unlock(&d->mu);
     return value;
 }

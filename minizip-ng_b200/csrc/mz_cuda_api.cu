@@ -34,16 +34,17 @@ struct DeviceCtx {
     bool ready = false;
     int sm_count = 0;
     CrcConsts *d_consts = nullptr;
-    uint8_t *d_words = nullptr;
-    uint32_t *d_word_off = nullptr;
-    uint32_t nwords = 0;
     uint32_t *d_crc_scratch = nullptr; /* residues for mz_cuda_crc32_device */
-    uint32_t *d_work = nullptr;        /* ring of work counters for dynamically scheduled launches */
+    uint32_t *d_work = nullptr;        /* ring of work-counter pairs for dynamically scheduled launches */
     unsigned work_next = 0;
     size_t crc_scratch_n = 0;
 };
 
 constexpr int kMaxDev = 16;
+/* work-counter pairs for dynamically scheduled launches. A launch takes the next pair of the ring; the kernel's last CTA
+ * leaves it zeroed, so a pair is only ever shared if more than kWorkRing launches are in flight on one device at once
+ * (the driver's launch queue is far shorter). */
+constexpr unsigned kWorkRing = 4096;
 DeviceCtx g_dev[kMaxDev];
 std::mutex g_mu;
 std::mutex g_crc_mu;
@@ -60,26 +61,6 @@ int32_t fail(cudaError_t e, const char *what) {
         cudaError_t e_ = (call);                       \
         if (e_ != cudaSuccess) return fail(e_, #call); \
     } while (0)
-
-/* vocabulary for the text generator: 50k pseudo-words of 2..10 lowercase letters, fixed seed */
-void make_vocab(std::vector<uint8_t> &words, std::vector<uint32_t> &off, uint32_t n) {
-    uint64_t s = 1234;
-    off.resize(n + 1);
-    for (uint32_t i = 0; i < n; i++) {
-        off[i] = (uint32_t)words.size();
-        s = s * 6364136223846793005ull + 1442695040888963407ull;
-        uint32_t len = 2 + (uint32_t)((s >> 33) % 9);
-        for (uint32_t k = 0; k < len; k++) {
-            s = s * 6364136223846793005ull + 1442695040888963407ull;
-            /* skewed letter frequencies so words share n-grams like a natural language */
-            uint32_t r = (uint32_t)(s >> 40) % 100;
-            static const char alpha[] = "etaoinshrdlcumwfgypbvkjxqz";
-            uint32_t idx = r < 60 ? r % 8 : (r < 90 ? 8 + r % 10 : 18 + r % 8);
-            words.push_back((uint8_t)alpha[idx]);
-        }
-    }
-    off[n] = (uint32_t)words.size();
-}
 
 int32_t get_ctx(DeviceCtx **out) {
     int dev = 0;
@@ -106,14 +87,6 @@ int32_t get_ctx(DeviceCtx **out) {
             c.sm_count = prop.multiProcessorCount;
             CK(cudaMalloc(&c.d_consts, sizeof(CrcConsts)));
             CK(cudaMemcpy(c.d_consts, &g_consts, sizeof(CrcConsts), cudaMemcpyHostToDevice));
-            std::vector<uint8_t> words;
-            std::vector<uint32_t> off;
-            make_vocab(words, off, 50000);
-            c.nwords = 50000;
-            CK(cudaMalloc(&c.d_words, words.size()));
-            CK(cudaMalloc(&c.d_word_off, off.size() * 4));
-            CK(cudaMemcpy(c.d_words, words.data(), words.size(), cudaMemcpyHostToDevice));
-            CK(cudaMemcpy(c.d_word_off, off.data(), off.size() * 4, cudaMemcpyHostToDevice));
             CK(cudaFuncSetAttribute(deflate_chunks_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_SMEM_BYTES));
             CK(cudaFuncSetAttribute(deflate_chunks_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_SMEM_BYTES));
             CK(cudaFuncSetAttribute(deflate_chunks_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_SMEM_BYTES));
@@ -123,7 +96,8 @@ int32_t get_ctx(DeviceCtx **out) {
             CK(cudaFuncSetAttribute(inflate_spec_compose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SPEC_COMPOSE_SMEM));
             CK(cudaFuncSetAttribute(inflate_spec_link_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
             CK(cudaFuncSetAttribute(inflate_spec_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SPEC_MAX_SEGMENTS * 16));
-            CK(cudaMalloc(&c.d_work, 256 * sizeof(uint32_t)));
+            CK(cudaMalloc(&c.d_work, kWorkRing * 2 * sizeof(uint32_t)));
+            CK(cudaMemset(c.d_work, 0, kWorkRing * 2 * sizeof(uint32_t)));
             c.ready = true;
         }
     }
@@ -379,9 +353,8 @@ int32_t mz_cuda_deflate_chunks(const void *d_in, uint64_t total_len, uint32_t ch
     P.out_len = d_out_len;
     {
         std::lock_guard<std::mutex> lk(g_mu);
-        P.work_counter = c->d_work + (c->work_next++ & 255u);
+        P.work_counter = c->d_work + 2 * (c->work_next++ % kWorkRing);
     }
-    CK(cudaMemsetAsync(P.work_counter, 0, sizeof(uint32_t), (cudaStream_t)stream));
     const uint32_t resident = (uint32_t)c->sm_count * 2u; /* two 512-thread CTAs of 111 KB shared memory per SM */
     uint32_t grid = nchunks < resident ? nchunks : resident;
     if (deflate_stride_for_level(level) == 2)
@@ -419,9 +392,8 @@ int32_t mz_cuda_inflate_streams(const mz_cuda_inflate_job *d_jobs, mz_cuda_infla
     uint32_t *counter;
     {
         std::lock_guard<std::mutex> lk(g_mu);
-        counter = c->d_work + (c->work_next++ & 255u);
+        counter = c->d_work + 2 * (c->work_next++ % kWorkRing);
     }
-    CK(cudaMemsetAsync(counter, 0, sizeof(uint32_t), (cudaStream_t)stream));
     MZ_LAUNCH(inflate_streams_kernel, dim3(grid), dim3(INF_THREADS), INF_SMEM_BYTES, (cudaStream_t)stream, (const InflateJob *)d_jobs,
               (InflateState *)d_states, nstreams, counter);
     CK(cudaGetLastError());
@@ -496,20 +468,6 @@ int32_t mz_cuda_inflate_spec_round(const void *d_in, uint64_t in_base, uint64_t 
         fprintf(stderr, "mz_cuda: K6 kernels ms: find %.3f scan %.3f chain %.3f compose+link+resolve %.3f emit %.3f (%u segments)\n", t[0], t[1], t[2], t[3], t[4], nseg);
         for (int i = 0; i < 6; i++) cudaEventDestroy(ev[i]);
     }
-    return MZ_OK;
-}
-
-int32_t mz_cuda_textgen(void *d_out, uint64_t nbytes, uint64_t seed, void *stream) {
-    DeviceCtx *c;
-    int32_t err = get_ctx(&c);
-    if (err) return err;
-    if (nbytes == 0) return MZ_OK;
-    uint64_t pieces = (nbytes + TEXT_PIECE - 1) / TEXT_PIECE;
-    uint64_t blocks = (pieces + 255) / 256;
-    uint32_t grid = blocks < (uint64_t)c->sm_count * 32 ? (uint32_t)blocks : (uint32_t)c->sm_count * 32u;
-    MZ_LAUNCH(textgen_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (uint8_t *)d_out, nbytes, seed, (const uint8_t *)c->d_words,
-              (const uint32_t *)c->d_word_off, c->nwords);
-    CK(cudaGetLastError());
     return MZ_OK;
 }
 

@@ -43,6 +43,7 @@ typedef struct cu_slot_s {
 } cu_slot;
 
 typedef struct cu_ws_s {
+    int device; /* CUDA device the buffers, streams and events belong to */
     struct cu_ws_s *next;
     int kind; /* 1 write, 2 read */
     size_t batch;
@@ -115,13 +116,15 @@ static void ws_destroy(cu_ws *w) {
     free(w);
 }
 
+#define CU_POOL_MAX 8
 static cu_ws *ws_acquire(int kind) {
     cu_ws *w = NULL, **pp;
     size_t batch = env_size("MZ_CUDA_BATCH_KB", 32u << 20, 1024);
     batch = (batch + CU_CHUNK - 1) / CU_CHUNK * CU_CHUNK;
+    const int device = mz_cuda_get_device();
     pthread_mutex_lock(&g_pool_mu);
     for (pp = &g_pool; *pp; pp = &(*pp)->next)
-        if ((*pp)->kind == kind && (*pp)->batch == batch) {
+        if ((*pp)->kind == kind && (*pp)->batch == batch && (*pp)->device == device) { /* never hand out another device's workspace */
             w = *pp;
             *pp = w->next;
             break;
@@ -134,6 +137,7 @@ static cu_ws *ws_acquire(int kind) {
         return NULL;
     w->kind = kind;
     w->batch = batch;
+    w->device = device;
     if (kind == 1) {
         w->max_chunks = (uint32_t)(batch / CU_CHUNK);
         w->slot_stride = mz_cuda_deflate_slot_bound(CU_CHUNK);
@@ -197,10 +201,22 @@ static void ws_release(cu_ws *w) {
         }
         w->cur = 0;
     }
+    /* keep the pool bounded: at most CU_POOL_MAX idle workspaces per kind, and at most one of the big read workspaces
+     * (128 MiB pinned + ~640 MiB device, taken by one long stream) -- the rest is given back */
+    int same = 0, large = 0;
     pthread_mutex_lock(&g_pool_mu);
-    w->next = g_pool;
-    g_pool = w;
+    for (cu_ws *q = g_pool; q; q = q->next) {
+        same += q->kind == w->kind;
+        large += q->kind == 2 && q->large;
+    }
+    const int keep = same < CU_POOL_MAX && !(w->kind == 2 && w->large && large >= 1);
+    if (keep) {
+        w->next = g_pool;
+        g_pool = w;
+    }
     pthread_mutex_unlock(&g_pool_mu);
+    if (!keep)
+        ws_destroy(w);
 }
 
 /* ---- the stream object ------------------------------------------------------------------------------ */
@@ -908,10 +924,18 @@ static int32_t cu_decode_more(mz_stream_cuda *cu) {
         uint64_t need = w->d_spec ? w->win_cap / 2 : 65536;
         if (out_pos - cu->win_base + need > w->win_cap) {
             uint64_t keep = out_pos - cu->win_base < 32768 ? out_pos - cu->win_base : 32768;
-            /* ranges cannot overlap: the window is much larger than 64 KiB */
-            err = mz_cuda_memcpy_d2d(w->d_win, w->d_win + (out_pos - cu->win_base - keep), keep, w->rstream);
-            if (err)
-                return err;
+            /* cudaMemcpy of overlapping ranges is undefined: with a tiny window (MZ_CUDA_BATCH_KB <= 64) source and
+             * destination can overlap, then move front to back in pieces no longer than the gap between them */
+            const uint64_t gap = out_pos - cu->win_base - keep;
+            for (uint64_t o = 0; gap > 0 && o < keep;) {
+                uint64_t k = keep - o;
+                if (gap < keep && k > gap)
+                    k = gap;
+                err = mz_cuda_memcpy_d2d(w->d_win + o, w->d_win + gap + o, k, w->rstream);
+                if (err)
+                    return err;
+                o += k;
+            }
             cu->win_base = out_pos - keep;
         }
         if (cu_spec_eligible(cu)) {
@@ -998,6 +1022,17 @@ int32_t mz_stream_cuda_read(void *stream, void *buf, int32_t size) {
     }
     if (done == 0 && cu->error != 0)
         return cu->error;
+    /* zlib reaches Z_STREAM_END in the call that hands out the last byte, so TOTAL_IN is final and the trailer is checked
+     * by then (mz_zip_entry_read_close compares TOTAL_IN with the compressed size right after reading exactly the
+     * uncompressed size, mz_zip.c:2100-2128). Do the same: when everything decoded has been delivered and the decoder
+     * stands at the end of the stream, finish now instead of on an extra read() call. A bad trailer surfaces on the
+     * next call, like every other error that follows cleanly decoded bytes. */
+    if (cu->error == 0 && !cu->ended && cu->ws && cu->hdr_parsed && cu->dec_pos == cu->dec_len && !cu->ws->pending &&
+        cu->ws->h_state->status == 1 && cu->deliv_pos == cu->ws->h_state->out_pos) {
+        int32_t ferr = cu_finish_stream(cu);
+        if (ferr != MZ_OK)
+            cu->error = ferr;
+    }
     cu->total_out += done;
     return done;
 #endif

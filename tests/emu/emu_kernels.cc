@@ -19,7 +19,8 @@ static void ensure() {
     }
 }
 
-static uint32_t emu_work_counter;
+static uint32_t emu_work_counter2[2];
+#define emu_work_counter emu_work_counter2[0]
 
 extern "C" {
 
@@ -49,9 +50,9 @@ int64_t emu_deflate(const uint8_t *in, uint64_t len, uint32_t chunk_size, int le
     P.out = sl;
     P.slot_stride = stride;
     P.out_len = out_len.data();
-    static uint32_t work_counter;
-    work_counter = 0;
-    P.work_counter = (grid & 0x80000000u) ? nullptr : &work_counter; /* high bit of grid selects static striding */
+    static uint32_t work_counter[2];
+    work_counter[0] = work_counter[1] = 0;
+    P.work_counter = (grid & 0x80000000u) ? nullptr : work_counter; /* high bit of grid selects static striding */
     grid &= 0x7fffffffu;
     if (grid == 0 || grid > nchunks) grid = nchunks;
     if (deflate_stride_for_level(level) == 2) MZ_LAUNCH((deflate_chunks_kernel<2, false>), dim3(grid), dim3(DF_THREADS), DF_SMEM_BYTES, 0, P);
@@ -119,7 +120,7 @@ int32_t emu_inflate(const uint8_t *in, uint64_t in_len, uint8_t *out, uint64_t o
         job.out_base = 0;
         job.out_cap = out_limit;
         job.in_final = fed == in_len;
-        emu_work_counter = 0;
+        emu_work_counter2[0] = emu_work_counter2[1] = 0;
         MZ_LAUNCH(inflate_streams_kernel, dim3(1), dim3(INF_THREADS), INF_SMEM_BYTES, 0, (const InflateJob *)&job, &st, 1u, &emu_work_counter);
         if (st.status != INF_ST_RUN) break;
         if (st.why == INF_WHY_INPUT) {
@@ -218,7 +219,7 @@ int32_t emu_inflate_spec(const uint8_t *in, uint64_t in_len, uint8_t *out, uint6
         job.out_cap = out_cap;
         job.in_final = 1;
         job.flags = INF_JOB_STOP_AT_BOUNDARY;
-        emu_work_counter = 0;
+        emu_work_counter2[0] = emu_work_counter2[1] = 0;
         MZ_LAUNCH(inflate_streams_kernel, dim3(1), dim3(INF_THREADS), INF_SMEM_BYTES, 0, (const InflateJob *)&job, &st, 1u, &emu_work_counter);
         stats[2]++;
         if (st.status == INF_ST_RUN && st.why != INF_WHY_BOUNDARY) { st.status = st.why == INF_WHY_OUTPUT ? INF_ST_BUF_ERROR : -99; break; }
@@ -228,7 +229,4 @@ int32_t emu_inflate_spec(const uint8_t *in, uint64_t in_len, uint8_t *out, uint6
     return st.status;
 }
 
-void emu_textgen(uint8_t *out, uint64_t n, uint64_t seed, const uint8_t *words, const uint32_t *word_off, uint32_t nwords) {
-    MZ_LAUNCH(textgen_kernel, dim3(4), dim3(256), 0, 0, out, n, seed, words, word_off, nwords);
-}
 }

@@ -116,6 +116,21 @@ def scenario_crc():
     v = lib.mz_crypt_crc32_update(0, buf, half)
     v = lib.mz_crypt_crc32_update(v, C.byref(buf, half), len(data) - half)
     assert v == zlib.crc32(data)
+    # the host path (slice-by-16, calls below the threshold): every length 0..70, odd alignments, chaining, known answers
+    assert lib.mz_crypt_crc32_update(0, C.create_string_buffer(b"123456789", 9), 9) == 0xCBF43926
+    assert lib.mz_crypt_crc32_update(0x1234, buf, 0) == 0x1234  # size 0 returns value unchanged (mz_os.c:340)
+    for n in list(range(0, 71)) + [255, 256, 257, 4095, 65535]:
+        for a in (0, 1, 3, 7, 13):
+            want = zlib.crc32(data[a:a + n])
+            assert lib.mz_crypt_crc32_update(0, C.byref(buf, a), n) == want, (n, a)
+            k = n // 3
+            v = lib.mz_crypt_crc32_update(0, C.byref(buf, a), k)
+            assert lib.mz_crypt_crc32_update(v, C.byref(buf, a + k), n - k) == want, (n, a, "chained")
+    # pieces: more than one 8 MiB staging piece, uneven tail
+    big = datagen.random_bytes(19_000_003, 10)
+    bb = C.create_string_buffer(big, len(big))
+    assert lib.mz_crypt_crc32_update(0, bb, len(big)) == zlib.crc32(big)
+    assert lib.mz_crypt_crc32_update(0xDEADBEEF, bb, len(big)) == zlib.crc32(big, 0xDEADBEEF)
 
 
 if __name__ == "__main__":

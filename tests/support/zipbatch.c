@@ -24,6 +24,20 @@
 
 #include "mz_zip_cuda.h"
 
+#ifdef ZIPBATCH_NO_CUDA
+/* reference-only build (oracle/_ref/zipbatch_ref: the reference arm of bench.py, which must not map the product library):
+ * the modes `ref` and `extract_ref` work, the product's entry points are absent */
+int32_t mz_zip_cuda_add_buffers(void *z, const mz_cuda_zip_item *it, uint32_t n, int16_t level, mz_cuda_zip_stats *st) {
+    (void)z; (void)it; (void)n; (void)level; (void)st;
+    return MZ_SUPPORT_ERROR;
+}
+int32_t mz_zip_cuda_extract_all(void *z, mz_cuda_zip_entry_cb cb, void *u, mz_cuda_zip_stats *st) {
+    (void)z; (void)cb; (void)u; (void)st;
+    return MZ_SUPPORT_ERROR;
+}
+uint32_t mz_zip_cuda_abi_file_info_size(void) { return (uint32_t)sizeof(mz_zip_file); }
+#endif
+
 static uint64_t rng_state;
 static inline uint64_t rng(void) { /* splitmix64 */
     uint64_t z = (rng_state += 0x9e3779b97f4a7c15ull);

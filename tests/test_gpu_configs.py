@@ -7,6 +7,7 @@ import zlib
 import pytest
 
 import datagen
+import textgen
 import refshim
 
 pytestmark = pytest.mark.gpu
@@ -33,7 +34,7 @@ def test_c1_crc32_64mib_through_the_replaced_symbol(env, orc):
     """configs[0]: CRC32 of a 64 MiB buffer via mz_crypt_crc32_update (one call, host pointer)."""
     p, lib, tl, torch = env
     n = 64 * MiB
-    src = p.textgen(n, seed=5)
+    src = textgen.device(n, seed=5)
     torch.cuda.synchronize()
     host = _host_bytes(src)
     buf = C.create_string_buffer(host, n)
@@ -49,7 +50,7 @@ def test_c2_minigzip_level6_text_through_vtbl(env, ref):
     the reference's own reader must reproduce the input (size 64 MiB here instead of 256 MiB)."""
     p, lib, tl, torch = env
     n = 64 * MiB
-    host = _host_bytes(p.textgen(n, seed=6))
+    host = _host_bytes(textgen.device(n, seed=6))
     comp, info = tl.compress(lib.mz_stream_cuda_create, host, level=6, window_bits=31, write_size=16384)
     assert info["total_in"] == n and info["total_out"] == len(comp) and info["close"] == 0
     assert comp[:4] == b"\x1f\x8b\x08\x00" and int.from_bytes(comp[-4:], "little") == n
@@ -65,7 +66,7 @@ def test_c3_inflate_reference_gz_through_vtbl(env, ref):
     mz_stream_cuda_read in 16 KiB reads (128 MiB here instead of 4 GiB; ISIZE-mod-2^32 is covered by the trailer logic)."""
     p, lib, tl, torch = env
     n = 128 * MiB
-    host = _host_bytes(p.textgen(n, seed=7))
+    host = _host_bytes(textgen.device(n, seed=7))
     comp = ref.zlib_compress(host, level=6, window_bits=31, write_size=1 << 20)
     out, info = tl.decompress(lib.mz_stream_cuda_create, comp, n, window_bits=31, read_size=16384)
     assert info["read"] == n and info["total_in"] == len(comp) and info["total_out"] == n and info["close"] == 0
@@ -78,7 +79,7 @@ def test_c4_zip_entries_batch(env, orc):
     n_ent, ent = 4000, 65536
     total = n_ent * ent
     src = torch.empty(total, dtype=torch.uint8, device="cuda")
-    p.check(lib.mz_cuda_textgen(src.data_ptr(), total * 7 // 10, 11, None))
+    textgen.device_into(src.data_ptr(), total * 7 // 10, 11)
     src[total * 7 // 10:] = torch.randint(0, 256, (total - total * 7 // 10,), dtype=torch.uint8, device="cuda")  # incompressible tail
     d_off = torch.arange(n_ent, dtype=torch.int64, device="cuda") * ent
     d_len = torch.full((n_ent,), ent, dtype=torch.int32, device="cuda")
@@ -127,7 +128,7 @@ def test_c5_chunked_level1_with_crc_fold(env, ref):
     p, lib, tl, torch = env
     n = 512 * MiB
     half = n // 2
-    src = p.textgen(n, seed=8)
+    src = textgen.device(n, seed=8)
     torch.cuda.synchronize()
     b = p.DeflateBatch(half)
     parts, crcs = [], []
@@ -160,7 +161,7 @@ def test_c3_long_member_speculative_rounds_match_serial(env, ref, monkeypatch):
     foreign member; zlib level 1/6/9 members, Z_FULL_FLUSH-riddled members and a member with a long stored run inside"""
     p, lib, tl, torch = env
     n = 48 * MiB
-    text = _host_bytes(p.textgen(n, seed=17))
+    text = _host_bytes(textgen.device(n, seed=17))
     noise = datagen.random_bytes(6 * MiB, seed=5)
     cases = []
     for level in (1, 6, 9):
@@ -208,7 +209,7 @@ def test_c3_abandoned_long_read_leaves_the_workspace_usable(env):
     return cleanly and the pooled workspace must serve the next streams -- a long one, then a tiny one -- correctly"""
     p, lib, tl, torch = env
     import cuharness
-    text = _host_bytes(p.textgen(40 * MiB, seed=23))
+    text = _host_bytes(textgen.device(40 * MiB, seed=23))
     co = zlib.compressobj(6, zlib.DEFLATED, 31)
     comp = co.compress(text) + co.flush()
     src, keep = tl.source(comp)

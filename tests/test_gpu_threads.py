@@ -49,3 +49,40 @@ def test_concurrent_streams_and_crc_calls(env):
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+def test_crc_symbol_hammered_from_eight_threads(env):
+    """mz_crypt_crc32_update is a pure, re-entrant function in the reference (mz_crypt.c:35-92): eight threads call the
+    replacement at once with different buffers between 1 and 4 MiB (all on the device path, which shares per-device staging),
+    chained in uneven pieces, and every single result is checked. Also below the threshold (host slice-by-16 path)."""
+    p, lib = env
+    import numpy as np
+    errors = []
+
+    def worker(k):
+        try:
+            rng = np.random.default_rng(1000 + k)
+            for rep in range(12):
+                n = int(rng.integers(1 << 20, 4 << 20))
+                data = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+                buf = C.create_string_buffer(data, n)
+                want = zlib.crc32(data)
+                got = lib.mz_crypt_crc32_update(0, buf, n)
+                assert got == want, ("whole", k, rep, n, hex(got), hex(want))
+                cut = int(rng.integers(1 << 20, n)) if n > (1 << 20) + 1 else n
+                part = lib.mz_crypt_crc32_update(0, buf, cut)           # device path
+                tail = C.create_string_buffer(data[cut:], n - cut)     # may be short: host path
+                got2 = lib.mz_crypt_crc32_update(part, tail, n - cut)
+                assert got2 == want, ("chained", k, rep, n, cut)
+                small = data[: int(rng.integers(1, 70000))]
+                sb = C.create_string_buffer(small, len(small))
+                assert lib.mz_crypt_crc32_update(0, sb, len(small)) == zlib.crc32(small)
+        except Exception as e:  # noqa: BLE001
+            errors.append((k, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors

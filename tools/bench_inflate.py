@@ -20,6 +20,7 @@ import numpy as np
 import torch
 
 import __graft_entry__ as ge
+import textgen
 
 pkg = ge._load_pkg()
 lib = pkg.load()
@@ -47,7 +48,7 @@ def dev(data):
 
 def single(n_mib):
     n = n_mib * MiB
-    host = bytes(pkg.textgen(n, seed=3).cpu().numpy().tobytes())
+    host = bytes(textgen.device(n, seed=3).cpu().numpy().tobytes())
     co = zlib.compressobj(6, zlib.DEFLATED, -15)
     comp = co.compress(host) + co.flush()
     d_in = torch.zeros(len(comp) + 64, dtype=torch.uint8, device="cuda")
@@ -70,7 +71,7 @@ def single(n_mib):
 
 def batch(m):
     ent = 65536
-    src = pkg.textgen(m * ent, seed=4)
+    src = textgen.device(m * ent, seed=4)
     b = pkg.DeflateBatch(m * ent)
     s = pkg._stream_ptr()
     d_off = torch.arange(m, dtype=torch.int64, device="cuda") * ent
@@ -100,7 +101,7 @@ def batch(m):
 
 def crc(n_mib):
     n = n_mib * MiB
-    src = pkg.textgen(n, seed=5)
+    src = textgen.device(n, seed=5)
     nseg = (n + 65535) // 65536
     res = torch.empty(nseg, dtype=torch.int32, device="cuda")
     out2 = torch.empty(2, dtype=torch.int32, device="cuda")
@@ -121,7 +122,7 @@ def vtbl_long(n_mib, read_size=1 << 20, spec=True):
     import cuharness
     tl = cuharness.TestLib()
     n = n_mib * MiB
-    host = bytes(pkg.textgen(n, seed=9).cpu().numpy().tobytes())
+    host = bytes(textgen.device(n, seed=9).cpu().numpy().tobytes())
     co = zlib.compressobj(6, zlib.DEFLATED, 31)
     comp = co.compress(host) + co.flush()
     os.environ["MZ_CUDA_SPEC"] = "1" if spec else "0"
