@@ -78,6 +78,12 @@ int32_t mz_cuda_deflate_chunks(const void *d_in, uint64_t total_len, uint32_t ch
 int32_t mz_cuda_concat(const void *d_slots, uint64_t slot_stride, const uint32_t *d_out_len, uint32_t nchunks,
                        uint64_t *d_offsets, void *d_dst, void *stream);
 
+/* ---- K7: SHA-256 of independent buffers ----------------------------------------------------------------------
+ * Message i = d_in[d_off[i] .. d_off[i] + d_len[i]); d_digest receives n x 32 bytes (the digest as the standard prints it).
+ * This is the per-entry hash of the reference's zip writer / reader (MZ_ZIP_EXTENSION_HASH, mz_zip_rw.c:1339-1420, :410-450),
+ * batched like the per-entry CRC. */
+int32_t mz_cuda_sha256_batch(const void *d_in, const uint64_t *d_off, const uint64_t *d_len, uint32_t n, void *d_digest, void *stream);
+
 /* ---- K5: DEFLATE decode of independent raw streams (resumable) ---------------------------------------- */
 typedef struct mz_cuda_inflate_job {
     const void *d_in;    /* d_in[0] = stream byte `in_base`; readable (zero padded) 16 bytes past in_avail */

@@ -44,6 +44,14 @@ typedef struct mz_cuda_zip_stats {
 int32_t mz_zip_cuda_add_buffers(void *zip_handle, const mz_cuda_zip_item *items, uint32_t count, int16_t level,
                                 mz_cuda_zip_stats *stats);
 
+/* Same, with options. MZ_ZIP_CUDA_HASH_SHA256: every entry also gets the SHA-256 of its plain bytes, computed on the GPU in
+ * the same round (K7) and stored in the MZ_ZIP_EXTENSION_HASH extra field (id 0x1a51: algorithm 23, digest size 32, digest)
+ * exactly as the reference's zip writer stores it when built with a crypto provider (mz_zip_rw.c:1339-1420); the reference's
+ * reader then verifies it on extraction (mz_zip_rw.c:410-450), and so does mz_zip_cuda_extract_all. */
+#define MZ_ZIP_CUDA_HASH_SHA256 1u
+int32_t mz_zip_cuda_add_buffers_ex(void *zip_handle, const mz_cuda_zip_item *items, uint32_t count, int16_t level, uint32_t flags,
+                                   mz_cuda_zip_stats *stats);
+
 /* ---- batch extraction (scope row f2): the reverse direction ---------------------------------------------------
  * The reference extracts entry by entry: mz_zip_entry_read_open(raw=0) creates a mz_stream_zlib, the caller's loop
  * reads through it, mz_zip_entry_close compares the CRC (mz_zip_rw.c:818-909, mz_zip.c:2116-2128). Here the central
@@ -51,7 +59,9 @@ int32_t mz_zip_cuda_add_buffers(void *zip_handle, const mz_cuda_zip_item *items,
  * mz_zip_entry_get_info, mz_zip.c:2320-2400) and the compressed bytes are fetched through the raw seam
  * (mz_zip_entry_read_open(raw=1) / mz_zip_entry_read, mz_zip.c:1874,2031), but all entries of a round are inflated by
  * ONE K5 launch and checksummed by ONE K1 launch; the CRCs are compared with the headers on the host (MZ_CRC_ERROR on
- * the first mismatch, MZ_DATA_ERROR if a stream does not decode to exactly its recorded size).
+ * the first mismatch, MZ_DATA_ERROR if a stream does not decode to exactly its recorded size). An entry that carries a
+ * SHA-256 in a MZ_ZIP_EXTENSION_HASH extra field has that verified too (K7 over the round's plain bytes; MZ_CRC_ERROR on a
+ * mismatch, as mz_zip_reader_entry_close reports it, mz_zip_rw.c:430-450).
  * `cb` is called once per entry in archive order with the plain bytes (valid during the call only); a non-zero return
  * stops the extraction and is returned. Entries that are encrypted, use another method than STORE/DEFLATE, or exceed
  * 1 GiB are not batched: the call returns MZ_SUPPORT_ERROR (use the per-entry stream path for such archives). */

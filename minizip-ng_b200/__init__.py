@@ -51,7 +51,7 @@ EXPORTS = [
     "mz_cuda_event_create", "mz_cuda_event_destroy", "mz_cuda_event_record", "mz_cuda_event_sync", "mz_cuda_event_elapsed_ms",
     "mz_cuda_crc32_segments", "mz_cuda_crc32_fold", "mz_cuda_crc32_device", "mz_cuda_crc32_device_stream", "mz_cuda_crc32_combine",
     "mz_cuda_deflate_slot_bound", "mz_cuda_deflate_chunks", "mz_cuda_concat", "mz_cuda_inflate_streams",
-    "mz_cuda_inflate_spec_workspace_bytes", "mz_cuda_inflate_spec_round",
+    "mz_cuda_inflate_spec_workspace_bytes", "mz_cuda_inflate_spec_round", "mz_cuda_sha256_batch",
     # include/mz_zip_cuda.h
     "mz_zip_cuda_add_buffers", "mz_zip_cuda_extract_all", "mz_zip_cuda_abi_file_info_size",
 ]
@@ -123,6 +123,7 @@ def configure(L):
     sig("mz_cuda_deflate_chunks", i32, [vp, u64, u32, vp, vp, vp, u32, u32, i32, vp, u64, vp, vp])
     sig("mz_cuda_concat", i32, [vp, u64, vp, u32, vp, vp, vp])
     sig("mz_cuda_inflate_streams", i32, [vp, vp, u32, vp])
+    sig("mz_cuda_sha256_batch", i32, [vp, vp, vp, u32, vp, vp])
     return L
 
 

@@ -15,6 +15,7 @@
 #include <cstdio>
 #include "inflate_kernel.cuh"
 #include "inflate_spec_kernel.cuh"
+#include "sha256_kernel.cuh"
 
 #define MZ_OK 0
 #define MZ_MEM_ERROR (-4)
@@ -468,6 +469,26 @@ int32_t mz_cuda_inflate_spec_round(const void *d_in, uint64_t in_base, uint64_t 
         fprintf(stderr, "mz_cuda: K6 kernels ms: find %.3f scan %.3f chain %.3f compose+link+resolve %.3f emit %.3f (%u segments)\n", t[0], t[1], t[2], t[3], t[4], nseg);
         for (int i = 0; i < 6; i++) cudaEventDestroy(ev[i]);
     }
+    return MZ_OK;
+}
+
+int32_t mz_cuda_sha256_batch(const void *d_in, const uint64_t *d_off, const uint64_t *d_len, uint32_t n, void *d_digest, void *stream) {
+    DeviceCtx *c;
+    int32_t err = get_ctx(&c);
+    if (err) return err;
+    if (n == 0) return MZ_OK;
+    if (!d_in || !d_off || !d_len || !d_digest || ((uintptr_t)d_digest & 3)) return MZ_PARAM_ERROR;
+    Sha256Params P;
+    P.in = (const uint8_t *)d_in;
+    P.off = d_off;
+    P.len = d_len;
+    P.n = n;
+    P.digest = (uint8_t *)d_digest;
+    uint32_t blocks = (n + SHA_THREADS - 1) / SHA_THREADS;
+    const uint32_t cap = (uint32_t)c->sm_count * 16u;
+    if (blocks > cap) blocks = cap;
+    MZ_LAUNCH(sha256_batch_kernel, dim3(blocks), dim3(SHA_THREADS), 0, (cudaStream_t)stream, P);
+    CK(cudaGetLastError());
     return MZ_OK;
 }
 

@@ -77,6 +77,8 @@ typedef struct zc_bufs_s {
     uint64_t *h_off, *d_off, *d_joined_off, *h_joined_off;
     uint32_t *h_len, *d_len, *d_out_len, *d_residue, *d_crc, *h_crc;
     uint8_t *h_flags, *d_flags;
+    uint64_t *h_eoff, *d_eoff, *h_elen, *d_elen; /* per ENTRY: offset / size of the plain bytes (K7) */
+    uint8_t *d_digest, *h_digest;                 /* per entry: 32 bytes */
 } zc_bufs;
 
 static void zc_free(zc_bufs *b) {
@@ -97,6 +99,12 @@ static void zc_free(zc_bufs *b) {
     mz_cuda_host_free(b->h_crc);
     mz_cuda_host_free(b->h_flags);
     mz_cuda_free(b->d_flags);
+    mz_cuda_host_free(b->h_eoff);
+    mz_cuda_free(b->d_eoff);
+    mz_cuda_host_free(b->h_elen);
+    mz_cuda_free(b->d_elen);
+    mz_cuda_free(b->d_digest);
+    mz_cuda_host_free(b->h_digest);
     memset(b, 0, sizeof(*b));
 }
 
@@ -123,8 +131,15 @@ static int zc_alloc(zc_bufs *b, size_t round_bytes, uint32_t max_chunks) {
     b->h_crc = (uint32_t *)mz_cuda_host_alloc((size_t)max_chunks * 4);
     b->h_flags = (uint8_t *)mz_cuda_host_alloc(max_chunks);
     b->d_flags = (uint8_t *)mz_cuda_malloc(max_chunks);
+    b->h_eoff = (uint64_t *)mz_cuda_host_alloc((size_t)max_chunks * 8); /* an entry has at least one chunk */
+    b->d_eoff = (uint64_t *)mz_cuda_malloc((size_t)max_chunks * 8);
+    b->h_elen = (uint64_t *)mz_cuda_host_alloc((size_t)max_chunks * 8);
+    b->d_elen = (uint64_t *)mz_cuda_malloc((size_t)max_chunks * 8);
+    b->d_digest = (uint8_t *)mz_cuda_malloc((size_t)max_chunks * 32);
+    b->h_digest = (uint8_t *)mz_cuda_host_alloc((size_t)max_chunks * 32);
     if (!b->h_in || !b->d_in || !b->d_slots || !b->d_out || !b->h_out || !b->h_off || !b->d_off || !b->d_joined_off || !b->h_joined_off ||
-        !b->h_len || !b->d_len || !b->d_out_len || !b->d_residue || !b->d_crc || !b->h_crc || !b->h_flags || !b->d_flags) {
+        !b->h_len || !b->d_len || !b->d_out_len || !b->d_residue || !b->d_crc || !b->h_crc || !b->h_flags || !b->d_flags || !b->h_eoff ||
+        !b->d_eoff || !b->h_elen || !b->d_elen || !b->d_digest || !b->h_digest) {
         zc_free(b);
         return 0;
     }
@@ -142,6 +157,7 @@ typedef struct zc_round_s {
     const mz_cuda_zip_item *items;
     uint32_t count, first, last, nch;
     int16_t level;
+    uint32_t flags;
     int32_t device, err;
     double pack_ms, gpu_ms;
 } zc_round;
@@ -160,6 +176,8 @@ static void *zc_prepare(void *arg) {
             break;
         if (r->items[last].size > 0)
             memcpy(b->h_in + pos, r->items[last].data, (size_t)r->items[last].size);
+        b->h_eoff[last - r->first] = pos;
+        b->h_elen[last - r->first] = (uint64_t)r->items[last].size;
         int64_t left = r->items[last].size;
         for (uint32_t k = 0; k < c; k++) {
             const uint32_t n = left > (int64_t)ZC_CHUNK ? ZC_CHUNK : (uint32_t)left;
@@ -183,6 +201,13 @@ static void *zc_prepare(void *arg) {
     if (!err) err = mz_cuda_deflate_chunks(b->d_in, 0, 0, b->d_off, b->d_len, b->d_flags, nch, 0, r->level, b->d_slots, b->stride, b->d_out_len, NULL);
     if (!err) err = mz_cuda_crc32_segments(b->d_in, 0, 0, b->d_off, b->d_len, nch, b->d_residue, b->d_crc, NULL);
     if (!err) err = mz_cuda_concat(b->d_slots, b->stride, b->d_out_len, nch, b->d_joined_off, b->d_out, NULL);
+    if (!err && (r->flags & MZ_ZIP_CUDA_HASH_SHA256)) { /* K7: SHA-256 of every entry's plain bytes */
+        const uint32_t ne = last - r->first;
+        err = mz_cuda_memcpy_h2d(b->d_eoff, b->h_eoff, (size_t)ne * 8, NULL);
+        if (!err) err = mz_cuda_memcpy_h2d(b->d_elen, b->h_elen, (size_t)ne * 8, NULL);
+        if (!err) err = mz_cuda_sha256_batch(b->d_in, b->d_eoff, b->d_elen, ne, b->d_digest, NULL);
+        if (!err) err = mz_cuda_memcpy_d2h(b->h_digest, b->d_digest, (size_t)ne * 32, NULL);
+    }
     if (!err) err = mz_cuda_memcpy_d2h(b->h_joined_off, b->d_joined_off, ((size_t)nch + 1) * 8, NULL);
     if (!err) err = mz_cuda_memcpy_d2h(b->h_crc, b->d_crc, (size_t)nch * 4, NULL);
     if (!err) err = mz_cuda_stream_sync(NULL);
@@ -195,6 +220,11 @@ static void *zc_prepare(void *arg) {
 }
 
 int32_t mz_zip_cuda_add_buffers(void *zip_handle, const mz_cuda_zip_item *items, uint32_t count, int16_t level, mz_cuda_zip_stats *stats) {
+    return mz_zip_cuda_add_buffers_ex(zip_handle, items, count, level, 0, stats);
+}
+
+int32_t mz_zip_cuda_add_buffers_ex(void *zip_handle, const mz_cuda_zip_item *items, uint32_t count, int16_t level, uint32_t flags,
+                                   mz_cuda_zip_stats *stats) {
     zc_round rd[2];
     int32_t err = MZ_OK;
     mz_cuda_zip_stats st;
@@ -259,6 +289,7 @@ int32_t mz_zip_cuda_add_buffers(void *zip_handle, const mz_cuda_zip_item *items,
         rd[k].items = items;
         rd[k].count = count;
         rd[k].level = level;
+        rd[k].flags = flags;
         rd[k].device = device < 0 ? 0 : device;
     }
     /* round r is prepared by a worker while this thread feeds round r-1 to the container */
@@ -304,6 +335,16 @@ int32_t mz_zip_cuda_add_buffers(void *zip_handle, const mz_cuda_zip_item *items,
             fi.uncompressed_size = items[i].size;
             fi.external_fa = items[i].external_fa ? items[i].external_fa : (0100644u << 16);
             fi.filename = items[i].filename;
+            uint8_t xf[40];
+            if (flags & MZ_ZIP_CUDA_HASH_SHA256) {
+                /* MZ_ZIP_EXTENSION_HASH (mz.h:93): id, field length 4 + 32, algorithm MZ_HASH_SHA256 (mz.h:131), digest size, digest --
+                 * the bytes mz_zip_writer_entry_close assembles (mz_zip_rw.c:1398-1408) */
+                static const uint8_t head[8] = {0x51, 0x1a, 36, 0, 23, 0, 32, 0};
+                memcpy(xf, head, 8);
+                memcpy(xf + 8, b->h_digest + (size_t)(i - r->first) * 32, 32);
+                fi.extrafield = xf;
+                fi.extrafield_size = 40;
+            }
             err = mz_zip_entry_write_open(zip_handle, &fi, level, 1, NULL);
             uint64_t done = 0;
             while (err == MZ_OK && done < csize) {
@@ -342,6 +383,8 @@ typedef struct zx_entry_s {
     uint64_t coff, csize, ooff, usize; /* offsets inside the round's compressed / plain buffers */
     uint32_t crc, name_off;
     uint16_t method;
+    uint8_t has_sha;
+    uint8_t sha[32]; /* expected SHA-256 from the MZ_ZIP_EXTENSION_HASH extra field */
 } zx_entry;
 
 typedef struct zx_bufs_s {
@@ -352,6 +395,8 @@ typedef struct zx_bufs_s {
     mz_cuda_inflate_state *h_state, *d_state;
     uint64_t *h_off, *d_off;
     uint32_t *h_len, *d_len, *d_residue, *d_crc, *h_crc;
+    uint64_t *h_len64, *d_len64;
+    uint8_t *d_digest, *h_digest;
     zx_entry *ent;
     char *names;
     size_t names_cap;
@@ -373,6 +418,10 @@ static void zx_free(zx_bufs *b) {
     mz_cuda_free(b->d_residue);
     mz_cuda_free(b->d_crc);
     mz_cuda_host_free(b->h_crc);
+    mz_cuda_host_free(b->h_len64);
+    mz_cuda_free(b->d_len64);
+    mz_cuda_free(b->d_digest);
+    mz_cuda_host_free(b->h_digest);
     free(b->ent);
     free(b->names);
     memset(b, 0, sizeof(*b));
@@ -399,10 +448,15 @@ static int zx_alloc(zx_bufs *b, size_t comp_cap, size_t out_cap, uint32_t max_en
     b->d_residue = (uint32_t *)mz_cuda_malloc((size_t)max_entries * 4);
     b->d_crc = (uint32_t *)mz_cuda_malloc((size_t)max_entries * 4);
     b->h_crc = (uint32_t *)mz_cuda_host_alloc((size_t)max_entries * 4);
+    b->h_len64 = (uint64_t *)mz_cuda_host_alloc((size_t)max_entries * 8);
+    b->d_len64 = (uint64_t *)mz_cuda_malloc((size_t)max_entries * 8);
+    b->d_digest = (uint8_t *)mz_cuda_malloc((size_t)max_entries * 32);
+    b->h_digest = (uint8_t *)mz_cuda_host_alloc((size_t)max_entries * 32);
     b->ent = (zx_entry *)malloc((size_t)max_entries * sizeof(zx_entry));
     b->names = (char *)malloc(b->names_cap);
     if (!b->h_comp || !b->d_comp || !b->d_out || !b->h_out || !b->h_job || !b->d_job || !b->h_state || !b->d_state || !b->h_off || !b->d_off ||
-        !b->h_len || !b->d_len || !b->d_residue || !b->d_crc || !b->h_crc || !b->ent || !b->names) {
+        !b->h_len || !b->d_len || !b->d_residue || !b->d_crc || !b->h_crc || !b->h_len64 || !b->d_len64 || !b->d_digest || !b->h_digest ||
+        !b->ent || !b->names) {
         zx_free(b);
         return 0;
     }
@@ -449,6 +503,16 @@ static int32_t zx_flush(zx_bufs *b, uint32_t n, size_t comp_used, size_t out_use
     if (!err) err = mz_cuda_memcpy_h2d(b->d_len, b->h_len, (size_t)n * 4, NULL);
     if (!err) err = mz_cuda_crc32_segments(b->d_out, 0, 0, b->d_off, b->d_len, n, b->d_residue, b->d_crc, NULL);
     if (!err) err = mz_cuda_memcpy_d2h(b->h_crc, b->d_crc, (size_t)n * 4, NULL);
+    int any_sha = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        any_sha |= b->ent[i].has_sha;
+        b->h_len64[i] = b->ent[i].usize;
+    }
+    if (!err && any_sha) { /* K7 over the round's plain bytes */
+        err = mz_cuda_memcpy_h2d(b->d_len64, b->h_len64, (size_t)n * 8, NULL);
+        if (!err) err = mz_cuda_sha256_batch(b->d_out, b->d_off, b->d_len64, n, b->d_digest, NULL);
+        if (!err) err = mz_cuda_memcpy_d2h(b->h_digest, b->d_digest, (size_t)n * 32, NULL);
+    }
     if (!err) err = mz_cuda_memcpy_d2h(b->h_out, b->d_out, out_used, NULL);
     if (!err) err = mz_cuda_stream_sync(NULL);
     double t1 = now_ms();
@@ -467,6 +531,8 @@ static int32_t zx_flush(zx_bufs *b, uint32_t n, size_t comp_used, size_t out_use
         const uint32_t crc = e->usize ? b->h_crc[i] : 0u;
         if (crc != e->crc)
             return MZ_CRC_ERROR;
+        if (e->has_sha && memcmp(b->h_digest + (size_t)i * 32, e->sha, 32) != 0)
+            return MZ_CRC_ERROR; /* mz_zip_reader_entry_close: hash mismatch -> MZ_CRC_ERROR (mz_zip_rw.c:444-447) */
     }
     double t2 = now_ms();
     for (uint32_t i = 0; i < n; i++) {
@@ -551,6 +617,20 @@ int32_t mz_zip_cuda_extract_all(void *zip_handle, mz_cuda_zip_entry_cb cb, void 
         e->crc = fi->crc;
         e->method = fi->compression_method;
         e->name_off = (uint32_t)names_used;
+        e->has_sha = 0;
+        /* extra fields are {id u16, size u16, data}; find MZ_ZIP_EXTENSION_HASH with algorithm SHA-256 (mz_zip_rw.c:478-510) */
+        for (uint32_t xo = 0; fi->extrafield && xo + 4 <= fi->extrafield_size;) {
+            const uint8_t *x = fi->extrafield + xo;
+            const uint32_t id = x[0] | (x[1] << 8), xs = x[2] | (x[3] << 8);
+            if (xo + 4 + xs > fi->extrafield_size)
+                break;
+            if (id == 0x1a51 && xs >= 4 + 32 && (x[4] | (x[5] << 8)) == 23 && (x[6] | (x[7] << 8)) == 32) {
+                memcpy(e->sha, x + 8, 32);
+                e->has_sha = 1;
+                break;
+            }
+            xo += 4 + xs;
+        }
         memcpy(b.names + names_used, fi->filename, nlen);
         /* the compressed bytes, untouched, through the raw seam */
         if (csz) {

@@ -7,6 +7,7 @@
 #include "../../minizip-ng_b200/csrc/deflate_kernel.cuh"
 #include "../../minizip-ng_b200/csrc/inflate_kernel.cuh"
 #include "../../minizip-ng_b200/csrc/inflate_spec_kernel.cuh"
+#include "../../minizip-ng_b200/csrc/sha256_kernel.cuh"
 
 using namespace mzc;
 
@@ -229,4 +230,15 @@ int32_t emu_inflate_spec(const uint8_t *in, uint64_t in_len, uint8_t *out, uint6
     return st.status;
 }
 
+
+/* n messages packed at the given offsets of one buffer -> n x 32 digest bytes */
+void emu_sha256(const uint8_t *in, const uint64_t *off, const uint64_t *len, uint32_t n, uint8_t *digest) {
+    Sha256Params P;
+    P.in = in;
+    P.off = off;
+    P.len = len;
+    P.n = n;
+    P.digest = digest;
+    MZ_LAUNCH(sha256_batch_kernel, dim3(2), dim3(SHA_THREADS), 0, 0, P);
+}
 }

@@ -19,6 +19,8 @@ class EmuLib:
         L.emu_inflate.argtypes = [vp, u64, vp, u64, u64, u64, C.POINTER(u64), C.POINTER(u64), C.POINTER(u32)]
         L.emu_inflate_spec.restype = C.c_int32
         L.emu_inflate_spec.argtypes = [vp, u64, vp, u64, u64, u32, u64, C.POINTER(u64), C.POINTER(u64), C.POINTER(u32)]
+        L.emu_sha256.restype = None
+        L.emu_sha256.argtypes = [vp, vp, vp, u32, vp]
 
     def deflate(self, data, level=1, chunk=65536, final=True, grid=0):
         data = bytes(data)
@@ -54,3 +56,23 @@ class EmuLib:
         st = self.lib.emu_inflate_spec(comp, len(comp), out, out_cap, seg_bytes, max_seg, window, C.byref(cons), C.byref(prod), stats)
         names = ["rounds", "chain", "serial", "candidates", "discarded"]
         return st, out.raw[:prod.value], cons.value, dict(zip(names, list(stats)))
+
+    def sha256(self, messages, align=16, shift=0):
+        """digests of a list of byte strings packed at `align`-aligned offsets (+ shift) of one buffer"""
+        offs, pos = [], shift
+        for m in messages:
+            offs.append(pos)
+            pos += (len(m) + align - 1) // align * align + (0 if align > 1 else 0)
+        buf = bytearray(pos + 64)
+        for o, m in zip(offs, messages):
+            buf[o:o + len(m)] = m
+        n = len(messages)
+        base = (C.c_uint8 * (len(buf) + 16))()
+        a = (16 - C.addressof(base) % 16) % 16  # 16-byte aligned base so that aligned offsets take the fast path
+        C.memmove(C.addressof(base) + a, bytes(buf), len(buf))
+        off = (C.c_uint64 * max(n, 1))(*offs)
+        ln = (C.c_uint64 * max(n, 1))(*[len(m) for m in messages])
+        dig = (C.c_uint8 * (32 * max(n, 1)))()
+        self.lib.emu_sha256(C.addressof(base) + a, off, ln, n, dig)
+        raw = bytes(dig)
+        return [raw[32 * i:32 * i + 32] for i in range(n)]

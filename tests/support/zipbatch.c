@@ -4,7 +4,7 @@
  * Compiled against the reference's own headers and objects by oracle/Makefile (-> oracle/_ref/zipbatch_cuda); the
  * container code in both modes is the reference's.
  *
- *   zipbatch_cuda <out.zip> <entries> <entry_bytes> <level> <cuda|ref> [dump_dir dump_every]
+ *   zipbatch_cuda <out.zip> <entries> <entry_bytes> <level> <cuda|cuda_sha|ref> [dump_dir dump_every]
  *   zipbatch_cuda <in.zip>  <entries> <entry_bytes> <level> <extract|extract_ref>   (batch extractor / the reference's loop)
  *
  * Entry i: i%10 < 7 text-like, < 9 binary records, else incompressible; name e/%06d.
@@ -27,8 +27,8 @@
 #ifdef ZIPBATCH_NO_CUDA
 /* reference-only build (oracle/_ref/zipbatch_ref: the reference arm of bench.py, which must not map the product library):
  * the modes `ref` and `extract_ref` work, the product's entry points are absent */
-int32_t mz_zip_cuda_add_buffers(void *z, const mz_cuda_zip_item *it, uint32_t n, int16_t level, mz_cuda_zip_stats *st) {
-    (void)z; (void)it; (void)n; (void)level; (void)st;
+int32_t mz_zip_cuda_add_buffers_ex(void *z, const mz_cuda_zip_item *it, uint32_t n, int16_t level, uint32_t flags, mz_cuda_zip_stats *st) {
+    (void)z; (void)it; (void)n; (void)level; (void)flags; (void)st;
     return MZ_SUPPORT_ERROR;
 }
 int32_t mz_zip_cuda_extract_all(void *z, mz_cuda_zip_entry_cb cb, void *u, mz_cuda_zip_stats *st) {
@@ -187,7 +187,8 @@ int main(int argc, char **argv) {
     const uint32_t n = (uint32_t)atoi(argv[2]);
     const size_t esz = (size_t)atoll(argv[3]);
     const int16_t level = (int16_t)atoi(argv[4]);
-    const int use_cuda = strcmp(argv[5], "cuda") == 0;
+    const int use_sha = strcmp(argv[5], "cuda_sha") == 0; /* + SHA-256 extra field per entry (scope row f3) */
+    const int use_cuda = strcmp(argv[5], "cuda") == 0 || use_sha;
     const char *dump_dir = argc > 7 ? argv[6] : NULL;
     const uint32_t dump_every = argc > 7 ? (uint32_t)atoi(argv[7]) : 0;
     if (sizeof(mz_zip_file) != mz_zip_cuda_abi_file_info_size()) {
@@ -234,7 +235,7 @@ int main(int argc, char **argv) {
     uint64_t bytes_in = 0;
     t0 = now_s();
     if (use_cuda) {
-        err = mz_zip_cuda_add_buffers(zip, items, n, level, &st);
+        err = mz_zip_cuda_add_buffers_ex(zip, items, n, level, use_sha ? MZ_ZIP_CUDA_HASH_SHA256 : 0u, &st);
         bytes_in = st.bytes_in;
     } else {
         for (uint32_t i = 0; i < n && err == MZ_OK; i++) {

@@ -106,3 +106,57 @@ def test_zip_batch_writer_and_extractor(emu_bins, tmp_path):
     (tmp_path / "bad.zip").write_bytes(bytes(raw))
     r = _run([exe, "bad.zip", str(n), str(esz), "0", "extract"], tmp_path, ok=False)
     assert r.returncode != 0 and json.loads(r.stdout.decode().strip().splitlines()[-1])["err"] in (-3, -105)
+
+
+def _sha_roundtrip(exe, refc, tmp_path, run):
+    """scope row f3: per-entry SHA-256 computed by K7 and stored in MZ_ZIP_EXTENSION_HASH exactly as the reference's writer stores
+    it (mz_zip_rw.c:1398-1408); checked three ways -- hashlib over every entry, the reference built WITH its crypto provider
+    (oracle/_ref/minizip_refc verifies the hash while extracting, mz_zip_rw.c:430-450), and the product's own batch extractor --
+    in both directions (the reference's hashes are verified by K7 too), and a damaged digest must be refused by both."""
+    import hashlib
+    n, esz = 120, 20_000
+    st = json.loads(run([exe, "h.zip", str(n), str(esz), "6", "cuda_sha"], tmp_path).stdout.decode().strip().splitlines()[-1])
+    assert st["err"] == 0 and st["close_err"] == 0 and st["entries"] == n
+    with zipfile.ZipFile(tmp_path / "h.zip") as z:
+        assert z.testzip() is None
+        for info in z.infolist():
+            x = info.extra
+            assert x[:8] == bytes([0x51, 0x1a, 36, 0, 23, 0, 32, 0]), x.hex()
+            assert x[8:40] == hashlib.sha256(z.read(info)).digest(), info.filename
+        victim = z.getinfo("e/000050")
+    run([refc, "-x", "-o", "-d", "out_h", "h.zip"], tmp_path)                      # the reference verifies every hash
+    got = json.loads(run([exe, "h.zip", str(n), str(esz), "0", "extract"], tmp_path).stdout.decode().strip().splitlines()[-1])
+    assert got["err"] == 0 and got["entries"] == n and got["mismatches"] == 0
+    # the other direction: an archive whose hashes the REFERENCE computed (OpenSSL) is verified by K7
+    (tmp_path / "src").mkdir()
+    for k, v in _corpus().items():
+        (tmp_path / "src" / k).write_bytes(v)
+    run([refc, "-o", "-6", "../r_h.zip"] + sorted(_corpus()), tmp_path / "src")
+    with zipfile.ZipFile(tmp_path / "r_h.zip") as z:
+        assert all(i.extra[:2] == b"\x51\x1a" for i in z.infolist())
+    got = json.loads(run([exe, "r_h.zip", "0", str(1 << 20), "0", "extract"], tmp_path).stdout.decode().strip().splitlines()[-1])
+    assert got["err"] == 0 and got["entries"] == len(_corpus())
+    # one flipped digest bit in the central directory: refused by the reference reader and by the batch extractor (MZ_CRC_ERROR)
+    raw = bytearray((tmp_path / "h.zip").read_bytes())
+    cd = raw.rfind(b"PK\x01\x02" + b"", 0)
+    pos = 0
+    while True:  # walk the central directory to the victim's record
+        pos = raw.find(b"PK\x01\x02", pos)
+        assert pos >= 0
+        nlen = int.from_bytes(raw[pos + 28:pos + 30], "little")
+        if raw[pos + 46:pos + 46 + nlen] == victim.filename.encode():
+            break
+        pos += 46
+    raw[pos + 46 + nlen + 8 + 5] ^= 0x01
+    (tmp_path / "bad_h.zip").write_bytes(bytes(raw))
+    r = run([exe, "bad_h.zip", str(n), str(esz), "0", "extract"], tmp_path, ok=False)
+    assert r.returncode != 0 and json.loads(r.stdout.decode().strip().splitlines()[-1])["err"] == -105
+    r = run([refc, "-x", "-o", "-d", "out_bad", "bad_h.zip"], tmp_path, ok=False)
+    assert r.returncode != 0 or b"rror" in r.stdout + r.stderr
+
+
+def test_zip_batch_sha256_extrafield(emu_bins, tmp_path):
+    refc = os.path.join(REFDIR, "minizip_refc")
+    if not os.path.exists(refc):
+        pytest.skip("oracle/_ref/minizip_refc not built (no OpenSSL headers)")
+    _sha_roundtrip(emu_bins["zipbatch_emu"], refc, tmp_path, _run)

@@ -229,6 +229,25 @@ def test_emu_deflate_literal_heavy_blocks_take_the_split_path(emu):
             assert len(comp) < 0.6 * len(data)
 
 
+def test_emu_sha256_known_answers_and_every_padding_case(emu):
+    """K7 against FIPS 180-4 known answers and hashlib: every length around the one-/two-block padding boundary (55, 56, 63, 64),
+    aligned (16-byte loads) and unaligned (byte loads) starts, empty and multi-block messages, many messages per launch."""
+    import hashlib
+    assert emu.sha256([b"abc"])[0].hex() == "ba7816bf8f01cfea414140de5dae2223b00361a396177a9cb410ff61f20015ad"
+    assert emu.sha256([b""])[0].hex() == "e3b0c44298fc1c149afbf4c8996fb92427ae41e4649b934ca495991b7852b855"
+    assert emu.sha256([b"abcdbcdecdefdefgefghfghighijhijkijkljklmklmnlmnomnopnopq"])[0].hex() == \
+        "248d6a61d20638b8e5c026930c3e6039a33ce45964ff2167f6ecedd419db06c1"
+    base = datagen.random_bytes(70_000, 5)
+    msgs = [base[:n] for n in list(range(0, 130)) + [255, 256, 4095, 4096, 65535, 65536, 70_000]]
+    for shift in (0, 1, 7):
+        got = emu.sha256(msgs, align=16, shift=shift)
+        for m, g in zip(msgs, got):
+            assert g == hashlib.sha256(m).digest(), (len(m), shift)
+    many = [datagen.text_like(1000 + 37 * i, seed=i)[: 1000 + 37 * i] for i in range(300)]
+    for m, g in zip(many, emu.sha256(many)):
+        assert g == hashlib.sha256(m).digest()
+
+
 def test_emu_kernels_under_sanitizers():
     """the same kernel sources built with AddressSanitizer + UBSan: out-of-bounds global accesses, shifts by >= 32,
     signed overflow ... in the deflate, CRC, inflate and K6 kernels abort the run"""

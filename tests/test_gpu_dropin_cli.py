@@ -219,3 +219,18 @@ def test_zip_batch_extractor_reads_every_kind_of_archive(built, tmp_path):
     r = _run([exe, "bad.zip", "301", "200000", "0", "extract"], tmp_path, ok=False)
     bad = json.loads(r.stdout.decode().strip().splitlines()[-1])
     assert r.returncode != 0 and bad["err"] in (-3, -105)  # MZ_DATA_ERROR or MZ_CRC_ERROR
+
+
+@pytest.mark.gpu
+def test_zip_batch_sha256_extrafield_on_the_gpu(built, tmp_path):
+    """scope row f3 on the device: K7 hashes stored in MZ_ZIP_EXTENSION_HASH are verified by hashlib, by the reference built with
+    its crypto provider (minizip_refc) and by the batch extractor; the reference's own hashes are verified by K7; a damaged
+    digest is refused (same scenario as the CPU suite runs on the emulator)."""
+    import test_emu_dropin_cli as emu_cli
+    refc = os.path.join(REFDIR, "minizip_refc")
+    if not os.path.exists(refc):
+        pytest.skip("oracle/_ref/minizip_refc not built (no OpenSSL headers)")
+
+    def run(args, cwd, ok=True):
+        return _run([str(a) for a in args], cwd, ok)
+    emu_cli._sha_roundtrip(_bin("zipbatch_cuda"), refc, tmp_path, run)
