@@ -426,12 +426,47 @@ def run_ours(args, rank, world, local_rank):
     nshard_chunks = c1 - c0
     bounds = [nshard_chunks * j // NB for j in range(NB + 1)]
     subs = [(bounds[j] * 65536, (bounds[j + 1] - bounds[j]) * 65536) for j in range(NB)]  # (byte offset in shard, bytes)
+    bounds_chunks = bounds
     batches = [pkg.DeflateBatch(max(nb, 65536)) for _, nb in subs]
     stream = torch.cuda.current_stream()
     comm_stream = torch.cuda.Stream() if world > 1 else None
     ev_done = [torch.cuda.Event() for _ in range(NB)]
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    state = {"cap": None, "gathered": [None] * NB, "tbl_all": None}
+    # ---- N > 1: the all-gather runs on the COPY ENGINES. Every rank owns one `gathered` buffer (cudaMalloc through the library,
+    # exported by IPC handle, mapped by every peer): rank r's joined stream lives at region_off[r] in all of them, its per-chunk
+    # {crc32, out_len} rows at chunk index c0 in the global tables. A finished piece is pushed to the N-1 peers with
+    # cudaMemcpyAsync on a second stream while the SMs compress the next piece; no SM-based collective competes with the
+    # 2 x 111 KB deflate CTAs. Piece offsets come from the warm-up pass: the encoder is bit-reproducible, so they do not change.
+    state = {"ready": False, "base": [0] * (NB + 1)}
+    if world > 1:
+        rbounds = [int(lib.mz_cuda_gather_region_bound(((r + 1) * nchunks_total // world - r * nchunks_total // world) * 65536)) for r in range(world)]
+        region_off = [sum(rbounds[:r]) for r in range(world)]
+        cap_total = sum(rbounds)
+        g_mine = lib.mz_cuda_malloc(cap_total + 256)
+        t_crc = lib.mz_cuda_malloc(nchunks_total * 4 + 256)
+        t_len = lib.mz_cuda_malloc(nchunks_total * 4 + 256)
+        assert g_mine and t_crc and t_len, "cudaMalloc of the gathered buffers failed"
+        handles = []
+        for ptr in (g_mine, t_crc, t_len):
+            h = C.create_string_buffer(64)
+            pkg.check(lib.mz_cuda_ipc_export(ptr, h), "ipc_export")
+            handles.append(h.raw)
+        allh = [None] * world
+        dist.all_gather_object(allh, handles)
+        peers = []
+        for r in range(world):
+            if r == rank:
+                peers.append((g_mine, t_crc, t_len))
+                continue
+            got = []
+            for hb in allh[r]:
+                pp = C.c_void_p()
+                pkg.check(lib.mz_cuda_ipc_open(C.create_string_buffer(hb, 64), C.byref(pp)), "ipc_open")
+                got.append(pp.value)
+            peers.append(tuple(got))
+        copy_stream_t = torch.cuda.Stream()
+        copy_s = copy_stream_t.cuda_stream
+        ev_piece = [lib.mz_cuda_event_create() for _ in range(NB)]
 
     def compress_sub(j, kev=None):
         off, nb = subs[j]
@@ -446,32 +481,37 @@ def run_ours(args, rank, world, local_rank):
                                              b.out_len.data_ptr(), s), "deflate")
         if kev is not None:
             kev[1].record(stream)
-        pkg.check(lib.mz_cuda_crc32_segments(base, nb, 65536, None, None, n, b.residue.data_ptr(), b.chunk_crc.data_ptr(), s), "crc")
+        cbase = c0 + bounds_chunks[j]  # global index of the piece's first chunk
+        crc_dst = b.chunk_crc.data_ptr() if world == 1 else t_crc + 4 * cbase
+        pkg.check(lib.mz_cuda_crc32_segments(base, nb, 65536, None, None, n, b.residue.data_ptr(), crc_dst, s), "crc")
         pkg.check(lib.mz_cuda_crc32_fold(b.residue.data_ptr(), n, 65536, nb, b.crc_out.data_ptr(), s), "fold")
-        pkg.check(lib.mz_cuda_concat(b.slots.data_ptr(), b.stride, b.out_len.data_ptr(), n, b.offsets.data_ptr(), b.joined.data_ptr(), s), "concat")
+        # the join writes straight into this rank's region of its own gathered buffer (N > 1, once the offsets are known)
+        dst = b.joined.data_ptr() if not state["ready"] else g_mine + region_off[rank] + state["base"][j]
+        pkg.check(lib.mz_cuda_concat(b.slots.data_ptr(), b.stride, b.out_len.data_ptr(), n, b.offsets.data_ptr(), dst, s), "concat")
         return 5
 
     def step(kevs=None):
         launches = 0
         for j in range(NB):
             launches += compress_sub(j, kevs[j] if kevs else None)
-            if world > 1 and state["cap"] is not None:
-                ev_done[j].record(stream)
-                with torch.cuda.stream(comm_stream):
-                    comm_stream.wait_event(ev_done[j])
-                    # THE collective of the path: every rank's joined bitstream of piece j (fixed capacity, sized in warm-up)
-                    dist.all_gather_into_tensor(state["gathered"][j], batches[j].joined[:state["cap"]])
-                launches += 1
-        if world > 1 and state["cap"] is not None:
-            with torch.cuda.stream(comm_stream):
-                comm_stream.wait_event(ev_done[NB - 1])
-                tbl = torch.cat([torch.stack([b.chunk_crc[:b.nchunks(nb)], b.out_len[:b.nchunks(nb)], b.offsets[:b.nchunks(nb)].to(torch.int32)], 1)
-                                 for b, (_, nb) in zip(batches, subs)]).contiguous()
-                if state["tbl_all"] is None:
-                    state["tbl_all"] = torch.empty((world * tbl.shape[0], 3), dtype=torch.int32, device=dev)
-                dist.all_gather_into_tensor(state["tbl_all"], tbl)  # per-chunk {crc32, out_len, offset} table
-            stream.wait_stream(comm_stream)
-            launches += 1
+            if world > 1 and state["ready"]:
+                off, nb = subs[j]
+                n = batches[j].nchunks(nb)
+                cbase = c0 + bounds_chunks[j]
+                L = state["base"][j + 1] - state["base"][j]
+                pkg.check(lib.mz_cuda_memcpy_d2d(t_len + 4 * cbase, batches[j].out_len.data_ptr(), 4 * n, pkg._stream_ptr()), "rows")
+                pkg.check(lib.mz_cuda_event_record(ev_piece[j], pkg._stream_ptr()), "event")
+                pkg.check(lib.mz_cuda_stream_wait_event(copy_s, ev_piece[j]), "wait")
+                for r in range(world):  # THE exchange of the path: piece j of this rank's stream + its rows, to every peer
+                    if r == rank:
+                        continue
+                    pg, pc, pl = peers[r]
+                    o = region_off[rank] + state["base"][j]
+                    pkg.check(lib.mz_cuda_memcpy_peer(pg + o, g_mine + o, L, copy_s), "peer copy")
+                    pkg.check(lib.mz_cuda_memcpy_peer(pc + 4 * cbase, t_crc + 4 * cbase, 4 * n, copy_s), "peer copy")
+                    pkg.check(lib.mz_cuda_memcpy_peer(pl + 4 * cbase, t_len + 4 * cbase, 4 * n, copy_s), "peer copy")
+        if world > 1 and state["ready"]:
+            stream.wait_stream(copy_stream_t)  # the step ends when this rank's pieces have left
         return launches
 
     def barrier():
@@ -482,15 +522,15 @@ def run_ours(args, rank, world, local_rank):
     def piece_totals():
         return [int(b.offsets[b.nchunks(nb)].item()) for b, (_, nb) in zip(batches, subs)]
 
-    # warm-up: first pass sizes the gather slabs (max piece over all ranks + margin), the rest run the full pipeline
+    # warm-up: the first pass measures the pieces (their sizes fix where each lands in the gathered buffers), the rest run the full pipeline
     step()
     barrier()
     if world > 1:
-        mx = torch.tensor([max(piece_totals())], dtype=torch.int64, device=dev)
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        state["cap"] = (int(mx.item()) * 51 // 50 + 4096 + 255) // 256 * 256
+        tot = piece_totals()
         for j in range(NB):
-            state["gathered"][j] = torch.empty(state["cap"] * world, dtype=torch.uint8, device=dev)
+            state["base"][j + 1] = state["base"][j] + tot[j]
+        assert state["base"][NB] <= rbounds[rank], "region too small"
+        state["ready"] = True
     for i in range(max(0, args.warmup - 1) + (1 if world > 1 else 0)):
         step()
     barrier()
@@ -515,11 +555,18 @@ def run_ours(args, rank, world, local_rank):
     kms = sum(a.elapsed_time(b) for row in kev for a, b in row) / max(1, args.steps)
     clk = clocks.stop()
     if world > 1:
-        assert max(piece_totals()) <= state["cap"], "gather slab too small"
-        # the gathered slabs really hold every rank's stream: spot-check piece 0 of the next rank against the table
+        assert piece_totals() == [state["base"][j + 1] - state["base"][j] for j in range(NB)], "piece sizes changed between passes"
+        # the gathered buffer really holds every rank's stream: the next rank's region must start with a valid block header and its
+        # rows must be filled in (spot check), and the rank-ordered concatenation of all regions is checked against the CRC table
         nxt = (rank + 1) % world
-        rows = state["tbl_all"].view(world, -1, 3)[nxt]
-        assert int(rows[0, 2]) == 0 and int(rows[0, 1]) > 0
+        head = torch.empty(16, dtype=torch.uint8, device=dev)
+        pkg.check(lib.mz_cuda_memcpy_d2d(head.data_ptr(), g_mine + region_off[nxt], 16, pkg._stream_ptr()), "check")
+        nxt_c0 = nxt * nchunks_total // world
+        rows = torch.empty(2, dtype=torch.int32, device=dev)
+        pkg.check(lib.mz_cuda_memcpy_d2d(rows.data_ptr(), t_len + 4 * nxt_c0, 4, pkg._stream_ptr()), "check")
+        torch.cuda.synchronize()
+        assert int(head[0].item()) & 6 in (0, 4), "peer region does not start with a stored/dynamic block header"
+        assert 0 < int(rows[0].item()) <= 65632, "peer rows missing"
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -630,7 +677,8 @@ def run_ours(args, rank, world, local_rank):
         "data": "synthetic",
         "config": {"workload": workload_text(args),
                    "chunk_bytes": 65536, "level": args.level, "l2": "inputs (%.1f GiB per GPU) are far larger than L2; no flush needed" % (shard / GiB),
-                   "parallelism": ("chunk-sharded x%d; per step one NCCL all-gather of the bitstreams (in %d pieces overlapped with compression) + one of the per-chunk {crc,len,offset} table" % (world, NB)) if world > 1 else "single GPU"},
+                   "parallelism": ("chunk-sharded x%d; per step one all-gather of the bitstreams + per-chunk {crc32, out_len} rows, done with peer-to-peer copies on the copy engines "
+                                   "(IPC-mapped gathered buffers, %d pieces per shard overlapped with compression, exact lengths); NCCL only for setup and barriers" % (world, NB)) if world > 1 else "single GPU"},
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clk, "e2e": e2e, "gpu_launches": launches,
         "ratio": round(comp_bytes / shard, 4), "crc32": "%08x" % crc_whole,
     }

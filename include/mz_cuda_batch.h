@@ -78,6 +78,41 @@ int32_t mz_cuda_deflate_chunks(const void *d_in, uint64_t total_len, uint32_t ch
 int32_t mz_cuda_concat(const void *d_slots, uint64_t slot_stride, const uint32_t *d_out_len, uint32_t nchunks,
                        uint64_t *d_offsets, void *d_dst, void *stream);
 
+/* ---- multi-GPU: chunk-sharded DEFLATE, all-gather on the copy engines ---------------------------------------------------
+ * Chunks are independent, so device r of N owns a contiguous chunk range; the only exchange is the all-gather of the joined
+ * bitstreams and of the per-chunk {crc32, in_len, out_len} rows. It is done with peer-to-peer copies (cudaMemcpyPeerAsync /
+ * IPC-mapped destinations): the copy engines move the bytes over NVLink while every SM keeps compressing -- an SM-based
+ * collective cannot co-reside with the 2 x 111 KB deflate CTAs and serialises with them.
+ *
+ * (a) one process, N devices (a C host):  mz_cuda_deflate_sharded()
+ * (b) one process per device (torchrun):  export / open IPC handles of the gathered buffers once, then mz_cuda_memcpy_peer(). */
+typedef struct mz_cuda_shard {
+    int32_t device;          /* CUDA ordinal */
+    const void *d_in;        /* this device's shard of the input (on `device`), 16-byte aligned */
+    uint64_t len;            /* bytes; every shard but the last must be a multiple of 64 KiB */
+    void *d_gathered;        /* on `device`: receives EVERY device's joined stream; device r's stream starts at region_off[r] */
+    uint64_t gathered_cap;
+    uint32_t *d_rows;        /* on `device`: receives every device's rows {crc32, in_len, out_len} (3 x uint32 per chunk), in
+                                global chunk order (device r's rows start at chunk index = sum of earlier devices' chunks) */
+} mz_cuda_shard;
+/* Compress + CRC + join every shard on its device (level 0..9, BFINAL on the globally last chunk) and all-gather: after the
+ * call every device holds all streams and all rows. region_off[r], stream_len[r] (arrays of ndev, host) describe where device
+ * r's stream lies in every gathered buffer: region_off[r] = sum over earlier devices of mz_cuda_gather_region_bound(len);
+ * the rank-ordered concatenation of the N streams is ONE valid raw DEFLATE stream. *crc32 = CRC-32 of the whole input
+ * (host fold of the per-device CRCs). `pieces` >= 1: each shard is compressed in that many pieces and a finished piece
+ * travels while the next one is being compressed. Synchronous. */
+uint64_t mz_cuda_gather_region_bound(uint64_t shard_len);
+int32_t mz_cuda_deflate_sharded(const mz_cuda_shard *shards, int32_t ndev, int32_t level, int32_t pieces, uint64_t *region_off,
+                                uint64_t *stream_len, uint32_t *crc32);
+/* IPC: handle64 = 64 opaque bytes to hand to the other processes; open() maps a peer's allocation into this process (peer
+ * access is enabled lazily); memcpy_peer() = cudaMemcpyAsync between any two device pointers of this process's address space
+ * (own or IPC-mapped), executed by a copy engine. The exported pointer must come from mz_cuda_malloc(). */
+int32_t mz_cuda_ipc_export(const void *dptr, void *handle64);
+int32_t mz_cuda_ipc_open(const void *handle64, void **dptr);
+int32_t mz_cuda_ipc_close(void *dptr);
+int32_t mz_cuda_memcpy_peer(void *dst, const void *src, size_t bytes, void *stream);
+int32_t mz_cuda_stream_wait_event(void *stream, void *event);
+
 /* ---- K7: SHA-256 of independent buffers ----------------------------------------------------------------------
  * Message i = d_in[d_off[i] .. d_off[i] + d_len[i]); d_digest receives n x 32 bytes (the digest as the standard prints it).
  * This is the per-entry hash of the reference's zip writer / reader (MZ_ZIP_EXTENSION_HASH, mz_zip_rw.c:1339-1420, :410-450),

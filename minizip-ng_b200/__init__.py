@@ -52,6 +52,8 @@ EXPORTS = [
     "mz_cuda_crc32_segments", "mz_cuda_crc32_fold", "mz_cuda_crc32_device", "mz_cuda_crc32_device_stream", "mz_cuda_crc32_combine",
     "mz_cuda_deflate_slot_bound", "mz_cuda_deflate_chunks", "mz_cuda_concat", "mz_cuda_inflate_streams",
     "mz_cuda_inflate_spec_workspace_bytes", "mz_cuda_inflate_spec_round", "mz_cuda_sha256_batch",
+    "mz_cuda_gather_region_bound", "mz_cuda_deflate_sharded", "mz_cuda_ipc_export", "mz_cuda_ipc_open", "mz_cuda_ipc_close", "mz_cuda_memcpy_peer",
+    "mz_cuda_stream_wait_event",
     # include/mz_zip_cuda.h
     "mz_zip_cuda_add_buffers", "mz_zip_cuda_extract_all", "mz_zip_cuda_abi_file_info_size",
 ]
@@ -124,7 +126,20 @@ def configure(L):
     sig("mz_cuda_concat", i32, [vp, u64, vp, u32, vp, vp, vp])
     sig("mz_cuda_inflate_streams", i32, [vp, vp, u32, vp])
     sig("mz_cuda_sha256_batch", i32, [vp, vp, vp, u32, vp, vp])
+    sig("mz_cuda_gather_region_bound", u64, [u64])
+    sig("mz_cuda_deflate_sharded", i32, [vp, i32, i32, i32, C.POINTER(u64), C.POINTER(u64), C.POINTER(u32)])
+    sig("mz_cuda_ipc_export", i32, [vp, vp])
+    sig("mz_cuda_ipc_open", i32, [vp, C.POINTER(vp)])
+    sig("mz_cuda_ipc_close", i32, [vp])
+    sig("mz_cuda_memcpy_peer", i32, [vp, vp, sz, vp])
+    sig("mz_cuda_stream_wait_event", i32, [vp, vp])
     return L
+
+
+class Shard(C.Structure):
+    """mz_cuda_shard (include/mz_cuda_batch.h)"""
+    _fields_ = [("device", C.c_int32), ("d_in", C.c_void_p), ("len", C.c_uint64), ("d_gathered", C.c_void_p), ("gathered_cap", C.c_uint64),
+                ("d_rows", C.c_void_p)]
 
 
 def check(err, what="call"):

@@ -69,5 +69,17 @@ __global__ void __launch_bounds__(GATHER_THREADS) gather_slots_kernel(const uint
     }
 }
 
+/* per-chunk rows {crc32, in_len, out_len} for the multi-GPU table (one thread per chunk) */
+__global__ void __launch_bounds__(256) pack_rows_kernel(const uint32_t *chunk_crc, const uint32_t *out_len, uint32_t nchunks, uint64_t total_len,
+                                                        uint32_t chunk_size, uint32_t *rows) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nchunks) return;
+    const uint64_t off = (uint64_t)c * chunk_size;
+    const uint64_t rem = total_len - off;
+    rows[3 * c] = chunk_crc[c];
+    rows[3 * c + 1] = rem < chunk_size ? (uint32_t)rem : chunk_size;
+    rows[3 * c + 2] = out_len[c];
+}
+
 } // namespace mzc
 #endif

@@ -492,4 +492,211 @@ int32_t mz_cuda_sha256_batch(const void *d_in, const uint64_t *d_off, const uint
     return MZ_OK;
 }
 
+/* ---- multi-GPU --------------------------------------------------------------------------------------------- */
+int32_t mz_cuda_ipc_export(const void *dptr, void *handle64) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CK(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)handle64, (void *)dptr));
+    return MZ_OK;
+}
+int32_t mz_cuda_ipc_open(const void *handle64, void **dptr) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    CK(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return MZ_OK;
+}
+int32_t mz_cuda_ipc_close(void *dptr) {
+    CK(cudaIpcCloseMemHandle(dptr));
+    return MZ_OK;
+}
+int32_t mz_cuda_memcpy_peer(void *dst, const void *src, size_t bytes, void *stream) {
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream)); /* UVA: the driver routes it over NVLink on a copy engine */
+    return MZ_OK;
+}
+int32_t mz_cuda_stream_wait_event(void *stream, void *event) {
+    CK(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)event, 0));
+    return MZ_OK;
+}
+
+uint64_t mz_cuda_gather_region_bound(uint64_t shard_len) {
+    const uint64_t nch = shard_len == 0 ? 1 : (shard_len + MZ_CUDA_CHUNK_MAX - 1) / MZ_CUDA_CHUNK_MAX;
+    return (nch * deflate_slot_bound(MZ_CUDA_CHUNK_MAX) + 255) & ~255ull;
+}
+
+namespace {
+struct ShardCtx { /* per shard slot (= per device in real use), grown on demand, kept for the life of the process */
+    int device = -1;
+    cudaStream_t compute = nullptr, copy = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    uint8_t *d_slots = nullptr;
+    uint32_t *d_out_len = nullptr, *d_residue = nullptr, *d_chunk_crc = nullptr, *d_crc2 = nullptr, *d_rows = nullptr;
+    uint64_t *d_offsets = nullptr;
+    uint64_t *h_total = nullptr; /* pinned: [2] joined bytes of the piece in flight */
+    uint32_t *h_crc = nullptr;   /* pinned: [2][2] */
+    uint32_t cap_chunks = 0;
+};
+ShardCtx g_shard[kMaxDev];
+std::mutex g_shard_mu;
+}
+
+int32_t mz_cuda_deflate_sharded(const mz_cuda_shard *sh, int32_t ndev, int32_t level, int32_t pieces, uint64_t *region_off, uint64_t *stream_len,
+                                uint32_t *crc32) {
+    if (!sh || ndev < 1 || ndev > kMaxDev || level < 0 || level > 9 || !region_off || !stream_len) return MZ_PARAM_ERROR;
+    if (pieces < 1) pieces = 1;
+    std::lock_guard<std::mutex> lk(g_shard_mu);
+    int prev_dev = 0;
+    cudaGetDevice(&prev_dev);
+    const uint64_t stride = deflate_slot_bound(MZ_CUDA_CHUNK_MAX);
+    std::vector<uint32_t> nch(ndev), chunk_base(ndev);
+    uint64_t roff = 0;
+    uint32_t cb = 0;
+    for (int i = 0; i < ndev; i++) {
+        if (sh[i].device < 0 || sh[i].device >= kMaxDev || !sh[i].d_gathered || ((uintptr_t)sh[i].d_in & 15) || ((uintptr_t)sh[i].d_gathered & 15)) return MZ_PARAM_ERROR;
+        if (i + 1 < ndev && (sh[i].len == 0 || sh[i].len % MZ_CUDA_CHUNK_MAX)) return MZ_PARAM_ERROR;
+        nch[i] = (uint32_t)(sh[i].len == 0 ? 1 : (sh[i].len + MZ_CUDA_CHUNK_MAX - 1) / MZ_CUDA_CHUNK_MAX);
+        region_off[i] = roff;
+        roff += mz_cuda_gather_region_bound(sh[i].len);
+        chunk_base[i] = cb;
+        cb += nch[i];
+    }
+    for (int i = 0; i < ndev; i++)
+        if (sh[i].gathered_cap < roff) return MZ_PARAM_ERROR;
+    /* contexts, scratch, peer access */
+    for (int i = 0; i < ndev; i++) {
+        CK(cudaSetDevice(sh[i].device));
+        DeviceCtx *c;
+        int32_t err = get_ctx(&c);
+        if (err) return err;
+        ShardCtx &x = g_shard[i];
+        if (x.compute && x.device != sh[i].device) return MZ_PARAM_ERROR; /* slot i stays with the device it was first used with */
+        if (!x.compute) {
+            x.device = sh[i].device;
+            CK(cudaStreamCreateWithFlags(&x.compute, cudaStreamNonBlocking));
+            CK(cudaStreamCreateWithFlags(&x.copy, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&x.ev[0], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&x.ev[1], cudaEventDisableTiming));
+            CK(cudaHostAlloc((void **)&x.h_total, 16, cudaHostAllocDefault));
+            CK(cudaHostAlloc((void **)&x.h_crc, 16, cudaHostAllocDefault));
+            CK(cudaMalloc(&x.d_crc2, 16));
+        }
+        const uint32_t need = (nch[i] + (uint32_t)pieces - 1) / (uint32_t)pieces + 1; /* chunks of the largest piece */
+        if (x.cap_chunks < need || !x.d_rows) {
+            cudaFree(x.d_slots); cudaFree(x.d_out_len); cudaFree(x.d_residue); cudaFree(x.d_chunk_crc); cudaFree(x.d_offsets); cudaFree(x.d_rows);
+            x.cap_chunks = 0;
+            CK(cudaMalloc(&x.d_slots, (size_t)need * stride));
+            CK(cudaMalloc(&x.d_out_len, (size_t)need * 4));
+            CK(cudaMalloc(&x.d_residue, (size_t)need * 4));
+            CK(cudaMalloc(&x.d_chunk_crc, (size_t)need * 4));
+            CK(cudaMalloc(&x.d_offsets, ((size_t)need + 1) * 8));
+            CK(cudaMalloc(&x.d_rows, (size_t)need * 12));
+            x.cap_chunks = need;
+        }
+        for (int j = 0; j < ndev; j++)
+            if (j != i && sh[j].device != sh[i].device) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(sh[j].device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(e, "cudaDeviceEnablePeerAccess");
+                cudaGetLastError();
+            }
+    }
+    std::vector<uint64_t> base(ndev, 0);            /* bytes of device i's stream produced so far */
+    std::vector<uint32_t> crc_dev(ndev, 0);
+    std::vector<uint64_t> done_len(ndev, 0);        /* input bytes folded into crc_dev */
+    auto piece_range = [&](int i, int k, uint32_t &c0, uint32_t &c1) {
+        c0 = (uint32_t)((uint64_t)nch[i] * k / pieces);
+        c1 = (uint32_t)((uint64_t)nch[i] * (k + 1) / pieces);
+    };
+    /* finish piece k of device i: learn its size, send it (and its rows) to every other device on the copy stream */
+    auto finish = [&](int i, int k) -> int32_t {
+        ShardCtx &x = g_shard[i];
+        CK(cudaSetDevice(sh[i].device));
+        CK(cudaEventSynchronize(x.ev[k & 1]));
+        uint32_t c0, c1;
+        piece_range(i, k, c0, c1);
+        const uint64_t L = x.h_total[k & 1];
+        const uint64_t in0 = (uint64_t)c0 * MZ_CUDA_CHUNK_MAX;
+        const uint64_t inl = ((uint64_t)c1 * MZ_CUDA_CHUNK_MAX < sh[i].len ? (uint64_t)c1 * MZ_CUDA_CHUNK_MAX : sh[i].len) - (in0 < sh[i].len ? in0 : sh[i].len);
+        const uint32_t pc = x.h_crc[(k & 1) * 2 + 1];
+        if (inl) {
+            crc_dev[i] = done_len[i] == 0 ? pc : mz_cuda_crc32_combine(crc_dev[i], pc, inl);
+            done_len[i] += inl;
+        }
+        if (c1 > c0) {
+            const uint8_t *src = (const uint8_t *)sh[i].d_gathered + region_off[i] + base[i];
+            for (int j = 0; j < ndev; j++) {
+                if (j == i) continue;
+                CK(cudaMemcpyPeerAsync((uint8_t *)sh[j].d_gathered + region_off[i] + base[i], sh[j].device, src, sh[i].device, (size_t)L, x.copy));
+                if (sh[j].d_rows && sh[i].d_rows)
+                    CK(cudaMemcpyPeerAsync(sh[j].d_rows + 3ull * (chunk_base[i] + c0), sh[j].device, sh[i].d_rows + 3ull * (chunk_base[i] + c0), sh[i].device,
+                                           (size_t)(c1 - c0) * 12, x.copy));
+            }
+        }
+        base[i] += L;
+        return MZ_OK;
+    };
+    for (int k = 0; k <= pieces; k++) {
+        if (k < pieces) {
+            for (int i = 0; i < ndev; i++) { /* compression of piece k: does not depend on where the piece will land */
+                ShardCtx &x = g_shard[i];
+                CK(cudaSetDevice(sh[i].device));
+                uint32_t c0, c1;
+                piece_range(i, k, c0, c1);
+                if (c1 == c0) continue;
+                const uint64_t in0 = (uint64_t)c0 * MZ_CUDA_CHUNK_MAX;
+                const uint64_t inl = ((uint64_t)c1 * MZ_CUDA_CHUNK_MAX < sh[i].len ? (uint64_t)c1 * MZ_CUDA_CHUNK_MAX : sh[i].len) - in0;
+                const uint32_t lastf = (i == ndev - 1 && k == pieces - 1) ? MZ_CUDA_FLAG_FINAL : 0u;
+                int32_t err = mz_cuda_deflate_chunks((const uint8_t *)sh[i].d_in + in0, inl, MZ_CUDA_CHUNK_MAX, nullptr, nullptr, nullptr, c1 - c0, lastf, level,
+                                                     x.d_slots, stride, x.d_out_len, x.compute);
+                if (!err) err = mz_cuda_crc32_segments((const uint8_t *)sh[i].d_in + in0, inl, MZ_CUDA_CHUNK_MAX, nullptr, nullptr, c1 - c0, x.d_residue, x.d_chunk_crc, x.compute);
+                if (!err) err = mz_cuda_crc32_fold(x.d_residue, c1 - c0, MZ_CUDA_CHUNK_MAX, inl, x.d_crc2, x.compute);
+                if (err) return err;
+            }
+        }
+        if (k > 0)
+            for (int i = 0; i < ndev; i++) {
+                int32_t err = finish(i, k - 1);
+                if (err) return err;
+            }
+        if (k < pieces) {
+            for (int i = 0; i < ndev; i++) { /* join piece k straight into the device's own region of its gathered buffer */
+                ShardCtx &x = g_shard[i];
+                CK(cudaSetDevice(sh[i].device));
+                uint32_t c0, c1;
+                piece_range(i, k, c0, c1);
+                x.h_total[k & 1] = 0;
+                if (c1 > c0) {
+                    uint8_t *dst = (uint8_t *)sh[i].d_gathered + region_off[i] + base[i];
+                    const uint64_t in0 = (uint64_t)c0 * MZ_CUDA_CHUNK_MAX;
+                    const uint64_t inl = ((uint64_t)c1 * MZ_CUDA_CHUNK_MAX < sh[i].len ? (uint64_t)c1 * MZ_CUDA_CHUNK_MAX : sh[i].len) - in0;
+                    int32_t err = mz_cuda_concat(x.d_slots, stride, x.d_out_len, c1 - c0, x.d_offsets, dst, x.compute);
+                    if (err) return err;
+                    if (sh[i].d_rows) {
+                        MZ_LAUNCH(pack_rows_kernel, dim3((c1 - c0 + 255) / 256), dim3(256), 0, x.compute, (const uint32_t *)x.d_chunk_crc, (const uint32_t *)x.d_out_len,
+                                  c1 - c0, inl, (uint32_t)MZ_CUDA_CHUNK_MAX, sh[i].d_rows + 3ull * (chunk_base[i] + c0));
+                        CK(cudaGetLastError());
+                    }
+                    CK(cudaMemcpyAsync(&x.h_total[k & 1], x.d_offsets + (c1 - c0), 8, cudaMemcpyDeviceToHost, x.compute));
+                    CK(cudaMemcpyAsync(&x.h_crc[(k & 1) * 2], x.d_crc2, 8, cudaMemcpyDeviceToHost, x.compute));
+                }
+                CK(cudaEventRecord(x.ev[k & 1], x.compute));
+                CK(cudaStreamWaitEvent(x.copy, x.ev[k & 1], 0)); /* the copies of this piece (issued later) follow its join */
+            }
+        }
+    }
+    uint32_t crc = 0;
+    uint64_t folded = 0;
+    for (int i = 0; i < ndev; i++) {
+        ShardCtx &x = g_shard[i];
+        CK(cudaSetDevice(sh[i].device));
+        CK(cudaStreamSynchronize(x.copy));
+        CK(cudaStreamSynchronize(x.compute));
+        stream_len[i] = base[i];
+        if (done_len[i]) {
+            crc = folded == 0 ? crc_dev[i] : mz_cuda_crc32_combine(crc, crc_dev[i], done_len[i]);
+            folded += done_len[i];
+        }
+    }
+    if (crc32) *crc32 = crc;
+    cudaSetDevice(prev_dev);
+    return MZ_OK;
+}
+
 } /* extern "C" */

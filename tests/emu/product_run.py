@@ -133,6 +133,69 @@ def scenario_crc():
     assert lib.mz_crypt_crc32_update(0xDEADBEEF, bb, len(big)) == zlib.crc32(big, 0xDEADBEEF)
 
 
+def scenario_sharded():
+    """mz_cuda_deflate_sharded with three shards (all on the emulator's one device): region layout, piece pipeline, rows, CRC fold"""
+    pkg = p
+    text = datagen.text_like(11 * 65536 - 4321, 77)
+    cuts = [0, 5 * 65536, 8 * 65536, len(text)]
+    n = 3
+    bound = [lib.mz_cuda_gather_region_bound(cuts[i + 1] - cuts[i]) for i in range(n)]
+    cap = sum(bound)
+    nch_all = sum((cuts[i + 1] - cuts[i] + 65535) // 65536 for i in range(n))
+    ins = [C.create_string_buffer(text[cuts[i]:cuts[i + 1]] + bytes(64), cuts[i + 1] - cuts[i] + 64) for i in range(n)]
+    gath = [C.create_string_buffer(cap + 64) for _ in range(n)]
+    rows = [(C.c_uint32 * (3 * nch_all))() for _ in range(n)]
+
+    def al(b):  # 16-byte aligned view into a ctypes buffer
+        a = C.addressof(b)
+        return (a + 15) & ~15
+    # ctypes buffers are not 16-byte aligned by contract: copy into aligned storage
+    store = []
+
+    def aligned(data, extra=64):
+        raw = C.create_string_buffer(len(data) + extra + 16)
+        p = al(raw)
+        C.memmove(p, data, len(data))
+        store.append(raw)
+        return p
+    shards = (pkg.Shard * n)()
+    gp = []
+    for i in range(n):
+        shards[i].device = 0
+        shards[i].d_in = aligned(text[cuts[i]:cuts[i + 1]])
+        shards[i].len = cuts[i + 1] - cuts[i]
+        g = aligned(bytes(cap), 0)
+        gp.append(g)
+        shards[i].d_gathered = g
+        shards[i].gathered_cap = cap
+        shards[i].d_rows = C.addressof(rows[i])
+    roff = (C.c_uint64 * n)()
+    slen = (C.c_uint64 * n)()
+    crc = C.c_uint32(0)
+    for pieces in (1, 2, 3):
+        err = lib.mz_cuda_deflate_sharded(shards, n, 1, pieces, roff, slen, C.byref(crc))
+        assert err == 0, (err, lib.mz_cuda_last_error())
+        assert crc.value == zlib.crc32(text)
+        streams = []
+        for j in range(n):  # every device's gathered buffer holds every stream at the same place
+            parts = [C.string_at(gp[j] + roff[i], slen[i]) for i in range(n)]
+            streams.append(b"".join(parts))
+        assert streams[0] == streams[1] == streams[2]
+        d = zlib.decompressobj(-15)
+        assert d.decompress(streams[0]) == text and d.eof and d.unused_data == b""
+        # rows: {crc32, in_len, out_len} per chunk in global order, identical everywhere
+        r0 = list(rows[0])
+        assert list(rows[1]) == r0 and list(rows[2]) == r0
+        pos = 0
+        total_out = 0
+        for c in range(nch_all):
+            ln = r0[3 * c + 1]
+            assert r0[3 * c] == zlib.crc32(text[pos:pos + ln])
+            pos += ln
+            total_out += r0[3 * c + 2]
+        assert pos == len(text) and total_out == sum(slen)
+
+
 if __name__ == "__main__":
     name = sys.argv[1]
     if name == "write":
@@ -143,6 +206,8 @@ if __name__ == "__main__":
         scenario_long()
     elif name == "crc":
         scenario_crc()
+    elif name == "sharded":
+        scenario_sharded()
     else:
         raise SystemExit("unknown scenario " + name)
     print("scenario %s ok" % name)

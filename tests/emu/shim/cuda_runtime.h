@@ -14,7 +14,7 @@ typedef int cudaError_t;
 enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1 };
 typedef struct emu_stream_s *cudaStream_t;
 typedef struct emu_event_s { double t; } *cudaEvent_t;
-enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
+enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3, cudaMemcpyDefault = 4 };
 enum { cudaStreamNonBlocking = 1, cudaHostAllocDefault = 0 };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2 };
@@ -53,5 +53,17 @@ static inline cudaError_t cudaEventSynchronize(cudaEvent_t e) { (void)e; return 
 static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)(b->t - a->t); return cudaSuccess; }
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F f, enum cudaFuncAttribute a, int v) { (void)f; (void)a; (void)v; return cudaSuccess; }
 static inline cudaError_t cudaPointerGetAttributes(struct cudaPointerAttributes *a, const void *p) { (void)p; a->type = cudaMemoryTypeUnregistered; return cudaSuccess; }
+
+/* multi-device / IPC entry points: the emulator has one "device" whose memory is the host's, so several shards can be run on
+ * ordinal 0 (tests exercise the piece pipeline, the region layout and the CRC fold of mz_cuda_deflate_sharded that way) */
+enum { cudaErrorPeerAccessAlreadyEnabled = 704, cudaEventDisableTiming = 2, cudaIpcMemLazyEnablePeerAccess = 1 };
+typedef struct { char reserved[64]; } cudaIpcMemHandle_t;
+static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) { memset(h, 0, sizeof(*h)); memcpy(h->reserved, &p, sizeof(p)); return cudaSuccess; }
+static inline cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned flags) { (void)flags; memcpy(p, h.reserved, sizeof(*p)); return cudaSuccess; }
+static inline cudaError_t cudaIpcCloseMemHandle(void *p) { (void)p; return cudaSuccess; }
+static inline cudaError_t cudaDeviceEnablePeerAccess(int peer, unsigned flags) { (void)peer; (void)flags; return cudaSuccess; }
+static inline cudaError_t cudaMemcpyPeerAsync(void *d, int dd, const void *s, int sd, size_t n, cudaStream_t st) { (void)dd; (void)sd; (void)st; memmove(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned flags) { (void)s; (void)e; (void)flags; return cudaSuccess; }
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned flags) { (void)flags; return cudaEventCreate(e); }
 
 #endif

@@ -50,6 +50,11 @@ def test_crc_symbol_device_path(emulib):
     _scenario("crc", MZ_CUDA_CRC_MIN_BYTES=65536)
 
 
+def test_sharded_deflate_layout_pieces_rows_and_crc(emulib):
+    """mz_cuda_deflate_sharded (the multi-GPU entry point of the C library) with three shards on the emulator's device"""
+    _scenario("sharded")
+
+
 def test_host_paths_under_sanitizers(emulib):
     """the same scenarios with the whole library (host C included) built with AddressSanitizer + UBSan: window arithmetic that
     runs off a staging buffer, a stale pointer after the workspace switches windows, a shift by 32 ... abort the run"""
