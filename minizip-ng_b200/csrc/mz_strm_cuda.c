@@ -33,6 +33,7 @@
 typedef struct cu_slot_s {
     void *stream;   /* cudaStream_t */
     void *ev_h2d;   /* input upload finished: caller memory may be reused */
+    void *ev_d2h[2]; /* download pieces: piece i+1 travels while piece i is handed to base */
     uint8_t *h_in;  /* pinned staging for pageable / small writes */
     uint8_t *d_in, *d_slots, *d_out, *h_out;
     uint32_t *d_out_len, *d_residue, *d_crc2;
@@ -97,6 +98,8 @@ static void ws_destroy(cu_ws *w) {
         mz_cuda_free(s->d_offsets);
         mz_cuda_host_free(s->h_total);
         mz_cuda_event_destroy(s->ev_h2d);
+        mz_cuda_event_destroy(s->ev_d2h[0]);
+        mz_cuda_event_destroy(s->ev_d2h[1]);
         mz_cuda_stream_destroy(s->stream);
     }
     mz_cuda_host_free(w->h_cin);
@@ -146,6 +149,8 @@ static cu_ws *ws_acquire(int kind) {
             cu_slot *s = &w->slot[i];
             s->stream = mz_cuda_stream_create();
             s->ev_h2d = mz_cuda_event_create();
+            s->ev_d2h[0] = mz_cuda_event_create();
+            s->ev_d2h[1] = mz_cuda_event_create();
             s->h_in = (uint8_t *)mz_cuda_host_alloc(batch);
             s->d_in = (uint8_t *)mz_cuda_malloc(batch + 64);
             s->d_slots = (uint8_t *)mz_cuda_malloc(slots);
@@ -156,7 +161,7 @@ static cu_ws *ws_acquire(int kind) {
             s->d_crc2 = (uint32_t *)mz_cuda_malloc(8);
             s->d_offsets = (uint64_t *)mz_cuda_malloc(((size_t)w->max_chunks + 1) * 8);
             s->h_total = (uint64_t *)mz_cuda_host_alloc(16);
-            if (!s->stream || !s->ev_h2d || !s->h_in || !s->d_in || !s->d_slots || !s->d_out || !s->h_out || !s->d_out_len ||
+            if (!s->stream || !s->ev_h2d || !s->ev_d2h[0] || !s->ev_d2h[1] || !s->h_in || !s->d_in || !s->d_slots || !s->d_out || !s->h_out || !s->d_out_len ||
                 !s->d_residue || !s->d_crc2 || !s->d_offsets || !s->h_total) {
                 ws_destroy(w);
                 return NULL;
@@ -192,6 +197,7 @@ static void ws_release(cu_ws *w) {
         if (w->pending)
             mz_cuda_stream_sync(w->rstream);
         w->pending = 0;
+        mz_cuda_stream_sync(w->dstream); /* a piece may still be on its way into h_dec (abandoned read) */
     }
     if (w->kind == 1) {
         for (int i = 0; i < CU_NSLOT; i++) {
@@ -244,7 +250,9 @@ typedef struct mz_stream_cuda_s {
     uint64_t cin_base;  /* raw-stream offset of ws->h_cin[0] */
     size_t cin_len;     /* valid bytes in ws->h_cin */
     uint64_t win_base;  /* output offset of ws->d_win[0] */
-    size_t dec_pos, dec_len; /* decoded bytes waiting in ws->h_dec */
+    size_t dec_pos, dec_len; /* decoded bytes waiting in ws->h_dec + dec_base */
+    size_t dec_base;         /* which half of h_dec the caller is reading */
+    size_t pre_len;          /* bytes of the NEXT piece already on their way into the other half (0 = none) */
     uint64_t fed_in;    /* compressed bytes pulled from base (framing included) */
     uint64_t deliv_pos; /* output bytes already copied out of ws->d_win */
     uint64_t spec_resume_bit; /* no speculative round before the decoder has passed this stream bit */
@@ -313,6 +321,7 @@ int32_t mz_stream_cuda_open(void *stream, const char *path, int32_t mode) {
     cu->cin_len = 0;
     cu->win_base = 0;
     cu->dec_pos = cu->dec_len = 0;
+    cu->dec_base = cu->pre_len = 0;
     cu->fed_in = 0;
     cu->deliv_pos = 0;
     cu->spec_resume_bit = 0;
@@ -430,16 +439,37 @@ static int32_t cu_retire(mz_stream_cuda *cu, cu_slot *s) {
     if (err)
         return err;
     uint64_t total = s->h_total[0];
-    err = mz_cuda_memcpy_d2h(s->h_out, s->d_out, total, s->stream);
-    if (err)
-        return err;
-    err = mz_cuda_stream_sync(s->stream);
-    if (err)
-        return err;
     if (cu->wrap == 2 && s->n > 0) /* crc(A||B) from crc(A), crc(B), |B| */
         cu->crc = cu->crc_bytes == 0 ? (uint32_t)s->h_total[1] : mz_cuda_crc32_combine(cu->crc, (uint32_t)s->h_total[1], s->n);
     cu->crc_bytes += s->n;
-    return cu_emit(cu, s->h_out, total);
+    /* the joined stream comes down in pieces: while base (the caller's thread, usually a memcpy or a file write) takes piece i,
+     * piece i+1 is already crossing PCIe */
+    const uint64_t piece = 4u << 20;
+    const uint64_t np = (total + piece - 1) / piece;
+    for (uint64_t i = 0; i < np && i < 2; i++) {
+        const uint64_t o = i * piece, k = total - o < piece ? total - o : piece;
+        err = mz_cuda_memcpy_d2h(s->h_out + o, s->d_out + o, k, s->stream);
+        if (!err) err = mz_cuda_event_record(s->ev_d2h[i & 1], s->stream);
+        if (err)
+            return err;
+    }
+    for (uint64_t i = 0; i < np; i++) {
+        const uint64_t o = i * piece, k = total - o < piece ? total - o : piece;
+        err = mz_cuda_event_sync(s->ev_d2h[i & 1]);
+        if (err)
+            return err;
+        if (i + 2 < np) {
+            const uint64_t o2 = (i + 2) * piece, k2 = total - o2 < piece ? total - o2 : piece;
+            err = mz_cuda_memcpy_d2h(s->h_out + o2, s->d_out + o2, k2, s->stream);
+            if (!err) err = mz_cuda_event_record(s->ev_d2h[i & 1], s->stream);
+            if (err)
+                return err;
+        }
+        err = cu_emit(cu, s->h_out + o, k);
+        if (err)
+            return err;
+    }
+    return MZ_OK;
 }
 
 /* submit the slot being filled and advance the ring; the next slot is the oldest in flight */
@@ -846,6 +876,28 @@ static int32_t cu_spec_collect(mz_stream_cuda *cu) {
     return 1;
 }
 
+/* enqueue (on the delivery stream) the download of the next undelivered bytes into h_dec + base; advances deliv_pos */
+static int32_t cu_fetch_piece(mz_stream_cuda *cu, size_t base, size_t cap) {
+    cu_ws *w = cu->ws;
+    const mz_cuda_inflate_state *st = w->h_state;
+    uint64_t n = st->out_pos - cu->deliv_pos;
+    int32_t err;
+    if (n > cap)
+        n = cap;
+    const uint8_t *src = w->d_win + (cu->deliv_pos - cu->win_base);
+    if (cu->wrap == 2) {
+        err = mz_cuda_crc32_device_stream(src, n, cu->crc, &cu->crc, w->dstream);
+        if (err)
+            return err;
+    }
+    err = mz_cuda_memcpy_d2h(w->h_dec + base, src, n, w->dstream);
+    if (err)
+        return err;
+    cu->pre_len = (size_t)n;
+    cu->deliv_pos += n;
+    return MZ_OK;
+}
+
 /* Make ws->h_dec[0..dec_len) hold fresh output, or finish the stream. Decoded bytes stay in the device window until
  * they are delivered, at most one host buffer (`batch`) per call; while they are being delivered the next K6 round
  * is already running on the decode stream. */
@@ -865,8 +917,9 @@ static int32_t cu_decode_more(mz_stream_cuda *cu) {
             ws_read_upgrade(w, cu->cin_len);
     }
     for (;;) {
-        /* 1. deliver what is already decoded */
-        if (cu->deliv_pos < st->out_pos) {
+        /* 1. deliver what is already decoded. h_dec is two halves: the piece the caller is copying out of one half has its
+         * successor already crossing PCIe into the other (enqueued before this function returned last time). */
+        if (cu->deliv_pos < st->out_pos || cu->pre_len) {
             /* keep the GPU busy meanwhile: if the decoder stands at a block boundary and the output window still has
              * room behind the undelivered bytes, start the next round now */
             if (w->d_spec && !w->pending && st->status == 0 && st->phase == 0 &&
@@ -880,26 +933,30 @@ static int32_t cu_decode_more(mz_stream_cuda *cu) {
                         return err;
                 }
             }
-            uint64_t n = st->out_pos - cu->deliv_pos;
-            if (n > w->batch)
-                n = w->batch;
-            const uint8_t *src = w->d_win + (cu->deliv_pos - cu->win_base);
-            if (cu->wrap == 2) {
-                err = mz_cuda_crc32_device_stream(src, n, cu->crc, &cu->crc, w->dstream);
+            const size_t half = w->batch / 2;
+            if (!cu->pre_len) { /* nothing in flight: fetch the next piece now */
+                cu->dec_base = 0;
+                err = cu_fetch_piece(cu, cu->dec_base, half);
                 if (err)
                     return err;
+            } else {
+                cu->dec_base = cu->dec_base ? 0 : half; /* the piece in flight landed in the other half */
             }
-            err = mz_cuda_memcpy_d2h(w->h_dec, src, n, w->dstream);
-            if (err)
-                return err;
             err = mz_cuda_stream_sync(w->dstream);
             if (err)
                 return err;
+            const size_t n = cu->pre_len;
+            cu->pre_len = 0;
             if (cu->wrap == 1)
-                cu_adler_update(cu, w->h_dec, n);
+                cu_adler_update(cu, w->h_dec + cu->dec_base, n);
             cu->dec_pos = 0;
-            cu->dec_len = (size_t)n;
-            cu->deliv_pos += n;
+            cu->dec_len = n;
+            /* and send the piece after it on its way before the caller starts copying this one */
+            if (cu->deliv_pos < st->out_pos) {
+                err = cu_fetch_piece(cu, cu->dec_base ? 0 : half, half);
+                if (err)
+                    return err;
+            }
             return MZ_OK;
         }
         /* 2. a round in flight: its result decides what comes next */
@@ -1005,7 +1062,7 @@ int32_t mz_stream_cuda_read(void *stream, void *buf, int32_t size) {
             size_t k = cu->dec_len - cu->dec_pos;
             if (k > (size_t)(size - done))
                 k = (size_t)(size - done);
-            memcpy(out + done, cu->ws->h_dec + cu->dec_pos, k);
+            memcpy(out + done, cu->ws->h_dec + cu->dec_base + cu->dec_pos, k);
             cu->dec_pos += k;
             done += (int32_t)k;
             continue;
@@ -1028,7 +1085,7 @@ int32_t mz_stream_cuda_read(void *stream, void *buf, int32_t size) {
      * stands at the end of the stream, finish now instead of on an extra read() call. A bad trailer surfaces on the
      * next call, like every other error that follows cleanly decoded bytes. */
     if (cu->error == 0 && !cu->ended && cu->ws && cu->hdr_parsed && cu->dec_pos == cu->dec_len && !cu->ws->pending &&
-        cu->ws->h_state->status == 1 && cu->deliv_pos == cu->ws->h_state->out_pos) {
+        cu->ws->h_state->status == 1 && cu->deliv_pos == cu->ws->h_state->out_pos && cu->pre_len == 0) {
         int32_t ferr = cu_finish_stream(cu);
         if (ferr != MZ_OK)
             cu->error = ferr;
