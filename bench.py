@@ -995,46 +995,59 @@ def run_c3(args, rank, world, local_rank):
 
 
 def run_c4(args, rank, world, local_rank):
-    """zip of N x 64 KiB entries (70 % text, 20 % records, 10 % incompressible), level 6: the product's batch writer
-    (mz_zip_cuda_add_buffers) through the reference's own container code, archive on tmpfs, driven by the C program
-    oracle/_ref/zipbatch_cuda (tests/support/zipbatch.c). With N GPUs every rank writes its own archive of entries/N entries
-    (the zip container is a serial byte stream: entries shard, archives do not merge without rewriting offsets)."""
+    """zip of N x 64 KiB entries (70 % text, 20 % records, 10 % incompressible), level 6, archive on tmpfs, driven by the C program
+    oracle/_ref/zipbatch_cuda (tests/support/zipbatch.c). The product's native archive writer (mz_zip_cuda_write_archive: headers,
+    streams, central directory by the library, a round's region assembled on the device) is the measured path; the batch writer on
+    the reference's raw-entry seam (mz_zip_cuda_add_buffers) is reported beside it. With N GPUs the ENTRIES shard across the GPUs
+    inside one writer (rounds go round-robin to the devices, flag MZ_ZIP_CUDA_ALL_DEVICES): a zip archive is one serial byte
+    stream, so rank 0 drives all N devices from one process and the other ranks only take part in the barriers."""
     torch, pkg, lib, dev = _setup(local_rank)
     exe = os.path.join(ROOT, "oracle", "_ref", "zipbatch_cuda")
-    entries = int(round(args.size_gib * GiB / 65536)) // world
-    d = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
-    env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", ",".join(str(i) for i in range(torch.cuda.device_count()))).split(",")[local_rank])
-    runs = []
+    entries = int(round(args.size_gib * GiB / 65536))
+    runs, seam = [], None
     clocks = ClockSampler(local_rank)
-    try:
-        for i in range(min(args.warmup, 1) + min(args.steps, 3)):
-            if i == min(args.warmup, 1):
-                clocks.start()
-            _barrier(world)
-            r = subprocess.run([exe, os.path.join(d, "c4_%d.zip" % rank), str(entries), "65536", str(args.level), "cuda"], stdout=subprocess.PIPE, text=True, env=env, timeout=900)
-            j = json.loads(r.stdout.strip().splitlines()[-1])
-            assert j["err"] == 0 and j["close_err"] == 0, j
-            if i >= min(args.warmup, 1):
-                runs.append(j)
-        clk = clocks.stop()
-        # the archive is a valid zip: CPython's zipfile checks every entry's CRC
-        import zipfile
-        with zipfile.ZipFile(os.path.join(d, "c4_%d.zip" % rank)) as zf:
-            assert len(zf.namelist()) == entries and zf.testzip() is None
-    finally:
-        subprocess.run(["rm", "-rf", d])
+    clk = None
+    if rank == 0:
+        d = tempfile.mkdtemp(dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        env = dict(os.environ)  # under torchrun every rank sees all devices: the writer takes them all
+        mode = "native_all" if world > 1 else "native"
+        try:
+            for i in range(min(args.warmup, 1) + min(args.steps, 3)):
+                if i == min(args.warmup, 1):
+                    clocks.start()
+                r = subprocess.run([exe, os.path.join(d, "c4.zip"), str(entries), "65536", str(args.level), mode], stdout=subprocess.PIPE, text=True, env=env, timeout=900)
+                j = json.loads(r.stdout.strip().splitlines()[-1])
+                assert j["err"] == 0 and j["close_err"] == 0, j
+                if i >= min(args.warmup, 1):
+                    runs.append(j)
+            clk = clocks.stop()
+            import zipfile
+            with zipfile.ZipFile(os.path.join(d, "c4.zip")) as zf:  # a valid zip: CPython's zipfile checks every entry's CRC
+                assert len(zf.namelist()) == entries and zf.testzip() is None
+            if world == 1:
+                r = subprocess.run([exe, os.path.join(d, "c4s.zip"), str(entries), "65536", str(args.level), "cuda"], stdout=subprocess.PIPE, text=True, env=env, timeout=900)
+                seam = json.loads(r.stdout.strip().splitlines()[-1])
+        finally:
+            subprocess.run(["rm", "-rf", d])
+    _barrier(world)
+    if rank != 0:
+        return
     add_s = sum(j["add_s"] + j["close_s"] for j in runs) / len(runs)
     gpu_ms = sum(j["gpu_ms"] for j in runs) / len(runs)
     nbytes = runs[-1]["bytes_in"]
     peak, psrc = _peak()
-    roofline = {"bound": "hbm", "kernel": "deflate_chunks_kernel (+ crc32_segments, gather)", "achieved": round(nbytes / gpu_ms / 1e6, 2), "peak": peak, "unit": "GB/s",
-                "frac": round(nbytes / gpu_ms / 1e6 / peak, 5), "traffic": None, "peak_source": psrc, "algorithmic_bytes_per_launch": nbytes // max(runs[-1]["rounds"], 1),
-                "ms_per_launch": round(gpu_ms / max(runs[-1]["rounds"], 1), 3), "launches_per_step": runs[-1]["rounds"],
-                "note": "gpu_ms = upload + kernels + download per round as timed by the writer's worker thread (host clock around stream syncs)"}
-    value = nbytes * world / GiB / add_s
+    roofline = {"bound": "hbm", "kernel": "deflate_chunks_kernel (+ crc32_segments, gather, header scatter)", "achieved": round(nbytes / gpu_ms / 1e6, 2), "peak": peak,
+                "unit": "GB/s", "frac": round(nbytes / gpu_ms / 1e6 / peak, 5), "traffic": None, "peak_source": psrc,
+                "algorithmic_bytes_per_launch": nbytes // max(runs[-1]["rounds"], 1), "ms_per_launch": round(gpu_ms / max(runs[-1]["rounds"], 1), 3),
+                "launches_per_step": runs[-1]["rounds"],
+                "note": "gpu_ms = per round: kernels + table download + layout + region assembly + region download, host clock of the worker thread (summed over devices)"}
+    value = nbytes / GiB / add_s
     e2e = {"value": round(value, 4), "unit": "GiB/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": runs[-1]["bytes_out"],
-           "api": "mz_zip_cuda_add_buffers(zip handle, %d host buffers) + mz_zip_close, archive file on tmpfs" % entries,
-           "entries_per_s": round(entries * world / add_s, 1), "pack_ms": runs[-1]["pack_ms"], "gpu_ms": runs[-1]["gpu_ms"], "container_ms": runs[-1]["container_ms"]}
+           "api": "mz_zip_cuda_write_archive(file stream, %d host buffers, flags %s), archive file on tmpfs" % (entries, "ALL_DEVICES" if world > 1 else "0"),
+           "entries_per_s": round(entries / add_s, 1), "pack_ms": runs[-1]["pack_ms"], "gpu_ms": runs[-1]["gpu_ms"], "write_ms": runs[-1]["container_ms"]}
+    if seam:
+        e2e["raw_entry_seam"] = {"entries_per_s": seam["entries_per_s"], "GiB_per_s": seam["GiB_per_s"], "container_ms": seam["container_ms"],
+                                 "api": "mz_zip_cuda_add_buffers: the reference's container writes every header (three calls per entry)"}
     cpu = None
     if not args.no_cpu and world == 1:
         ref_exe = os.path.join(ROOT, "oracle", "_ref", "zipbatch_ref")
@@ -1047,8 +1060,14 @@ def run_c4(args, rank, world, local_rank):
                        "sample": "6000 entries x 64 KiB through the reference's zip writer (mz_zip_entry_write_open raw=0, zlib level %d, CRC per 64 KiB), one core" % args.level}
             finally:
                 subprocess.run(["rm", "-rf", d2])
-    _emit(args, rank, world, value, add_s * 1000, roofline, cpu, clk, e2e, 3 * runs[-1]["rounds"],
-          {"entries": entries * world, "entries_per_s": round(entries * world / add_s, 1), "ratio": round(runs[-1]["bytes_out"] / nbytes, 4)})
+    metric, unit = METRICS[args.config]
+    line = {"metric": metric, "value": round(value, 4), "unit": unit, "n_gpus": world, "steps": len(runs), "warmup": min(args.warmup, 1),
+            "ms_per_step": round(add_s * 1000, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": workload_text(args), "level": args.level, "l2": "inputs are larger than L2; no flush needed",
+                       "parallelism": "single GPU" if world == 1 else "entries sharded over %d GPUs inside one archive writer (rounds round-robin); one process drives all devices" % world},
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clk, "e2e": e2e, "gpu_launches": 5 * runs[-1]["rounds"],
+            "entries": entries, "entries_per_s": round(entries / add_s, 1), "ratio": round(runs[-1]["bytes_out"] / nbytes, 4)}
+    print(json.dumps(line), flush=True)
 
 
 def main():

@@ -119,6 +119,13 @@ int32_t mz_cuda_stream_wait_event(void *stream, void *event);
  * batched like the per-entry CRC. */
 int32_t mz_cuda_sha256_batch(const void *d_in, const uint64_t *d_off, const uint64_t *d_len, uint32_t n, void *d_digest, void *stream);
 
+/* K4 with caller-given destinations: slot i goes to d_dst + d_offsets[i] (no scan) -- the zip archive writer interleaves the
+ * entries' streams with their local headers; and n small blobs (blob i = d_blob[d_blob_off[i] .. d_blob_off[i+1])) scattered to
+ * d_dst + d_dst_off[i] (the headers themselves). */
+int32_t mz_cuda_gather(const void *d_slots, uint64_t slot_stride, const uint32_t *d_out_len, uint32_t nchunks, const uint64_t *d_offsets,
+                       void *d_dst, void *stream);
+int32_t mz_cuda_scatter_blobs(const void *d_blob, const uint32_t *d_blob_off, const uint64_t *d_dst_off, uint32_t n, void *d_dst, void *stream);
+
 /* ---- K5: DEFLATE decode of independent raw streams (resumable) ---------------------------------------- */
 typedef struct mz_cuda_inflate_job {
     const void *d_in;    /* d_in[0] = stream byte `in_base`; readable (zero padded) 16 bytes past in_avail */

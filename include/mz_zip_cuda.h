@@ -52,6 +52,20 @@ int32_t mz_zip_cuda_add_buffers(void *zip_handle, const mz_cuda_zip_item *items,
 int32_t mz_zip_cuda_add_buffers_ex(void *zip_handle, const mz_cuda_zip_item *items, uint32_t count, int16_t level, uint32_t flags,
                                    mz_cuda_zip_stats *stats);
 
+/* ---- a whole archive, natively (scope row f1, "if the container is the limit") ------------------------------------------
+ * With 100 000 small entries the reference's per-entry container calls (mz_zip_entry_write_open / _write / _close_raw: three
+ * calls and ~28 us per entry) cost ten times the GPU work. This call writes the COMPLETE archive itself to `base_stream` (any
+ * mz_stream object: file, buffered, memory): local headers (mz_zip.c:594-919 layout: no data descriptor -- sizes and CRC are
+ * known before a byte is written --, UTF-8 flag, version 20, or 45 with a zip64 extra field), the entries' DEFLATE streams,
+ * the central directory and the end records incl. the zip64 end record + locator when there are >= 65535 entries or the
+ * directory starts beyond 4 GiB (mz_zip.c:1102-1234, zip64 rules :551-592). A round's region [header | stream | header | ...]
+ * is assembled ON THE DEVICE (K4 gather with explicit destinations + a header scatter) and goes to base in one write.
+ * MZ_ZIP_CUDA_ALL_DEVICES: rounds are prepared round-robin on every visible GPU (entries shard across the GPUs; the archive
+ * itself is one serial byte stream written in order). Entries must be smaller than 4 GiB - 64 KiB. */
+#define MZ_ZIP_CUDA_ALL_DEVICES 2u
+int32_t mz_zip_cuda_write_archive(void *base_stream, const mz_cuda_zip_item *items, uint32_t count, int16_t level, uint32_t flags,
+                                  mz_cuda_zip_stats *stats);
+
 /* ---- batch extraction (scope row f2): the reverse direction ---------------------------------------------------
  * The reference extracts entry by entry: mz_zip_entry_read_open(raw=0) creates a mz_stream_zlib, the caller's loop
  * reads through it, mz_zip_entry_close compares the CRC (mz_zip_rw.c:818-909, mz_zip.c:2116-2128). Here the central

@@ -53,9 +53,9 @@ EXPORTS = [
     "mz_cuda_deflate_slot_bound", "mz_cuda_deflate_chunks", "mz_cuda_concat", "mz_cuda_inflate_streams",
     "mz_cuda_inflate_spec_workspace_bytes", "mz_cuda_inflate_spec_round", "mz_cuda_sha256_batch",
     "mz_cuda_gather_region_bound", "mz_cuda_deflate_sharded", "mz_cuda_ipc_export", "mz_cuda_ipc_open", "mz_cuda_ipc_close", "mz_cuda_memcpy_peer",
-    "mz_cuda_stream_wait_event",
+    "mz_cuda_stream_wait_event", "mz_cuda_gather", "mz_cuda_scatter_blobs",
     # include/mz_zip_cuda.h
-    "mz_zip_cuda_add_buffers", "mz_zip_cuda_extract_all", "mz_zip_cuda_abi_file_info_size",
+    "mz_zip_cuda_add_buffers", "mz_zip_cuda_add_buffers_ex", "mz_zip_cuda_write_archive", "mz_zip_cuda_extract_all", "mz_zip_cuda_abi_file_info_size",
 ]
 
 
@@ -133,6 +133,8 @@ def configure(L):
     sig("mz_cuda_ipc_close", i32, [vp])
     sig("mz_cuda_memcpy_peer", i32, [vp, vp, sz, vp])
     sig("mz_cuda_stream_wait_event", i32, [vp, vp])
+    sig("mz_cuda_gather", i32, [vp, u64, vp, u32, vp, vp, vp])
+    sig("mz_cuda_scatter_blobs", i32, [vp, vp, vp, u32, vp, vp])
     return L
 
 

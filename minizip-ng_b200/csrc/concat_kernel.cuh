@@ -69,6 +69,17 @@ __global__ void __launch_bounds__(GATHER_THREADS) gather_slots_kernel(const uint
     }
 }
 
+/* copy n small blobs (zip local headers) from a packed source to dst + dst_off[i]: one warp per blob, byte copies */
+__global__ void __launch_bounds__(256) scatter_blobs_kernel(const uint8_t *blob, const uint32_t *blob_off, const uint64_t *dst_off, uint32_t n, uint8_t *dst) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t i = warp; i < n; i += nwarps) {
+        const uint32_t a = blob_off[i], b = blob_off[i + 1];
+        uint8_t *d = dst + dst_off[i];
+        for (uint32_t k = a + lane; k < b; k += 32) d[k - a] = blob[k];
+    }
+}
+
 /* per-chunk rows {crc32, in_len, out_len} for the multi-GPU table (one thread per chunk) */
 __global__ void __launch_bounds__(256) pack_rows_kernel(const uint32_t *chunk_crc, const uint32_t *out_len, uint32_t nchunks, uint64_t total_len,
                                                         uint32_t chunk_size, uint32_t *rows) {

@@ -383,6 +383,31 @@ int32_t mz_cuda_concat(const void *d_slots, uint64_t slot_stride, const uint32_t
     return MZ_OK;
 }
 
+int32_t mz_cuda_gather(const void *d_slots, uint64_t slot_stride, const uint32_t *d_out_len, uint32_t nchunks, const uint64_t *d_offsets, void *d_dst,
+                       void *stream) {
+    DeviceCtx *c;
+    int32_t err = get_ctx(&c);
+    if (err) return err;
+    if (nchunks == 0) return MZ_OK;
+    uint32_t grid = nchunks < (uint32_t)c->sm_count * 16u ? nchunks : (uint32_t)c->sm_count * 16u;
+    MZ_LAUNCH(gather_slots_kernel, dim3(grid), dim3(GATHER_THREADS), 0, (cudaStream_t)stream, (const uint8_t *)d_slots, slot_stride, d_out_len, d_offsets,
+              nchunks, (uint8_t *)d_dst);
+    CK(cudaGetLastError());
+    return MZ_OK;
+}
+
+int32_t mz_cuda_scatter_blobs(const void *d_blob, const uint32_t *d_blob_off, const uint64_t *d_dst_off, uint32_t n, void *d_dst, void *stream) {
+    DeviceCtx *c;
+    int32_t err = get_ctx(&c);
+    if (err) return err;
+    if (n == 0) return MZ_OK;
+    uint32_t grid = (n + 7) / 8;
+    if (grid > (uint32_t)c->sm_count * 8u) grid = (uint32_t)c->sm_count * 8u;
+    MZ_LAUNCH(scatter_blobs_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const uint8_t *)d_blob, d_blob_off, d_dst_off, n, (uint8_t *)d_dst);
+    CK(cudaGetLastError());
+    return MZ_OK;
+}
+
 int32_t mz_cuda_inflate_streams(const mz_cuda_inflate_job *d_jobs, mz_cuda_inflate_state *d_states, uint32_t nstreams, void *stream) {
     DeviceCtx *c;
     int32_t err = get_ctx(&c);

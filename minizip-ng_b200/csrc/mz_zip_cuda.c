@@ -378,6 +378,476 @@ int32_t mz_zip_cuda_add_buffers_ex(void *zip_handle, const mz_cuda_zip_item *ite
     return err;
 }
 
+/* ---- the native archive writer (mz_zip_cuda_write_archive) ------------------------------------------------------------- */
+typedef struct za_meta_s { /* per entry of a round, filled by the worker */
+    uint64_t csize, lh_rel; /* compressed bytes; offset of the local header inside the round's region */
+    uint32_t crc, lh_size;
+} za_meta;
+
+typedef struct za_slot_s {
+    zc_bufs b;
+    uint32_t *h_out_len;               /* pinned: per chunk */
+    uint64_t *h_dst_off, *d_dst_off;   /* per chunk: where its stream goes inside the region */
+    uint64_t *h_hdr_off, *d_hdr_off;   /* per entry: where its local header goes */
+    uint32_t *h_blob_off, *d_blob_off; /* per entry + 1: header bytes inside the blob */
+    uint8_t *h_blob, *d_blob;
+    size_t blob_cap;
+    uint8_t *d_region, *h_region;
+    size_t region_cap;
+    za_meta *meta;
+    /* the round in flight */
+    const mz_cuda_zip_item *items;
+    uint32_t first, last, nch;
+    uint32_t flags;
+    int16_t level;
+    int32_t device, err;
+    uint64_t region_len;
+    double pack_ms, gpu_ms;
+    pthread_t th;
+    int running;
+} za_slot;
+
+static void put16(uint8_t *p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); }
+static void put32(uint8_t *p, uint32_t v) { put16(p, v); put16(p + 2, v >> 16); }
+static void put64(uint8_t *p, uint64_t v) { put32(p, (uint32_t)v); put32(p + 4, (uint32_t)(v >> 32)); }
+
+/* mz_zip_time_t_to_dos_date (mz_zip.c): local time, 2-second resolution, years from 1980 */
+static uint32_t za_dos_date(int64_t t) {
+    time_t tt = (time_t)(t ? t : time(NULL));
+    struct tm tmv;
+    if (!localtime_r(&tt, &tmv))
+        return 0;
+    int year = tmv.tm_year >= 1980 ? tmv.tm_year - 1980 : (tmv.tm_year >= 80 ? tmv.tm_year - 80 : 0);
+    return ((uint32_t)((tmv.tm_mday) + 32 * (tmv.tm_mon + 1) + 512 * year) << 16) |
+           (uint32_t)(tmv.tm_sec / 2 + 32 * tmv.tm_min + 2048 * tmv.tm_hour);
+}
+
+static void za_free(za_slot *z) {
+    zc_free(&z->b);
+    mz_cuda_host_free(z->h_out_len);
+    mz_cuda_host_free(z->h_dst_off);
+    mz_cuda_free(z->d_dst_off);
+    mz_cuda_host_free(z->h_hdr_off);
+    mz_cuda_free(z->d_hdr_off);
+    mz_cuda_host_free(z->h_blob_off);
+    mz_cuda_free(z->d_blob_off);
+    mz_cuda_host_free(z->h_blob);
+    mz_cuda_free(z->d_blob);
+    mz_cuda_free(z->d_region);
+    mz_cuda_host_free(z->h_region);
+    free(z->meta);
+    memset(z, 0, sizeof(*z));
+}
+
+static int za_alloc(za_slot *z, size_t round_bytes, uint32_t max_chunks, size_t blob_cap) {
+    memset(z, 0, sizeof(*z));
+    if (!zc_alloc(&z->b, round_bytes, max_chunks))
+        return 0;
+    z->blob_cap = blob_cap;
+    z->region_cap = (size_t)max_chunks * z->b.stride + blob_cap + 64;
+    z->h_out_len = (uint32_t *)mz_cuda_host_alloc((size_t)max_chunks * 4);
+    z->h_dst_off = (uint64_t *)mz_cuda_host_alloc((size_t)max_chunks * 8);
+    z->d_dst_off = (uint64_t *)mz_cuda_malloc((size_t)max_chunks * 8);
+    z->h_hdr_off = (uint64_t *)mz_cuda_host_alloc((size_t)max_chunks * 8);
+    z->d_hdr_off = (uint64_t *)mz_cuda_malloc((size_t)max_chunks * 8);
+    z->h_blob_off = (uint32_t *)mz_cuda_host_alloc(((size_t)max_chunks + 1) * 4);
+    z->d_blob_off = (uint32_t *)mz_cuda_malloc(((size_t)max_chunks + 1) * 4);
+    z->h_blob = (uint8_t *)mz_cuda_host_alloc(blob_cap + 16);
+    z->d_blob = (uint8_t *)mz_cuda_malloc(blob_cap + 16);
+    z->d_region = (uint8_t *)mz_cuda_malloc(z->region_cap);
+    z->h_region = (uint8_t *)mz_cuda_host_alloc(z->region_cap);
+    z->meta = (za_meta *)malloc((size_t)max_chunks * sizeof(za_meta));
+    if (!z->h_out_len || !z->h_dst_off || !z->d_dst_off || !z->h_hdr_off || !z->d_hdr_off || !z->h_blob_off || !z->d_blob_off || !z->h_blob ||
+        !z->d_blob || !z->d_region || !z->h_region || !z->meta) {
+        za_free(z);
+        return 0;
+    }
+    return 1;
+}
+
+/* the hash extra field of an entry (40 bytes) -- the bytes mz_zip_writer_entry_close assembles (mz_zip_rw.c:1398-1408) */
+static void za_hash_field(uint8_t *xf, const uint8_t *digest) {
+    static const uint8_t head[8] = {0x51, 0x1a, 36, 0, 23, 0, 32, 0};
+    memcpy(xf, head, 8);
+    memcpy(xf + 8, digest, 32);
+}
+
+/* one round: pack, upload, compress + checksum (+ hash), lay the region out, assemble it on the device, download it */
+static void *za_prepare(void *arg) {
+    za_slot *z = (za_slot *)arg;
+    zc_bufs *b = &z->b;
+    int32_t err = mz_cuda_set_device(z->device);
+    double t0 = now_ms();
+    uint32_t nch = 0;
+    size_t pos = 0;
+    const uint32_t ne = z->last - z->first;
+    for (uint32_t i = z->first; i < z->last; i++) {
+        const mz_cuda_zip_item *it = &z->items[i];
+        const uint32_t c = chunks_of(it->size);
+        if (it->size > 0)
+            memcpy(b->h_in + pos, it->data, (size_t)it->size);
+        b->h_eoff[i - z->first] = pos;
+        b->h_elen[i - z->first] = (uint64_t)it->size;
+        int64_t left = it->size;
+        for (uint32_t k = 0; k < c; k++) {
+            const uint32_t n = left > (int64_t)ZC_CHUNK ? ZC_CHUNK : (uint32_t)left;
+            b->h_off[nch] = pos + (uint64_t)k * ZC_CHUNK;
+            b->h_len[nch] = n;
+            b->h_flags[nch] = k + 1 == c ? 1u : 0u;
+            left -= n;
+            nch++;
+        }
+        pos += ((size_t)it->size + 15) & ~(size_t)15;
+    }
+    z->nch = nch;
+    if (!err) err = mz_cuda_memcpy_h2d(b->d_in, b->h_in, pos + 16, NULL);
+    if (!err) err = mz_cuda_memcpy_h2d(b->d_off, b->h_off, (size_t)nch * 8, NULL);
+    if (!err) err = mz_cuda_memcpy_h2d(b->d_len, b->h_len, (size_t)nch * 4, NULL);
+    if (!err) err = mz_cuda_memcpy_h2d(b->d_flags, b->h_flags, nch, NULL);
+    double t1 = now_ms();
+    if (!err) err = mz_cuda_deflate_chunks(b->d_in, 0, 0, b->d_off, b->d_len, b->d_flags, nch, 0, z->level, b->d_slots, b->stride, b->d_out_len, NULL);
+    if (!err) err = mz_cuda_crc32_segments(b->d_in, 0, 0, b->d_off, b->d_len, nch, b->d_residue, b->d_crc, NULL);
+    if (!err && (z->flags & MZ_ZIP_CUDA_HASH_SHA256)) {
+        err = mz_cuda_memcpy_h2d(b->d_eoff, b->h_eoff, (size_t)ne * 8, NULL);
+        if (!err) err = mz_cuda_memcpy_h2d(b->d_elen, b->h_elen, (size_t)ne * 8, NULL);
+        if (!err) err = mz_cuda_sha256_batch(b->d_in, b->d_eoff, b->d_elen, ne, b->d_digest, NULL);
+        if (!err) err = mz_cuda_memcpy_d2h(b->h_digest, b->d_digest, (size_t)ne * 32, NULL);
+    }
+    if (!err) err = mz_cuda_memcpy_d2h(z->h_out_len, b->d_out_len, (size_t)nch * 4, NULL);
+    if (!err) err = mz_cuda_memcpy_d2h(b->h_crc, b->d_crc, (size_t)nch * 4, NULL);
+    if (!err) err = mz_cuda_stream_sync(NULL);
+    /* host: sizes, CRCs, local headers, the region's layout */
+    uint64_t cur = 0;
+    uint32_t c0 = 0, bo = 0;
+    for (uint32_t e = 0; e < ne && !err; e++) {
+        const mz_cuda_zip_item *it = &z->items[z->first + e];
+        const uint32_t c = chunks_of(it->size);
+        uint32_t crc = b->h_crc[c0];
+        uint64_t csize = z->h_out_len[c0];
+        for (uint32_t k = 1; k < c; k++) {
+            crc = mz_cuda_crc32_combine(crc, b->h_crc[c0 + k], b->h_len[c0 + k]);
+            csize += z->h_out_len[c0 + k];
+        }
+        if (it->size == 0)
+            crc = 0;
+        const size_t nlen = strlen(it->filename);
+        const uint32_t xlen = (z->flags & MZ_ZIP_CUDA_HASH_SHA256) ? 40u : 0u;
+        const uint32_t lh = 30 + (uint32_t)nlen + xlen;
+        if (bo + lh > z->blob_cap || csize >= 0xffffffffull) {
+            err = MZ_INTERNAL_ERROR;
+            break;
+        }
+        uint8_t *h = z->h_blob + bo;
+        put32(h, 0x04034b50u);                       /* MZ_ZIP_MAGIC_LOCALHEADER */
+        put16(h + 4, 20);                            /* version needed (mz_zip.c:706) */
+        put16(h + 6, 1u << 11);                      /* MZ_ZIP_FLAG_UTF8; no data descriptor: everything is known */
+        put16(h + 8, 8);                             /* MZ_COMPRESS_METHOD_DEFLATE */
+        put32(h + 10, za_dos_date(it->modified_date));
+        put32(h + 14, crc);
+        put32(h + 18, (uint32_t)csize);
+        put32(h + 22, (uint32_t)it->size);
+        put16(h + 26, (uint32_t)nlen);
+        put16(h + 28, xlen);
+        memcpy(h + 30, it->filename, nlen);
+        if (xlen)
+            za_hash_field(h + 30 + nlen, b->h_digest + (size_t)e * 32);
+        z->h_blob_off[e] = bo;
+        z->h_hdr_off[e] = cur;
+        z->meta[e].csize = csize;
+        z->meta[e].crc = crc;
+        z->meta[e].lh_rel = cur;
+        z->meta[e].lh_size = lh;
+        bo += lh;
+        cur += lh;
+        for (uint32_t k = 0; k < c; k++) {
+            z->h_dst_off[c0 + k] = cur;
+            cur += z->h_out_len[c0 + k];
+        }
+        c0 += c;
+    }
+    z->h_blob_off[ne] = bo;
+    z->region_len = cur;
+    if (!err && cur > z->region_cap)
+        err = MZ_INTERNAL_ERROR;
+    /* device: streams and headers into place; the finished region comes down in one copy */
+    if (!err) err = mz_cuda_memcpy_h2d(z->d_dst_off, z->h_dst_off, (size_t)nch * 8, NULL);
+    if (!err) err = mz_cuda_memcpy_h2d(z->d_hdr_off, z->h_hdr_off, (size_t)ne * 8, NULL);
+    if (!err) err = mz_cuda_memcpy_h2d(z->d_blob_off, z->h_blob_off, ((size_t)ne + 1) * 4, NULL);
+    if (!err) err = mz_cuda_memcpy_h2d(z->d_blob, z->h_blob, (size_t)bo + 16, NULL);
+    if (!err) err = mz_cuda_gather(b->d_slots, b->stride, b->d_out_len, nch, z->d_dst_off, z->d_region, NULL);
+    if (!err) err = mz_cuda_scatter_blobs(z->d_blob, z->d_blob_off, z->d_hdr_off, ne, z->d_region, NULL);
+    if (!err) err = mz_cuda_memcpy_d2h(z->h_region, z->d_region, (size_t)cur, NULL);
+    if (!err) err = mz_cuda_stream_sync(NULL);
+    z->pack_ms = t1 - t0;
+    z->gpu_ms = now_ms() - t1;
+    z->err = err;
+    return NULL;
+}
+
+typedef struct za_cd_s {
+    uint8_t *p;
+    size_t len, cap;
+} za_cd;
+static uint8_t *za_cd_room(za_cd *cd, size_t n) {
+    if (cd->len + n > cd->cap) {
+        size_t ncap = cd->cap ? cd->cap * 2 : (1u << 20);
+        while (ncap < cd->len + n)
+            ncap *= 2;
+        uint8_t *q = (uint8_t *)realloc(cd->p, ncap);
+        if (!q)
+            return NULL;
+        cd->p = q;
+        cd->cap = ncap;
+    }
+    uint8_t *r = cd->p + cd->len;
+    cd->len += n;
+    return r;
+}
+
+static int32_t za_write(void *base, const uint8_t *p, uint64_t n) {
+    while (n > 0) {
+        const int32_t part = n > (1u << 30) ? (int32_t)(1u << 30) : (int32_t)n;
+        if (mz_abi_base_write(base, p, part) != part)
+            return MZ_WRITE_ERROR;
+        p += part;
+        n -= (uint64_t)part;
+    }
+    return MZ_OK;
+}
+
+int32_t mz_zip_cuda_write_archive(void *base_stream, const mz_cuda_zip_item *items, uint32_t count, int16_t level, uint32_t flags,
+                                  mz_cuda_zip_stats *stats) {
+    mz_cuda_zip_stats st;
+    int32_t err = MZ_OK;
+    memset(&st, 0, sizeof(st));
+    if (!base_stream || (!items && count))
+        return MZ_PARAM_ERROR;
+    if (level == MZ_COMPRESS_LEVEL_DEFAULT)
+        level = 6;
+    if (level < 0 || level > 9)
+        return MZ_PARAM_ERROR;
+    if (mz_cuda_init() != MZ_OK) {
+        fprintf(stderr, "mz_zip_cuda: no usable sm_100 GPU (%s); there is no CPU fallback\n", mz_cuda_last_error());
+        return MZ_SUPPORT_ERROR;
+    }
+    size_t round_bytes = 256u << 20;
+    {
+        const char *v = getenv("MZ_CUDA_ZIP_ROUND_MB");
+        if (v && atoll(v) > 0)
+            round_bytes = (size_t)atoll(v) << 20;
+    }
+    size_t max_name = 0;
+    for (uint32_t i = 0; i < count; i++) {
+        if (!items[i].filename || items[i].size < 0 || (items[i].size > 0 && !items[i].data))
+            return MZ_PARAM_ERROR;
+        const size_t nl = strlen(items[i].filename);
+        if (nl == 0 || nl > 65535)
+            return MZ_PARAM_ERROR;
+        if (nl > max_name)
+            max_name = nl;
+        if (items[i].size >= 0xffff0000ll)
+            return MZ_SUPPORT_ERROR; /* zip64-sized ENTRIES take the per-entry path (mz_zip_cuda_add_buffers) */
+        if ((size_t)items[i].size + 16 > round_bytes)
+            round_bytes = ((size_t)items[i].size + 16 + 65535) & ~(size_t)65535;
+    }
+    /* rounds: consecutive entries that fit the staging buffers; boundaries depend on the sizes alone, so they are fixed up
+     * front and several rounds can be prepared at once */
+    uint32_t nrounds = 0, rcap = 16;
+    uint32_t *rfirst = (uint32_t *)malloc((rcap + 1) * sizeof(uint32_t));
+    uint32_t max_chunks = 1, max_entries = 1;
+    size_t max_blob = 64;
+    if (!rfirst)
+        return MZ_MEM_ERROR;
+    {
+        uint32_t i = 0;
+        while (i < count) {
+            size_t bytes = 0, blob = 0;
+            uint32_t ch = 0, j = i;
+            while (j < count) {
+                const size_t need = ((size_t)items[j].size + 15) & ~(size_t)15;
+                if (j > i && bytes + need > round_bytes)
+                    break;
+                bytes += need;
+                ch += chunks_of(items[j].size);
+                blob += 30 + strlen(items[j].filename) + 40;
+                j++;
+            }
+            if (nrounds == rcap) {
+                rcap *= 2;
+                uint32_t *q = (uint32_t *)realloc(rfirst, (rcap + 1) * sizeof(uint32_t));
+                if (!q) {
+                    free(rfirst);
+                    return MZ_MEM_ERROR;
+                }
+                rfirst = q;
+            }
+            rfirst[nrounds++] = i;
+            if (ch > max_chunks) max_chunks = ch;
+            if (j - i > max_entries) max_entries = j - i;
+            if (blob > max_blob) max_blob = blob;
+            i = j;
+        }
+        rfirst[nrounds] = count;
+    }
+    int32_t ndev = 1;
+    const int32_t dev0 = mz_cuda_get_device() < 0 ? 0 : mz_cuda_get_device();
+    if (flags & MZ_ZIP_CUDA_ALL_DEVICES) {
+        ndev = mz_cuda_device_count();
+        if (ndev < 1) ndev = 1;
+        if (ndev > 8) ndev = 8;
+    }
+    const uint32_t nslots = (uint32_t)ndev * 2 < nrounds ? (uint32_t)ndev * 2 : (nrounds ? nrounds : 1);
+    za_slot *slots = (za_slot *)calloc(nslots, sizeof(za_slot));
+    za_cd cd = {NULL, 0, 0};
+    if (!slots) {
+        free(rfirst);
+        return MZ_MEM_ERROR;
+    }
+    for (uint32_t k = 0; k < nslots && err == MZ_OK; k++) {
+        const int32_t dev = ndev > 1 ? (int32_t)(k % (uint32_t)ndev) : dev0;
+        if (mz_cuda_set_device(dev) != MZ_OK || !za_alloc(&slots[k], round_bytes, max_chunks + 1, max_blob)) {
+            err = MZ_MEM_ERROR;
+            break;
+        }
+        slots[k].device = dev;
+        slots[k].items = items;
+        slots[k].level = level;
+        slots[k].flags = flags;
+    }
+    mz_cuda_set_device(dev0);
+    uint64_t abs_off = 0;
+    uint32_t issued = 0;
+    const double t_all = now_ms();
+    for (uint32_t r = 0; r < nrounds && err == MZ_OK; r++) {
+        /* keep every slot busy: rounds r .. r + nslots - 1 are in preparation */
+        while (issued < nrounds && issued < r + nslots) {
+            za_slot *z = &slots[issued % nslots];
+            z->first = rfirst[issued];
+            z->last = rfirst[issued + 1];
+            z->running = pthread_create(&z->th, NULL, za_prepare, z) == 0;
+            if (!z->running)
+                za_prepare(z);
+            issued++;
+        }
+        za_slot *z = &slots[r % nslots];
+        if (z->running) {
+            pthread_join(z->th, NULL);
+            z->running = 0;
+        }
+        err = z->err;
+        if (err)
+            break;
+        const double t2 = now_ms();
+        err = za_write(base_stream, z->h_region, z->region_len);
+        /* central directory records of the round (mz_zip.c:594-919 with local = 0) */
+        for (uint32_t e = 0; e < z->last - z->first && err == MZ_OK; e++) {
+            const mz_cuda_zip_item *it = &items[z->first + e];
+            const za_meta *m = &z->meta[e];
+            const uint64_t lh_off = abs_off + m->lh_rel;
+            const int z64 = lh_off >= 0xffffffffull;
+            const size_t nlen = strlen(it->filename);
+            const uint32_t xhash = (flags & MZ_ZIP_CUDA_HASH_SHA256) ? 40u : 0u;
+            const uint32_t xlen = (z64 ? 4u + 24u : 0u) + xhash;
+            uint8_t *h = za_cd_room(&cd, 46 + nlen + xlen);
+            if (!h) {
+                err = MZ_MEM_ERROR;
+                break;
+            }
+            put32(h, 0x02014b50u);                   /* MZ_ZIP_MAGIC_CENTRALHEADER */
+            put16(h + 4, (3u << 8) | 45u);           /* made by: MZ_HOST_SYSTEM_UNIX, 4.5 */
+            put16(h + 6, z64 ? 45 : 20);
+            put16(h + 8, 1u << 11);
+            put16(h + 10, 8);
+            put32(h + 12, za_dos_date(it->modified_date));
+            put32(h + 16, m->crc);
+            put32(h + 20, z64 ? 0xffffffffu : (uint32_t)m->csize); /* with a zip64 field both sizes move into it (mz_zip.c:519-548) */
+            put32(h + 24, z64 ? 0xffffffffu : (uint32_t)it->size);
+            put16(h + 28, (uint32_t)nlen);
+            put16(h + 30, xlen);
+            put16(h + 32, 0);                        /* comment */
+            put16(h + 34, 0);                        /* disk number start */
+            put16(h + 36, 0);                        /* internal attributes */
+            put32(h + 38, it->external_fa ? it->external_fa : (0100644u << 16));
+            put32(h + 42, z64 ? 0xffffffffu : (uint32_t)lh_off);
+            memcpy(h + 46, it->filename, nlen);
+            uint8_t *x = h + 46 + nlen;
+            if (z64) {                               /* MZ_ZIP_EXTENSION_ZIP64: uncompressed, compressed, header offset */
+                put16(x, 0x0001);
+                put16(x + 2, 24);
+                put64(x + 4, (uint64_t)it->size);
+                put64(x + 12, m->csize);
+                put64(x + 20, lh_off);
+                x += 28;
+            }
+            if (xhash)
+                za_hash_field(x, z->b.h_digest + (size_t)e * 32);
+            st.bytes_in += (uint64_t)it->size;
+            st.bytes_out += m->csize;
+        }
+        abs_off += z->region_len;
+        st.container_ms += now_ms() - t2;
+        st.pack_ms += z->pack_ms;
+        st.gpu_ms += z->gpu_ms;
+        st.entries += z->last - z->first;
+        st.rounds++;
+    }
+    for (uint32_t k = 0; k < nslots; k++)
+        if (slots[k].running) {
+            pthread_join(slots[k].th, NULL);
+            slots[k].running = 0;
+        }
+    /* central directory + end records (mz_zip.c:1102-1234) */
+    if (err == MZ_OK) {
+        const uint64_t cd_off = abs_off, cd_size = cd.len;
+        uint8_t tail[56 + 20 + 22];
+        size_t tl = 0;
+        err = za_write(base_stream, cd.p, cd.len);
+        if (cd_off >= 0xffffffffull || count >= 0xffffu) {
+            uint8_t *q = tail;
+            put32(q, 0x06064b50u);                   /* MZ_ZIP_MAGIC_ENDHEADER64 */
+            put64(q + 4, 44);
+            put16(q + 12, (3u << 8) | 45u);
+            put16(q + 14, 45);
+            put32(q + 16, 0);
+            put32(q + 20, 0);
+            put64(q + 24, count);
+            put64(q + 32, count);
+            put64(q + 40, cd_size);
+            put64(q + 48, cd_off);
+            q += 56;
+            put32(q, 0x07064b50u);                   /* MZ_ZIP_MAGIC_ENDLOCHEADER64 */
+            put32(q + 4, 0);
+            put64(q + 8, cd_off + cd_size);
+            put32(q + 16, 1);
+            tl = 76;
+        }
+        uint8_t *q = tail + tl;
+        put32(q, 0x06054b50u);                       /* MZ_ZIP_MAGIC_ENDHEADER */
+        put16(q + 4, 0);
+        put16(q + 6, 0);
+        put16(q + 8, count >= 0xffffu ? 0xffffu : count);
+        put16(q + 10, count >= 0xffffu ? 0xffffu : count);
+        put32(q + 12, (uint32_t)cd_size);
+        put32(q + 16, cd_off >= 0xffffffffull ? 0xffffffffu : (uint32_t)cd_off);
+        put16(q + 20, 0);
+        tl += 22;
+        if (err == MZ_OK)
+            err = za_write(base_stream, tail, tl);
+    }
+    (void)t_all;
+    for (uint32_t k = 0; k < nslots; k++) {
+        mz_cuda_set_device(slots[k].device);
+        za_free(&slots[k]);
+    }
+    mz_cuda_set_device(dev0);
+    free(slots);
+    free(cd.p);
+    free(rfirst);
+    if (stats)
+        *stats = st;
+    return err;
+}
+
 /* ---- batch extraction ------------------------------------------------------------------------------------------ */
 typedef struct zx_entry_s {
     uint64_t coff, csize, ooff, usize; /* offsets inside the round's compressed / plain buffers */

@@ -4,7 +4,7 @@
  * Compiled against the reference's own headers and objects by oracle/Makefile (-> oracle/_ref/zipbatch_cuda); the
  * container code in both modes is the reference's.
  *
- *   zipbatch_cuda <out.zip> <entries> <entry_bytes> <level> <cuda|cuda_sha|ref> [dump_dir dump_every]
+ *   zipbatch_cuda <out.zip> <entries> <entry_bytes> <level> <cuda|cuda_sha|native|native_sha|native_all|ref> [dump_dir dump_every]
  *   zipbatch_cuda <in.zip>  <entries> <entry_bytes> <level> <extract|extract_ref>   (batch extractor / the reference's loop)
  *
  * Entry i: i%10 < 7 text-like, < 9 binary records, else incompressible; name e/%06d.
@@ -33,6 +33,10 @@ int32_t mz_zip_cuda_add_buffers_ex(void *z, const mz_cuda_zip_item *it, uint32_t
 }
 int32_t mz_zip_cuda_extract_all(void *z, mz_cuda_zip_entry_cb cb, void *u, mz_cuda_zip_stats *st) {
     (void)z; (void)cb; (void)u; (void)st;
+    return MZ_SUPPORT_ERROR;
+}
+int32_t mz_zip_cuda_write_archive(void *b, const mz_cuda_zip_item *it, uint32_t n, int16_t level, uint32_t flags, mz_cuda_zip_stats *st) {
+    (void)b; (void)it; (void)n; (void)level; (void)flags; (void)st;
     return MZ_SUPPORT_ERROR;
 }
 uint32_t mz_zip_cuda_abi_file_info_size(void) { return (uint32_t)sizeof(mz_zip_file); }
@@ -188,6 +192,9 @@ int main(int argc, char **argv) {
     const size_t esz = (size_t)atoll(argv[3]);
     const int16_t level = (int16_t)atoi(argv[4]);
     const int use_sha = strcmp(argv[5], "cuda_sha") == 0; /* + SHA-256 extra field per entry (scope row f3) */
+    /* native / native_sha / native_all: the product writes the WHOLE archive itself (mz_zip_cuda_write_archive) to the file stream */
+    const int use_native = strncmp(argv[5], "native", 6) == 0;
+    const uint32_t native_flags = (strstr(argv[5], "sha") ? MZ_ZIP_CUDA_HASH_SHA256 : 0u) | (strstr(argv[5], "all") ? MZ_ZIP_CUDA_ALL_DEVICES : 0u);
     const int use_cuda = strcmp(argv[5], "cuda") == 0 || use_sha;
     const char *dump_dir = argc > 7 ? argv[6] : NULL;
     const uint32_t dump_every = argc > 7 ? (uint32_t)atoi(argv[7]) : 0;
@@ -228,13 +235,16 @@ int main(int argc, char **argv) {
     void *zip = mz_zip_create();
     mz_stream_set_base(stream, file_stream);
     int32_t err = mz_stream_open(stream, path, MZ_OPEN_MODE_CREATE | MZ_OPEN_MODE_WRITE);
-    if (err == MZ_OK) err = mz_zip_open(zip, stream, MZ_OPEN_MODE_WRITE);
+    if (err == MZ_OK && !use_native) err = mz_zip_open(zip, stream, MZ_OPEN_MODE_WRITE);
     if (err != MZ_OK) { fprintf(stderr, "open failed %d\n", err); return 5; }
     mz_cuda_zip_stats st;
     memset(&st, 0, sizeof(st));
     uint64_t bytes_in = 0;
     t0 = now_s();
-    if (use_cuda) {
+    if (use_native) {
+        err = mz_zip_cuda_write_archive(stream, items, n, level, native_flags, &st);
+        bytes_in = st.bytes_in;
+    } else if (use_cuda) {
         err = mz_zip_cuda_add_buffers_ex(zip, items, n, level, use_sha ? MZ_ZIP_CUDA_HASH_SHA256 : 0u, &st);
         bytes_in = st.bytes_in;
     } else {
@@ -261,7 +271,7 @@ int main(int argc, char **argv) {
     }
     double t_add = now_s() - t0;
     t0 = now_s();
-    int32_t cerr = mz_zip_close(zip);
+    int32_t cerr = use_native ? MZ_OK : mz_zip_close(zip);
     mz_stream_close(stream);
     double t_close = now_s() - t0;
     mz_zip_delete(&zip);
@@ -270,7 +280,7 @@ int main(int argc, char **argv) {
     printf("{\"mode\": \"%s\", \"entries\": %u, \"entry_bytes\": %zu, \"level\": %d, \"err\": %d, \"close_err\": %d, \"bytes_in\": %llu, "
            "\"bytes_out\": %llu, \"gen_s\": %.3f, \"add_s\": %.4f, \"close_s\": %.4f, \"entries_per_s\": %.0f, \"GiB_per_s\": %.3f, "
            "\"pack_ms\": %.1f, \"gpu_ms\": %.1f, \"container_ms\": %.1f, \"rounds\": %u}\n",
-           use_cuda ? "cuda" : "ref", n, esz, level, err, cerr, (unsigned long long)bytes_in, (unsigned long long)st.bytes_out, t_gen, t_add,
+           use_native ? argv[5] : (use_cuda ? "cuda" : "ref"), n, esz, level, err, cerr, (unsigned long long)bytes_in, (unsigned long long)st.bytes_out, t_gen, t_add,
            t_close, n / (t_add + t_close), (double)bytes_in / (1ull << 30) / (t_add + t_close), st.pack_ms, st.gpu_ms, st.container_ms, st.rounds);
     free(data);
     free(names);

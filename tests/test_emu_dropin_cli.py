@@ -160,3 +160,30 @@ def test_zip_batch_sha256_extrafield(emu_bins, tmp_path):
     if not os.path.exists(refc):
         pytest.skip("oracle/_ref/minizip_refc not built (no OpenSSL headers)")
     _sha_roundtrip(emu_bins["zipbatch_emu"], refc, tmp_path, _run)
+
+
+def _native_archive_checks(exe, ref_bins, tmp_path, run, n=260, esz=30_000):
+    """mz_zip_cuda_write_archive: the product writes local headers, streams, central directory and end records itself; the
+    archive must be what the reference's container would have produced as far as any reader can tell: same names / CRCs / sizes
+    as the reference-written archive, extractable by the unmodified reference CLI and by CPython's zipfile, readable by the
+    batch extractor."""
+    (tmp_path / "dumpn").mkdir()
+    st = json.loads(run([exe, "n.zip", str(n), str(esz), "6", "native", "dumpn", "17"], tmp_path).stdout.decode().strip().splitlines()[-1])
+    assert st["err"] == 0 and st["entries"] == n
+    run([exe, "rn.zip", str(n), str(esz), "6", "ref"], tmp_path)
+    with zipfile.ZipFile(tmp_path / "n.zip") as zn, zipfile.ZipFile(tmp_path / "rn.zip") as zr:
+        assert zn.testzip() is None and zn.namelist() == zr.namelist()
+        for a, b in zip(zn.infolist(), zr.infolist()):
+            assert (a.CRC, a.file_size, a.compress_type, a.date_time) == (b.CRC, b.file_size, b.compress_type, b.date_time), a.filename
+            assert a.flag_bits & 0x808 == 0x800 and a.external_attr >> 16 == 0o100644
+        for i in range(0, n, 17):
+            assert zn.read("e/%06d" % i) == (tmp_path / "dumpn" / ("%06d" % i)).read_bytes()
+    run([ref_bins["minizip_ref"], "-x", "-o", "-d", "outn", "n.zip"], tmp_path)
+    assert (tmp_path / "outn" / "e" / "000034").read_bytes() == (tmp_path / "dumpn" / "000034").read_bytes()
+    got = json.loads(run([exe, "n.zip", str(n), str(esz), "0", "extract"], tmp_path).stdout.decode().strip().splitlines()[-1])
+    want = json.loads(run([exe, "n.zip", str(n), str(esz), "0", "extract_ref"], tmp_path).stdout.decode().strip().splitlines()[-1])
+    assert got["err"] == 0 and want["err"] == 0 and got["entries"] == want["entries"] == n and got["bytes_out"] == want["bytes_out"]
+
+
+def test_native_archive_writer(emu_bins, tmp_path):
+    _native_archive_checks(emu_bins["zipbatch_emu"], emu_bins, tmp_path, _run)

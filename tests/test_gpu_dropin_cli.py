@@ -234,3 +234,19 @@ def test_zip_batch_sha256_extrafield_on_the_gpu(built, tmp_path):
     def run(args, cwd, ok=True):
         return _run([str(a) for a in args], cwd, ok)
     emu_cli._sha_roundtrip(_bin("zipbatch_cuda"), refc, tmp_path, run)
+
+
+@pytest.mark.gpu
+def test_native_archive_writer_on_the_gpu(built, tmp_path):
+    """mz_zip_cuda_write_archive on the device (region assembly by K4 gather + header scatter), same checks as on the emulator,
+    plus the hash variant verified by the crypto-enabled reference"""
+    import test_emu_dropin_cli as emu_cli
+
+    def run(args, cwd, ok=True):
+        return _run([str(a) for a in args], cwd, ok)
+    bins = {"minizip_ref": _bin("minizip_ref")}
+    emu_cli._native_archive_checks(_bin("zipbatch_cuda"), bins, tmp_path, run, n=3000, esz=65536)
+    refc = os.path.join(REFDIR, "minizip_refc")
+    if os.path.exists(refc):
+        run([_bin("zipbatch_cuda"), "ns.zip", "500", "40000", "6", "native_sha"], tmp_path)
+        run([refc, "-x", "-o", "-d", "out_ns", "ns.zip"], tmp_path)

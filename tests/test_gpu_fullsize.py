@@ -118,3 +118,45 @@ def test_c4_hundred_thousand_entries_checked_by_the_reference_reader(built, tmp_
         assert r.returncode == 0 and m["err"] == 0 and m["entries"] == 100000 and m["mismatches"] == 0, (m, r.stderr[-400:])
     finally:
         subprocess.run(["rm", "-rf", d])
+
+
+def test_c4_native_archive_zip64_paths(built, tmp_path):
+    """The native writer's zip64 branches: more than 65535 entries (zip64 end record + locator) AND an archive larger than 4 GiB
+    (zip64 extra field with the 64-bit header offset in the late central-directory records): 70 000 x 64 KiB at level 0. Read back
+    by the reference's own loop (every CRC checked by mz_zip_entry_close) and opened by CPython's zipfile."""
+    import zipfile
+    exe, ref = _bin("zipbatch_cuda"), _bin("zipbatch_ref")
+    d = os.path.join(_shm(tmp_path), "mz_c4n_%d" % os.getpid())
+    os.makedirs(d, exist_ok=True)
+    try:
+        arc = os.path.join(d, "big.zip")
+        r = subprocess.run([exe, arc, "70000", "65536", "0", "native"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=1200)
+        j = json.loads(r.stdout.strip().splitlines()[-1])
+        assert r.returncode == 0 and j["err"] == 0 and j["entries"] == 70000, (j, r.stderr[-400:])
+        assert os.path.getsize(arc) > (1 << 32)
+        r = subprocess.run([ref, arc, "70000", "65536", "0", "extract_ref"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=1800)
+        k = json.loads(r.stdout.strip().splitlines()[-1])
+        assert r.returncode == 0 and k["err"] == 0 and k["entries"] == 70000 and k["mismatches"] == 0 and k["bytes_out"] == j["bytes_in"], (k, r.stderr[-400:])
+        with zipfile.ZipFile(arc) as z:
+            infos = z.infolist()
+            assert len(infos) == 70000 and infos[-1].header_offset > (1 << 32)
+            assert z.read(infos[-1]) is not None and z.read(infos[0]) is not None
+    finally:
+        subprocess.run(["rm", "-rf", d])
+
+
+def test_c4_native_hundred_thousand_entries(built, tmp_path):
+    """configs[3] through the native writer: 100 000 x 64 KiB at level 6, checked entry by entry by the reference's reader"""
+    exe, ref = _bin("zipbatch_cuda"), _bin("zipbatch_ref")
+    d = os.path.join(_shm(tmp_path), "mz_c4m_%d" % os.getpid())
+    os.makedirs(d, exist_ok=True)
+    try:
+        arc = os.path.join(d, "c4n.zip")
+        r = subprocess.run([exe, arc, "100000", "65536", "6", "native"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+        j = json.loads(r.stdout.strip().splitlines()[-1])
+        assert r.returncode == 0 and j["err"] == 0 and j["entries"] == 100000, (j, r.stderr[-400:])
+        r = subprocess.run([ref, arc, "100000", "65536", "6", "extract_ref"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=1800)
+        k = json.loads(r.stdout.strip().splitlines()[-1])
+        assert r.returncode == 0 and k["err"] == 0 and k["entries"] == 100000 and k["mismatches"] == 0 and k["bytes_out"] == j["bytes_in"], (k, r.stderr[-400:])
+    finally:
+        subprocess.run(["rm", "-rf", d])
