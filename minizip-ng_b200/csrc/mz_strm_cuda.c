@@ -789,11 +789,13 @@ static int32_t cu_prepare_input(mz_stream_cuda *cu) {
     return MZ_OK;
 }
 
-/* enough compressed input ahead of the decoder for a speculative round to pay off (16 segments) */
+/* enough compressed input ahead of the decoder for a speculative round to pay off: 4 segments (64 KiB). One warp decodes
+ * ~13 MB/s of output, so even the two or three zlib blocks of such a window, decoded side by side, beat the serial decoder;
+ * below that the round's seven launches cost more than they save. */
 static int cu_spec_worthwhile(const mz_stream_cuda *cu) {
     const cu_ws *w = cu->ws;
     const uint64_t seg = w->spec_seg_bytes ? w->spec_seg_bytes : 16384;
-    return (cu->cin_base + cu->cin_len) * 8 > w->h_state->in_bitpos + 8 * 16 * seg;
+    return (cu->cin_base + cu->cin_len) * 8 > w->h_state->in_bitpos + 8 * 4 * seg;
 }
 
 static int cu_spec_eligible(mz_stream_cuda *cu) {
