@@ -71,7 +71,10 @@ constexpr int DF_OFF_BITS = DF_OFF_LENS + (288 + 32);        /* u8[288 + 32] cod
 constexpr int DF_OFF_SCAN = DF_OFF_BITS + (288 + 32);        /* u32[256]: [0,128) per (batch, warp) partials, [128,256) scanned */
 constexpr int DF_OFF_BB = DF_OFF_SCAN + 256 * 4;             /* u32[512] code-builder scratch */
 constexpr int DF_OFF_MISC = DF_OFF_BB + 512 * 4;             /* u32[32] + mbarrier */
-constexpr int DF_SMEM_BYTES = DF_OFF_MISC + 32 * 4 + 16;
+constexpr int DF_OFF_SINK = DF_OFF_MISC + 32 * 4 + 16;       /* u32[32]: one word per lane, the target of atomics that have nothing to do
+                                                              * (ptxas branches around a predicated ATOMS; a select on the address is one instruction) */
+constexpr int DF_SMEM_BYTES = DF_OFF_SINK + 32 * 4;
+constexpr uint32_t DF_ZERO_SYM = 286;                        /* literal/length symbol that never occurs: its table entries are all zero */
 static_assert(DF_HASH_ENTRIES * 4 <= DF_STAGE_WORDS * 4, "hash fits the staging region");
 static_assert(DF_SMEM_BYTES <= 113 * 1024, "shared memory budget for two CTAs per SM");
 
@@ -189,7 +192,24 @@ __device__ inline uint32_t block_excl_sum(uint32_t v, uint32_t *scan, uint32_t &
  * and bits (u8: code length + extra bits = what one entry of that symbol costs). */
 constexpr int DF_BB_THREADS = 320;
 enum { BB_STAT = 0 /* [2][4]: used,total,first */, BB_KRAFT = 8 /* [2 sweeps][2 alph][16] */, BB_K = 72 /* [2][16] */,
-       BB_NEXT = 104 /* [2][16] */, BB_SLACK = 136 /* [2] */, BB_CNTW = 144 /* [2 bufs][10 warps][16] */ };
+       BB_NEXT = 104 /* [2][16] */, BB_SLACK = 136 /* [2] */, BB_CNTW = 144 /* [2 bufs][10 warps][16] */,
+       BB_NZ = 464 /* [10] ballots: length != 0 */, BB_ST = 474 /* [10] ballots: a run of equal lengths starts here */,
+       BB_HSUM = 484 /* [10] header bits per warp */, BB_HDRBITS = 494 /* size of the block header in bits */ };
+
+/* ---- block header (RFC 1951 3.2.7): HLIT/HDIST trimmed, code lengths run-length coded (symbols 16/17/18) under a STATIC
+ * code-length code. A code chosen per block would save another 0.01-0.09 % of the input (tools/sim/lzsim hdr=0 vs hdr=3) and cost
+ * a third code construction on the critical path. The static code is complete (Kraft sum exactly 1; zlib's inflate rejects
+ * anything else) and gives every one of the 19 symbols a code, so any length 1..15 can be sent:
+ *   3 bits: lengths 7 8 9 | 4 bits: 0 5 6 10 11 and run symbol 18 | 5 bits: 3 4 12 13, 16, 17 | 6 bits: 1 2 14 15.
+ * Packed per symbol 0..18: CL_LENS 3 bits each; CL_CODE_* the canonical codes bit-reversed (sent LSB first), 6 bits each;
+ * CL_ORDER57 the nineteen 3-bit lengths in the header's transmission order 16,17,18,0,8,7,9,6,10,5,11,4,12,3,13,2,14,1,15. */
+constexpr uint64_t CL_LENS = 0x12ddad91b725bb4ull;
+constexpr uint64_t CL_CODE_LO = 0x840013930ef3c6ull, CL_CODE_HI = 0xd5c7fdf6cb149ull;
+constexpr uint64_t CL_ORDER57 = 0x1b6d6db248db92dull;
+__device__ __forceinline__ uint32_t cl_len(uint32_t s) { return (uint32_t)(CL_LENS >> (3 * s)) & 7u; }
+__device__ __forceinline__ uint32_t cl_code(uint32_t s) {
+    return s < 10 ? (uint32_t)(CL_CODE_LO >> (6 * s)) & 63u : (uint32_t)(CL_CODE_HI >> (6 * (s - 10))) & 63u;
+}
 
 __device__ __forceinline__ void bb_count_lengths(uint32_t *cntw_row, uint32_t L, unsigned lane, unsigned &m) {
     if (lane < 16) cntw_row[lane] = 0;
@@ -200,7 +220,8 @@ __device__ __forceinline__ void bb_count_lengths(uint32_t *cntw_row, uint32_t L,
 }
 
 __device__ inline void block_build_codes(const uint32_t *hist_ll, const uint32_t *hist_lit2, const uint32_t *hist_d, uint8_t *lens_ll, uint8_t *lens_d,
-                                         uint32_t *code_ll, uint32_t *code_d, uint8_t *bits_ll, uint8_t *bits_d, uint32_t *bb) {
+                                         uint32_t *code_ll, uint32_t *code_d, uint8_t *bits_ll, uint8_t *bits_d, uint32_t *bb,
+                                         uint32_t *stage, uint32_t hdrpos, uint32_t bfinal) {
     const uint32_t tid = threadIdx.x;
     const unsigned lane = lane_id(), w = warp_id();
     const int a = tid < 288 ? 0 : (tid < 320 ? 1 : 2);
@@ -344,21 +365,65 @@ __device__ inline void block_build_codes(const uint32_t *hist_ll, const uint32_t
             bits_d[sym] = (uint8_t)(L + dist_extra_bits(sym));
         }
     }
-}
-
-/* Dynamic block header with a FIXED code-length code (all sixteen length values 0..15 coded in 4 bits:
- * a complete prefix code, so zlib accepts it) and no run-length symbols: constant size, every field at a
- * known bit position, written by 317 threads in parallel. */
-constexpr uint32_t DF_HDR_BITS = 17 + 19 * 3 + 4 * (286 + 30);
-__device__ __forceinline__ void emit_block_header(uint32_t *stage, uint32_t pos, uint32_t bfinal, const uint8_t *lens_ll,
-                                                  const uint8_t *lens_d, uint32_t tid) {
-    if (tid == 0) stage_put(stage, pos, bfinal | (2u << 1) | (29u << 3) | (29u << 8) | (15u << 13), 17);
-    /* code-length code lengths in the order 16,17,18,0,8,7,...: three zeros, then sixteen 4s */
-    if (tid >= 1 && tid <= 16) stage_put(stage, pos + 17 + 9 + 3 * (tid - 1), 4u, 3);
-    if (tid < 286 + 30) {
-        uint32_t v = tid < 286 ? lens_ll[tid] : lens_d[tid - 286];
-        stage_put(stage, pos + 17 + 57 + 4 * tid, __brev(v) >> 28, 4); /* canonical 4-bit code of value v, MSB first */
+    /* ---- the block header, written straight into the (clean) staging buffer at bit hdrpos. One thread per code length;
+     * runs of equal lengths are found from per-warp ballots (a run never crosses from the literal/length lengths into the
+     * distance lengths: the RFC allows it, zlib never writes it, so neither do we). ---- */
+    const unsigned nz = __ballot_sync(MZ_FULL_MASK, L != 0);
+    if (lane == 0) bb[BB_NZ + w] = nz;
+    bar_sync(1, DF_BB_THREADS);
+    const uint32_t hlit = 256u + 32u - (uint32_t)__clz((int)bb[BB_NZ + 8]); /* the end-of-block symbol always has a code: >= 257 */
+    const uint32_t hdw = bb[BB_NZ + 9];
+    const uint32_t hdist = hdw ? 32u - (uint32_t)__clz((int)hdw) : 1u;
+    const uint32_t nlen = a == 0 ? hlit : hdist;
+    const bool valid = sym < nlen;
+    const uint32_t prevL = sym == 0 ? 0xffu : (a == 0 ? lens_ll[sym - 1] : lens_d[sym - 1]);
+    const unsigned st = __ballot_sync(MZ_FULL_MASK, (valid && prevL != L) || sym == nlen); /* + a sentinel start behind the last length */
+    if (lane == 0) bb[BB_ST + w] = st;
+    bar_sync(1, DF_BB_THREADS);
+    uint32_t nb = 0, val = 0;
+    if (valid) {
+        uint32_t m = st & (0xffffffffu >> (31u - lane)), ww = w;
+        while (m == 0) m = bb[BB_ST + --ww];                   /* symbol 0 starts a run: terminates inside my alphabet */
+        const uint32_t s0 = (ww - w0) * 32u + 31u - (uint32_t)__clz((int)m);
+        m = lane == 31 ? 0u : st & (0xfffffffeu << lane);
+        ww = w;
+        while (m == 0) m = bb[BB_ST + ++ww];                   /* the sentinel ends the last run */
+        const uint32_t e0 = (ww - w0) * 32u + (uint32_t)__ffs((int)m) - 1u;
+        const uint32_t k = sym - s0, R = e0 - s0;                /* my place in a run of R equal lengths */
+        uint32_t cs = L, ev = 0, eb = 0;
+        bool tok = true;
+        if (L == 0) { /* zeros: 18 = 11..138 of them, 17 = 3..10, else one by one */
+            const uint32_t full = (R / 138u) * 138u, rem = R - full;
+            if (k < full) { tok = k % 138u == 0; cs = 18; ev = 127; eb = 7; }
+            else if (rem >= 11) { tok = k == full; cs = 18; ev = rem - 11; eb = 7; }
+            else if (rem >= 3) { tok = k == full; cs = 17; ev = rem - 3; eb = 3; }
+        } else if (k > 0) { /* the length itself, then 16 = repeat it 3..6 times, else one by one */
+            const uint32_t k1 = k - 1, rest = R - 1, full = (rest / 6u) * 6u, rem = rest - full;
+            if (k1 < full) { tok = k1 % 6u == 0; cs = 16; ev = 3; eb = 2; }
+            else if (rem >= 3) { tok = k1 == full; cs = 16; ev = rem - 3; eb = 2; }
+        }
+        if (tok) {
+            const uint32_t cl = cl_len(cs);
+            nb = cl + eb;
+            val = cl_code(cs) | (ev << cl);
+        }
     }
+    const uint32_t incl = warp_incl_sum(nb);
+    if (lane == 31) bb[BB_HSUM + w] = incl;
+    bar_sync(1, DF_BB_THREADS);
+    uint32_t off = incl - nb, total = 0;
+    for (uint32_t ww = 0; ww < 10; ww++) {
+        const uint32_t t = bb[BB_HSUM + ww];
+        off += ww < w ? t : 0u;
+        total += t;
+    }
+    if (nb) stage_put(stage, hdrpos + 17 + 57 + off, val, nb);
+    if (tid == 0) {
+        stage_put(stage, hdrpos, bfinal | (2u << 1) | ((hlit - 257u) << 3) | ((hdist - 1u) << 8) | (15u << 13), 17);
+        bb[BB_HDRBITS] = 17 + 57 + total;
+    }
+    if (tid == 32) stage_put(stage, hdrpos + 17, (uint32_t)CL_ORDER57, 32);
+    if (tid == 64) stage_put(stage, hdrpos + 17 + 32, (uint32_t)(CL_ORDER57 >> 32), 25);
 }
 
 /* ---- A: match helpers ----------------------------------------------------------------------------------- */
@@ -454,7 +519,7 @@ __device__ __forceinline__ void put_match_bits(const Smem &sm, uint32_t pos, uin
     const uint32_t wa = DF_OFF_STAGE + (pos >> 5) * 4;
     const uint32_t w0 = lo << sh, w1 = __funnelshift_l(lo, hi, sh), w2 = __funnelshift_l(hi, 0u, sh);
     sm.red_or32(wa, w0);
-    if (w1) sm.red_or32(wa + 4, w1);
+    sm.red_or32(wa + 4, w1);
     if (w2) sm.red_or32(wa + 8, w2);
 }
 
@@ -749,6 +814,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) deflate_chunks_kernel(DeflatePa
 
                 /* ---- T: classify every span once -> final records in registers; symbol counts ---------------------- */
                 const uint32_t hist_lit = (lane & 1u) ? (uint32_t)DF_OFF_HIST2 : (uint32_t)DF_OFF_HIST; /* two copies halve the same-address traffic */
+                const uint32_t sink = DF_OFF_SINK + lane * 4;
 #pragma unroll
                 for (int b = 0; b < DF_NBATCH; b++) {
                     uint32_t F = 0, MA = 0, MB = 0;
@@ -770,7 +836,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) deflate_chunks_kernel(DeflatePa
                                                : j < 4 ? (x.x >> (8 * j - 2)) & 0x3fcu
                                                : j == 4 ? (x.y << 2) & 0x3fcu
                                                         : (x.y >> (8 * (j - 4) - 2)) & 0x3fcu; /* byte * 4 */
-                            sm.red_add32_if(((F >> j) & 1u) != 0, hist_lit + by4, 1u);
+                            sm.red_add32(((F >> j) & 1u) ? hist_lit + by4 : sink, 1u);
                         }
                         if (MA) MA = match_symbols(sm, MA);
                         if (!ONEM && MB) MB = match_symbols(sm, MB);
@@ -781,8 +847,10 @@ __global__ void __launch_bounds__(DF_THREADS, 2) deflate_chunks_kernel(DeflatePa
                 __syncthreads(); /* S4 */
                 /* ---- D: codes (10 warps on a named barrier; the rest wait here) ------------------------- */
                 if (tid < DF_BB_THREADS)
-                    block_build_codes(s_hist_ll, (const uint32_t *)(smem + DF_OFF_HIST2), s_hist_d, s_lens_ll, s_lens_d, s_code_ll, s_code_d, s_bits_ll, s_bits_d, s_bb);
+                    block_build_codes(s_hist_ll, (const uint32_t *)(smem + DF_OFF_HIST2), s_hist_d, s_lens_ll, s_lens_d, s_code_ll, s_code_d, s_bits_ll, s_bits_d, s_bb,
+                                      s_stage, bitpos, bfinal);
                 __syncthreads(); /* S5 */
+                const uint32_t hdrbits = s_bb[BB_HDRBITS]; /* (the scratch is reused below) */
                 /* ---- E: bits per span -> offsets ------------------------------------------------------------------- */
 #pragma unroll
                 for (int b = 0; b < DF_NBATCH; b++) {
@@ -822,17 +890,20 @@ __global__ void __launch_bounds__(DF_THREADS, 2) deflate_chunks_kernel(DeflatePa
                     s_bb[tid] = mybase;
                 }
                 __syncthreads(); /* S9: offsets visible */
-                const uint32_t hdrbits = DF_HDR_BITS;
                 const uint32_t eob = s_code_ll[256];
                 const uint32_t dyn_bits = hdrbits + tokbits + ((eob >> 16) & 15u);
                 const uint32_t stored_bits = (((bitpos + 3 + 7) & ~7u) - bitpos) + 32 + ulen * 8;
                 if (dyn_bits >= stored_bits) {
                     stored = true;
+                    /* take the header back out of the staging buffer (rare path) */
+                    const uint32_t w0 = bitpos >> 5;
+                    for (uint32_t i = tid; i <= (hdrbits + 31) / 32 + 1; i += DF_THREADS)
+                        s_stage[w0 + i] = i == 0 ? s_stage[w0] & ((1u << (bitpos & 31u)) - 1u) : 0u;
+                    __syncthreads();
                 } else {
                     /* ---- F: emit. Literals of a span go through a bit accumulator in slot order; a match leaves a gap of
                      * its size in that stream (its slot puts zeros) and is OR-ed in afterwards at the recorded position. ---- */
                     const uint32_t base = bitpos + hdrbits;
-                    emit_block_header(s_stage, bitpos, bfinal, s_lens_ll, s_lens_d, tid);
 #pragma unroll
                     for (int b = 0; b < DF_NBATCH; b++) {
                         if ((uint32_t)b < nb) {
@@ -860,20 +931,20 @@ __global__ void __launch_bounds__(DF_THREADS, 2) deflate_chunks_kernel(DeflatePa
                                 const uint32_t xw = jj < 2 ? x.x : x.y;
                                 const uint32_t b0 = jj & 1 ? (xw >> 14) & 0x3fcu : (xw << 2) & 0x3fcu;   /* byte * 4 */
                                 const uint32_t b1 = jj & 1 ? (xw >> 22) & 0x3fcu : (xw >> 6) & 0x3fcu;
-                                const uint32_t cw0 = sm.ld32(DF_OFF_CODE + b0), cw1 = sm.ld32(DF_OFF_CODE + b1);
                                 const bool l0 = ((F >> (2 * jj)) & 1u) != 0, l1 = ((F >> (2 * jj + 1)) & 1u) != 0;
-                                const uint32_t n0 = l0 ? (cw0 >> 16) & 15u : 0u, n1 = l1 ? (cw1 >> 16) & 15u : 0u;
+                                /* a position that is not a literal looks up the all-zero entry: no selects on the results */
+                                const uint32_t cw0 = sm.ld32(DF_OFF_CODE + (l0 ? b0 : DF_ZERO_SYM * 4)), cw1 = sm.ld32(DF_OFF_CODE + (l1 ? b1 : DF_ZERO_SYM * 4));
+                                const uint32_t n0 = cw0 >> 16, n1 = cw1 >> 16; /* (a literal's entry has no extra-bits field) */
                                 const uint32_t g0 = slotA == 2u * jj ? nA : (slotB == 2u * jj ? nB : 0u);            /* a match ordered here leaves a gap */
                                 const uint32_t g1 = slotA == 2u * jj + 1 ? nA : (slotB == 2u * jj + 1 ? nB : 0u);
                                 posA = slotA == 2u * jj ? pos : (slotA == 2u * jj + 1 ? pos + n0 : posA);
                                 posB = slotB == 2u * jj ? pos : (slotB == 2u * jj + 1 ? pos + n0 : posB);
                                 /* at most the two literals are in-band, and then they are adjacent (a match start covers its neighbour) */
-                                const uint32_t v = (l0 ? cw0 & 0x7fffu : 0u) | ((l1 ? cw1 & 0x7fffu : 0u) << n0);
+                                const uint32_t v = (cw0 & 0xffffu) | ((cw1 & 0xffffu) << n0);
                                 const uint32_t sh = pos & 31u, wa = DF_OFF_STAGE + ((pos >> 5) << 2);
-                                if (l0 || l1) {
-                                    sm.red_or32(wa, v << sh);
-                                    if (sh + n0 + n1 > 32) sm.red_or32(wa + 4, v >> (32 - sh));
-                                }
+                                /* both words unconditionally (an OR of zero is harmless): cheaper than the branches around them */
+                                sm.red_or32(wa, v << sh);
+                                sm.red_or32(wa + 4, __funnelshift_l(v, 0u, sh));
                                 pos += n0 + n1 + g0 + g1;
                             }
                             if (MA) put_match_bits(sm, posA, MA);

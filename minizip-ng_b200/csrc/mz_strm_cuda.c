@@ -21,6 +21,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "mz_abi.h"
 #include "mz_cuda_batch.h"
@@ -55,6 +56,7 @@ typedef struct cu_ws_s {
     uint64_t slot_stride;
     /* read */
     uint8_t *h_cin, *d_cin, *d_win, *h_dec;
+    uint8_t *d_win2; /* long streams: second output window, so that decoding can go on while the first is still being delivered */
     size_t cin_cap, win_cap;
     mz_cuda_inflate_job *h_job, *d_job;
     mz_cuda_inflate_state *h_state, *d_state;
@@ -105,6 +107,7 @@ static void ws_destroy(cu_ws *w) {
     mz_cuda_host_free(w->h_cin);
     mz_cuda_free(w->d_cin);
     mz_cuda_free(w->d_win);
+    mz_cuda_free(w->d_win2);
     mz_cuda_host_free(w->h_dec);
     mz_cuda_host_free(w->h_job);
     mz_cuda_free(w->d_job);
@@ -249,7 +252,10 @@ typedef struct mz_stream_cuda_s {
     int64_t hdr_size;   /* framing bytes before the raw stream */
     uint64_t cin_base;  /* raw-stream offset of ws->h_cin[0] */
     size_t cin_len;     /* valid bytes in ws->h_cin */
-    uint64_t win_base;  /* output offset of ws->d_win[0] */
+    uint64_t win_base;  /* output offset of byte 0 of the window being decoded into */
+    int dwin, lwin;     /* which window (0 = ws->d_win, 1 = ws->d_win2) is decoded into / delivered from */
+    uint64_t lwin_base; /* output offset of byte 0 of the delivery window, while it is not the decode window */
+    uint64_t lwin_end;  /* ... and where its bytes end */
     size_t dec_pos, dec_len; /* decoded bytes waiting in ws->h_dec + dec_base */
     size_t dec_base;         /* which half of h_dec the caller is reading */
     size_t pre_len;          /* bytes of the NEXT piece already on their way into the other half (0 = none) */
@@ -258,7 +264,26 @@ typedef struct mz_stream_cuda_s {
     uint64_t spec_resume_bit; /* no speculative round before the decoder has passed this stream bit */
     double ratio_est;   /* output bytes per compressed byte seen so far (sizes the rounds) */
     int8_t cin_dirty;   /* ws->h_cin changed since the last upload */
+    /* MZ_CUDA_TRACE: where the caller's thread spent its time on the read path (ns), printed by close() */
+    int8_t trace;
+    uint64_t t_base, t_move, t_round, t_piece, t_serial, t_copy, n_round, n_serial;
 } mz_stream_cuda;
+
+static inline uint64_t now_ns(void) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec;
+}
+#define CU_TIMED(cu, acc, stmt)          \
+    do {                                 \
+        if ((cu)->trace) {               \
+            const uint64_t t0_ = now_ns(); \
+            stmt;                        \
+            (cu)->acc += now_ns() - t0_; \
+        } else {                         \
+            stmt;                        \
+        }                                \
+    } while (0)
 
 static mz_stream_vtbl mz_stream_cuda_vtbl = {
     mz_stream_cuda_open,   mz_stream_cuda_is_open, mz_stream_cuda_read,           mz_stream_cuda_write,
@@ -320,6 +345,8 @@ int32_t mz_stream_cuda_open(void *stream, const char *path, int32_t mode) {
     cu->cin_base = 0;
     cu->cin_len = 0;
     cu->win_base = 0;
+    cu->dwin = cu->lwin = 0;
+    cu->lwin_base = cu->lwin_end = 0;
     cu->dec_pos = cu->dec_len = 0;
     cu->dec_base = cu->pre_len = 0;
     cu->fed_in = 0;
@@ -327,6 +354,8 @@ int32_t mz_stream_cuda_open(void *stream, const char *path, int32_t mode) {
     cu->spec_resume_bit = 0;
     cu->ratio_est = 4.0;
     cu->cin_dirty = 1;
+    cu->trace = getenv("MZ_CUDA_TRACE") != NULL;
+    cu->t_base = cu->t_move = cu->t_round = cu->t_piece = cu->t_serial = cu->t_copy = cu->n_round = cu->n_serial = 0;
     cu->initialized = 1;
     cu->mode = mode;
     return MZ_OK;
@@ -575,7 +604,8 @@ static int32_t cu_refill(mz_stream_cuda *cu) {
             cu->base_eof = 1;
             break;
         }
-        int32_t got = mz_abi_base_read(cu->stream.base, w->h_cin + cu->cin_len, (int32_t)want);
+        int32_t got;
+        CU_TIMED(cu, t_base, got = mz_abi_base_read(cu->stream.base, w->h_cin + cu->cin_len, (int32_t)want));
         if (got < 0)
             return got;
         if (got == 0) {
@@ -648,13 +678,15 @@ static void ws_read_upgrade(cu_ws *w, size_t cin_len) {
     size_t seg = env_size("MZ_CUDA_SPEC_SEG_KB", 16u << 10, 1024);
     if (cin_cap <= w->cin_cap || seg < 1024)
         return;
-    size_t win_cap = 32768 + 4 * cin_cap;
+    size_t mult = env_size("MZ_CUDA_READ_OUT_MULT", 4, 1); /* output window = this many compressed windows (tests shrink it) */
+    size_t win_cap = 32768 + (mult ? mult : 4) * cin_cap;
     uint32_t max_seg = (uint32_t)(cin_cap / seg) + 1;
     if (max_seg > 12288) /* K6c keeps 16 bytes of shared memory per segment */
         max_seg = 12288;
     uint8_t *h_cin = (uint8_t *)mz_cuda_host_alloc(cin_cap + 64);
     uint8_t *d_cin = (uint8_t *)mz_cuda_malloc(cin_cap + 64);
     uint8_t *d_win = (uint8_t *)mz_cuda_malloc(win_cap + 512);
+    uint8_t *d_win2 = (uint8_t *)mz_cuda_malloc(win_cap + 512); /* (optional: without it rounds simply wait for the delivery) */
     void *d_spec = mz_cuda_malloc((size_t)mz_cuda_inflate_spec_workspace_bytes(max_seg));
     mz_cuda_spec_summary *h_sum = (mz_cuda_spec_summary *)mz_cuda_host_alloc(sizeof(mz_cuda_spec_summary));
     mz_cuda_spec_summary *d_sum = (mz_cuda_spec_summary *)mz_cuda_malloc(sizeof(mz_cuda_spec_summary));
@@ -662,6 +694,7 @@ static void ws_read_upgrade(cu_ws *w, size_t cin_len) {
         mz_cuda_host_free(h_cin);
         mz_cuda_free(d_cin);
         mz_cuda_free(d_win);
+        mz_cuda_free(d_win2);
         mz_cuda_free(d_spec);
         mz_cuda_host_free(h_sum);
         mz_cuda_free(d_sum);
@@ -677,6 +710,8 @@ static void ws_read_upgrade(cu_ws *w, size_t cin_len) {
     w->h_cin = h_cin;
     w->d_cin = d_cin;
     w->d_win = d_win;
+    mz_cuda_free(w->d_win2);
+    w->d_win2 = d_win2;
     w->cin_cap = cin_cap;
     w->win_cap = win_cap;
     w->d_spec = d_spec;
@@ -771,7 +806,7 @@ static int32_t cu_prepare_input(mz_stream_cuda *cu) {
         size_t drop = (size_t)(pos_byte - cu->cin_base);
         if (drop > cu->cin_len)
             drop = cu->cin_len;
-        memmove(w->h_cin, w->h_cin + drop, cu->cin_len - drop);
+        CU_TIMED(cu, t_move, memmove(w->h_cin, w->h_cin + drop, cu->cin_len - drop));
         cu->cin_len -= drop;
         cu->cin_base += drop;
         cu->cin_dirty = 1;
@@ -788,6 +823,8 @@ static int32_t cu_prepare_input(mz_stream_cuda *cu) {
     }
     return MZ_OK;
 }
+
+static inline uint8_t *cu_window(const mz_stream_cuda *cu, int which) { return which ? cu->ws->d_win2 : cu->ws->d_win; }
 
 /* enough compressed input ahead of the decoder for a speculative round to pay off: 4 segments (64 KiB). One warp decodes
  * ~13 MB/s of output, so even the two or three zlib blocks of such a window, decoded side by side, beat the serial decoder;
@@ -825,7 +862,7 @@ static int32_t cu_spec_launch(mz_stream_cuda *cu) {
     if (nseg < 2)
         return 0;
     err = mz_cuda_inflate_spec_round(w->d_cin, cu->cin_base, cu->cin_len, cu->base_eof ? 1u : 0u, st->in_bitpos, w->spec_seg_bytes,
-                                     (uint32_t)nseg, w->d_win, cu->win_base, st->out_pos, out_end, w->d_spec, w->spec_max_seg, w->d_sum,
+                                     (uint32_t)nseg, cu_window(cu, cu->dwin), cu->win_base, st->out_pos, out_end, w->d_spec, w->spec_max_seg, w->d_sum,
                                      w->rstream);
     if (err)
         return err;
@@ -846,7 +883,9 @@ static int32_t cu_spec_collect(mz_stream_cuda *cu) {
     cu_ws *w = cu->ws;
     mz_cuda_inflate_state *st = w->h_state;
     const uint64_t seg_bits = (uint64_t)w->spec_seg_bytes * 8;
-    int32_t err = mz_cuda_event_sync(w->rev);
+    int32_t err;
+    CU_TIMED(cu, t_round, err = mz_cuda_event_sync(w->rev));
+    cu->n_round += 1;
     w->pending = 0;
     if (err)
         return err;
@@ -882,11 +921,14 @@ static int32_t cu_spec_collect(mz_stream_cuda *cu) {
 static int32_t cu_fetch_piece(mz_stream_cuda *cu, size_t base, size_t cap) {
     cu_ws *w = cu->ws;
     const mz_cuda_inflate_state *st = w->h_state;
-    uint64_t n = st->out_pos - cu->deliv_pos;
     int32_t err;
+    if (cu->lwin != cu->dwin && cu->deliv_pos >= cu->lwin_end)
+        cu->lwin = cu->dwin; /* the old window is empty: it may be decoded into again */
+    const int old = cu->lwin != cu->dwin;
+    uint64_t n = (old ? cu->lwin_end : st->out_pos) - cu->deliv_pos;
     if (n > cap)
         n = cap;
-    const uint8_t *src = w->d_win + (cu->deliv_pos - cu->win_base);
+    const uint8_t *src = cu_window(cu, cu->lwin) + (cu->deliv_pos - (old ? cu->lwin_base : cu->win_base));
     if (cu->wrap == 2) {
         err = mz_cuda_crc32_device_stream(src, n, cu->crc, &cu->crc, w->dstream);
         if (err)
@@ -924,6 +966,22 @@ static int32_t cu_decode_more(mz_stream_cuda *cu) {
         if (cu->deliv_pos < st->out_pos || cu->pre_len) {
             /* keep the GPU busy meanwhile: if the decoder stands at a block boundary and the output window still has
              * room behind the undelivered bytes, start the next round now */
+            if (w->d_spec && w->d_win2 && !w->pending && st->status == 0 && st->phase == 0 && cu->lwin == cu->dwin &&
+                cu->win_base + w->win_cap - st->out_pos < w->win_cap / 4) {
+                /* no room for another round behind the undelivered bytes, and the other window is idle: carry the last
+                 * 32 KiB of history over and decode into it; the delivery drains this window meanwhile */
+                const uint64_t have = st->out_pos - cu->win_base, keep = have < 32768 ? have : 32768;
+                err = mz_cuda_memcpy_d2d(cu_window(cu, cu->dwin ^ 1), cu_window(cu, cu->dwin) + (have - keep), keep, w->rstream);
+                if (err)
+                    return err;
+                if (cu->trace)
+                    fprintf(stderr, "mz_strm_cuda: output window %d full at byte %llu with %llu bytes to deliver: decoding on in window %d\n", cu->dwin,
+                            (unsigned long long)st->out_pos, (unsigned long long)(st->out_pos - cu->deliv_pos), cu->dwin ^ 1);
+                cu->lwin_base = cu->win_base;
+                cu->lwin_end = st->out_pos;
+                cu->dwin ^= 1;
+                cu->win_base = st->out_pos - keep;
+            }
             if (w->d_spec && !w->pending && st->status == 0 && st->phase == 0 &&
                 cu->win_base + w->win_cap - st->out_pos >= w->win_cap / 4) {
                 err = cu_prepare_input(cu);
@@ -944,7 +1002,7 @@ static int32_t cu_decode_more(mz_stream_cuda *cu) {
             } else {
                 cu->dec_base = cu->dec_base ? 0 : half; /* the piece in flight landed in the other half */
             }
-            err = mz_cuda_stream_sync(w->dstream);
+            CU_TIMED(cu, t_piece, err = mz_cuda_stream_sync(w->dstream));
             if (err)
                 return err;
             const size_t n = cu->pre_len;
@@ -990,7 +1048,7 @@ static int32_t cu_decode_more(mz_stream_cuda *cu) {
                 uint64_t k = keep - o;
                 if (gap < keep && k > gap)
                     k = gap;
-                err = mz_cuda_memcpy_d2d(w->d_win + o, w->d_win + gap + o, k, w->rstream);
+                err = mz_cuda_memcpy_d2d(cu_window(cu, cu->dwin) + o, cu_window(cu, cu->dwin) + gap + o, k, w->rstream);
                 if (err)
                     return err;
                 o += k;
@@ -1007,7 +1065,7 @@ static int32_t cu_decode_more(mz_stream_cuda *cu) {
         w->h_job->d_in = w->d_cin;
         w->h_job->in_base = cu->cin_base;
         w->h_job->in_avail = cu->cin_len;
-        w->h_job->d_out = w->d_win;
+        w->h_job->d_out = cu_window(cu, cu->dwin);
         w->h_job->out_base = cu->win_base;
         /* at most one host buffer (`batch` bytes) of fresh output per launch */
         w->h_job->out_cap = (out_pos - cu->win_base) + w->batch < w->win_cap ? (out_pos - cu->win_base) + w->batch : w->win_cap;
@@ -1025,7 +1083,8 @@ static int32_t cu_decode_more(mz_stream_cuda *cu) {
         err = mz_cuda_memcpy_d2h(st, w->d_state, sizeof(*st), w->rstream);
         if (err)
             return err;
-        err = mz_cuda_stream_sync(w->rstream);
+        CU_TIMED(cu, t_serial, err = mz_cuda_stream_sync(w->rstream));
+        cu->n_serial += 1;
         if (err)
             return err;
         if (st->status == 0)
@@ -1064,7 +1123,7 @@ int32_t mz_stream_cuda_read(void *stream, void *buf, int32_t size) {
             size_t k = cu->dec_len - cu->dec_pos;
             if (k > (size_t)(size - done))
                 k = (size_t)(size - done);
-            memcpy(out + done, cu->ws->h_dec + cu->dec_base + cu->dec_pos, k);
+            CU_TIMED(cu, t_copy, memcpy(out + done, cu->ws->h_dec + cu->dec_base + cu->dec_pos, k));
             cu->dec_pos += k;
             done += (int32_t)k;
             continue;
@@ -1145,6 +1204,11 @@ int32_t mz_stream_cuda_close(void *stream) {
 #ifdef MZ_ZIP_NO_DECOMPRESSION
         return MZ_SUPPORT_ERROR;
 #endif
+        if (cu->trace)
+            fprintf(stderr, "mz_strm_cuda: read side, caller's thread (ms): base reads %.1f, window moves %.1f, waiting for speculative rounds %.1f (%llu), "
+                            "for serial K5 steps %.1f (%llu), for output pieces %.1f, copying to the caller %.1f; %lld bytes out\n",
+                    cu->t_base / 1e6, cu->t_move / 1e6, cu->t_round / 1e6, (unsigned long long)cu->n_round, cu->t_serial / 1e6,
+                    (unsigned long long)cu->n_serial, cu->t_piece / 1e6, cu->t_copy / 1e6, (long long)cu->total_out);
     }
     if (cu->ws) {
         ws_release(cu->ws);

@@ -46,6 +46,13 @@ def test_read_path_long_member_switches_windows_and_overlaps_rounds(emulib):
     assert out.count("K6 round") >= 3
 
 
+def test_read_path_long_member_alternates_output_windows(emulib):
+    """output window as small as the compressed one: every other round finds it full while bytes are still being delivered, and
+    decoding moves on in the second window (history carried over)"""
+    out = _scenario("long", MZ_CUDA_SPEC_SEG_KB=4, MZ_CUDA_BATCH_KB=1024, MZ_CUDA_READ_WINDOW_KB=1100, MZ_CUDA_READ_OUT_MULT=1, MZ_CUDA_TRACE=1)
+    assert out.count("decoding on in window") >= 4
+
+
 def test_crc_symbol_device_path(emulib):
     _scenario("crc", MZ_CUDA_CRC_MIN_BYTES=65536)
 
@@ -67,3 +74,4 @@ def test_host_paths_under_sanitizers(emulib):
     _scenario("write", MZ_CUDA_BATCH_KB=256, **san)
     _scenario("read", MZ_CUDA_SPEC=1, MZ_CUDA_SPEC_SEG_KB=4, MZ_CUDA_BATCH_KB=1024, **san)
     _scenario("long", MZ_CUDA_SPEC_SEG_KB=4, MZ_CUDA_BATCH_KB=1024, MZ_CUDA_READ_WINDOW_KB=2048, **san)
+    _scenario("long", MZ_CUDA_SPEC_SEG_KB=4, MZ_CUDA_BATCH_KB=1024, MZ_CUDA_READ_WINDOW_KB=1100, MZ_CUDA_READ_OUT_MULT=1, **san)

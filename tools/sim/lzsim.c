@@ -103,7 +103,9 @@ static const uint8_t dext[30] = {0,0,0,0,1,1,2,2,3,3,4,4,5,5,6,6,7,7,8,8,9,9,10,
 static int lsym(int len) { int l = len - 3; if (l < 8) return l; if (len == 258) return 28; int msb = 31 - __builtin_clz(l); int eb = msb - 2; return 4 * (eb + 1) + ((l >> eb) & 3); }
 static int dsym(int dist) { int d = dist - 1; if (d < 4) return d; int msb = 31 - __builtin_clz(d); int eb = msb - 1; return 2 * msb + ((d >> eb) & 1); }
 
-static int g_hdrmode = 0; /* 0 = optimal RLE header, 1 = fixed 1338-bit header (v2 kernel) , 2 = flat 4-bit CL code, trimmed, with RLE symbols at fixed lengths */
+static int g_hdrmode = 0; /* 0 = optimal RLE header, 1 = fixed 1338-bit header (v2/v3.1 kernel), 3 = run-length symbols with the kernel's STATIC code-length code */
+static uint64_t g_cf[19]; /* code-length symbol counts over all blocks (printed with cf=1: the input for choosing the static code) */
+static uint8_t g_static_cl[19] = {4, 6, 6, 5, 5, 4, 4, 3, 3, 3, 4, 4, 5, 5, 6, 6, 5, 5, 4};
 static uint64_t block_cost(const uint32_t *fl, const uint32_t *fd, uint64_t *hdr_out) {
     uint8_t ll[288], dl[32];
     uint32_t f2[288]; memcpy(f2, fl, sizeof(f2)); f2[256] = 1;
@@ -131,8 +133,8 @@ static uint64_t block_cost(const uint32_t *fl, const uint32_t *fd, uint64_t *hdr
             i = j;
         }
         uint8_t cl[19];
-        if (g_hdrmode == 2) { for (int i = 0; i < 19; i++) cl[i] = 0; /* fixed CL code: 0..15 -> 4 bits?? not complete with 16-18; model: symbols 0-15: 5 bits except common; */
-            huff_lengths(cf, 19, 7, cl); }
+        for (int i = 0; i < 19; i++) g_cf[i] += cf[i];
+        if (g_hdrmode == 3) memcpy(cl, g_static_cl, 19);
         else huff_lengths(cf, 19, 7, cl);
         static const int ord[19] = {16,17,18,0,8,7,9,6,10,5,11,4,12,3,13,2,14,1,15};
         int hclen = 19; while (hclen > 4 && cl[ord[hclen - 1]] == 0) hclen--;
@@ -272,6 +274,7 @@ int main(int argc, char **argv) {
         else if (!strncmp(argv[i], "chunk=", 6)) M.chunk = atoi(argv[i] + 6);
         else if (!strncmp(argv[i], "hdr=", 4)) g_hdrmode = atoi(argv[i] + 4);
         else if (!strcmp(argv[i], "zlib")) zl = 1;
+        else if (!strncmp(argv[i], "cl=", 3)) { const char *q = argv[i] + 3; for (int k = 0; k < 19 && *q; k++) { g_static_cl[k] = (uint8_t)strtol(q, (char **)&q, 10); if (*q == ',') q++; } }
     }
     uint8_t *buf;
     if (file) { FILE *f = fopen(file, "rb"); fseek(f, 0, SEEK_END); n = ftell(f); fseek(f, 0, SEEK_SET); buf = malloc(n + 64); if (fread(buf, 1, n, f) != n) return 1; fclose(f); }
@@ -290,5 +293,6 @@ int main(int argc, char **argv) {
     }
     printf("lstride=%d chunk=%d ", M.lstride, M.chunk); printf("mode=%d hbits=%d hbytes=%d min=%d span=%d lazy=%d batch=%d cap=%d sb=%d dict=%d ways=%d hdr=%d : ratio %.4f  (lit/B %.3f match/B %.4f avgmatch %.2f hdr %.4f)\n", M.hashmode, M.hbits, M.hbytes, M.minmatch, M.span,
            M.lazy, M.batch, M.cap, M.sbsize, M.dict, M.ways, g_hdrmode, bits / 8.0 / n, (double)g_tok_lit / n, (double)g_tok_match / n, (double)g_matchbytes / (g_tok_match ? g_tok_match : 1), g_hdrbits / 8.0 / n);
+    printf("cf:"); for (int i = 0; i < 19; i++) printf(" %llu", (unsigned long long)g_cf[i]); printf("\n");
     return 0;
 }
