@@ -354,7 +354,7 @@ int32_t mz_stream_cuda_open(void *stream, const char *path, int32_t mode) {
     cu->spec_resume_bit = 0;
     cu->ratio_est = 4.0;
     cu->cin_dirty = 1;
-    cu->trace = getenv("MZ_CUDA_TRACE") != NULL;
+    cu->trace = getenv("MZ_CUDA_TRACE") != NULL || getenv("MZ_CUDA_READ_STATS") != NULL; /* (TRACE also serialises the K6 kernels to time them) */
     cu->t_base = cu->t_move = cu->t_round = cu->t_piece = cu->t_serial = cu->t_copy = cu->n_round = cu->n_serial = 0;
     cu->initialized = 1;
     cu->mode = mode;

@@ -403,6 +403,7 @@ typedef struct za_slot_s {
     int32_t device, err;
     uint64_t region_len;
     double pack_ms, gpu_ms;
+    void *stream; /* the slot's own CUDA stream: rounds of different slots (and devices) overlap */
     pthread_t th;
     int running;
 } za_slot;
@@ -413,17 +414,25 @@ static void put64(uint8_t *p, uint64_t v) { put32(p, (uint32_t)v); put32(p + 4, 
 
 /* mz_zip_time_t_to_dos_date (mz_zip.c): local time, 2-second resolution, years from 1980 */
 static uint32_t za_dos_date(int64_t t) {
+    static __thread int64_t last_t = -1; /* archives carry few distinct dates: localtime_r once per run of equal ones */
+    static __thread uint32_t last_v;
+    if (t && t == last_t)
+        return last_v;
     time_t tt = (time_t)(t ? t : time(NULL));
     struct tm tmv;
     if (!localtime_r(&tt, &tmv))
         return 0;
     int year = tmv.tm_year >= 1980 ? tmv.tm_year - 1980 : (tmv.tm_year >= 80 ? tmv.tm_year - 80 : 0);
-    return ((uint32_t)((tmv.tm_mday) + 32 * (tmv.tm_mon + 1) + 512 * year) << 16) |
-           (uint32_t)(tmv.tm_sec / 2 + 32 * tmv.tm_min + 2048 * tmv.tm_hour);
+    last_v = ((uint32_t)((tmv.tm_mday) + 32 * (tmv.tm_mon + 1) + 512 * year) << 16) |
+             (uint32_t)(tmv.tm_sec / 2 + 32 * tmv.tm_min + 2048 * tmv.tm_hour);
+    last_t = t;
+    return last_v;
 }
 
 static void za_free(za_slot *z) {
     zc_free(&z->b);
+    if (z->stream)
+        mz_cuda_stream_destroy(z->stream);
     mz_cuda_host_free(z->h_out_len);
     mz_cuda_host_free(z->h_dst_off);
     mz_cuda_free(z->d_dst_off);
@@ -457,7 +466,8 @@ static int za_alloc(za_slot *z, size_t round_bytes, uint32_t max_chunks, size_t 
     z->d_region = (uint8_t *)mz_cuda_malloc(z->region_cap);
     z->h_region = (uint8_t *)mz_cuda_host_alloc(z->region_cap);
     z->meta = (za_meta *)malloc((size_t)max_chunks * sizeof(za_meta));
-    if (!z->h_out_len || !z->h_dst_off || !z->d_dst_off || !z->h_hdr_off || !z->d_hdr_off || !z->h_blob_off || !z->d_blob_off || !z->h_blob ||
+    z->stream = mz_cuda_stream_create();
+    if (!z->stream || !z->h_out_len || !z->h_dst_off || !z->d_dst_off || !z->h_hdr_off || !z->d_hdr_off || !z->h_blob_off || !z->d_blob_off || !z->h_blob ||
         !z->d_blob || !z->d_region || !z->h_region || !z->meta) {
         za_free(z);
         return 0;
@@ -500,22 +510,22 @@ static void *za_prepare(void *arg) {
         pos += ((size_t)it->size + 15) & ~(size_t)15;
     }
     z->nch = nch;
-    if (!err) err = mz_cuda_memcpy_h2d(b->d_in, b->h_in, pos + 16, NULL);
-    if (!err) err = mz_cuda_memcpy_h2d(b->d_off, b->h_off, (size_t)nch * 8, NULL);
-    if (!err) err = mz_cuda_memcpy_h2d(b->d_len, b->h_len, (size_t)nch * 4, NULL);
-    if (!err) err = mz_cuda_memcpy_h2d(b->d_flags, b->h_flags, nch, NULL);
+    if (!err) err = mz_cuda_memcpy_h2d(b->d_in, b->h_in, pos + 16, z->stream);
+    if (!err) err = mz_cuda_memcpy_h2d(b->d_off, b->h_off, (size_t)nch * 8, z->stream);
+    if (!err) err = mz_cuda_memcpy_h2d(b->d_len, b->h_len, (size_t)nch * 4, z->stream);
+    if (!err) err = mz_cuda_memcpy_h2d(b->d_flags, b->h_flags, nch, z->stream);
     double t1 = now_ms();
-    if (!err) err = mz_cuda_deflate_chunks(b->d_in, 0, 0, b->d_off, b->d_len, b->d_flags, nch, 0, z->level, b->d_slots, b->stride, b->d_out_len, NULL);
-    if (!err) err = mz_cuda_crc32_segments(b->d_in, 0, 0, b->d_off, b->d_len, nch, b->d_residue, b->d_crc, NULL);
+    if (!err) err = mz_cuda_deflate_chunks(b->d_in, 0, 0, b->d_off, b->d_len, b->d_flags, nch, 0, z->level, b->d_slots, b->stride, b->d_out_len, z->stream);
+    if (!err) err = mz_cuda_crc32_segments(b->d_in, 0, 0, b->d_off, b->d_len, nch, b->d_residue, b->d_crc, z->stream);
     if (!err && (z->flags & MZ_ZIP_CUDA_HASH_SHA256)) {
-        err = mz_cuda_memcpy_h2d(b->d_eoff, b->h_eoff, (size_t)ne * 8, NULL);
-        if (!err) err = mz_cuda_memcpy_h2d(b->d_elen, b->h_elen, (size_t)ne * 8, NULL);
-        if (!err) err = mz_cuda_sha256_batch(b->d_in, b->d_eoff, b->d_elen, ne, b->d_digest, NULL);
-        if (!err) err = mz_cuda_memcpy_d2h(b->h_digest, b->d_digest, (size_t)ne * 32, NULL);
+        err = mz_cuda_memcpy_h2d(b->d_eoff, b->h_eoff, (size_t)ne * 8, z->stream);
+        if (!err) err = mz_cuda_memcpy_h2d(b->d_elen, b->h_elen, (size_t)ne * 8, z->stream);
+        if (!err) err = mz_cuda_sha256_batch(b->d_in, b->d_eoff, b->d_elen, ne, b->d_digest, z->stream);
+        if (!err) err = mz_cuda_memcpy_d2h(b->h_digest, b->d_digest, (size_t)ne * 32, z->stream);
     }
-    if (!err) err = mz_cuda_memcpy_d2h(z->h_out_len, b->d_out_len, (size_t)nch * 4, NULL);
-    if (!err) err = mz_cuda_memcpy_d2h(b->h_crc, b->d_crc, (size_t)nch * 4, NULL);
-    if (!err) err = mz_cuda_stream_sync(NULL);
+    if (!err) err = mz_cuda_memcpy_d2h(z->h_out_len, b->d_out_len, (size_t)nch * 4, z->stream);
+    if (!err) err = mz_cuda_memcpy_d2h(b->h_crc, b->d_crc, (size_t)nch * 4, z->stream);
+    if (!err) err = mz_cuda_stream_sync(z->stream);
     /* host: sizes, CRCs, local headers, the region's layout */
     uint64_t cur = 0;
     uint32_t c0 = 0, bo = 0;
@@ -570,14 +580,14 @@ static void *za_prepare(void *arg) {
     if (!err && cur > z->region_cap)
         err = MZ_INTERNAL_ERROR;
     /* device: streams and headers into place; the finished region comes down in one copy */
-    if (!err) err = mz_cuda_memcpy_h2d(z->d_dst_off, z->h_dst_off, (size_t)nch * 8, NULL);
-    if (!err) err = mz_cuda_memcpy_h2d(z->d_hdr_off, z->h_hdr_off, (size_t)ne * 8, NULL);
-    if (!err) err = mz_cuda_memcpy_h2d(z->d_blob_off, z->h_blob_off, ((size_t)ne + 1) * 4, NULL);
-    if (!err) err = mz_cuda_memcpy_h2d(z->d_blob, z->h_blob, (size_t)bo + 16, NULL);
-    if (!err) err = mz_cuda_gather(b->d_slots, b->stride, b->d_out_len, nch, z->d_dst_off, z->d_region, NULL);
-    if (!err) err = mz_cuda_scatter_blobs(z->d_blob, z->d_blob_off, z->d_hdr_off, ne, z->d_region, NULL);
-    if (!err) err = mz_cuda_memcpy_d2h(z->h_region, z->d_region, (size_t)cur, NULL);
-    if (!err) err = mz_cuda_stream_sync(NULL);
+    if (!err) err = mz_cuda_memcpy_h2d(z->d_dst_off, z->h_dst_off, (size_t)nch * 8, z->stream);
+    if (!err) err = mz_cuda_memcpy_h2d(z->d_hdr_off, z->h_hdr_off, (size_t)ne * 8, z->stream);
+    if (!err) err = mz_cuda_memcpy_h2d(z->d_blob_off, z->h_blob_off, ((size_t)ne + 1) * 4, z->stream);
+    if (!err) err = mz_cuda_memcpy_h2d(z->d_blob, z->h_blob, (size_t)bo + 16, z->stream);
+    if (!err) err = mz_cuda_gather(b->d_slots, b->stride, b->d_out_len, nch, z->d_dst_off, z->d_region, z->stream);
+    if (!err) err = mz_cuda_scatter_blobs(z->d_blob, z->d_blob_off, z->d_hdr_off, ne, z->d_region, z->stream);
+    if (!err) err = mz_cuda_memcpy_d2h(z->h_region, z->d_region, (size_t)cur, z->stream);
+    if (!err) err = mz_cuda_stream_sync(z->stream);
     z->pack_ms = t1 - t0;
     z->gpu_ms = now_ms() - t1;
     z->err = err;
@@ -630,7 +640,9 @@ int32_t mz_zip_cuda_write_archive(void *base_stream, const mz_cuda_zip_item *ite
         fprintf(stderr, "mz_zip_cuda: no usable sm_100 GPU (%s); there is no CPU fallback\n", mz_cuda_last_error());
         return MZ_SUPPORT_ERROR;
     }
-    size_t round_bytes = 256u << 20;
+    /* 64 MiB rounds, four in preparation: each round's entries are packed into pinned staging by its own worker thread (that copy is
+     * the slowest stage of a round), and small rounds keep the page-locked allocations -- and the time to make them -- small */
+    size_t round_bytes = 64u << 20;
     {
         const char *v = getenv("MZ_CUDA_ZIP_ROUND_MB");
         if (v && atoll(v) > 0)
@@ -696,7 +708,8 @@ int32_t mz_zip_cuda_write_archive(void *base_stream, const mz_cuda_zip_item *ite
         if (ndev < 1) ndev = 1;
         if (ndev > 8) ndev = 8;
     }
-    const uint32_t nslots = (uint32_t)ndev * 2 < nrounds ? (uint32_t)ndev * 2 : (nrounds ? nrounds : 1);
+    const uint32_t want = ndev > 1 ? (uint32_t)ndev * 2 : 4u;
+    const uint32_t nslots = want < nrounds ? want : (nrounds ? nrounds : 1);
     za_slot *slots = (za_slot *)calloc(nslots, sizeof(za_slot));
     za_cd cd = {NULL, 0, 0};
     if (!slots) {

@@ -2,6 +2,7 @@
 #define MZ_EMU 1
 #include "cuda_emu.h"
 
+#include <pthread.h>
 #include <sys/mman.h>
 
 emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
@@ -97,6 +98,10 @@ static void trampoline(void) {
     emu_switch(&f->sp, g_sched_sp);
     abort();
 }
+
+static pthread_mutex_t g_launch_mu = PTHREAD_MUTEX_INITIALIZER;
+void emu_launch_lock(void) { pthread_mutex_lock(&g_launch_mu); }
+void emu_launch_unlock(void) { pthread_mutex_unlock(&g_launch_mu); }
 
 void emu_run_block(unsigned nthreads, void (*entry)(void *), void *arg, size_t dyn_smem) {
     if (g_fibers.size() < nthreads) {

@@ -253,7 +253,12 @@ template <typename F> struct emu_thunk {
     static void call(void *p) { (*(F *)p)(); }
 };
 
+/* one kernel at a time: the emulator's state (fibers, the built-in index variables, shared memory) is global, while the product
+ * launches from several host threads (the zip writer's round workers) */
+void emu_launch_lock(void);
+void emu_launch_unlock(void);
 template <typename F> static inline void emu_launch(dim3 grid, dim3 block, size_t smem, F body) {
+    emu_launch_lock();
     gridDim = grid;
     blockDim = block;
     for (unsigned bz = 0; bz < grid.z; bz++)
@@ -262,6 +267,7 @@ template <typename F> static inline void emu_launch(dim3 grid, dim3 block, size_
                 blockIdx = emu_dim3(bx, by, bz);
                 emu_run_block(block.x * block.y * block.z, &emu_thunk<F>::call, &body, smem);
             }
+    emu_launch_unlock();
 }
 /* MZ_LAUNCH(kernel, grid, block, smem, stream, args...) */
 #define MZ_LAUNCH(kernel, grid, block, smem, stream, ...) emu_launch((grid), (block), (smem), [&]() { kernel(__VA_ARGS__); })

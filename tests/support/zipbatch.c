@@ -234,6 +234,10 @@ int main(int argc, char **argv) {
     void *stream = mz_stream_buffered_create();
     void *zip = mz_zip_create();
     mz_stream_set_base(stream, file_stream);
+    if (use_native) { /* the native writer hands over whole rounds (tens of MiB per call): no 32 KiB buffering layer in between */
+        mz_stream_buffered_delete(&stream);
+        stream = file_stream;
+    }
     int32_t err = mz_stream_open(stream, path, MZ_OPEN_MODE_CREATE | MZ_OPEN_MODE_WRITE);
     if (err == MZ_OK && !use_native) err = mz_zip_open(zip, stream, MZ_OPEN_MODE_WRITE);
     if (err != MZ_OK) { fprintf(stderr, "open failed %d\n", err); return 5; }
@@ -275,7 +279,8 @@ int main(int argc, char **argv) {
     mz_stream_close(stream);
     double t_close = now_s() - t0;
     mz_zip_delete(&zip);
-    mz_stream_buffered_delete(&stream);
+    if (stream != file_stream)
+        mz_stream_buffered_delete(&stream);
     mz_stream_os_delete(&file_stream);
     printf("{\"mode\": \"%s\", \"entries\": %u, \"entry_bytes\": %zu, \"level\": %d, \"err\": %d, \"close_err\": %d, \"bytes_in\": %llu, "
            "\"bytes_out\": %llu, \"gen_s\": %.3f, \"add_s\": %.4f, \"close_s\": %.4f, \"entries_per_s\": %.0f, \"GiB_per_s\": %.3f, "

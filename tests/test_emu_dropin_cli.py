@@ -187,3 +187,8 @@ def _native_archive_checks(exe, ref_bins, tmp_path, run, n=260, esz=30_000):
 
 def test_native_archive_writer(emu_bins, tmp_path):
     _native_archive_checks(emu_bins["zipbatch_emu"], emu_bins, tmp_path, _run)
+    # 1 MiB rounds: eight of them, four in preparation at a time on their own worker threads
+    st = json.loads(_run(["env", "MZ_CUDA_ZIP_ROUND_MB=1", emu_bins["zipbatch_emu"], "n8.zip", "260", "30000", "6", "native"], tmp_path).stdout.decode().strip().splitlines()[-1])
+    assert st["err"] == 0 and st["rounds"] >= 8
+    with zipfile.ZipFile(tmp_path / "n8.zip") as z8, zipfile.ZipFile(tmp_path / "n.zip") as z1:
+        assert z8.testzip() is None and [(i.filename, i.CRC, i.file_size) for i in z8.infolist()] == [(i.filename, i.CRC, i.file_size) for i in z1.infolist()]
