@@ -643,18 +643,21 @@ def run_ours(args, rank, world, local_rank):
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = shard / (kms / 1000.0) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "r1_deflate_kernel.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_input_byte")
-            traffic = None if traffic is None else round(traffic * shard / NB)
-        except Exception:
-            traffic = None
+    traffic, tsrc = None, None
+    for tp in ("r2_deflate_kernel.json", "r1_deflate_kernel.json"):  # the newest committed ncu --set full capture of the kernel
+        tp = os.path.join(ROOT, "profiles", tp)
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_input_byte")
+                traffic = None if traffic is None else round(traffic * shard / NB)
+                tsrc = "profiles/" + os.path.basename(tp)
+                break
+            except Exception:
+                traffic = None
     roofline = {"bound": "hbm", "kernel": "deflate_chunks_kernel", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": shard // NB, "ms_per_launch": round(kms / NB, 4), "launches_per_step": NB,
-                "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per input byte x bytes per launch (profiles/r1_deflate_kernel.json)"}
+                "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum per input byte x bytes per launch (%s)" % tsrc}
     cpu = None
     if not args.no_cpu and world == 1:  # reported baseline: rank 0 at N=1 only
         import refshim

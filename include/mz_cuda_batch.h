@@ -119,6 +119,20 @@ int32_t mz_cuda_stream_wait_event(void *stream, void *event);
  * batched like the per-entry CRC. */
 int32_t mz_cuda_sha256_batch(const void *d_in, const uint64_t *d_off, const uint64_t *d_len, uint32_t n, void *d_digest, void *stream);
 
+/* K8: the arithmetic of WinZip AES entries (mz_strm_wzaes.c) for a batch of zip entries, every entry with its own salt.
+ * strength = MZ_AES_STRENGTH_128 / _192 / _256 (1 / 2 / 3, mz.h:117-119): key 16 / 24 / 32 bytes, salt 8 / 12 / 16 bytes.
+ *   derive: PBKDF2-HMAC-SHA1, 1000 iterations (mz_strm_wzaes.c:95-97) of the password with salt e (d_salts + 16 e) into the key
+ *           record d_keys + MZ_CUDA_WZAES_KEYREC * e: encryption key at +0, authentication key at +32, 2-byte verifier at +64.
+ *   ctr:    XOR entry e's bytes d_data[d_off[e] .. + d_len[e]) in place with the AES-CTR key stream of its encryption key
+ *           (counter little-endian, first block 1, mz_strm_wzaes.c:147-171) -- encrypts and decrypts. max_len >= every d_len[e].
+ *   hmac:   HMAC-SHA1 (authentication key) of entry e's bytes -> d_mac + 20 e; the entry stores the first 10 (:236-256). */
+#define MZ_CUDA_WZAES_KEYREC 80
+int32_t mz_cuda_wzaes_derive(const void *d_password, uint32_t pw_len, const void *d_salts, uint32_t n, uint32_t strength, void *d_keys, void *stream);
+int32_t mz_cuda_wzaes_ctr(void *d_data, const uint64_t *d_off, const uint64_t *d_len, uint32_t n, uint64_t max_len, const void *d_keys, uint32_t strength,
+                          void *stream);
+int32_t mz_cuda_wzaes_hmac(const void *d_data, const uint64_t *d_off, const uint64_t *d_len, uint32_t n, const void *d_keys, uint32_t strength, void *d_mac,
+                           void *stream);
+
 /* K4 with caller-given destinations: slot i goes to d_dst + d_offsets[i] (no scan) -- the zip archive writer interleaves the
  * entries' streams with their local headers; and n small blobs (blob i = d_blob[d_blob_off[i] .. d_blob_off[i+1])) scattered to
  * d_dst + d_dst_off[i] (the headers themselves). */

@@ -66,6 +66,18 @@ int32_t mz_zip_cuda_add_buffers_ex(void *zip_handle, const mz_cuda_zip_item *ite
 int32_t mz_zip_cuda_write_archive(void *base_stream, const mz_cuda_zip_item *items, uint32_t count, int16_t level, uint32_t flags,
                                   mz_cuda_zip_stats *stats);
 
+/* The same archive with every entry WinZip-AES encrypted after compression (scope row f4, the part that follows the codec): what
+ * the reference does per entry by stacking mz_stream_wzaes under the codec (mz_zip.c:1734-1741, mz_strm_wzaes.c) -- a random salt,
+ * PBKDF2-HMAC-SHA1 (1000 iterations) of the password, AES in counter mode over the compressed stream, HMAC-SHA1 of the ciphertext
+ * -- done for all entries of a round by three kernels (K8, include/mz_cuda_batch.h). Entry layout and headers as the reference
+ * writes them: method 99 + the 0x9901 extra field (AE-1, strength, real method 8), flag bit 0, version needed 51, stored size =
+ * salt + 2-byte verifier + ciphertext + 10-byte authentication code, CRC kept (mz_zip.c:703-733, :870-885).
+ * flags must contain MZ_ZIP_CUDA_AES; aes_strength = 1 / 2 / 3 (AES-128 / 192 / 256; 0 = 3, the reference's default);
+ * password up to 128 bytes. */
+#define MZ_ZIP_CUDA_AES 4u
+int32_t mz_zip_cuda_write_archive_aes(void *base_stream, const mz_cuda_zip_item *items, uint32_t count, int16_t level, uint32_t flags,
+                                      const char *password, uint8_t aes_strength, mz_cuda_zip_stats *stats);
+
 /* ---- batch extraction (scope row f2): the reverse direction ---------------------------------------------------
  * The reference extracts entry by entry: mz_zip_entry_read_open(raw=0) creates a mz_stream_zlib, the caller's loop
  * reads through it, mz_zip_entry_close compares the CRC (mz_zip_rw.c:818-909, mz_zip.c:2116-2128). Here the central
@@ -81,6 +93,15 @@ int32_t mz_zip_cuda_write_archive(void *base_stream, const mz_cuda_zip_item *ite
  * 1 GiB are not batched: the call returns MZ_SUPPORT_ERROR (use the per-entry stream path for such archives). */
 typedef int32_t (*mz_cuda_zip_entry_cb)(void *userdata, const char *filename, const void *data, int64_t size, uint32_t crc32);
 int32_t mz_zip_cuda_extract_all(void *zip_handle, mz_cuda_zip_entry_cb cb, void *userdata, mz_cuda_zip_stats *stats);
+
+/* The same for archives whose entries are WinZip-AES encrypted (any strength; written by this library, by the reference or by
+ * WinZip): the stored bytes still come through the raw seam (mz_zip_entry_read_open(raw = 1, password = NULL) hands out the
+ * encrypted bytes, mz_zip.c:1727-1731), K8 derives every entry's keys from password + salt, the 2-byte verifier is compared
+ * (MZ_PASSWORD_ERROR, mz_strm_wzaes.c:133-134), the HMAC-SHA1 of the ciphertext is compared with the stored authentication code
+ * (MZ_CRC_ERROR, :252-254), the ciphertext is decrypted in place and decoded like any other entry. The HOST program's container
+ * must be built with HAVE_WZAES (otherwise its reader refuses such entries before this code sees them). PKWARE-encrypted entries
+ * return MZ_SUPPORT_ERROR; encrypted entries without a password MZ_PASSWORD_ERROR. */
+int32_t mz_zip_cuda_extract_all_aes(void *zip_handle, const char *password, mz_cuda_zip_entry_cb cb, void *userdata, mz_cuda_zip_stats *stats);
 
 /* sizeof the mz_zip_file mirror this library was built with: the host asserts it equals sizeof(mz_zip_file) */
 uint32_t mz_zip_cuda_abi_file_info_size(void);

@@ -16,6 +16,7 @@
 #include "inflate_kernel.cuh"
 #include "inflate_spec_kernel.cuh"
 #include "sha256_kernel.cuh"
+#include "wzaes_kernel.cuh"
 
 #define MZ_OK 0
 #define MZ_MEM_ERROR (-4)
@@ -37,6 +38,7 @@ struct DeviceCtx {
     CrcConsts *d_consts = nullptr;
     uint32_t *d_crc_scratch = nullptr; /* residues for mz_cuda_crc32_device */
     uint32_t *d_work = nullptr;        /* ring of work-counter pairs for dynamically scheduled launches */
+    uint32_t *d_aes = nullptr;         /* K8 tables: 256 words of T-table, then the S-box (256 bytes); made on first use */
     unsigned work_next = 0;
     size_t crc_scratch_n = 0;
 };
@@ -513,6 +515,119 @@ int32_t mz_cuda_sha256_batch(const void *d_in, const uint64_t *d_off, const uint
     const uint32_t cap = (uint32_t)c->sm_count * 16u;
     if (blocks > cap) blocks = cap;
     MZ_LAUNCH(sha256_batch_kernel, dim3(blocks), dim3(SHA_THREADS), 0, (cudaStream_t)stream, P);
+    CK(cudaGetLastError());
+    return MZ_OK;
+}
+
+/* ---- K8: WinZip AES for a batch of entries ------------------------------------------------------------------- */
+namespace {
+/* FIPS 197 4.2 / 5.1.1: S[x] = affine(inverse of x in GF(2^8) mod x^8 + x^4 + x^3 + x + 1); T[x] = (2 S, S, S, 3 S) */
+int32_t aes_tables(DeviceCtx *c) {
+    if (c->d_aes) return MZ_OK;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (c->d_aes) return MZ_OK;
+    uint32_t h[256 + 64];
+    uint8_t sbox[256];
+    uint8_t p = 1, q = 1;
+    do { /* p runs over the multiplicative group (generator 3), q over the inverses */
+        p = (uint8_t)(p ^ (p << 1) ^ ((p & 0x80) ? 0x1b : 0));
+        q ^= (uint8_t)(q << 1);
+        q ^= (uint8_t)(q << 2);
+        q ^= (uint8_t)(q << 4);
+        if (q & 0x80) q ^= 0x09;
+        const uint8_t x = (uint8_t)(q ^ (uint8_t)((q << 1) | (q >> 7)) ^ (uint8_t)((q << 2) | (q >> 6)) ^ (uint8_t)((q << 3) | (q >> 5)) ^ (uint8_t)((q << 4) | (q >> 4)));
+        sbox[p] = (uint8_t)(x ^ 0x63);
+    } while (p != 1);
+    sbox[0] = 0x63;
+    for (int i = 0; i < 256; i++) {
+        const uint32_t s1 = sbox[i], s2 = ((s1 << 1) ^ ((s1 & 0x80) ? 0x11b : 0)) & 0xff, s3 = s2 ^ s1;
+        h[i] = (s2 << 24) | (s1 << 16) | (s1 << 8) | s3;
+    }
+    memcpy(h + 256, sbox, 256);
+    uint32_t *d = nullptr;
+    CK(cudaMalloc(&d, sizeof(h)));
+    CK(cudaMemcpy(d, h, sizeof(h), cudaMemcpyHostToDevice));
+    c->d_aes = d;
+    return MZ_OK;
+}
+bool wz_strength(uint32_t strength, uint32_t *key_len, uint32_t *salt_len) {
+    if (strength < 1 || strength > 3) return false;
+    *key_len = 8 * strength + 8;   /* MZ_AES_KEY_LENGTH, mz_strm_wzaes.c:19 */
+    *salt_len = 4 * strength + 4;  /* MZ_AES_SALT_LENGTH, :21 */
+    return true;
+}
+} // namespace
+
+int32_t mz_cuda_wzaes_derive(const void *d_password, uint32_t pw_len, const void *d_salts, uint32_t n, uint32_t strength, void *d_keys, void *stream) {
+    DeviceCtx *c;
+    int32_t err = get_ctx(&c);
+    if (err) return err;
+    WzDeriveParams P;
+    if (!wz_strength(strength, &P.key_len, &P.salt_len) || pw_len > 128) return MZ_PARAM_ERROR;
+    if (n == 0) return MZ_OK;
+    if (!d_password || !d_salts || !d_keys) return MZ_PARAM_ERROR;
+    P.password = (const uint8_t *)d_password;
+    P.pw_len = pw_len;
+    P.salts = (const uint8_t *)d_salts;
+    P.iterations = 1000; /* MZ_AES_KEYING_ITERATIONS, mz_strm_wzaes.c:20 */
+    P.n = n;
+    P.keys = (uint8_t *)d_keys;
+    const uint32_t threads = n * ((2 * P.key_len + 2 + 19) / 20);
+    uint32_t blocks = (threads + 127) / 128;
+    const uint32_t cap = (uint32_t)c->sm_count * 16u;
+    if (blocks > cap) blocks = cap;
+    MZ_LAUNCH(wzaes_derive_kernel, dim3(blocks), dim3(128), 0, (cudaStream_t)stream, P);
+    CK(cudaGetLastError());
+    return MZ_OK;
+}
+
+int32_t mz_cuda_wzaes_ctr(void *d_data, const uint64_t *d_off, const uint64_t *d_len, uint32_t n, uint64_t max_len, const void *d_keys, uint32_t strength,
+                          void *stream) {
+    DeviceCtx *c;
+    int32_t err = get_ctx(&c);
+    if (err) return err;
+    WzCtrParams P;
+    uint32_t salt_len;
+    if (!wz_strength(strength, &P.key_len, &salt_len)) return MZ_PARAM_ERROR;
+    if (n == 0 || max_len == 0) return MZ_OK;
+    if (!d_data || !d_off || !d_len || !d_keys) return MZ_PARAM_ERROR;
+    err = aes_tables(c);
+    if (err) return err;
+    P.data = (uint8_t *)d_data;
+    P.off = d_off;
+    P.len = d_len;
+    P.n = n;
+    P.parts = (uint32_t)((max_len + WZ_CTR_PART - 1) / WZ_CTR_PART);
+    if (P.parts > 65535) return MZ_PARAM_ERROR; /* entries up to 4 GiB */
+    P.keys = (const uint8_t *)d_keys;
+    P.te0 = c->d_aes;
+    P.sbox = (const uint8_t *)(c->d_aes + 256);
+    const uint32_t gx = n < (uint32_t)c->sm_count * 64u ? n : (uint32_t)c->sm_count * 64u;
+    MZ_LAUNCH(wzaes_ctr_kernel, dim3(gx, P.parts), dim3(WZ_CTR_THREADS), 0, (cudaStream_t)stream, P);
+    CK(cudaGetLastError());
+    return MZ_OK;
+}
+
+int32_t mz_cuda_wzaes_hmac(const void *d_data, const uint64_t *d_off, const uint64_t *d_len, uint32_t n, const void *d_keys, uint32_t strength, void *d_mac,
+                           void *stream) {
+    DeviceCtx *c;
+    int32_t err = get_ctx(&c);
+    if (err) return err;
+    WzHmacParams P;
+    uint32_t salt_len;
+    if (!wz_strength(strength, &P.key_len, &salt_len)) return MZ_PARAM_ERROR;
+    if (n == 0) return MZ_OK;
+    if (!d_data || !d_off || !d_len || !d_keys || !d_mac) return MZ_PARAM_ERROR;
+    P.data = (const uint8_t *)d_data;
+    P.off = d_off;
+    P.len = d_len;
+    P.n = n;
+    P.keys = (const uint8_t *)d_keys;
+    P.mac = (uint8_t *)d_mac;
+    uint32_t blocks = (n + 127) / 128;
+    const uint32_t cap = (uint32_t)c->sm_count * 16u;
+    if (blocks > cap) blocks = cap;
+    MZ_LAUNCH(wzaes_hmac_kernel, dim3(blocks), dim3(128), 0, (cudaStream_t)stream, P);
     CK(cudaGetLastError());
     return MZ_OK;
 }

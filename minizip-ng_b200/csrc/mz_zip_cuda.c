@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <sys/random.h>
 
 #include "mz_abi.h"
 #include "mz_cuda_batch.h"
@@ -108,7 +109,7 @@ static void zc_free(zc_bufs *b) {
     memset(b, 0, sizeof(*b));
 }
 
-static int zc_alloc(zc_bufs *b, size_t round_bytes, uint32_t max_chunks) {
+static int zc_alloc(zc_bufs *b, size_t round_bytes, uint32_t max_chunks, int with_join) {
     memset(b, 0, sizeof(*b));
     b->round_bytes = round_bytes;
     b->max_chunks = max_chunks;
@@ -117,8 +118,8 @@ static int zc_alloc(zc_bufs *b, size_t round_bytes, uint32_t max_chunks) {
     b->h_in = (uint8_t *)mz_cuda_host_alloc(round_bytes + 64);
     b->d_in = (uint8_t *)mz_cuda_malloc(round_bytes + 64);
     b->d_slots = (uint8_t *)mz_cuda_malloc(slots);
-    b->d_out = (uint8_t *)mz_cuda_malloc(slots);
-    b->h_out = (uint8_t *)mz_cuda_host_alloc(slots);
+    b->d_out = with_join ? (uint8_t *)mz_cuda_malloc(slots) : NULL; /* (the native writer assembles its own region instead) */
+    b->h_out = with_join ? (uint8_t *)mz_cuda_host_alloc(slots) : NULL;
     b->h_off = (uint64_t *)mz_cuda_host_alloc((size_t)max_chunks * 8);
     b->d_off = (uint64_t *)mz_cuda_malloc((size_t)max_chunks * 8);
     b->d_joined_off = (uint64_t *)mz_cuda_malloc(((size_t)max_chunks + 1) * 8);
@@ -137,7 +138,7 @@ static int zc_alloc(zc_bufs *b, size_t round_bytes, uint32_t max_chunks) {
     b->d_elen = (uint64_t *)mz_cuda_malloc((size_t)max_chunks * 8);
     b->d_digest = (uint8_t *)mz_cuda_malloc((size_t)max_chunks * 32);
     b->h_digest = (uint8_t *)mz_cuda_host_alloc((size_t)max_chunks * 32);
-    if (!b->h_in || !b->d_in || !b->d_slots || !b->d_out || !b->h_out || !b->h_off || !b->d_off || !b->d_joined_off || !b->h_joined_off ||
+    if (!b->h_in || !b->d_in || !b->d_slots || (with_join && (!b->d_out || !b->h_out)) || !b->h_off || !b->d_off || !b->d_joined_off || !b->h_joined_off ||
         !b->h_len || !b->d_len || !b->d_out_len || !b->d_residue || !b->d_crc || !b->h_crc || !b->h_flags || !b->d_flags || !b->h_eoff ||
         !b->d_eoff || !b->h_elen || !b->d_elen || !b->d_digest || !b->h_digest) {
         zc_free(b);
@@ -282,7 +283,7 @@ int32_t mz_zip_cuda_add_buffers_ex(void *zip_handle, const mz_cuda_zip_item *ite
     }
     const int32_t device = mz_cuda_get_device();
     for (int k = 0; k < 2; k++) {
-        if (!zc_alloc(&rd[k].b, round_bytes, max_chunks)) {
+        if (!zc_alloc(&rd[k].b, round_bytes, max_chunks, 1)) {
             zc_free(&rd[0].b);
             return MZ_MEM_ERROR;
         }
@@ -404,6 +405,11 @@ typedef struct za_slot_s {
     uint64_t region_len;
     double pack_ms, gpu_ms;
     void *stream; /* the slot's own CUDA stream: rounds of different slots (and devices) overlap */
+    /* WinZip AES (flag MZ_ZIP_CUDA_AES): per entry a salt, derived keys, where its ciphertext lies in the region, its HMAC */
+    const char *password;
+    uint32_t strength, pw_len;
+    uint8_t *h_salt, *d_salt, *h_keys, *d_keys, *d_pw, *h_mac, *d_mac;
+    uint64_t *h_coff, *d_coff, *h_clen, *d_clen;
     pthread_t th;
     int running;
 } za_slot;
@@ -444,13 +450,24 @@ static void za_free(za_slot *z) {
     mz_cuda_free(z->d_blob);
     mz_cuda_free(z->d_region);
     mz_cuda_host_free(z->h_region);
+    mz_cuda_host_free(z->h_salt);
+    mz_cuda_free(z->d_salt);
+    mz_cuda_host_free(z->h_keys);
+    mz_cuda_free(z->d_keys);
+    mz_cuda_free(z->d_pw);
+    mz_cuda_host_free(z->h_mac);
+    mz_cuda_free(z->d_mac);
+    mz_cuda_host_free(z->h_coff);
+    mz_cuda_free(z->d_coff);
+    mz_cuda_host_free(z->h_clen);
+    mz_cuda_free(z->d_clen);
     free(z->meta);
     memset(z, 0, sizeof(*z));
 }
 
-static int za_alloc(za_slot *z, size_t round_bytes, uint32_t max_chunks, size_t blob_cap) {
+static int za_alloc(za_slot *z, size_t round_bytes, uint32_t max_chunks, size_t blob_cap, int aes) {
     memset(z, 0, sizeof(*z));
-    if (!zc_alloc(&z->b, round_bytes, max_chunks))
+    if (!zc_alloc(&z->b, round_bytes, max_chunks, 0))
         return 0;
     z->blob_cap = blob_cap;
     z->region_cap = (size_t)max_chunks * z->b.stride + blob_cap + 64;
@@ -467,6 +484,24 @@ static int za_alloc(za_slot *z, size_t round_bytes, uint32_t max_chunks, size_t 
     z->h_region = (uint8_t *)mz_cuda_host_alloc(z->region_cap);
     z->meta = (za_meta *)malloc((size_t)max_chunks * sizeof(za_meta));
     z->stream = mz_cuda_stream_create();
+    if (aes) {
+        z->h_salt = (uint8_t *)mz_cuda_host_alloc((size_t)max_chunks * 16);
+        z->d_salt = (uint8_t *)mz_cuda_malloc((size_t)max_chunks * 16);
+        z->h_keys = (uint8_t *)mz_cuda_host_alloc((size_t)max_chunks * MZ_CUDA_WZAES_KEYREC);
+        z->d_keys = (uint8_t *)mz_cuda_malloc((size_t)max_chunks * MZ_CUDA_WZAES_KEYREC);
+        z->d_pw = (uint8_t *)mz_cuda_malloc(256);
+        z->h_mac = (uint8_t *)mz_cuda_host_alloc((size_t)max_chunks * 20);
+        z->d_mac = (uint8_t *)mz_cuda_malloc((size_t)max_chunks * 20);
+        z->h_coff = (uint64_t *)mz_cuda_host_alloc((size_t)max_chunks * 8);
+        z->d_coff = (uint64_t *)mz_cuda_malloc((size_t)max_chunks * 8);
+        z->h_clen = (uint64_t *)mz_cuda_host_alloc((size_t)max_chunks * 8);
+        z->d_clen = (uint64_t *)mz_cuda_malloc((size_t)max_chunks * 8);
+        if (!z->h_salt || !z->d_salt || !z->h_keys || !z->d_keys || !z->d_pw || !z->h_mac || !z->d_mac || !z->h_coff || !z->d_coff || !z->h_clen ||
+            !z->d_clen) {
+            za_free(z);
+            return 0;
+        }
+    }
     if (!z->stream || !z->h_out_len || !z->h_dst_off || !z->d_dst_off || !z->h_hdr_off || !z->d_hdr_off || !z->h_blob_off || !z->d_blob_off || !z->h_blob ||
         !z->d_blob || !z->d_region || !z->h_region || !z->meta) {
         za_free(z);
@@ -480,6 +515,13 @@ static void za_hash_field(uint8_t *xf, const uint8_t *digest) {
     static const uint8_t head[8] = {0x51, 0x1a, 36, 0, 23, 0, 32, 0};
     memcpy(xf, head, 8);
     memcpy(xf + 8, digest, 32);
+}
+
+/* the AES extra field of an entry (11 bytes): id 0x9901, size 7, AE version, vendor "AE", strength, the real method
+ * (mz_zip.c:870-885) */
+static void za_aes_field(uint8_t *xf, uint32_t strength) {
+    const uint8_t f[11] = {0x01, 0x99, 7, 0, 1, 0, 'A', 'E', (uint8_t)strength, 8, 0};
+    memcpy(xf, f, 11);
 }
 
 /* one round: pack, upload, compress + checksum (+ hash), lay the region out, assemble it on the device, download it */
@@ -515,6 +557,20 @@ static void *za_prepare(void *arg) {
     if (!err) err = mz_cuda_memcpy_h2d(b->d_len, b->h_len, (size_t)nch * 4, z->stream);
     if (!err) err = mz_cuda_memcpy_h2d(b->d_flags, b->h_flags, nch, z->stream);
     double t1 = now_ms();
+    const int aes = (z->flags & MZ_ZIP_CUDA_AES) != 0;
+    const uint32_t slen = aes ? 4 * z->strength + 4 : 0; /* MZ_AES_SALT_LENGTH */
+    if (!err && aes) { /* a fresh salt per entry (mz_strm_wzaes.c:85-86), then every entry's keys and password verifier by K8 */
+        size_t got = 0;
+        while (got < (size_t)ne * 16) {
+            ssize_t k = getrandom(z->h_salt + got, (size_t)ne * 16 - got, 0);
+            if (k <= 0) { err = MZ_INTERNAL_ERROR; break; }
+            got += (size_t)k;
+        }
+        if (!err) err = mz_cuda_memcpy_h2d(z->d_salt, z->h_salt, (size_t)ne * 16, z->stream);
+        if (!err) err = mz_cuda_memcpy_h2d(z->d_pw, z->password, z->pw_len ? z->pw_len : 1, z->stream);
+        if (!err) err = mz_cuda_wzaes_derive(z->d_pw, z->pw_len, z->d_salt, ne, z->strength, z->d_keys, z->stream);
+        if (!err) err = mz_cuda_memcpy_d2h(z->h_keys, z->d_keys, (size_t)ne * MZ_CUDA_WZAES_KEYREC, z->stream);
+    }
     if (!err) err = mz_cuda_deflate_chunks(b->d_in, 0, 0, b->d_off, b->d_len, b->d_flags, nch, 0, z->level, b->d_slots, b->stride, b->d_out_len, z->stream);
     if (!err) err = mz_cuda_crc32_segments(b->d_in, 0, 0, b->d_off, b->d_len, nch, b->d_residue, b->d_crc, z->stream);
     if (!err && (z->flags & MZ_ZIP_CUDA_HASH_SHA256)) {
@@ -527,7 +583,7 @@ static void *za_prepare(void *arg) {
     if (!err) err = mz_cuda_memcpy_d2h(b->h_crc, b->d_crc, (size_t)nch * 4, z->stream);
     if (!err) err = mz_cuda_stream_sync(z->stream);
     /* host: sizes, CRCs, local headers, the region's layout */
-    uint64_t cur = 0;
+    uint64_t cur = 0, max_clen = 0;
     uint32_t c0 = 0, bo = 0;
     for (uint32_t e = 0; e < ne && !err; e++) {
         const mz_cuda_zip_item *it = &z->items[z->first + e];
@@ -541,38 +597,53 @@ static void *za_prepare(void *arg) {
         if (it->size == 0)
             crc = 0;
         const size_t nlen = strlen(it->filename);
-        const uint32_t xlen = (z->flags & MZ_ZIP_CUDA_HASH_SHA256) ? 40u : 0u;
+        const uint32_t xaes = aes ? 11u : 0u;
+        const uint32_t xlen = xaes + ((z->flags & MZ_ZIP_CUDA_HASH_SHA256) ? 40u : 0u);
         const uint32_t lh = 30 + (uint32_t)nlen + xlen;
-        if (bo + lh > z->blob_cap || csize >= 0xffffffffull) {
+        const uint64_t stored = csize + (aes ? slen + 2 + 10 : 0); /* salt | verifier | ciphertext | authentication code */
+        if (bo + lh + slen + 2 > z->blob_cap || stored >= 0xffffffffull) {
             err = MZ_INTERNAL_ERROR;
             break;
         }
         uint8_t *h = z->h_blob + bo;
         put32(h, 0x04034b50u);                       /* MZ_ZIP_MAGIC_LOCALHEADER */
-        put16(h + 4, 20);                            /* version needed (mz_zip.c:706) */
-        put16(h + 6, 1u << 11);                      /* MZ_ZIP_FLAG_UTF8; no data descriptor: everything is known */
-        put16(h + 8, 8);                             /* MZ_COMPRESS_METHOD_DEFLATE */
+        put16(h + 4, aes ? 51 : 20);                 /* version needed (mz_zip.c:703-725) */
+        put16(h + 6, (1u << 11) | (aes ? 1u : 0u));  /* MZ_ZIP_FLAG_UTF8 (| MZ_ZIP_FLAG_ENCRYPTED); no data descriptor: everything is known */
+        put16(h + 8, aes ? 99 : 8);                  /* MZ_COMPRESS_METHOD_DEFLATE, or _AES with the real method in the extra field (:728-733) */
         put32(h + 10, za_dos_date(it->modified_date));
-        put32(h + 14, crc);
-        put32(h + 18, (uint32_t)csize);
+        put32(h + 14, crc);                          /* AE-1 (MZ_AES_VERSION 1) keeps the CRC (mz_zip.c:2117-2121) */
+        put32(h + 18, (uint32_t)stored);
         put32(h + 22, (uint32_t)it->size);
         put16(h + 26, (uint32_t)nlen);
         put16(h + 28, xlen);
         memcpy(h + 30, it->filename, nlen);
-        if (xlen)
-            za_hash_field(h + 30 + nlen, b->h_digest + (size_t)e * 32);
+        if (aes)
+            za_aes_field(h + 30 + nlen, z->strength);
+        if (xlen > xaes)
+            za_hash_field(h + 30 + nlen + xaes, b->h_digest + (size_t)e * 32);
+        if (aes) { /* salt and password verifier travel with the header blob (mz_strm_wzaes.c:116-125) */
+            memcpy(h + lh, z->h_salt + (size_t)e * 16, slen);
+            memcpy(h + lh + slen, z->h_keys + (size_t)e * MZ_CUDA_WZAES_KEYREC + 64, 2);
+        }
         z->h_blob_off[e] = bo;
         z->h_hdr_off[e] = cur;
-        z->meta[e].csize = csize;
+        z->meta[e].csize = stored;
         z->meta[e].crc = crc;
         z->meta[e].lh_rel = cur;
         z->meta[e].lh_size = lh;
-        bo += lh;
-        cur += lh;
+        bo += lh + (aes ? slen + 2 : 0);
+        cur += lh + (aes ? slen + 2 : 0);
+        if (aes) {
+            z->h_coff[e] = cur;
+            z->h_clen[e] = csize;
+            if (csize > max_clen) max_clen = csize;
+        }
         for (uint32_t k = 0; k < c; k++) {
             z->h_dst_off[c0 + k] = cur;
             cur += z->h_out_len[c0 + k];
         }
+        if (aes)
+            cur += 10; /* MZ_AES_AUTHCODE_SIZE */
         c0 += c;
     }
     z->h_blob_off[ne] = bo;
@@ -586,8 +657,17 @@ static void *za_prepare(void *arg) {
     if (!err) err = mz_cuda_memcpy_h2d(z->d_blob, z->h_blob, (size_t)bo + 16, z->stream);
     if (!err) err = mz_cuda_gather(b->d_slots, b->stride, b->d_out_len, nch, z->d_dst_off, z->d_region, z->stream);
     if (!err) err = mz_cuda_scatter_blobs(z->d_blob, z->d_blob_off, z->d_hdr_off, ne, z->d_region, z->stream);
+    if (!err && aes) { /* the assembled streams become ciphertext in place; their HMACs follow them down */
+        err = mz_cuda_memcpy_h2d(z->d_coff, z->h_coff, (size_t)ne * 8, z->stream);
+        if (!err) err = mz_cuda_memcpy_h2d(z->d_clen, z->h_clen, (size_t)ne * 8, z->stream);
+        if (!err) err = mz_cuda_wzaes_ctr(z->d_region, z->d_coff, z->d_clen, ne, max_clen, z->d_keys, z->strength, z->stream);
+        if (!err) err = mz_cuda_wzaes_hmac(z->d_region, z->d_coff, z->d_clen, ne, z->d_keys, z->strength, z->d_mac, z->stream);
+        if (!err) err = mz_cuda_memcpy_d2h(z->h_mac, z->d_mac, (size_t)ne * 20, z->stream);
+    }
     if (!err) err = mz_cuda_memcpy_d2h(z->h_region, z->d_region, (size_t)cur, z->stream);
     if (!err) err = mz_cuda_stream_sync(z->stream);
+    for (uint32_t e = 0; e < ne && !err && aes; e++) /* authentication code = the first 10 bytes of the HMAC (mz_strm_wzaes.c:243-247) */
+        memcpy(z->h_region + z->h_coff[e] + z->h_clen[e], z->h_mac + (size_t)e * 20, 10);
     z->pack_ms = t1 - t0;
     z->gpu_ms = now_ms() - t1;
     z->err = err;
@@ -627,6 +707,13 @@ static int32_t za_write(void *base, const uint8_t *p, uint64_t n) {
 
 int32_t mz_zip_cuda_write_archive(void *base_stream, const mz_cuda_zip_item *items, uint32_t count, int16_t level, uint32_t flags,
                                   mz_cuda_zip_stats *stats) {
+    if (flags & MZ_ZIP_CUDA_AES)
+        return MZ_PARAM_ERROR; /* needs a password: mz_zip_cuda_write_archive_aes */
+    return mz_zip_cuda_write_archive_aes(base_stream, items, count, level, flags, NULL, 0, stats);
+}
+
+int32_t mz_zip_cuda_write_archive_aes(void *base_stream, const mz_cuda_zip_item *items, uint32_t count, int16_t level, uint32_t flags,
+                                      const char *password, uint8_t aes_strength, mz_cuda_zip_stats *stats) {
     mz_cuda_zip_stats st;
     int32_t err = MZ_OK;
     memset(&st, 0, sizeof(st));
@@ -636,6 +723,11 @@ int32_t mz_zip_cuda_write_archive(void *base_stream, const mz_cuda_zip_item *ite
         level = 6;
     if (level < 0 || level > 9)
         return MZ_PARAM_ERROR;
+    const int aes = (flags & MZ_ZIP_CUDA_AES) != 0;
+    if (aes_strength == 0)
+        aes_strength = 3; /* MZ_AES_STRENGTH_256, the reference's default (mz_zip.c:2007-2009) */
+    if (aes && (!password || strlen(password) > 128 || aes_strength > 3))
+        return MZ_PARAM_ERROR; /* MZ_AES_PW_LENGTH_MAX, mz_strm_wzaes.c:77-79 */
     if (mz_cuda_init() != MZ_OK) {
         fprintf(stderr, "mz_zip_cuda: no usable sm_100 GPU (%s); there is no CPU fallback\n", mz_cuda_last_error());
         return MZ_SUPPORT_ERROR;
@@ -681,7 +773,7 @@ int32_t mz_zip_cuda_write_archive(void *base_stream, const mz_cuda_zip_item *ite
                     break;
                 bytes += need;
                 ch += chunks_of(items[j].size);
-                blob += 30 + strlen(items[j].filename) + 40;
+                blob += 30 + strlen(items[j].filename) + 40 + 11 + 18; /* header, name, hash field, AES field, salt + verifier */
                 j++;
             }
             if (nrounds == rcap) {
@@ -718,7 +810,7 @@ int32_t mz_zip_cuda_write_archive(void *base_stream, const mz_cuda_zip_item *ite
     }
     for (uint32_t k = 0; k < nslots && err == MZ_OK; k++) {
         const int32_t dev = ndev > 1 ? (int32_t)(k % (uint32_t)ndev) : dev0;
-        if (mz_cuda_set_device(dev) != MZ_OK || !za_alloc(&slots[k], round_bytes, max_chunks + 1, max_blob)) {
+        if (mz_cuda_set_device(dev) != MZ_OK || !za_alloc(&slots[k], round_bytes, max_chunks + 1, max_blob, aes)) {
             err = MZ_MEM_ERROR;
             break;
         }
@@ -726,6 +818,9 @@ int32_t mz_zip_cuda_write_archive(void *base_stream, const mz_cuda_zip_item *ite
         slots[k].items = items;
         slots[k].level = level;
         slots[k].flags = flags;
+        slots[k].password = password;
+        slots[k].pw_len = aes ? (uint32_t)strlen(password) : 0;
+        slots[k].strength = aes_strength;
     }
     mz_cuda_set_device(dev0);
     uint64_t abs_off = 0;
@@ -760,7 +855,7 @@ int32_t mz_zip_cuda_write_archive(void *base_stream, const mz_cuda_zip_item *ite
             const int z64 = lh_off >= 0xffffffffull;
             const size_t nlen = strlen(it->filename);
             const uint32_t xhash = (flags & MZ_ZIP_CUDA_HASH_SHA256) ? 40u : 0u;
-            const uint32_t xlen = (z64 ? 4u + 24u : 0u) + xhash;
+            const uint32_t xlen = (z64 ? 4u + 24u : 0u) + (aes ? 11u : 0u) + xhash;
             uint8_t *h = za_cd_room(&cd, 46 + nlen + xlen);
             if (!h) {
                 err = MZ_MEM_ERROR;
@@ -768,9 +863,9 @@ int32_t mz_zip_cuda_write_archive(void *base_stream, const mz_cuda_zip_item *ite
             }
             put32(h, 0x02014b50u);                   /* MZ_ZIP_MAGIC_CENTRALHEADER */
             put16(h + 4, (3u << 8) | 45u);           /* made by: MZ_HOST_SYSTEM_UNIX, 4.5 */
-            put16(h + 6, z64 ? 45 : 20);
-            put16(h + 8, 1u << 11);
-            put16(h + 10, 8);
+            put16(h + 6, aes ? 51 : (z64 ? 45 : 20));
+            put16(h + 8, (1u << 11) | (aes ? 1u : 0u));
+            put16(h + 10, aes ? 99 : 8);
             put32(h + 12, za_dos_date(it->modified_date));
             put32(h + 16, m->crc);
             put32(h + 20, z64 ? 0xffffffffu : (uint32_t)m->csize); /* with a zip64 field both sizes move into it (mz_zip.c:519-548) */
@@ -791,6 +886,10 @@ int32_t mz_zip_cuda_write_archive(void *base_stream, const mz_cuda_zip_item *ite
                 put64(x + 12, m->csize);
                 put64(x + 20, lh_off);
                 x += 28;
+            }
+            if (aes) {
+                za_aes_field(x, aes_strength);
+                x += 11;
             }
             if (xhash)
                 za_hash_field(x, z->b.h_digest + (size_t)e * 32);
@@ -867,6 +966,7 @@ typedef struct zx_entry_s {
     uint32_t crc, name_off;
     uint16_t method;
     uint8_t has_sha;
+    uint8_t aes;     /* 0, or the WinZip AES strength 1..3: the stored bytes are salt | verifier | ciphertext | authentication code */
     uint8_t sha[32]; /* expected SHA-256 from the MZ_ZIP_EXTENSION_HASH extra field */
 } zx_entry;
 
@@ -880,6 +980,10 @@ typedef struct zx_bufs_s {
     uint32_t *h_len, *d_len, *d_residue, *d_crc, *h_crc;
     uint64_t *h_len64, *d_len64;
     uint8_t *d_digest, *h_digest;
+    /* WinZip AES entries of the round, grouped by strength (K8) */
+    uint8_t *h_salt, *d_salt, *h_keys, *d_keys, *d_pw, *h_mac, *d_mac;
+    uint64_t *h_coff, *d_coff, *h_clen, *d_clen;
+    uint32_t *aes_idx;
     zx_entry *ent;
     char *names;
     size_t names_cap;
@@ -905,9 +1009,42 @@ static void zx_free(zx_bufs *b) {
     mz_cuda_free(b->d_len64);
     mz_cuda_free(b->d_digest);
     mz_cuda_host_free(b->h_digest);
+    mz_cuda_host_free(b->h_salt);
+    mz_cuda_free(b->d_salt);
+    mz_cuda_host_free(b->h_keys);
+    mz_cuda_free(b->d_keys);
+    mz_cuda_free(b->d_pw);
+    mz_cuda_host_free(b->h_mac);
+    mz_cuda_free(b->d_mac);
+    mz_cuda_host_free(b->h_coff);
+    mz_cuda_free(b->d_coff);
+    mz_cuda_host_free(b->h_clen);
+    mz_cuda_free(b->d_clen);
+    free(b->aes_idx);
     free(b->ent);
     free(b->names);
     memset(b, 0, sizeof(*b));
+}
+
+/* the K8 tables, made when the first encrypted entry turns up */
+static int zx_alloc_aes(zx_bufs *b) {
+    const size_t n = b->max_entries;
+    if (b->aes_idx)
+        return 1;
+    b->h_salt = (uint8_t *)mz_cuda_host_alloc(n * 16);
+    b->d_salt = (uint8_t *)mz_cuda_malloc(n * 16);
+    b->h_keys = (uint8_t *)mz_cuda_host_alloc(n * MZ_CUDA_WZAES_KEYREC);
+    b->d_keys = (uint8_t *)mz_cuda_malloc(n * MZ_CUDA_WZAES_KEYREC);
+    b->d_pw = (uint8_t *)mz_cuda_malloc(256);
+    b->h_mac = (uint8_t *)mz_cuda_host_alloc(n * 20);
+    b->d_mac = (uint8_t *)mz_cuda_malloc(n * 20);
+    b->h_coff = (uint64_t *)mz_cuda_host_alloc(n * 8);
+    b->d_coff = (uint64_t *)mz_cuda_malloc(n * 8);
+    b->h_clen = (uint64_t *)mz_cuda_host_alloc(n * 8);
+    b->d_clen = (uint64_t *)mz_cuda_malloc(n * 8);
+    b->aes_idx = (uint32_t *)malloc(n * 4);
+    return b->h_salt && b->d_salt && b->h_keys && b->d_keys && b->d_pw && b->h_mac && b->d_mac && b->h_coff && b->d_coff && b->h_clen && b->d_clen &&
+           b->aes_idx;
 }
 
 static int zx_alloc(zx_bufs *b, size_t comp_cap, size_t out_cap, uint32_t max_entries) {
@@ -947,12 +1084,55 @@ static int zx_alloc(zx_bufs *b, size_t comp_cap, size_t out_cap, uint32_t max_en
 }
 
 /* decode + checksum + deliver the entries collected in b->ent[0..n) */
-static int32_t zx_flush(zx_bufs *b, uint32_t n, size_t comp_used, size_t out_used, mz_cuda_zip_entry_cb cb, void *userdata, mz_cuda_zip_stats *st) {
+static int32_t zx_flush(zx_bufs *b, uint32_t n, size_t comp_used, size_t out_used, const char *password, mz_cuda_zip_entry_cb cb, void *userdata,
+                        mz_cuda_zip_stats *st) {
     int32_t err = MZ_OK;
     uint32_t njobs = 0;
     double t0 = now_ms();
     if (n == 0)
         return MZ_OK;
+    err = mz_cuda_memcpy_h2d(b->d_comp, b->h_comp, comp_used + 32, NULL);
+    /* WinZip AES entries first (mz_strm_wzaes.c): keys from password + salt, verifier, HMAC of the ciphertext against the stored
+     * authentication code, then the ciphertext becomes the compressed stream in place. One pass per strength present. */
+    for (uint32_t strength = 1; strength <= 3 && !err; strength++) {
+        const uint32_t slen = 4 * strength + 4;
+        uint32_t m = 0;
+        uint64_t max_clen = 0;
+        for (uint32_t i = 0; i < n; i++) {
+            zx_entry *e = &b->ent[i];
+            if (e->aes != strength)
+                continue;
+            memcpy(b->h_salt + (size_t)m * 16, b->h_comp + e->coff, slen);
+            b->h_coff[m] = e->coff + slen + 2;
+            b->h_clen[m] = e->csize - slen - 12;
+            if (b->h_clen[m] > max_clen) max_clen = b->h_clen[m];
+            b->aes_idx[m++] = i;
+        }
+        if (m == 0)
+            continue;
+        const size_t pwl = strlen(password);
+        err = mz_cuda_memcpy_h2d(b->d_salt, b->h_salt, (size_t)m * 16, NULL);
+        if (!err) err = mz_cuda_memcpy_h2d(b->d_pw, password, pwl ? pwl : 1, NULL);
+        if (!err) err = mz_cuda_wzaes_derive(b->d_pw, (uint32_t)pwl, b->d_salt, m, strength, b->d_keys, NULL);
+        if (!err) err = mz_cuda_memcpy_d2h(b->h_keys, b->d_keys, (size_t)m * MZ_CUDA_WZAES_KEYREC, NULL);
+        if (!err) err = mz_cuda_memcpy_h2d(b->d_coff, b->h_coff, (size_t)m * 8, NULL);
+        if (!err) err = mz_cuda_memcpy_h2d(b->d_clen, b->h_clen, (size_t)m * 8, NULL);
+        if (!err) err = mz_cuda_wzaes_hmac(b->d_comp, b->d_coff, b->d_clen, m, b->d_keys, strength, b->d_mac, NULL);
+        if (!err) err = mz_cuda_memcpy_d2h(b->h_mac, b->d_mac, (size_t)m * 20, NULL);
+        if (!err) err = mz_cuda_wzaes_ctr(b->d_comp, b->d_coff, b->d_clen, m, max_clen, b->d_keys, strength, NULL);
+        if (!err) err = mz_cuda_stream_sync(NULL);
+        for (uint32_t k = 0; k < m && !err; k++) {
+            zx_entry *e = &b->ent[b->aes_idx[k]];
+            if (memcmp(b->h_keys + (size_t)k * MZ_CUDA_WZAES_KEYREC + 64, b->h_comp + e->coff + slen, 2) != 0)
+                err = MZ_PASSWORD_ERROR; /* mz_strm_wzaes.c:133-134 */
+            else if (memcmp(b->h_mac + (size_t)k * 20, b->h_comp + b->h_coff[k] + b->h_clen[k], 10) != 0)
+                err = MZ_CRC_ERROR;      /* :252-254 */
+            e->coff = b->h_coff[k];      /* from here on the entry is its compressed stream */
+            e->csize = b->h_clen[k];
+        }
+    }
+    if (err)
+        return err;
     memset(b->h_state, 0, (size_t)n * sizeof(mz_cuda_inflate_state));
     for (uint32_t i = 0; i < n; i++) {
         const zx_entry *e = &b->ent[i];
@@ -971,7 +1151,6 @@ static int32_t zx_flush(zx_bufs *b, uint32_t n, size_t comp_used, size_t out_use
             njobs++;
         }
     }
-    err = mz_cuda_memcpy_h2d(b->d_comp, b->h_comp, comp_used + 32, NULL);
     /* stored entries: their bytes are the plain bytes */
     for (uint32_t i = 0; i < n && !err; i++)
         if (b->ent[i].method == 0 && b->ent[i].usize)
@@ -1036,6 +1215,10 @@ static int32_t zx_flush(zx_bufs *b, uint32_t n, size_t comp_used, size_t out_use
 }
 
 int32_t mz_zip_cuda_extract_all(void *zip_handle, mz_cuda_zip_entry_cb cb, void *userdata, mz_cuda_zip_stats *stats) {
+    return mz_zip_cuda_extract_all_aes(zip_handle, NULL, cb, userdata, stats);
+}
+
+int32_t mz_zip_cuda_extract_all_aes(void *zip_handle, const char *password, mz_cuda_zip_entry_cb cb, void *userdata, mz_cuda_zip_stats *stats) {
     zx_bufs b;
     mz_cuda_zip_stats st;
     int32_t err;
@@ -1069,12 +1252,24 @@ int32_t mz_zip_cuda_extract_all(void *zip_handle, mz_cuda_zip_entry_cb cb, void 
         err = mz_zip_entry_get_info(zip_handle, &fi);
         if (err != MZ_OK)
             break;
-        if ((fi->flag & 1u) || (fi->compression_method != 0 && fi->compression_method != 8) || fi->compressed_size < 0 ||
-            fi->uncompressed_size < 0 || fi->uncompressed_size > (1ll << 30) || fi->compressed_size > (1ll << 30)) {
-            err = MZ_SUPPORT_ERROR; /* encrypted, another codec, or too large for the batch path */
+        const int enc = (fi->flag & 1u) != 0;
+        const uint32_t aes_over = enc ? 4u * fi->aes_strength + 4u + 12u : 0u; /* salt + verifier + authentication code */
+        if (enc && fi->aes_version && !password) {
+            err = MZ_PASSWORD_ERROR; /* encrypted and no password given */
             break;
         }
-        if (fi->compression_method == 0 && fi->compressed_size != fi->uncompressed_size) {
+        if ((enc && (!fi->aes_version || fi->aes_strength < 1 || fi->aes_strength > 3 || strlen(password) > 128 ||
+                     fi->compressed_size < (int64_t)aes_over)) ||
+            (fi->compression_method != 0 && fi->compression_method != 8) || fi->compressed_size < 0 ||
+            fi->uncompressed_size < 0 || fi->uncompressed_size > (1ll << 30) || fi->compressed_size > (1ll << 30)) {
+            err = MZ_SUPPORT_ERROR; /* PKWARE-encrypted, another codec, or too large for the batch path */
+            break;
+        }
+        if (enc && !zx_alloc_aes(&b)) {
+            err = MZ_MEM_ERROR;
+            break;
+        }
+        if (fi->compression_method == 0 && fi->compressed_size - (int64_t)aes_over != fi->uncompressed_size) {
             err = MZ_FORMAT_ERROR;
             break;
         }
@@ -1086,7 +1281,7 @@ int32_t mz_zip_cuda_extract_all(void *zip_handle, mz_cuda_zip_entry_cb cb, void 
             break;
         }
         if (n == b.max_entries || comp_used + cneed > b.comp_cap || out_used + oneed > b.out_cap || names_used + nlen > b.names_cap) {
-            err = zx_flush(&b, n, comp_used, out_used, cb, userdata, &st);
+            err = zx_flush(&b, n, comp_used, out_used, password, cb, userdata, &st);
             if (err)
                 break;
             n = 0;
@@ -1101,6 +1296,7 @@ int32_t mz_zip_cuda_extract_all(void *zip_handle, mz_cuda_zip_entry_cb cb, void 
         e->method = fi->compression_method;
         e->name_off = (uint32_t)names_used;
         e->has_sha = 0;
+        e->aes = enc ? fi->aes_strength : 0;
         /* extra fields are {id u16, size u16, data}; find MZ_ZIP_EXTENSION_HASH with algorithm SHA-256 (mz_zip_rw.c:478-510) */
         for (uint32_t xo = 0; fi->extrafield && xo + 4 <= fi->extrafield_size;) {
             const uint8_t *x = fi->extrafield + xo;
@@ -1143,7 +1339,7 @@ int32_t mz_zip_cuda_extract_all(void *zip_handle, mz_cuda_zip_entry_cb cb, void 
         err = mz_zip_goto_next_entry(zip_handle);
     }
     if (err == MZ_END_OF_LIST)
-        err = zx_flush(&b, n, comp_used, out_used, cb, userdata, &st);
+        err = zx_flush(&b, n, comp_used, out_used, password, cb, userdata, &st);
     zx_free(&b);
     if (stats)
         *stats = st;

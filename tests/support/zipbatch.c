@@ -4,8 +4,8 @@
  * Compiled against the reference's own headers and objects by oracle/Makefile (-> oracle/_ref/zipbatch_cuda); the
  * container code in both modes is the reference's.
  *
- *   zipbatch_cuda <out.zip> <entries> <entry_bytes> <level> <cuda|cuda_sha|native|native_sha|native_all|ref> [dump_dir dump_every]
- *   zipbatch_cuda <in.zip>  <entries> <entry_bytes> <level> <extract|extract_ref>   (batch extractor / the reference's loop)
+ *   zipbatch_cuda <out.zip> <entries> <entry_bytes> <level> <cuda|cuda_sha|native|native_sha|native_aes|native_all|ref> [dump_dir dump_every]
+ *   zipbatch_cuda <in.zip>  <entries> <entry_bytes> <level> <extract|extract_ref|extract_aes|extract_ref_aes>   (batch extractor / the reference's loop; _aes: password $ZIPBATCH_PASSWORD or "secret")
  *
  * Entry i: i%10 < 7 text-like, < 9 binary records, else incompressible; name e/%06d.
  * With dump_dir, every dump_every-th entry's plain bytes are also written to dump_dir/%06d for comparison.
@@ -35,8 +35,17 @@ int32_t mz_zip_cuda_extract_all(void *z, mz_cuda_zip_entry_cb cb, void *u, mz_cu
     (void)z; (void)cb; (void)u; (void)st;
     return MZ_SUPPORT_ERROR;
 }
+int32_t mz_zip_cuda_extract_all_aes(void *z, const char *pw, mz_cuda_zip_entry_cb cb, void *u, mz_cuda_zip_stats *st) {
+    (void)z; (void)pw; (void)cb; (void)u; (void)st;
+    return MZ_SUPPORT_ERROR;
+}
 int32_t mz_zip_cuda_write_archive(void *b, const mz_cuda_zip_item *it, uint32_t n, int16_t level, uint32_t flags, mz_cuda_zip_stats *st) {
     (void)b; (void)it; (void)n; (void)level; (void)flags; (void)st;
+    return MZ_SUPPORT_ERROR;
+}
+int32_t mz_zip_cuda_write_archive_aes(void *b, const mz_cuda_zip_item *it, uint32_t n, int16_t level, uint32_t flags, const char *pw, uint8_t strength,
+                                      mz_cuda_zip_stats *st) {
+    (void)b; (void)it; (void)n; (void)level; (void)flags; (void)pw; (void)strength; (void)st;
     return MZ_SUPPORT_ERROR;
 }
 uint32_t mz_zip_cuda_abi_file_info_size(void) { return (uint32_t)sizeof(mz_zip_file); }
@@ -120,7 +129,7 @@ static int32_t on_entry(void *ud, const char *name, const void *data, int64_t si
     return MZ_OK;
 }
 
-static int extract_main(const char *path, size_t esz, int use_cuda) {
+static int extract_main(const char *path, size_t esz, int use_cuda, const char *password) {
     void *file_stream = mz_stream_os_create();
     void *stream = mz_stream_buffered_create();
     void *zip = mz_zip_create();
@@ -137,7 +146,7 @@ static int extract_main(const char *path, size_t esz, int use_cuda) {
     memset(&st, 0, sizeof(st));
     double t0 = now_s();
     if (use_cuda) {
-        err = mz_zip_cuda_extract_all(zip, on_entry, &x, &st);
+        err = password ? mz_zip_cuda_extract_all_aes(zip, password, on_entry, &x, &st) : mz_zip_cuda_extract_all(zip, on_entry, &x, &st);
     } else { /* the reference's own loop: one mz_stream_zlib per entry, CRC checked by mz_zip_entry_close (mz_zip_rw.c:818-909) */
         uint8_t *buf = (uint8_t *)malloc(esz + 65536);
         err = mz_zip_goto_first_entry(zip);
@@ -145,7 +154,7 @@ static int extract_main(const char *path, size_t esz, int use_cuda) {
             mz_zip_file *fi = NULL;
             err = mz_zip_entry_get_info(zip, &fi);
             if (err != MZ_OK) break;
-            err = mz_zip_entry_read_open(zip, 0, NULL);
+            err = mz_zip_entry_read_open(zip, 0, password);
             if (err != MZ_OK) break;
             int64_t got = 0;
             for (;;) {
@@ -179,9 +188,10 @@ static int extract_main(const char *path, size_t esz, int use_cuda) {
 }
 
 int main(int argc, char **argv) {
-    if (argc >= 6 && (strcmp(argv[5], "extract") == 0 || strcmp(argv[5], "extract_ref") == 0)) {
+    if (argc >= 6 && strncmp(argv[5], "extract", 7) == 0) { /* extract | extract_ref | extract_aes | extract_ref_aes */
         if (sizeof(mz_zip_file) != mz_zip_cuda_abi_file_info_size()) return 3;
-        return extract_main(argv[1], (size_t)atoll(argv[3]), strcmp(argv[5], "extract") == 0);
+        const char *pw = strstr(argv[5], "aes") ? (getenv("ZIPBATCH_PASSWORD") ? getenv("ZIPBATCH_PASSWORD") : "secret") : NULL;
+        return extract_main(argv[1], (size_t)atoll(argv[3]), strstr(argv[5], "ref") == NULL, pw);
     }
     if (argc < 6) {
         fprintf(stderr, "usage: %s out.zip entries entry_bytes level cuda|ref [dump_dir dump_every]\n", argv[0]);
@@ -194,7 +204,9 @@ int main(int argc, char **argv) {
     const int use_sha = strcmp(argv[5], "cuda_sha") == 0; /* + SHA-256 extra field per entry (scope row f3) */
     /* native / native_sha / native_all: the product writes the WHOLE archive itself (mz_zip_cuda_write_archive) to the file stream */
     const int use_native = strncmp(argv[5], "native", 6) == 0;
-    const uint32_t native_flags = (strstr(argv[5], "sha") ? MZ_ZIP_CUDA_HASH_SHA256 : 0u) | (strstr(argv[5], "all") ? MZ_ZIP_CUDA_ALL_DEVICES : 0u);
+    const uint32_t native_flags = (strstr(argv[5], "sha") ? MZ_ZIP_CUDA_HASH_SHA256 : 0u) | (strstr(argv[5], "all") ? MZ_ZIP_CUDA_ALL_DEVICES : 0u) |
+                                  (strstr(argv[5], "aes") ? MZ_ZIP_CUDA_AES : 0u);
+    const char *password = getenv("ZIPBATCH_PASSWORD") ? getenv("ZIPBATCH_PASSWORD") : "secret";
     const int use_cuda = strcmp(argv[5], "cuda") == 0 || use_sha;
     const char *dump_dir = argc > 7 ? argv[6] : NULL;
     const uint32_t dump_every = argc > 7 ? (uint32_t)atoi(argv[7]) : 0;
@@ -246,7 +258,8 @@ int main(int argc, char **argv) {
     uint64_t bytes_in = 0;
     t0 = now_s();
     if (use_native) {
-        err = mz_zip_cuda_write_archive(stream, items, n, level, native_flags, &st);
+        err = (native_flags & MZ_ZIP_CUDA_AES) ? mz_zip_cuda_write_archive_aes(stream, items, n, level, native_flags, password, 0, &st)
+                                               : mz_zip_cuda_write_archive(stream, items, n, level, native_flags, &st);
         bytes_in = st.bytes_in;
     } else if (use_cuda) {
         err = mz_zip_cuda_add_buffers_ex(zip, items, n, level, use_sha ? MZ_ZIP_CUDA_HASH_SHA256 : 0u, &st);
