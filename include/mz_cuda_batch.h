@@ -44,6 +44,7 @@ void *mz_cuda_event_create(void);
 void mz_cuda_event_destroy(void *event);
 int32_t mz_cuda_event_record(void *event, void *stream);
 int32_t mz_cuda_event_sync(void *event);
+int32_t mz_cuda_event_query(void *event); /* 1 = complete, 0 = not yet, < 0 = MZ_* error */
 float mz_cuda_event_elapsed_ms(void *start, void *stop); /* syncs on stop */
 
 /* ---- K1: CRC-32 ---------------------------------------------------------------------------------

@@ -36,6 +36,7 @@ typedef struct mz_cuda_zip_stats {
     uint64_t bytes_in, bytes_out;
     uint32_t entries, rounds;
     double pack_ms, gpu_ms, container_ms; /* host packing + upload, device work + download, reference container calls */
+    double setup_ms;                      /* native writer: creating and releasing the page-locked / device staging of the call */
 } mz_cuda_zip_stats;
 
 /* Append `count` entries to the zip that `zip_handle` (an open mz_zip writer, mz_zip.c:1237 mz_zip_open) is writing.

@@ -224,6 +224,15 @@ int32_t mz_cuda_event_sync(void *e) {
     CK(cudaEventSynchronize((cudaEvent_t)e));
     return MZ_OK;
 }
+int32_t mz_cuda_event_query(void *e) { /* 1 = everything recorded before it has finished, 0 = not yet, < 0 = error */
+    const cudaError_t r = cudaEventQuery((cudaEvent_t)e);
+    if (r == cudaSuccess) return 1;
+    if (r == cudaErrorNotReady) {
+        cudaGetLastError();
+        return 0;
+    }
+    return fail(r, "cudaEventQuery");
+}
 float mz_cuda_event_elapsed_ms(void *a, void *b) {
     float ms = -1.f;
     if (cudaEventSynchronize((cudaEvent_t)b) != cudaSuccess) return -1.f;

@@ -18,6 +18,8 @@
 #include "mz_strm_cuda.h"
 
 #include <pthread.h>
+#include <sched.h>
+#include <stdatomic.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -30,6 +32,8 @@
 
 /* ---- workspaces: pinned + device buffers are expensive to create, so streams borrow them ---------- */
 #define CU_NSLOT 3 /* write pipeline depth: upload of batch k+1 overlaps compute of k and download of k-1 */
+#define CU_CRC_RING 64
+#define CU_CRC_SEG ((uint64_t)16384)
 
 typedef struct cu_slot_s {
     void *stream;   /* cudaStream_t */
@@ -69,6 +73,14 @@ typedef struct cu_ws_s {
     void *rstream;  /* decode stream: uploads, K5/K6 launches, state copies */
     void *dstream;  /* delivery stream: CRC + download of finished output, overlaps a round in flight */
     void *rev;      /* K6 round in flight finished (summary is in h_sum) */
+    /* gzip members: the CRC-32 of every delivered piece is computed on a THIRD stream and folded when it is there -- on the
+     * delivery stream the kernel would queue behind a K6 round that fills the SMs, and the caller's thread with it */
+    void *cstream;
+    void *cev[CU_CRC_RING];
+    uint32_t *d_cres;          /* per ring slot: segment residues + 2 words of fold output */
+    uint32_t *h_cres;          /* pinned, 2 words per slot: {residue, crc of the piece from 0} */
+    uint64_t clen[CU_CRC_RING];
+    uint64_t c_head, c_tail;   /* pieces folded / enqueued so far (slot = count % CU_CRC_RING) */
     int pending;    /* a K6 round is in flight */
     uint64_t pend_nseg;
 } cu_ws;
@@ -82,6 +94,11 @@ static size_t env_size(const char *name, size_t dflt, size_t unit) {
         return dflt;
     long long n = atoll(v);
     return n > 0 ? (size_t)n * unit : dflt;
+}
+
+/* words of CRC scratch per ring slot: one residue per 16 KiB segment of a delivery piece (half the host buffer) + fold output */
+static size_t cu_crc_slot_words(size_t batch) {
+    return (size_t)((batch / 2 + CU_CRC_SEG - 1) / CU_CRC_SEG) + 8;
 }
 
 static void ws_destroy(cu_ws *w) {
@@ -117,8 +134,13 @@ static void ws_destroy(cu_ws *w) {
     mz_cuda_host_free(w->h_sum);
     mz_cuda_free(w->d_sum);
     mz_cuda_event_destroy(w->rev);
+    for (int i = 0; i < CU_CRC_RING; i++)
+        mz_cuda_event_destroy(w->cev[i]);
+    mz_cuda_free(w->d_cres);
+    mz_cuda_host_free(w->h_cres);
     mz_cuda_stream_destroy(w->rstream);
     mz_cuda_stream_destroy(w->dstream);
+    mz_cuda_stream_destroy(w->cstream);
     free(w);
 }
 
@@ -184,7 +206,15 @@ static cu_ws *ws_acquire(int kind) {
         w->rstream = mz_cuda_stream_create();
         w->dstream = mz_cuda_stream_create();
         w->rev = mz_cuda_event_create();
-        if (!w->h_cin || !w->d_cin || !w->d_win || !w->h_dec || !w->h_job || !w->d_job || !w->h_state || !w->d_state || !w->rstream ||
+        w->cstream = mz_cuda_stream_create();
+        w->d_cres = (uint32_t *)mz_cuda_malloc((size_t)CU_CRC_RING * cu_crc_slot_words(batch) * 4);
+        w->h_cres = (uint32_t *)mz_cuda_host_alloc((size_t)CU_CRC_RING * 8);
+        int cev_ok = 1;
+        for (int i = 0; i < CU_CRC_RING; i++) {
+            w->cev[i] = mz_cuda_event_create();
+            cev_ok &= w->cev[i] != NULL;
+        }
+        if (!cev_ok || !w->cstream || !w->d_cres || !w->h_cres || !w->h_cin || !w->d_cin || !w->d_win || !w->h_dec || !w->h_job || !w->d_job || !w->h_state || !w->d_state || !w->rstream ||
             !w->dstream || !w->rev) {
             ws_destroy(w);
             return NULL;
@@ -201,6 +231,8 @@ static void ws_release(cu_ws *w) {
             mz_cuda_stream_sync(w->rstream);
         w->pending = 0;
         mz_cuda_stream_sync(w->dstream); /* a piece may still be on its way into h_dec (abandoned read) */
+        mz_cuda_stream_sync(w->cstream);
+        w->c_head = w->c_tail = 0;
     }
     if (w->kind == 1) {
         for (int i = 0; i < CU_NSLOT; i++) {
@@ -268,6 +300,96 @@ typedef struct mz_stream_cuda_s {
     int8_t trace;
     uint64_t t_base, t_move, t_round, t_piece, t_serial, t_copy, n_round, n_serial;
 } mz_stream_cuda;
+
+/* ---- copying decoded bytes to the caller --------------------------------------------------------------------------
+ * On a long member the caller's thread spends more time in this memcpy than in anything else (pinned staging -> the caller's
+ * pageable buffer, one core: ~8 GB/s). Copies of 256 KiB and more are therefore split over a few helper threads
+ * (MZ_CUDA_COPY_THREADS, default 4 including the caller; 1 = plain memcpy). The helpers spin for a moment after a job -- a
+ * reader that calls read() in a loop finds them awake -- and sleep on a condition variable otherwise. One parallel copy at a
+ * time per process; a second stream reading concurrently simply copies on its own thread. */
+#define CU_COPY_MAX 8
+static struct {
+    pthread_mutex_t use;  /* held by the stream that is copying */
+    pthread_mutex_t mu;
+    pthread_cond_t cv;
+    pthread_t th[CU_COPY_MAX];
+    int n;                /* helpers running */
+    int want;             /* -1 = environment not read yet */
+    atomic_uint gen, done;
+    uint8_t *dst;
+    const uint8_t *src;
+    size_t part, total;
+    int parts;
+} g_cp = {PTHREAD_MUTEX_INITIALIZER, PTHREAD_MUTEX_INITIALIZER, PTHREAD_COND_INITIALIZER, {0}, 0, -1, 0, 0, NULL, NULL, 0, 0, 0};
+
+static void cp_slice(int k) {
+    const size_t o = (size_t)k * g_cp.part;
+    if (o < g_cp.total)
+        memcpy(g_cp.dst + o, g_cp.src + o, g_cp.total - o < g_cp.part ? g_cp.total - o : g_cp.part);
+}
+
+static void *cp_helper(void *arg) {
+    const int me = (int)(intptr_t)arg; /* slice index 1.. */
+    unsigned seen = 0;
+    for (;;) {
+        unsigned g = atomic_load_explicit(&g_cp.gen, memory_order_acquire);
+        if (g == seen) { /* spin briefly, then sleep */
+            for (int i = 0; i < 20000 && g == seen; i++) {
+                if ((i & 63) == 63)
+                    sched_yield();
+                g = atomic_load_explicit(&g_cp.gen, memory_order_acquire);
+            }
+            if (g == seen) {
+                pthread_mutex_lock(&g_cp.mu);
+                while ((g = atomic_load_explicit(&g_cp.gen, memory_order_acquire)) == seen)
+                    pthread_cond_wait(&g_cp.cv, &g_cp.mu);
+                pthread_mutex_unlock(&g_cp.mu);
+            }
+        }
+        seen = g;
+        if (me < g_cp.parts)
+            cp_slice(me);
+        atomic_fetch_add_explicit(&g_cp.done, 1, memory_order_release);
+    }
+    return NULL;
+}
+
+static void cu_copy_out(uint8_t *dst, const uint8_t *src, size_t n) {
+    if (n < (256u << 10) || pthread_mutex_trylock(&g_cp.use) != 0) {
+        memcpy(dst, src, n);
+        return;
+    }
+    if (g_cp.want < 0) {
+        const char *v = getenv("MZ_CUDA_COPY_THREADS");
+        int w = (v && *v) ? atoi(v) : 4;
+        g_cp.want = w < 1 ? 1 : (w > CU_COPY_MAX ? CU_COPY_MAX : w);
+        for (int i = 1; i < g_cp.want; i++) {
+            if (pthread_create(&g_cp.th[i], NULL, cp_helper, (void *)(intptr_t)i) != 0)
+                break;
+            pthread_detach(g_cp.th[i]);
+            g_cp.n++;
+        }
+    }
+    if (g_cp.n == 0) {
+        memcpy(dst, src, n);
+        pthread_mutex_unlock(&g_cp.use);
+        return;
+    }
+    g_cp.parts = g_cp.n + 1;
+    g_cp.part = ((n / (size_t)g_cp.parts) + 4095) & ~(size_t)4095;
+    g_cp.total = n;
+    g_cp.dst = dst;
+    g_cp.src = src;
+    atomic_store_explicit(&g_cp.done, 0, memory_order_relaxed);
+    pthread_mutex_lock(&g_cp.mu);
+    atomic_fetch_add_explicit(&g_cp.gen, 1, memory_order_release);
+    pthread_cond_broadcast(&g_cp.cv);
+    pthread_mutex_unlock(&g_cp.mu);
+    cp_slice(0);
+    while (atomic_load_explicit(&g_cp.done, memory_order_acquire) < (unsigned)g_cp.n)
+        sched_yield();
+    pthread_mutex_unlock(&g_cp.use);
+}
 
 static inline uint64_t now_ns(void) {
     struct timespec ts;
@@ -753,6 +875,8 @@ static int ws_spec_ensure(cu_ws *w) {
     return 1;
 }
 
+static int32_t cu_crc_fold(mz_stream_cuda *cu, int wait, int one);
+
 /* end of the raw stream: account for consumed bytes, verify the trailer (gzip CRC-32 + ISIZE, zlib Adler-32) */
 static int32_t cu_finish_stream(mz_stream_cuda *cu) {
     cu_ws *w = cu->ws;
@@ -762,6 +886,11 @@ static int32_t cu_finish_stream(mz_stream_cuda *cu) {
     int32_t err;
     cu->ended = 1;
     cu->total_in = cu->hdr_size + (int64_t)raw_bytes + (int64_t)tsize;
+    if (cu->wrap == 2) {
+        err = cu_crc_fold(cu, 1, 0);
+        if (err)
+            return err;
+    }
     if (tsize) {
         size_t off = (size_t)(raw_bytes - cu->cin_base);
         if (off + tsize > cu->cin_len) {
@@ -917,6 +1046,40 @@ static int32_t cu_spec_collect(mz_stream_cuda *cu) {
     return 1;
 }
 
+/* Fold the CRCs of delivered pieces into the running value, oldest first: those whose kernels have finished, or (wait) all of
+ * them / (wait && one) just the oldest. */
+static int32_t cu_crc_fold(mz_stream_cuda *cu, int wait, int one) {
+    cu_ws *w = cu->ws;
+    while (w->c_head < w->c_tail) {
+        const uint32_t slot = (uint32_t)(w->c_head % CU_CRC_RING);
+        if (wait) {
+            int32_t err = mz_cuda_event_sync(w->cev[slot]);
+            if (err)
+                return err;
+        } else {
+            const int32_t q = mz_cuda_event_query(w->cev[slot]);
+            if (q < 0)
+                return q;
+            if (q == 0)
+                break;
+        }
+        cu->crc = mz_cuda_crc32_combine(cu->crc, w->h_cres[2 * slot + 1], w->clen[slot]); /* crc(v, A) (+) crc(0, B) -> crc(v, A || B) */
+        w->c_head++;
+        if (one)
+            break;
+    }
+    return MZ_OK;
+}
+
+/* the output window about to be written again must not be under a CRC kernel any more: the decode stream waits (on the device,
+ * not the caller) for the newest piece's CRC */
+static int32_t cu_crc_fence(mz_stream_cuda *cu) {
+    cu_ws *w = cu->ws;
+    if (w->c_tail == 0 || w->c_tail == w->c_head)
+        return MZ_OK;
+    return mz_cuda_stream_wait_event(w->rstream, w->cev[(w->c_tail - 1) % CU_CRC_RING]);
+}
+
 /* enqueue (on the delivery stream) the download of the next undelivered bytes into h_dec + base; advances deliv_pos */
 static int32_t cu_fetch_piece(mz_stream_cuda *cu, size_t base, size_t cap) {
     cu_ws *w = cu->ws;
@@ -929,14 +1092,27 @@ static int32_t cu_fetch_piece(mz_stream_cuda *cu, size_t base, size_t cap) {
     if (n > cap)
         n = cap;
     const uint8_t *src = cu_window(cu, cu->lwin) + (cu->deliv_pos - (old ? cu->lwin_base : cu->win_base));
-    if (cu->wrap == 2) {
-        err = mz_cuda_crc32_device_stream(src, n, cu->crc, &cu->crc, w->dstream);
-        if (err)
-            return err;
-    }
     err = mz_cuda_memcpy_d2h(w->h_dec + base, src, n, w->dstream);
     if (err)
         return err;
+    if (cu->wrap == 2 && n) { /* the piece's CRC-32, asynchronously on the third stream */
+        if (w->c_tail - w->c_head == CU_CRC_RING) {
+            err = cu_crc_fold(cu, 1, 1);
+            if (err)
+                return err;
+        }
+        const uint32_t slot = (uint32_t)(w->c_tail % CU_CRC_RING);
+        const uint32_t nseg = (uint32_t)((n + CU_CRC_SEG - 1) / CU_CRC_SEG);
+        uint32_t *res = w->d_cres + (size_t)slot * cu_crc_slot_words(w->batch);
+        err = mz_cuda_crc32_segments(src, n, CU_CRC_SEG, NULL, NULL, nseg, res, NULL, w->cstream);
+        if (!err) err = mz_cuda_crc32_fold(res, nseg, CU_CRC_SEG, n, res + nseg, w->cstream);
+        if (!err) err = mz_cuda_memcpy_d2h(w->h_cres + 2 * slot, res + nseg, 8, w->cstream);
+        if (!err) err = mz_cuda_event_record(w->cev[slot], w->cstream);
+        if (err)
+            return err;
+        w->clen[slot] = n;
+        w->c_tail++;
+    }
     cu->pre_len = (size_t)n;
     cu->deliv_pos += n;
     return MZ_OK;
@@ -971,7 +1147,8 @@ static int32_t cu_decode_more(mz_stream_cuda *cu) {
                 /* no room for another round behind the undelivered bytes, and the other window is idle: carry the last
                  * 32 KiB of history over and decode into it; the delivery drains this window meanwhile */
                 const uint64_t have = st->out_pos - cu->win_base, keep = have < 32768 ? have : 32768;
-                err = mz_cuda_memcpy_d2d(cu_window(cu, cu->dwin ^ 1), cu_window(cu, cu->dwin) + (have - keep), keep, w->rstream);
+                err = cu_crc_fence(cu); /* (the other window's last pieces may still be under their CRC kernels) */
+                if (!err) err = mz_cuda_memcpy_d2d(cu_window(cu, cu->dwin ^ 1), cu_window(cu, cu->dwin) + (have - keep), keep, w->rstream);
                 if (err)
                     return err;
                 if (cu->trace)
@@ -1007,6 +1184,11 @@ static int32_t cu_decode_more(mz_stream_cuda *cu) {
                 return err;
             const size_t n = cu->pre_len;
             cu->pre_len = 0;
+            if (cu->wrap == 2) {
+                err = cu_crc_fold(cu, 0, 0);
+                if (err)
+                    return err;
+            }
             if (cu->wrap == 1)
                 cu_adler_update(cu, w->h_dec + cu->dec_base, n);
             cu->dec_pos = 0;
@@ -1044,6 +1226,9 @@ static int32_t cu_decode_more(mz_stream_cuda *cu) {
             /* cudaMemcpy of overlapping ranges is undefined: with a tiny window (MZ_CUDA_BATCH_KB <= 64) source and
              * destination can overlap, then move front to back in pieces no longer than the gap between them */
             const uint64_t gap = out_pos - cu->win_base - keep;
+            err = cu_crc_fence(cu);
+            if (err)
+                return err;
             for (uint64_t o = 0; gap > 0 && o < keep;) {
                 uint64_t k = keep - o;
                 if (gap < keep && k > gap)
@@ -1123,7 +1308,7 @@ int32_t mz_stream_cuda_read(void *stream, void *buf, int32_t size) {
             size_t k = cu->dec_len - cu->dec_pos;
             if (k > (size_t)(size - done))
                 k = (size_t)(size - done);
-            CU_TIMED(cu, t_copy, memcpy(out + done, cu->ws->h_dec + cu->dec_base + cu->dec_pos, k));
+            CU_TIMED(cu, t_copy, cu_copy_out(out + done, cu->ws->h_dec + cu->dec_base + cu->dec_pos, k));
             cu->dec_pos += k;
             done += (int32_t)k;
             continue;

@@ -800,6 +800,7 @@ int32_t mz_zip_cuda_write_archive_aes(void *base_stream, const mz_cuda_zip_item 
         if (ndev < 1) ndev = 1;
         if (ndev > 8) ndev = 8;
     }
+    const double t_setup0 = now_ms();
     const uint32_t want = ndev > 1 ? (uint32_t)ndev * 2 : 4u;
     const uint32_t nslots = want < nrounds ? want : (nrounds ? nrounds : 1);
     za_slot *slots = (za_slot *)calloc(nslots, sizeof(za_slot));
@@ -825,7 +826,7 @@ int32_t mz_zip_cuda_write_archive_aes(void *base_stream, const mz_cuda_zip_item 
     mz_cuda_set_device(dev0);
     uint64_t abs_off = 0;
     uint32_t issued = 0;
-    const double t_all = now_ms();
+    st.setup_ms = now_ms() - t_setup0;
     for (uint32_t r = 0; r < nrounds && err == MZ_OK; r++) {
         /* keep every slot busy: rounds r .. r + nslots - 1 are in preparation */
         while (issued < nrounds && issued < r + nslots) {
@@ -946,12 +947,13 @@ int32_t mz_zip_cuda_write_archive_aes(void *base_stream, const mz_cuda_zip_item 
         if (err == MZ_OK)
             err = za_write(base_stream, tail, tl);
     }
-    (void)t_all;
+    const double t_setup1 = now_ms();
     for (uint32_t k = 0; k < nslots; k++) {
         mz_cuda_set_device(slots[k].device);
         za_free(&slots[k]);
     }
     mz_cuda_set_device(dev0);
+    st.setup_ms += now_ms() - t_setup1;
     free(slots);
     free(cd.p);
     free(rfirst);

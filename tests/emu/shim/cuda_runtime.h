@@ -11,7 +11,7 @@
 #include <time.h>
 
 typedef int cudaError_t;
-enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1 };
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1, cudaErrorNotReady = 600 };
 typedef struct emu_stream_s *cudaStream_t;
 typedef struct emu_event_s { double t; } *cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3, cudaMemcpyDefault = 4 };
@@ -50,6 +50,7 @@ static inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = (cudaEvent_t)ma
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { free(e); return cudaSuccess; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s) { (void)s; e->t = emu_now_ms(); return cudaSuccess; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t e) { (void)e; return cudaSuccess; }
+static inline cudaError_t cudaEventQuery(cudaEvent_t e) { (void)e; return cudaSuccess; }
 static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)(b->t - a->t); return cudaSuccess; }
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F f, enum cudaFuncAttribute a, int v) { (void)f; (void)a; (void)v; return cudaSuccess; }
 static inline cudaError_t cudaPointerGetAttributes(struct cudaPointerAttributes *a, const void *p) { (void)p; a->type = cudaMemoryTypeUnregistered; return cudaSuccess; }
