@@ -428,7 +428,7 @@ __device__ inline void block_build_codes(const uint32_t *hist_ll, const uint32_t
 
 /* ---- A: match helpers ----------------------------------------------------------------------------------- */
 /* in[q..] against in[c..] agree for 8 bytes already; extend to at most maxlen bytes (both inside the unit) */
-__device__ __noinline__ uint32_t extend_match8(Smem sm, uint32_t c, uint32_t q, uint32_t maxlen) {
+__device__ __forceinline__ uint32_t extend_match8(const Smem &sm, uint32_t c, uint32_t q, uint32_t maxlen) {
     uint32_t len = 8;
     while (len < maxlen) {
         uint32_t x = sm.ld32u(DF_OFF_IN, q + len) ^ sm.ld32u(DF_OFF_IN, c + len);
@@ -521,6 +521,31 @@ __device__ __forceinline__ void put_match_bits(const Smem &sm, uint32_t pos, uin
     sm.red_or32(wa, w0);
     sm.red_or32(wa + 4, w1);
     if (w2) sm.red_or32(wa + 8, w2);
+}
+
+/* The k-th (0-based) set bit over the eight ballot words bm[0..7] of this warp -> the span index b * 512 + warp * 32 + lane it
+ * stands for; 0xffffffff when there are fewer. (Once or twice per unit and warp: a popcount walk + a 5-step binary search.) */
+__device__ __forceinline__ uint32_t nth_parked(const uint32_t (&bm)[DF_NBATCH], uint32_t k, uint32_t warp) {
+    uint32_t r = k, word = 0, bsel = 0;
+    bool found = false;
+#pragma unroll
+    for (int b = 0; b < DF_NBATCH; b++) {
+        const uint32_t c = (uint32_t)__popc(bm[b]);
+        const bool here = !found && r < c;
+        word = here ? bm[b] : word;
+        bsel = here ? (uint32_t)b : bsel;
+        found = found || here;
+        r -= found ? 0u : c;
+    }
+    uint32_t base = 0;
+#pragma unroll
+    for (int st = 16; st; st >>= 1) {
+        const uint32_t c = (uint32_t)__popc((word >> base) & ((1u << st) - 1u));
+        const bool up = r >= c;
+        r -= up ? c : 0u;
+        base += up ? (uint32_t)st : 0u;
+    }
+    return found ? bsel * (uint32_t)DF_THREADS + warp * 32u + base : 0xffffffffu;
 }
 
 /* ---- the kernel ------------------------------------------------------------------------------- */
@@ -645,7 +670,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) deflate_chunks_kernel(DeflatePa
 #endif
             __syncthreads();
 
-            uint32_t fF[DF_NBATCH], fA[DF_NBATCH], fB[DF_NBATCH];
+            uint32_t fF[DF_NBATCH], fA[DF_NBATCH];
             bool stored = (P.level == 0);
             const uint32_t bfinal = (last_unit && (flags & DF_FLAG_FINAL)) ? 1u : 0u;
             uint32_t tokbits = 0;
@@ -729,21 +754,38 @@ __global__ void __launch_bounds__(DF_THREADS, 2) deflate_chunks_kernel(DeflatePa
                     }
                     lit &= (1u << nvalid) - 1u;
                     {
+                        /* a capped match (lockstep length 8) is the span's last token; its true length is found after the batches,
+                         * by the M0 pass, 32 such matches at a time (inline it kept the warp busy for the 8 lanes that have one) */
                         const uint32_t last = mB ? mB : mA;
-                        if (((last >> 3) & 255u) == (uint32_t)(DF_LOCKLEN - 3)) { /* capped: find the true length */
-                            const uint32_t j = last & 7u, c = (last >> 11) & 0x7fffu;
-                            uint32_t maxlen = ulen - (q0 + j);
-                            maxlen = maxlen < 258 ? maxlen : 258u;
-                            const uint32_t l = extend_match8(sm, c, q0 + j, maxlen);
-                            const uint32_t rec = (last & ~(255u << 3)) | ((l - 3) << 3);
-                            if (mB) mB = rec; else mA = rec;
-                            nxt = j + l;
-                        }
-                    }
-                    sm.st64(DF_OFF_REC + (b * DF_THREADS + tid) * 8, mA | ((lit & 63u) << 26), mB | ((lit >> 6) << 26));
-                    {
-                        const uint32_t last = mB ? mB : mA; /* start offset and end (relative to the span) of the span's last match */
+                        const uint32_t capped = __ballot_sync(MZ_FULL_MASK, ((last >> 3) & 255u) == (uint32_t)(DF_LOCKLEN - 3));
+                        if (lane == 0) s_scan[b * DF_WARPS + warp] = capped;
+                        sm.st64(DF_OFF_REC + (b * DF_THREADS + tid) * 8, mA | ((lit & 63u) << 26), mB | ((lit >> 6) << 26));
+                        /* start offset and end (relative to the span) of the span's last match */
                         sm.st16(DF_OFF_SPN + (b * DF_THREADS + tid) * 2, last ? ((last & 7u) << 9) | ((last & 7u) + rec_len(last)) : 0u);
+                    }
+                }
+                /* ---- M0: true lengths of the capped matches ----------------------------------------------------------------- */
+                {
+                    __syncwarp();
+                    uint32_t bmX[DF_NBATCH], totX = 0;
+#pragma unroll
+                    for (int b = 0; b < DF_NBATCH; b++) {
+                        bmX[b] = (uint32_t)b < nb ? s_scan[b * DF_WARPS + warp] : 0u;
+                        totX += (uint32_t)__popc(bmX[b]);
+                    }
+                    for (uint32_t k0 = 0; k0 < totX; k0 += 32) {
+                        const uint32_t sidx = nth_parked(bmX, k0 + lane, warp);
+                        if (sidx != 0xffffffffu) {
+                            const uint2 r = sm.ld64(DF_OFF_REC + sidx * 8);
+                            const bool second = (r.y & 0x03ffffffu) != 0;
+                            const uint32_t w = second ? r.y : r.x, last = w & 0x03ffffffu;
+                            const uint32_t j = last & 7u, c = (last >> 11) & 0x7fffu, q = sidx * DF_SPAN + j;
+                            uint32_t maxlen = ulen - q;
+                            maxlen = maxlen < 258 ? maxlen : 258u;
+                            const uint32_t l = extend_match8(sm, c, q, maxlen);
+                            sm.st32(DF_OFF_REC + sidx * 8 + (second ? 4u : 0u), (w & ~(255u << 3)) | ((l - 3) << 3));
+                            sm.st16(DF_OFF_SPN + sidx * 2, (j << 9) | (j + l));
+                        }
                     }
                 }
                 __syncthreads(); /* S1: records visible; the hash table is dead */
@@ -812,12 +854,17 @@ __global__ void __launch_bounds__(DF_THREADS, 2) deflate_chunks_kernel(DeflatePa
                 }
                 __syncthreads(); /* S3: covers visible */
 
-                /* ---- T: classify every span once -> final records in registers; symbol counts ---------------------- */
-                const uint32_t hist_lit = (lane & 1u) ? (uint32_t)DF_OFF_HIST2 : (uint32_t)DF_OFF_HIST; /* two copies halve the same-address traffic */
-                const uint32_t sink = DF_OFF_SINK + lane * 4;
+                /* ---- T: classify every span once -> final records; symbol counts. The first match of a span is turned into symbol
+                 * form here (36 % of the spans have one); the second one (7 %) would keep the whole warp busy for two or three
+                 * lanes, so it is parked in the record region (word 1 of the span's record, dead once it has been read) and the
+                 * warp's ballots remember where: the M1 pass below works through them 32 at a time. -------------------------- */
+                const uint32_t hist_lit = sm.addr((lane & 1u) ? (uint32_t)DF_OFF_HIST2 : (uint32_t)DF_OFF_HIST); /* two copies halve the same-address traffic */
+                const uint32_t sink = sm.addr(DF_OFF_SINK + lane * 4);
+                uint32_t bmB[DF_NBATCH]; /* per batch: the lanes of this warp whose span has a second match (warp-uniform) */
 #pragma unroll
                 for (int b = 0; b < DF_NBATCH; b++) {
                     uint32_t F = 0, MA = 0, MB = 0;
+                    bmB[b] = 0;
                     if ((uint32_t)b < nb) {
                         const uint32_t sidx = (uint32_t)b * DF_THREADS + tid;
                         const uint32_t q0 = sidx * DF_SPAN;
@@ -826,22 +873,36 @@ __global__ void __launch_bounds__(DF_THREADS, 2) deflate_chunks_kernel(DeflatePa
                         span_classify<ONEM>(sm, r.x, r.y, q0, cover, F, MA, MB);
                         const uint32_t ex = (F >> 8) & 3u;
                         if (ex) {
-                            sm.red_add32(hist_lit + ((F >> 16) & 0xffu) * 4, 1u);
-                            if (ex == 2) sm.red_add32(hist_lit + (F >> 24) * 4, 1u);
+                            sm.red_add32_a(hist_lit + ((F >> 16) & 0xffu) * 4, 1u);
+                            if (ex == 2) sm.red_add32_a(hist_lit + (F >> 24) * 4, 1u);
                         }
                         const uint2 x = sm.ld64(DF_OFF_IN + q0);
 #pragma unroll
                         for (int j = 0; j < 8; j++) {
-                            const uint32_t by4 = j == 0 ? (x.x << 2) & 0x3fcu
-                                               : j < 4 ? (x.x >> (8 * j - 2)) & 0x3fcu
-                                               : j == 4 ? (x.y << 2) & 0x3fcu
-                                                        : (x.y >> (8 * (j - 4) - 2)) & 0x3fcu; /* byte * 4 */
-                            sm.red_add32(((F >> j) & 1u) ? hist_lit + by4 : sink, 1u);
+                            const uint32_t by = MZ_BYTE(j < 4 ? x.x : x.y, j & 3);
+                            sm.red_add32_a(((F >> j) & 1u) ? by * 4u + hist_lit : sink, 1u);
                         }
                         if (MA) MA = match_symbols(sm, MA);
-                        if (!ONEM && MB) MB = match_symbols(sm, MB);
+                        if (!ONEM) {
+                            bmB[b] = __ballot_sync(MZ_FULL_MASK, MB != 0);
+                            sm.st32(DF_OFF_REC + sidx * 8 + 4, MB);
+                        }
                     }
-                    fF[b] = F; fA[b] = MA; fB[b] = MB;
+                    fF[b] = F; fA[b] = MA;
+                }
+                /* ---- M1: the parked second matches -> symbol form (+ their two symbol counts), one per lane ---------------- */
+                if (!ONEM) {
+                    uint32_t totB = 0;
+#pragma unroll
+                    for (int b = 0; b < DF_NBATCH; b++) totB += (uint32_t)__popc(bmB[b]);
+                    __syncwarp();
+                    for (uint32_t k0 = 0; k0 < totB; k0 += 32) {
+                        const uint32_t sidx = nth_parked(bmB, k0 + lane, warp);
+                        if (sidx != 0xffffffffu) {
+                            const uint32_t a = DF_OFF_REC + sidx * 8 + 4;
+                            sm.st32(a, match_symbols(sm, sm.ld32(a)));
+                        }
+                    }
                 }
                 if (tid == 0) sm.red_add32(DF_OFF_HIST + 256 * 4, 1u); /* end of block */
                 __syncthreads(); /* S4 */
@@ -852,20 +913,20 @@ __global__ void __launch_bounds__(DF_THREADS, 2) deflate_chunks_kernel(DeflatePa
                 __syncthreads(); /* S5 */
                 const uint32_t hdrbits = s_bb[BB_HDRBITS]; /* (the scratch is reused below) */
                 /* ---- E: bits per span -> offsets ------------------------------------------------------------------- */
+                const uint32_t bits_base = sm.addr(DF_OFF_BITS);
 #pragma unroll
                 for (int b = 0; b < DF_NBATCH; b++) {
                     if ((uint32_t)b < nb) {
                         const uint32_t sidx = (uint32_t)b * DF_THREADS + tid;
                         const uint32_t F = fF[b];
                         const uint2 x = sm.ld64(DF_OFF_IN + sidx * DF_SPAN);
-                        uint32_t nbits = match_bits(sm, fA[b]) + (ONEM ? 0u : match_bits(sm, fB[b]));
+                        uint32_t nbits = match_bits(sm, fA[b]) + (ONEM ? 0u : match_bits(sm, sm.ld32(DF_OFF_REC + sidx * 8 + 4)));
                         const uint32_t ex = (F >> 8) & 3u;
                         nbits += ex >= 1 ? sm.ld8(DF_OFF_BITS + ((F >> 16) & 0xffu)) : 0u;
                         nbits += ex == 2 ? sm.ld8(DF_OFF_BITS + (F >> 24)) : 0u;
 #pragma unroll
                         for (int j = 0; j < 8; j++) {
-                            const uint32_t by = ((j < 4 ? x.x : x.y) >> (8 * (j & 3))) & 0xffu;
-                            const uint32_t l = sm.ld8(DF_OFF_BITS + by);
+                            const uint32_t l = sm.ld8_a(bits_base + MZ_BYTE(j < 4 ? x.x : x.y, j & 3));
                             nbits += ((F >> j) & 1u) ? l : 0u;
                         }
                         sm.st16(DF_OFF_SPN + sidx * 2, nbits);
@@ -901,14 +962,20 @@ __global__ void __launch_bounds__(DF_THREADS, 2) deflate_chunks_kernel(DeflatePa
                         s_stage[w0 + i] = i == 0 ? s_stage[w0] & ((1u << (bitpos & 31u)) - 1u) : 0u;
                     __syncthreads();
                 } else {
-                    /* ---- F: emit. Literals of a span go through a bit accumulator in slot order; a match leaves a gap of
-                     * its size in that stream (its slot puts zeros) and is OR-ed in afterwards at the recorded position. ---- */
+                    /* ---- F: emit. The eight code words of a span are looked up first (a position that is not a literal looks
+                     * up the all-zero entry: no selects on the results); their lengths, packed one per byte, and the sizes of the
+                     * span's matches (added to the byte of the slot they are ordered at) give every bit offset of the span by
+                     * ONE multiplication per word: byte k of w * 0x01010101 is the sum of bytes 0..k of w (no byte overflows:
+                     * 8 x 15 + 2 x 48 < 256). Two literals go out per OR of <= 30 bits; both target words unconditionally (an OR
+                     * of zero is cheaper than the branches around it). The first match is OR-ed in by its span, the second
+                     * one's position is parked next to its record for the M3 pass. ------------------------------------------- */
                     const uint32_t base = bitpos + hdrbits;
+                    const uint32_t code_base = sm.addr(DF_OFF_CODE), zero_ent = sm.addr(DF_OFF_CODE + DF_ZERO_SYM * 4), stage_base = sm.addr(DF_OFF_STAGE);
 #pragma unroll
                     for (int b = 0; b < DF_NBATCH; b++) {
                         if ((uint32_t)b < nb) {
                             const uint32_t sidx = (uint32_t)b * DF_THREADS + tid;
-                            const uint32_t F = fF[b], MA = fA[b], MB = ONEM ? 0u : fB[b];
+                            const uint32_t F = fF[b], MA = fA[b], MB = ONEM ? 0u : sm.ld32(DF_OFF_REC + sidx * 8 + 4);
                             if ((F | MA | MB) == 0) continue;
                             const uint2 x = sm.ld64(DF_OFF_IN + sidx * DF_SPAN);
                             uint32_t pos = base + s_bb[sidx >> 3] + sm.ld16(DF_OFF_SPN + sidx * 2); /* bit position in the staging buffer */
@@ -923,32 +990,46 @@ __global__ void __launch_bounds__(DF_THREADS, 2) deflate_chunks_kernel(DeflatePa
                                     pos += (c1 >> 16) & 15u;
                                 }
                             }
-                            const uint32_t nA = match_bits(sm, MA), nB = ONEM ? 0u : match_bits(sm, MB);
-                            const uint32_t slotA = MA ? (MA >> 28) & 7u : 8u, slotB = MB ? (MB >> 28) & 7u : 8u;
-                            uint32_t posA = 0, posB = 0;
+                            uint32_t cw[8];
 #pragma unroll
-                            for (int jj = 0; jj < 4; jj++) { /* two positions per step: two literals go out as one OR of <= 30 bits */
-                                const uint32_t xw = jj < 2 ? x.x : x.y;
-                                const uint32_t b0 = jj & 1 ? (xw >> 14) & 0x3fcu : (xw << 2) & 0x3fcu;   /* byte * 4 */
-                                const uint32_t b1 = jj & 1 ? (xw >> 22) & 0x3fcu : (xw >> 6) & 0x3fcu;
-                                const bool l0 = ((F >> (2 * jj)) & 1u) != 0, l1 = ((F >> (2 * jj + 1)) & 1u) != 0;
-                                /* a position that is not a literal looks up the all-zero entry: no selects on the results */
-                                const uint32_t cw0 = sm.ld32(DF_OFF_CODE + (l0 ? b0 : DF_ZERO_SYM * 4)), cw1 = sm.ld32(DF_OFF_CODE + (l1 ? b1 : DF_ZERO_SYM * 4));
-                                const uint32_t n0 = cw0 >> 16, n1 = cw1 >> 16; /* (a literal's entry has no extra-bits field) */
-                                const uint32_t g0 = slotA == 2u * jj ? nA : (slotB == 2u * jj ? nB : 0u);            /* a match ordered here leaves a gap */
-                                const uint32_t g1 = slotA == 2u * jj + 1 ? nA : (slotB == 2u * jj + 1 ? nB : 0u);
-                                posA = slotA == 2u * jj ? pos : (slotA == 2u * jj + 1 ? pos + n0 : posA);
-                                posB = slotB == 2u * jj ? pos : (slotB == 2u * jj + 1 ? pos + n0 : posB);
-                                /* at most the two literals are in-band, and then they are adjacent (a match start covers its neighbour) */
-                                const uint32_t v = (cw0 & 0xffffu) | ((cw1 & 0xffffu) << n0);
-                                const uint32_t sh = pos & 31u, wa = DF_OFF_STAGE + ((pos >> 5) << 2);
-                                /* both words unconditionally (an OR of zero is harmless): cheaper than the branches around them */
-                                sm.red_or32(wa, v << sh);
-                                sm.red_or32(wa + 4, __funnelshift_l(v, 0u, sh));
-                                pos += n0 + n1 + g0 + g1;
+                            for (int j = 0; j < 8; j++) {
+                                const uint32_t by = MZ_BYTE(j < 4 ? x.x : x.y, j & 3);
+                                cw[j] = sm.ld32_a(((F >> j) & 1u) ? by * 4u + code_base : zero_ent); /* code | length << 16 (a literal's entry has no extra-bits field) */
                             }
-                            if (MA) put_match_bits(sm, posA, MA);
-                            if (!ONEM && MB) put_match_bits(sm, posB, MB);
+                            /* lengths, one per byte; a match leaves a gap of its size at its slot (slot 8 = none: the shifts clamp to 0) */
+                            const uint32_t nA = match_bits(sm, MA), nB = ONEM ? 0u : match_bits(sm, MB);
+                            const uint32_t sA = MA ? ((MA >> 28) & 7u) * 8u : 64u, sB = MB ? ((MB >> 28) & 7u) * 8u : 64u;
+                            const uint32_t L0 = __byte_perm(__byte_perm(cw[0], cw[1], 0x0062u), __byte_perm(cw[2], cw[3], 0x0062u), 0x5410u) + shl_clamp(nA, sA) + shl_clamp(nB, sB);
+                            const uint32_t L1 = __byte_perm(__byte_perm(cw[4], cw[5], 0x0062u), __byte_perm(cw[6], cw[7], 0x0062u), 0x5410u) + shl_clamp(nA, sA - 32u) + shl_clamp(nB, sB - 32u);
+                            const uint32_t P0 = L0 * 0x01010101u;                       /* inclusive sums of slots 0..3 */
+                            const uint32_t P1 = L1 * 0x01010101u + (P0 >> 24) * 0x01010101u;
+                            const uint32_t E0 = P0 << 8, E1 = __funnelshift_l(P0, P1, 8); /* exclusive: bits before slot k in byte k */
+#pragma unroll
+                            for (int jj = 0; jj < 4; jj++) {
+                                const uint32_t pp = pos + MZ_BYTE(jj < 2 ? E0 : E1, 2 * (jj & 1));
+                                const uint32_t c0 = cw[2 * jj], c1 = cw[2 * jj + 1];
+                                /* at most the two literals are in-band, and then they are adjacent (a match start covers its neighbour) */
+                                const uint32_t v = (c0 & 0xffffu) | ((c1 & 0xffffu) << (c0 >> 16));
+                                const uint32_t sh = pp & 31u, wa = stage_base + ((pp >> 5) << 2);
+                                sm.red_or32_a(wa, v << sh);
+                                sm.red_or32_a(wa + 4, __funnelshift_l(v, 0u, sh));
+                            }
+                            if (MA) put_match_bits(sm, pos + (shr_clamp(E0, sA) & 0xffu) + (shr_clamp(E1, sA - 32u) & 0xffu), MA);
+                            if (!ONEM) sm.st32(DF_OFF_REC + sidx * 8, pos + (shr_clamp(E0, sB) & 0xffu) + (shr_clamp(E1, sB - 32u) & 0xffu)); /* (only read back where MB != 0) */
+                        }
+                    }
+                    /* ---- M3: the parked second matches, one per lane ----------------------------------------------------- */
+                    if (!ONEM) {
+                        uint32_t totB = 0;
+#pragma unroll
+                        for (int b = 0; b < DF_NBATCH; b++) totB += (uint32_t)__popc(bmB[b]);
+                        __syncwarp();
+                        for (uint32_t k0 = 0; k0 < totB; k0 += 32) {
+                            const uint32_t sidx = nth_parked(bmB, k0 + lane, warp);
+                            if (sidx != 0xffffffffu) {
+                                const uint2 r = sm.ld64(DF_OFF_REC + sidx * 8);
+                                put_match_bits(sm, r.x, r.y);
+                            }
                         }
                     }
                     if (tid == DF_THREADS - 1) stage_put(s_stage, base + tokbits, eob & 0x7fffu, (eob >> 16) & 15u);

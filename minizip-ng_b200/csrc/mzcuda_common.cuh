@@ -65,6 +65,12 @@ struct Smem {
     __device__ __forceinline__ uint2 ld64(uint32_t off) const { return *(const uint2 *)(b + off); }
     __device__ __forceinline__ void st64(uint32_t off, uint32_t x, uint32_t y) const { *(uint2 *)(b + off) = make_uint2(x, y); }
     __device__ __forceinline__ void st128(uint32_t off, uint32_t x, uint32_t y, uint32_t z, uint32_t w) const { *(uint4 *)(b + off) = make_uint4(x, y, z, w); }
+    /* absolute forms: addr() folds the window base into a region base once, the *_a accessors then take that address as it is */
+    __device__ __forceinline__ uint32_t addr(uint32_t off) const { return off; }
+    __device__ __forceinline__ uint32_t ld32_a(uint32_t a) const { return ld32(a); }
+    __device__ __forceinline__ uint32_t ld8_a(uint32_t a) const { return ld8(a); }
+    __device__ __forceinline__ void red_or32_a(uint32_t a, uint32_t v) const { red_or32(a, v); }
+    __device__ __forceinline__ void red_add32_a(uint32_t a, uint32_t v) const { red_add32(a, v); }
 #else
     uint32_t b;
     __device__ __forceinline__ void init(uint8_t *base) {
@@ -110,6 +116,19 @@ struct Smem {
     __device__ __forceinline__ void st128(uint32_t off, uint32_t x, uint32_t y, uint32_t z, uint32_t w) const {
         asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(b + off), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
     }
+    __device__ __forceinline__ uint32_t addr(uint32_t off) const { return b + off; }
+    __device__ __forceinline__ uint32_t ld32_a(uint32_t a) const {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+        return v;
+    }
+    __device__ __forceinline__ uint32_t ld8_a(uint32_t a) const {
+        uint32_t v;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+        return v;
+    }
+    __device__ __forceinline__ void red_or32_a(uint32_t a, uint32_t v) const { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+    __device__ __forceinline__ void red_add32_a(uint32_t a, uint32_t v) const { asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 #endif
     /* unaligned little-endian 32-bit load at byte offset `off + p` (region base `off` is 4-byte aligned) */
     __device__ __forceinline__ uint32_t ld32u(uint32_t off, uint32_t p) const {
@@ -145,6 +164,28 @@ __device__ __forceinline__ uint32_t warp_incl_max(uint32_t v) {
     }
     return v;
 }
+
+/* v << s with PTX semantics: a shift amount of 32 or more (also a "negative" one that wrapped) gives 0 */
+__device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t s) {
+#ifdef MZ_EMU
+    return s >= 32u ? 0u : v << s;
+#else
+    uint32_t r;
+    asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(s));
+    return r;
+#endif
+}
+__device__ __forceinline__ uint32_t shr_clamp(uint32_t v, uint32_t s) {
+#ifdef MZ_EMU
+    return s >= 32u ? 0u : v >> s;
+#else
+    uint32_t r;
+    asm("shr.u32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(s));
+    return r;
+#endif
+}
+/* byte k (0..3, a constant) of a word */
+#define MZ_BYTE(x, k) __byte_perm((x), 0u, 0x4440u + (k))
 
 #ifndef MZ_EMU
 /* ---- mbarrier + TMA bulk copy (cp.async.bulk; SASS: UBLKCP) ------------------------------------ */
