@@ -1015,14 +1015,17 @@ def run_c4(args, rank, world, local_rank):
         env = dict(os.environ)  # under torchrun every rank sees all devices: the writer takes them all
         mode = "native_all" if world > 1 else "native"
         try:
-            for i in range(min(args.warmup, 1) + min(args.steps, 3)):
-                if i == min(args.warmup, 1):
-                    clocks.start()
-                r = subprocess.run([exe, os.path.join(d, "c4.zip"), str(entries), "65536", str(args.level), mode], stdout=subprocess.PIPE, text=True, env=env, timeout=900)
-                j = json.loads(r.stdout.strip().splitlines()[-1])
-                assert j["err"] == 0 and j["close_err"] == 0, j
-                if i >= min(args.warmup, 1):
-                    runs.append(j)
+            # ONE writer process writes the archive warm-up + steps times (ZIPBATCH_REPEAT): like the other configs' warm-up steps, the
+            # timed ones run in a warm process -- CUDA context up, the library's staging pool filled by the first archive
+            nw, ns = min(args.warmup, 1), min(args.steps, 3)
+            env["ZIPBATCH_REPEAT"] = str(nw + ns)
+            clocks.start()
+            r = subprocess.run([exe, os.path.join(d, "c4.zip"), str(entries), "65536", str(args.level), mode], stdout=subprocess.PIPE, text=True, env=env, timeout=1800)
+            lines = [json.loads(x) for x in r.stdout.strip().splitlines() if x.startswith("{")]
+            assert len(lines) == nw + ns and all(j["err"] == 0 and j["close_err"] == 0 for j in lines), r.stdout[-2000:]
+            first_archive = lines[0]
+            runs = lines[nw:]
+            env.pop("ZIPBATCH_REPEAT")
             clk = clocks.stop()
             import zipfile
             with zipfile.ZipFile(os.path.join(d, "c4.zip")) as zf:  # a valid zip: CPython's zipfile checks every entry's CRC
@@ -1049,8 +1052,10 @@ def run_c4(args, rank, world, local_rank):
            "api": "mz_zip_cuda_write_archive(file stream, %d host buffers, flags %s), archive file on tmpfs" % (entries, "ALL_DEVICES" if world > 1 else "0"),
            "entries_per_s": round(entries / add_s, 1), "pack_ms": runs[-1]["pack_ms"], "gpu_ms": runs[-1]["gpu_ms"], "write_ms": runs[-1]["container_ms"],
            "setup_ms": runs[-1].get("setup_ms"), "cuda_init_s_not_in_the_timed_region": runs[-1].get("cuda_init_s"),
-           "note": "timed: the whole mz_zip_cuda_write_archive call (staging allocation, rounds, central directory, release) + close of the file stream; "
-                   "CUDA context creation happens once per process before the timer starts; pack_ms is summed over the four round workers"}
+           "first_archive_of_the_process": {"entries_per_s": first_archive["entries_per_s"], "setup_ms": first_archive.get("setup_ms")},
+           "note": "timed: the whole mz_zip_cuda_write_archive call (staging from the library's pool, rounds, central directory, release) + close of the "
+                   "file stream, in a process that has written the archive once before (warm-up step: CUDA context, page-locked staging pool); the "
+                   "first archive of the process is reported beside it; pack_ms is summed over the four round workers"}
     if seam:
         e2e["raw_entry_seam"] = {"entries_per_s": seam["entries_per_s"], "GiB_per_s": seam["GiB_per_s"], "container_ms": seam["container_ms"],
                                  "api": "mz_zip_cuda_add_buffers: the reference's container writes every header (three calls per entry)"}

@@ -66,6 +66,9 @@ int32_t mz_zip_cuda_add_buffers_ex(void *zip_handle, const mz_cuda_zip_item *ite
 #define MZ_ZIP_CUDA_ALL_DEVICES 2u
 int32_t mz_zip_cuda_write_archive(void *base_stream, const mz_cuda_zip_item *items, uint32_t count, int16_t level, uint32_t flags,
                                   mz_cuda_zip_stats *stats);
+/* The native writer keeps the staging of finished calls (page-locked + device buffers, up to eight round slots per process) for
+ * the next call; this frees them. MZ_CUDA_ZIP_POOL=0 in the environment turns the pool off. */
+void mz_zip_cuda_trim(void);
 
 /* The same archive with every entry WinZip-AES encrypted after compression (scope row f4, the part that follows the codec): what
  * the reference does per entry by stacking mz_stream_wzaes under the codec (mz_zip.c:1734-1741, mz_strm_wzaes.c) -- a random salt,

@@ -56,7 +56,7 @@ EXPORTS = [
     "mz_cuda_gather_region_bound", "mz_cuda_deflate_sharded", "mz_cuda_ipc_export", "mz_cuda_ipc_open", "mz_cuda_ipc_close", "mz_cuda_memcpy_peer",
     "mz_cuda_stream_wait_event", "mz_cuda_gather", "mz_cuda_scatter_blobs",
     # include/mz_zip_cuda.h
-    "mz_zip_cuda_add_buffers", "mz_zip_cuda_add_buffers_ex", "mz_zip_cuda_write_archive", "mz_zip_cuda_write_archive_aes", "mz_zip_cuda_extract_all",
+    "mz_zip_cuda_add_buffers", "mz_zip_cuda_add_buffers_ex", "mz_zip_cuda_write_archive", "mz_zip_cuda_trim", "mz_zip_cuda_write_archive_aes", "mz_zip_cuda_extract_all",
     "mz_zip_cuda_extract_all_aes", "mz_zip_cuda_abi_file_info_size",
 ]
 

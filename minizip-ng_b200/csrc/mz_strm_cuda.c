@@ -62,6 +62,8 @@ typedef struct cu_ws_s {
     uint8_t *h_cin, *d_cin, *d_win, *h_dec;
     uint8_t *d_win2; /* long streams: second output window, so that decoding can go on while the first is still being delivered */
     size_t cin_cap, win_cap;
+    size_t ring_cap; /* h_cin is a ring of this many bytes (+ 64 zero bytes behind it): the compressed window is cin_cap of it at most, the
+                      * rest holds bytes read ahead from base while a round is in flight (long streams: 2 x cin_cap) */
     mz_cuda_inflate_job *h_job, *d_job;
     mz_cuda_inflate_state *h_state, *d_state;
     /* read, long streams: segment-speculative rounds (K6) */
@@ -195,7 +197,10 @@ static cu_ws *ws_acquire(int kind) {
     } else {
         w->cin_cap = batch / 4 > (1u << 20) ? batch / 4 : (1u << 20);
         w->win_cap = 32768 + batch;
-        w->h_cin = (uint8_t *)mz_cuda_host_alloc(w->cin_cap + 64);
+        w->ring_cap = w->cin_cap;
+        w->h_cin = (uint8_t *)mz_cuda_host_alloc(w->ring_cap + 64);
+        if (w->h_cin)
+            memset(w->h_cin + w->ring_cap, 0, 64); /* the pad uploaded behind the window; never written again */
         w->d_cin = (uint8_t *)mz_cuda_malloc(w->cin_cap + 64);
         w->d_win = (uint8_t *)mz_cuda_malloc(w->win_cap + 512);
         w->h_dec = (uint8_t *)mz_cuda_host_alloc(batch);
@@ -282,8 +287,11 @@ typedef struct mz_stream_cuda_s {
     int8_t hdr_parsed, ended, base_eof;
     int wrap;           /* 0 raw, 1 zlib, 2 gzip */
     int64_t hdr_size;   /* framing bytes before the raw stream */
-    uint64_t cin_base;  /* raw-stream offset of ws->h_cin[0] */
-    size_t cin_len;     /* valid bytes in ws->h_cin */
+    uint64_t cin_base;  /* raw-stream offset of the first byte of the compressed window */
+    size_t cin_len;     /* bytes in the window (what the kernels see: d_cin[0 .. cin_len)) */
+    size_t cin_off;     /* where the window starts in the ring ws->h_cin */
+    size_t ahead_len;   /* bytes read from base beyond the window (behind it in the ring), not yet uploaded */
+    int8_t ahead_force; /* MZ_CUDA_READ_AHEAD=2: read ahead whether or not the round is still running (tests: on the emulator it never is) */
     uint64_t win_base;  /* output offset of byte 0 of the window being decoded into */
     int dwin, lwin;     /* which window (0 = ws->d_win, 1 = ws->d_win2) is decoded into / delivered from */
     uint64_t lwin_base; /* output offset of byte 0 of the delivery window, while it is not the decode window */
@@ -298,7 +306,7 @@ typedef struct mz_stream_cuda_s {
     int8_t cin_dirty;   /* ws->h_cin changed since the last upload */
     /* MZ_CUDA_TRACE: where the caller's thread spent its time on the read path (ns), printed by close() */
     int8_t trace;
-    uint64_t t_base, t_move, t_round, t_piece, t_serial, t_copy, n_round, n_serial;
+    uint64_t t_base, t_move, t_round, t_piece, t_serial, t_copy, t_ahead, n_round, n_serial, n_ahead, n_wrap;
 } mz_stream_cuda;
 
 /* ---- copying decoded bytes to the caller --------------------------------------------------------------------------
@@ -466,6 +474,11 @@ int32_t mz_stream_cuda_open(void *stream, const char *path, int32_t mode) {
     cu->hdr_size = 0;
     cu->cin_base = 0;
     cu->cin_len = 0;
+    cu->cin_off = cu->ahead_len = 0;
+    {
+        const char *ra = getenv("MZ_CUDA_READ_AHEAD"); /* 0 = off, 1 = while a round is in flight (default), 2 = always (tests) */
+        cu->ahead_force = ra ? (ra[0] == '2' ? 1 : (ra[0] == '0' ? -1 : 0)) : 0;
+    }
     cu->win_base = 0;
     cu->dwin = cu->lwin = 0;
     cu->lwin_base = cu->lwin_end = 0;
@@ -477,7 +490,7 @@ int32_t mz_stream_cuda_open(void *stream, const char *path, int32_t mode) {
     cu->ratio_est = 4.0;
     cu->cin_dirty = 1;
     cu->trace = getenv("MZ_CUDA_TRACE") != NULL || getenv("MZ_CUDA_READ_STATS") != NULL; /* (TRACE also serialises the K6 kernels to time them) */
-    cu->t_base = cu->t_move = cu->t_round = cu->t_piece = cu->t_serial = cu->t_copy = cu->n_round = cu->n_serial = 0;
+    cu->t_base = cu->t_move = cu->t_round = cu->t_piece = cu->t_serial = cu->t_copy = cu->t_ahead = cu->n_round = cu->n_serial = cu->n_ahead = cu->n_wrap = 0;
     cu->initialized = 1;
     cu->mode = mode;
     return MZ_OK;
@@ -714,29 +727,76 @@ fail:
 /* ---- read side ------------------------------------------------------------------------------------------ */
 #ifndef MZ_ZIP_NO_DECOMPRESSION
 /* pull more compressed bytes from base into the pinned window; honours TOTAL_IN_MAX (mz_strm_zlib.c:140-144) */
+/* ring position of byte x of the compressed window (x may run past cin_len into the read-ahead bytes) */
+static inline size_t cu_ring_pos(const mz_stream_cuda *cu, size_t x) { return (cu->cin_off + x) % cu->ws->ring_cap; }
+
+/* one bounded read from base to ring offset x (relative to the window start): <= 1 MiB like the reference asks in bounded pieces,
+ * clipped by TOTAL_IN_MAX and by the end of the ring. Returns bytes read, 0 at the end of base (base_eof is set), < 0 on error. */
+static int32_t cu_base_read_at(mz_stream_cuda *cu, size_t x, size_t room) {
+    cu_ws *w = cu->ws;
+    const size_t p = cu_ring_pos(cu, x);
+    int64_t want = (int64_t)room;
+    if (want > (1 << 20))
+        want = 1 << 20;
+    if (want > (int64_t)(w->ring_cap - p))
+        want = (int64_t)(w->ring_cap - p);
+    if (cu->max_total_in > 0 && want > cu->max_total_in - (int64_t)cu->fed_in)
+        want = cu->max_total_in - (int64_t)cu->fed_in;
+    if (want <= 0) {
+        cu->base_eof = 1;
+        return 0;
+    }
+    int32_t got = mz_abi_base_read(cu->stream.base, w->h_cin + p, (int32_t)want);
+    if (got < 0)
+        return got;
+    if (got == 0) {
+        cu->base_eof = 1;
+        return 0;
+    }
+    cu->fed_in += (uint64_t)got;
+    return got;
+}
+
+/* top the compressed window up: first with the bytes already read ahead (they lie right behind it in the ring), then from base */
 static int32_t cu_refill(mz_stream_cuda *cu) {
     cu_ws *w = cu->ws;
-    while (cu->cin_len < w->cin_cap && !cu->base_eof) {
-        int64_t want = (int64_t)(w->cin_cap - cu->cin_len);
-        if (want > (1 << 20))
-            want = 1 << 20; /* like the reference, ask in bounded pieces */
-        if (cu->max_total_in > 0 && want > cu->max_total_in - (int64_t)cu->fed_in)
-            want = cu->max_total_in - (int64_t)cu->fed_in;
-        if (want <= 0) {
-            cu->base_eof = 1;
-            break;
-        }
+    if (cu->ahead_len && cu->cin_len < w->cin_cap) {
+        size_t take = w->cin_cap - cu->cin_len;
+        if (take > cu->ahead_len)
+            take = cu->ahead_len;
+        cu->cin_len += take;
+        cu->ahead_len -= take;
+        cu->cin_dirty = 1;
+    }
+    while (cu->cin_len < w->cin_cap && !cu->base_eof && cu->ahead_len == 0) {
         int32_t got;
-        CU_TIMED(cu, t_base, got = mz_abi_base_read(cu->stream.base, w->h_cin + cu->cin_len, (int32_t)want));
+        CU_TIMED(cu, t_base, got = cu_base_read_at(cu, cu->cin_len, w->cin_cap - cu->cin_len));
         if (got < 0)
             return got;
-        if (got == 0) {
-            cu->base_eof = 1;
+        if (got == 0)
             break;
-        }
         cu->cin_len += (size_t)got;
-        cu->fed_in += (uint64_t)got;
         cu->cin_dirty = 1;
+    }
+    return MZ_OK;
+}
+
+/* While a round is in flight the caller's thread has nothing to do but wait: pull the bytes the NEXT window will need from
+ * base meanwhile (into the part of the ring behind the window; the upload of the window in flight is long done -- its round
+ * has started). Stops as soon as the round has finished, the ring is full or base is at its end. */
+static int32_t cu_read_ahead(mz_stream_cuda *cu) {
+    cu_ws *w = cu->ws;
+    while (!cu->base_eof && cu->cin_len + cu->ahead_len + 4096 <= w->ring_cap && cu->ahead_len < w->cin_cap) {
+        if (!cu->ahead_force && mz_cuda_event_query(w->rev) != 0)
+            break;
+        int32_t got;
+        CU_TIMED(cu, t_ahead, got = cu_base_read_at(cu, cu->cin_len + cu->ahead_len, w->ring_cap - cu->cin_len - cu->ahead_len));
+        if (got < 0)
+            return got;
+        if (got == 0)
+            break;
+        cu->ahead_len += (size_t)got;
+        cu->n_ahead += (uint64_t)got;
     }
     return MZ_OK;
 }
@@ -744,7 +804,7 @@ static int32_t cu_refill(mz_stream_cuda *cu) {
 /* gzip / zlib framing in front of the raw stream (what inflateInit2's windowBits selects, :97) */
 static int32_t cu_parse_header(mz_stream_cuda *cu) {
     cu_ws *w = cu->ws;
-    const uint8_t *p = w->h_cin;
+    const uint8_t *p = w->h_cin + cu->cin_off; /* the first window starts at the ring's byte 0: contiguous */
     size_t n = cu->cin_len, i;
     if (cu->wrap == 0) {
         cu->hdr_size = 0;
@@ -781,8 +841,8 @@ static int32_t cu_parse_header(mz_stream_cuda *cu) {
             return MZ_BUF_ERROR;
         cu->hdr_size = (int64_t)i;
     }
-    /* drop the framing: h_cin[0] becomes raw-stream byte 0 */
-    memmove(w->h_cin, w->h_cin + cu->hdr_size, cu->cin_len - (size_t)cu->hdr_size);
+    /* drop the framing: the window starts at raw-stream byte 0 */
+    cu->cin_off = cu_ring_pos(cu, (size_t)cu->hdr_size);
     cu->cin_len -= (size_t)cu->hdr_size;
     cu->cin_base = 0;
     cu->hdr_parsed = 1;
@@ -792,7 +852,8 @@ static int32_t cu_parse_header(mz_stream_cuda *cu) {
 
 /* A stream that fills the first (small) compressed window is a long one: switch the workspace to big windows and
  * give it the scratch memory of the segment-speculative decoder (K6). Called before the first byte is decoded. */
-static void ws_read_upgrade(cu_ws *w, size_t cin_len) {
+static void ws_read_upgrade(mz_stream_cuda *cu) {
+    cu_ws *w = cu->ws;
     const char *off = getenv("MZ_CUDA_SPEC");
     if (off && off[0] == '0')
         return;
@@ -805,7 +866,8 @@ static void ws_read_upgrade(cu_ws *w, size_t cin_len) {
     uint32_t max_seg = (uint32_t)(cin_cap / seg) + 1;
     if (max_seg > 12288) /* K6c keeps 16 bytes of shared memory per segment */
         max_seg = 12288;
-    uint8_t *h_cin = (uint8_t *)mz_cuda_host_alloc(cin_cap + 64);
+    const size_t ring_cap = 2 * cin_cap; /* window + as much again read ahead while a round is in flight */
+    uint8_t *h_cin = (uint8_t *)mz_cuda_host_alloc(ring_cap + 64);
     uint8_t *d_cin = (uint8_t *)mz_cuda_malloc(cin_cap + 64);
     uint8_t *d_win = (uint8_t *)mz_cuda_malloc(win_cap + 512);
     uint8_t *d_win2 = (uint8_t *)mz_cuda_malloc(win_cap + 512); /* (optional: without it rounds simply wait for the delivery) */
@@ -822,7 +884,13 @@ static void ws_read_upgrade(cu_ws *w, size_t cin_len) {
         mz_cuda_free(d_sum);
         return;
     }
-    memcpy(h_cin, w->h_cin, cin_len);
+    {
+        const size_t n = cu->cin_len + cu->ahead_len, n1 = n < w->ring_cap - cu->cin_off ? n : w->ring_cap - cu->cin_off;
+        memcpy(h_cin, w->h_cin + cu->cin_off, n1);
+        memcpy(h_cin + n1, w->h_cin, n - n1);
+        memset(h_cin + ring_cap, 0, 64);
+        cu->cin_off = 0;
+    }
     mz_cuda_host_free(w->h_cin);
     mz_cuda_free(w->d_cin);
     mz_cuda_free(w->d_win);
@@ -835,6 +903,7 @@ static void ws_read_upgrade(cu_ws *w, size_t cin_len) {
     mz_cuda_free(w->d_win2);
     w->d_win2 = d_win2;
     w->cin_cap = cin_cap;
+    w->ring_cap = ring_cap;
     w->win_cap = win_cap;
     w->d_spec = d_spec;
     w->spec_max_seg = max_seg;
@@ -895,7 +964,7 @@ static int32_t cu_finish_stream(mz_stream_cuda *cu) {
         size_t off = (size_t)(raw_bytes - cu->cin_base);
         if (off + tsize > cu->cin_len) {
             /* trailer not in the window yet: slide and pull */
-            memmove(w->h_cin, w->h_cin + off, cu->cin_len - off);
+            cu->cin_off = cu_ring_pos(cu, off);
             cu->cin_len -= off;
             cu->cin_base += off;
             cu->cin_dirty = 1;
@@ -908,7 +977,9 @@ static int32_t cu_finish_stream(mz_stream_cuda *cu) {
                 return MZ_BUF_ERROR;
             }
         }
-        const uint8_t *t = w->h_cin + off;
+        uint8_t t[8];
+        for (size_t i = 0; i < (size_t)tsize; i++)
+            t[i] = w->h_cin[cu_ring_pos(cu, off + i)];
         if (cu->wrap == 2) {
             uint32_t crc = t[0] | (t[1] << 8) | (t[2] << 16) | ((uint32_t)t[3] << 24);
             uint32_t isz = t[4] | (t[5] << 8) | (t[6] << 16) | ((uint32_t)t[7] << 24);
@@ -935,7 +1006,7 @@ static int32_t cu_prepare_input(mz_stream_cuda *cu) {
         size_t drop = (size_t)(pos_byte - cu->cin_base);
         if (drop > cu->cin_len)
             drop = cu->cin_len;
-        CU_TIMED(cu, t_move, memmove(w->h_cin, w->h_cin + drop, cu->cin_len - drop));
+        cu->cin_off = cu_ring_pos(cu, drop); /* (a ring: nothing moves) */
         cu->cin_len -= drop;
         cu->cin_base += drop;
         cu->cin_dirty = 1;
@@ -944,8 +1015,14 @@ static int32_t cu_prepare_input(mz_stream_cuda *cu) {
     if (err != MZ_OK)
         return err;
     if (cu->cin_dirty) {
-        memset(w->h_cin + cu->cin_len, 0, 64); /* the kernels may read a few bytes past the end */
-        err = mz_cuda_memcpy_h2d(w->d_cin, w->h_cin, cu->cin_len + 64, w->rstream);
+        /* the window, in one or two pieces, and 64 zero bytes behind it (the kernels may read a few bytes past the end) */
+        const size_t n1 = cu->cin_len < w->ring_cap - cu->cin_off ? cu->cin_len : w->ring_cap - cu->cin_off;
+        err = n1 ? mz_cuda_memcpy_h2d(w->d_cin, w->h_cin + cu->cin_off, n1, w->rstream) : 0;
+        if (!err && cu->cin_len > n1) {
+            err = mz_cuda_memcpy_h2d(w->d_cin + n1, w->h_cin, cu->cin_len - n1, w->rstream);
+            cu->n_wrap += 1;
+        }
+        if (!err) err = mz_cuda_memcpy_h2d(w->d_cin + cu->cin_len, w->h_cin + w->ring_cap, 64, w->rstream);
         if (err)
             return err;
         cu->cin_dirty = 0;
@@ -1134,7 +1211,7 @@ static int32_t cu_decode_more(mz_stream_cuda *cu) {
             return err;
         cu->cin_dirty = 1;
         if (!w->large && cu->cin_len + (size_t)cu->hdr_size >= w->cin_cap && !cu->base_eof)
-            ws_read_upgrade(w, cu->cin_len);
+            ws_read_upgrade(cu);
     }
     for (;;) {
         /* 1. deliver what is already decoded. h_dec is two halves: the piece the caller is copying out of one half has its
@@ -1203,6 +1280,11 @@ static int32_t cu_decode_more(mz_stream_cuda *cu) {
         }
         /* 2. a round in flight: its result decides what comes next */
         if (w->pending) {
+            if (w->ring_cap > w->cin_cap && cu->ahead_force >= 0) {
+                err = cu_read_ahead(cu);
+                if (err < 0)
+                    return err;
+            }
             err = cu_spec_collect(cu);
             if (err < 0)
                 return err;
@@ -1390,9 +1472,9 @@ int32_t mz_stream_cuda_close(void *stream) {
         return MZ_SUPPORT_ERROR;
 #endif
         if (cu->trace)
-            fprintf(stderr, "mz_strm_cuda: read side, caller's thread (ms): base reads %.1f, window moves %.1f, waiting for speculative rounds %.1f (%llu), "
+            fprintf(stderr, "mz_strm_cuda: read side, caller's thread (ms): base reads %.1f (+ %.1f for %llu bytes read ahead under rounds in flight; %llu window uploads wrapped), waiting for speculative rounds %.1f (%llu), "
                             "for serial K5 steps %.1f (%llu), for output pieces %.1f, copying to the caller %.1f; %lld bytes out\n",
-                    cu->t_base / 1e6, cu->t_move / 1e6, cu->t_round / 1e6, (unsigned long long)cu->n_round, cu->t_serial / 1e6,
+                    cu->t_base / 1e6, cu->t_ahead / 1e6, (unsigned long long)cu->n_ahead, (unsigned long long)cu->n_wrap, cu->t_round / 1e6, (unsigned long long)cu->n_round, cu->t_serial / 1e6,
                     (unsigned long long)cu->n_serial, cu->t_piece / 1e6, cu->t_copy / 1e6, (long long)cu->total_out);
     }
     if (cu->ws) {

@@ -412,6 +412,7 @@ typedef struct za_slot_s {
     uint64_t *h_coff, *d_coff, *h_clen, *d_clen;
     pthread_t th;
     int running;
+    int has_aes; /* the AES buffers exist (pool matching) */
 } za_slot;
 
 static void put16(uint8_t *p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); }
@@ -467,6 +468,7 @@ static void za_free(za_slot *z) {
 
 static int za_alloc(za_slot *z, size_t round_bytes, uint32_t max_chunks, size_t blob_cap, int aes) {
     memset(z, 0, sizeof(*z));
+    z->has_aes = aes;
     if (!zc_alloc(&z->b, round_bytes, max_chunks, 0))
         return 0;
     z->blob_cap = blob_cap;
@@ -508,6 +510,77 @@ static int za_alloc(za_slot *z, size_t round_bytes, uint32_t max_chunks, size_t 
         return 0;
     }
     return 1;
+}
+
+/* Staging pool: a slot is ~130 MiB of page-locked and ~200 MiB of device memory, and making four of them costs more than half a
+ * second -- as much as compressing 2 GiB. A process that writes archive after archive keeps up to eight idle slots (per device,
+ * matched by capacity); MZ_CUDA_ZIP_POOL=0 turns the pool off, mz_zip_cuda_trim() empties it. */
+#define ZA_POOL_MAX 8
+static pthread_mutex_t g_za_mu = PTHREAD_MUTEX_INITIALIZER;
+static za_slot g_za_pool[ZA_POOL_MAX];
+static int g_za_n;
+
+static int za_pool_enabled(void) {
+    const char *v = getenv("MZ_CUDA_ZIP_POOL");
+    return !(v && v[0] == '0');
+}
+
+static int za_acquire(za_slot *z, int32_t dev, size_t round_bytes, uint32_t max_chunks, size_t blob_cap, int aes) {
+    int hit = 0;
+    pthread_mutex_lock(&g_za_mu);
+    for (int i = 0; i < g_za_n; i++) {
+        const za_slot *q = &g_za_pool[i];
+        if (q->device == dev && q->b.round_bytes >= round_bytes && q->b.max_chunks >= max_chunks && q->blob_cap >= blob_cap && (q->has_aes || !aes)) {
+            *z = *q;
+            g_za_pool[i] = g_za_pool[--g_za_n];
+            hit = 1;
+            break;
+        }
+    }
+    pthread_mutex_unlock(&g_za_mu);
+    if (hit) {
+        z->items = NULL;
+        z->first = z->last = z->nch = 0;
+        z->err = 0;
+        z->region_len = 0;
+        z->pack_ms = z->gpu_ms = 0;
+        z->running = 0;
+        z->password = NULL;
+        return 1;
+    }
+    if (!za_alloc(z, round_bytes, max_chunks, blob_cap, aes))
+        return 0;
+    z->device = dev;
+    return 1;
+}
+
+static void za_release(za_slot *z) {
+    int kept = 0;
+    if (z->b.h_in && za_pool_enabled()) {
+        pthread_mutex_lock(&g_za_mu);
+        if (g_za_n < ZA_POOL_MAX) {
+            g_za_pool[g_za_n++] = *z;
+            kept = 1;
+        }
+        pthread_mutex_unlock(&g_za_mu);
+    }
+    if (kept)
+        memset(z, 0, sizeof(*z));
+    else
+        za_free(z);
+}
+
+void mz_zip_cuda_trim(void) {
+    const int32_t dev0 = mz_cuda_get_device();
+    pthread_mutex_lock(&g_za_mu);
+    for (int i = 0; i < g_za_n; i++) {
+        mz_cuda_set_device(g_za_pool[i].device);
+        za_free(&g_za_pool[i]);
+    }
+    g_za_n = 0;
+    pthread_mutex_unlock(&g_za_mu);
+    if (dev0 >= 0)
+        mz_cuda_set_device(dev0);
 }
 
 /* the hash extra field of an entry (40 bytes) -- the bytes mz_zip_writer_entry_close assembles (mz_zip_rw.c:1398-1408) */
@@ -811,7 +884,7 @@ int32_t mz_zip_cuda_write_archive_aes(void *base_stream, const mz_cuda_zip_item 
     }
     for (uint32_t k = 0; k < nslots && err == MZ_OK; k++) {
         const int32_t dev = ndev > 1 ? (int32_t)(k % (uint32_t)ndev) : dev0;
-        if (mz_cuda_set_device(dev) != MZ_OK || !za_alloc(&slots[k], round_bytes, max_chunks + 1, max_blob, aes)) {
+        if (mz_cuda_set_device(dev) != MZ_OK || !za_acquire(&slots[k], dev, round_bytes, max_chunks + 1, max_blob, aes)) {
             err = MZ_MEM_ERROR;
             break;
         }
@@ -950,7 +1023,7 @@ int32_t mz_zip_cuda_write_archive_aes(void *base_stream, const mz_cuda_zip_item 
     const double t_setup1 = now_ms();
     for (uint32_t k = 0; k < nslots; k++) {
         mz_cuda_set_device(slots[k].device);
-        za_free(&slots[k]);
+        za_release(&slots[k]);
     }
     mz_cuda_set_device(dev0);
     st.setup_ms += now_ms() - t_setup1;

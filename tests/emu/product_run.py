@@ -108,6 +108,23 @@ def scenario_long():
     assert out == text and info["total_in"] == len(comp)
 
 
+def scenario_ring():
+    """the compressed window as a ring with read-ahead (MZ_CUDA_READ_AHEAD=2: bytes are pulled from base behind the window whether
+    or not a round is in flight -- on the emulator a launch has always finished): many wraps of a small ring, the trailer found
+    across a wrap, TOTAL_IN_MAX honoured by the read-ahead (bytes behind the member are never touched), truncation reported"""
+    text = datagen.text_like(8_000_000, 21) + datagen.random_bytes(400_000, 5) + datagen.text_like(4_000_000, 22)
+    for level, rsize in ((6, 300_000), (1, 65536)):
+        comp = gz(text, level, 31)
+        assert len(comp) > (4 << 20)
+        out, info = tl.decompress(CREATE, comp, len(text), window_bits=31, read_size=rsize)
+        assert info["read"] == len(text) and out == text and info["total_in"] == len(comp) and info["close"] == 0, info
+        junk = comp + datagen.random_bytes(1_500_000, 6)
+        out, info = tl.decompress(CREATE, junk, len(text), window_bits=31, read_size=rsize, total_in_max=len(comp))
+        assert out == text and info["total_in"] == len(comp) and info["base_tell"] == len(comp) and info["close"] == 0, info
+        out, info = tl.decompress(CREATE, comp[:len(comp) - 100_000], len(text), window_bits=31, read_size=rsize)
+        assert info["error"] == p.MZ_BUF_ERROR and info["read_again"] == p.MZ_BUF_ERROR and info["total_out"] > len(text) // 2, info
+
+
 def scenario_crc():
     data = datagen.random_bytes(3_000_001, 9)
     buf = C.create_string_buffer(data, len(data))
@@ -204,6 +221,8 @@ if __name__ == "__main__":
         scenario_read(os.environ.get("MZ_CUDA_SPEC", "1"))
     elif name == "long":
         scenario_long()
+    elif name == "ring":
+        scenario_ring()
     elif name == "crc":
         scenario_crc()
     elif name == "sharded":

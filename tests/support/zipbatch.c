@@ -247,71 +247,79 @@ int main(int argc, char **argv) {
     }
     double t_gen = now_s() - t0;
 
-    /* file <- buffered stream <- zip, as the reference's own writer stacks them (mz_zip_rw.c:1205-1222) */
-    void *file_stream = mz_stream_os_create();
-    void *stream = mz_stream_buffered_create();
-    void *zip = mz_zip_create();
-    mz_stream_set_base(stream, file_stream);
-    if (use_native) { /* the native writer hands over whole rounds (tens of MiB per call): no 32 KiB buffering layer in between */
-        mz_stream_buffered_delete(&stream);
-        stream = file_stream;
-    }
-    int32_t err = mz_stream_open(stream, path, MZ_OPEN_MODE_CREATE | MZ_OPEN_MODE_WRITE);
-    if (err == MZ_OK && !use_native) err = mz_zip_open(zip, stream, MZ_OPEN_MODE_WRITE);
-    if (err != MZ_OK) { fprintf(stderr, "open failed %d\n", err); return 5; }
-    mz_cuda_zip_stats st;
-    memset(&st, 0, sizeof(st));
-    uint64_t bytes_in = 0;
-    /* CUDA context creation (a few hundred ms, once per process) is reported on its own, not inside the throughput figure */
-    t0 = now_s();
-    if (use_native || use_cuda) zb_cuda_warm();
-    const double t_init = now_s() - t0;
-    t0 = now_s();
-    if (use_native) {
-        err = (native_flags & MZ_ZIP_CUDA_AES) ? mz_zip_cuda_write_archive_aes(stream, items, n, level, native_flags, password, 0, &st)
-                                               : mz_zip_cuda_write_archive(stream, items, n, level, native_flags, &st);
-        bytes_in = st.bytes_in;
-    } else if (use_cuda) {
-        err = mz_zip_cuda_add_buffers_ex(zip, items, n, level, use_sha ? MZ_ZIP_CUDA_HASH_SHA256 : 0u, &st);
-        bytes_in = st.bytes_in;
-    } else {
-        for (uint32_t i = 0; i < n && err == MZ_OK; i++) {
-            mz_zip_file fi;
-            memset(&fi, 0, sizeof(fi));
-            fi.version_madeby = MZ_VERSION_MADEBY;
-            fi.flag = MZ_ZIP_FLAG_UTF8;
-            fi.compression_method = MZ_COMPRESS_METHOD_DEFLATE;
-            fi.modified_date = 1700000000;
-            fi.filename = items[i].filename;
-            fi.uncompressed_size = items[i].size;
-            err = mz_zip_entry_write_open(zip, &fi, level, 0, NULL);
-            int64_t done = 0;
-            while (err == MZ_OK && done < items[i].size) { /* the reference's writers feed <= 64 KiB at a time (mz_zip_rw.c:1424) */
-                int32_t piece = items[i].size - done > 65536 ? 65536 : (int32_t)(items[i].size - done);
-                int32_t w = mz_zip_entry_write(zip, (const uint8_t *)items[i].data + done, piece);
-                if (w != piece) err = w < 0 ? w : MZ_WRITE_ERROR;
-                done += piece;
-            }
-            if (err == MZ_OK) err = mz_zip_entry_close(zip);
-            bytes_in += (uint64_t)items[i].size;
+    /* ZIPBATCH_REPEAT=N: write the archive N times in this process, one JSON line each (a long-lived writer: the library keeps its
+     * staging between calls; bench.py's warm-up and timed steps) */
+    const int repeat = getenv("ZIPBATCH_REPEAT") && atoi(getenv("ZIPBATCH_REPEAT")) > 0 ? atoi(getenv("ZIPBATCH_REPEAT")) : 1;
+    int rc = 0;
+    for (int rep = 0; rep < repeat && rc == 0; rep++) {
+        /* file <- buffered stream <- zip, as the reference's own writer stacks them (mz_zip_rw.c:1205-1222) */
+        void *file_stream = mz_stream_os_create();
+        void *stream = mz_stream_buffered_create();
+        void *zip = mz_zip_create();
+        mz_stream_set_base(stream, file_stream);
+        if (use_native) { /* the native writer hands over whole rounds (tens of MiB per call): no 32 KiB buffering layer in between */
+            mz_stream_buffered_delete(&stream);
+            stream = file_stream;
         }
+        int32_t err = mz_stream_open(stream, path, MZ_OPEN_MODE_CREATE | MZ_OPEN_MODE_WRITE);
+        if (err == MZ_OK && !use_native) err = mz_zip_open(zip, stream, MZ_OPEN_MODE_WRITE);
+        if (err != MZ_OK) { fprintf(stderr, "open failed %d\n", err); return 5; }
+        mz_cuda_zip_stats st;
+        memset(&st, 0, sizeof(st));
+        uint64_t bytes_in = 0;
+        /* CUDA context creation (a few hundred ms, once per process) is reported on its own, not inside the throughput figure */
+        t0 = now_s();
+        if (use_native || use_cuda) zb_cuda_warm();
+        const double t_init = now_s() - t0;
+        t0 = now_s();
+        if (use_native) {
+            err = (native_flags & MZ_ZIP_CUDA_AES) ? mz_zip_cuda_write_archive_aes(stream, items, n, level, native_flags, password, 0, &st)
+                                                   : mz_zip_cuda_write_archive(stream, items, n, level, native_flags, &st);
+            bytes_in = st.bytes_in;
+        } else if (use_cuda) {
+            err = mz_zip_cuda_add_buffers_ex(zip, items, n, level, use_sha ? MZ_ZIP_CUDA_HASH_SHA256 : 0u, &st);
+            bytes_in = st.bytes_in;
+        } else {
+            for (uint32_t i = 0; i < n && err == MZ_OK; i++) {
+                mz_zip_file fi;
+                memset(&fi, 0, sizeof(fi));
+                fi.version_madeby = MZ_VERSION_MADEBY;
+                fi.flag = MZ_ZIP_FLAG_UTF8;
+                fi.compression_method = MZ_COMPRESS_METHOD_DEFLATE;
+                fi.modified_date = 1700000000;
+                fi.filename = items[i].filename;
+                fi.uncompressed_size = items[i].size;
+                err = mz_zip_entry_write_open(zip, &fi, level, 0, NULL);
+                int64_t done = 0;
+                while (err == MZ_OK && done < items[i].size) { /* the reference's writers feed <= 64 KiB at a time (mz_zip_rw.c:1424) */
+                    int32_t piece = items[i].size - done > 65536 ? 65536 : (int32_t)(items[i].size - done);
+                    int32_t w = mz_zip_entry_write(zip, (const uint8_t *)items[i].data + done, piece);
+                    if (w != piece) err = w < 0 ? w : MZ_WRITE_ERROR;
+                    done += piece;
+                }
+                if (err == MZ_OK) err = mz_zip_entry_close(zip);
+                bytes_in += (uint64_t)items[i].size;
+            }
+        }
+        double t_add = now_s() - t0;
+        t0 = now_s();
+        int32_t cerr = use_native ? MZ_OK : mz_zip_close(zip);
+        mz_stream_close(stream);
+        double t_close = now_s() - t0;
+        mz_zip_delete(&zip);
+        if (stream != file_stream)
+            mz_stream_buffered_delete(&stream);
+        mz_stream_os_delete(&file_stream);
+        printf("{\"mode\": \"%s\", \"entries\": %u, \"entry_bytes\": %zu, \"level\": %d, \"err\": %d, \"close_err\": %d, \"bytes_in\": %llu, "
+               "\"bytes_out\": %llu, \"gen_s\": %.3f, \"add_s\": %.4f, \"close_s\": %.4f, \"entries_per_s\": %.0f, \"GiB_per_s\": %.3f, "
+               "\"pack_ms\": %.1f, \"gpu_ms\": %.1f, \"container_ms\": %.1f, \"setup_ms\": %.1f, \"cuda_init_s\": %.3f, \"rounds\": %u}\n",
+               use_native ? argv[5] : (use_cuda ? "cuda" : "ref"), n, esz, level, err, cerr, (unsigned long long)bytes_in, (unsigned long long)st.bytes_out, t_gen, t_add,
+               t_close, n / (t_add + t_close), (double)bytes_in / (1ull << 30) / (t_add + t_close), st.pack_ms, st.gpu_ms, st.container_ms, st.setup_ms, t_init, st.rounds);
+        fflush(stdout);
+        rc = err == MZ_OK && cerr == MZ_OK ? 0 : 1;
     }
-    double t_add = now_s() - t0;
-    t0 = now_s();
-    int32_t cerr = use_native ? MZ_OK : mz_zip_close(zip);
-    mz_stream_close(stream);
-    double t_close = now_s() - t0;
-    mz_zip_delete(&zip);
-    if (stream != file_stream)
-        mz_stream_buffered_delete(&stream);
-    mz_stream_os_delete(&file_stream);
-    printf("{\"mode\": \"%s\", \"entries\": %u, \"entry_bytes\": %zu, \"level\": %d, \"err\": %d, \"close_err\": %d, \"bytes_in\": %llu, "
-           "\"bytes_out\": %llu, \"gen_s\": %.3f, \"add_s\": %.4f, \"close_s\": %.4f, \"entries_per_s\": %.0f, \"GiB_per_s\": %.3f, "
-           "\"pack_ms\": %.1f, \"gpu_ms\": %.1f, \"container_ms\": %.1f, \"setup_ms\": %.1f, \"cuda_init_s\": %.3f, \"rounds\": %u}\n",
-           use_native ? argv[5] : (use_cuda ? "cuda" : "ref"), n, esz, level, err, cerr, (unsigned long long)bytes_in, (unsigned long long)st.bytes_out, t_gen, t_add,
-           t_close, n / (t_add + t_close), (double)bytes_in / (1ull << 30) / (t_add + t_close), st.pack_ms, st.gpu_ms, st.container_ms, st.setup_ms, t_init, st.rounds);
     free(data);
     free(names);
     free(items);
-    return err == MZ_OK && cerr == MZ_OK ? 0 : 1;
+    return rc;
 }
