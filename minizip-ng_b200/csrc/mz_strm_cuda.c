@@ -704,7 +704,7 @@ int32_t mz_stream_cuda_write(void *stream, const void *buf, int32_t size) {
         cu_slot *s = &cu->ws->slot[cu->ws->cur];
         size_t room = cu->ws->batch - cu->in_len;
         size_t k = (size_t)left < room ? (size_t)left : room;
-        memcpy(s->h_in + cu->in_len, p, k);
+        cu_copy_out(s->h_in + cu->in_len, p, k); /* (large writes: split over the copy helpers) */
         cu->in_len += k;
         p += k;
         left -= (int32_t)k;
