@@ -830,7 +830,7 @@ def run_c2(args, rank, world, local_rank):
     def step(ev=None):
         if ev:
             ev[0].record(stream)
-        pkg.check(lib.mz_cuda_deflate_chunks(src.data_ptr(), n, 65536, None, None, None, nch, pkg.FLAG_FINAL, args.level, b.slots.data_ptr(), b.stride,
+        pkg.check(lib.mz_cuda_deflate_chunks(src.data_ptr(), n, 65536, None, None, None, nch, pkg.FLAG_FINAL | pkg.FLAG_DICT, args.level, b.slots.data_ptr(), b.stride,
                                              b.out_len.data_ptr(), s), "deflate")
         if ev:
             ev[1].record(stream)

@@ -19,6 +19,9 @@ extern "C" {
 
 #define MZ_CUDA_CHUNK_MAX    65536u /* largest independent DEFLATE chunk */
 #define MZ_CUDA_FLAG_FINAL   1u     /* chunk ends its stream (BFINAL, no sync marker) */
+#define MZ_CUDA_FLAG_DICT    2u     /* the 32 KiB in front of the chunk (same buffer) are earlier bytes of the SAME stream: at levels 6-9 the
+                                    * chunk may refer back into them (zlib's sliding window across our chunk boundaries). In `last_flags` of a
+                                    * uniform partition it applies to every chunk: the buffer is one stream. */
 
 /* ---- runtime ---------------------------------------------------------------------------------- */
 int32_t mz_cuda_init(void);                 /* idempotent, thread-safe; MZ_SUPPORT_ERROR without a usable GPU */
@@ -69,7 +72,9 @@ uint32_t mz_cuda_crc32_combine(uint32_t crc_a, uint32_t crc_b, uint64_t len_b);
  * (slot_stride >= mz_cuda_deflate_slot_bound(chunk size), multiple of 16; d_slots 16-byte aligned);
  * d_out_len[i] = bytes written. Every slot is a byte-aligned piece of raw RFC1951 data: non-final
  * chunks end with a sync-flush marker, chunks flagged FINAL end with BFINAL. Uniform partition when
- * d_off == NULL (then only the last chunk gets `last_flags`). level 0 = stored, 1..9. */
+ * d_off == NULL (then only the last chunk gets the FINAL bit of `last_flags`). level 0 = stored, 1 = candidates at every second
+ * position, 2-3 = every position, 4-5 = + one-step lazy evaluation, 6-9 = + the previous 32 KiB as history (inside a chunk: its
+ * first half for its second; with MZ_CUDA_FLAG_DICT also the bytes in front of the chunk). */
 uint64_t mz_cuda_deflate_slot_bound(uint32_t chunk_size);
 int32_t mz_cuda_deflate_chunks(const void *d_in, uint64_t total_len, uint32_t chunk_size, const uint64_t *d_off,
                                const uint32_t *d_len, const uint8_t *d_flags, uint32_t nchunks, uint32_t last_flags,

@@ -23,6 +23,7 @@ MZ_STREAM_PROP_TOTAL_IN, MZ_STREAM_PROP_TOTAL_IN_MAX, MZ_STREAM_PROP_TOTAL_OUT =
 MZ_STREAM_PROP_COMPRESS_LEVEL, MZ_STREAM_PROP_COMPRESS_WINDOW = 9, 11
 CHUNK_MAX = 65536
 FLAG_FINAL = 1
+FLAG_DICT = 2  # the buffer is ONE stream: at levels 6-9 a chunk may refer back into the 32 KiB before it
 
 _lib = None
 
@@ -187,12 +188,12 @@ class DeflateBatch:
     def nchunks(self, nbytes):
         return max(1, (nbytes + self.chunk - 1) // self.chunk)
 
-    def compress(self, src, nbytes, level=1, final=True, join=True):
+    def compress(self, src, nbytes, level=1, final=True, join=True, one_stream=False):
         """Enqueue K2+K3 (+K1 per-chunk CRC and fold) (+K4 join). Returns number of chunks."""
         n = self.nchunks(nbytes)
         assert n <= self.max_chunks and src.is_cuda and src.dtype.itemsize == 1
         s = _stream_ptr()
-        check(self.lib.mz_cuda_deflate_chunks(src.data_ptr(), nbytes, self.chunk, None, None, None, n, FLAG_FINAL if final else 0,
+        check(self.lib.mz_cuda_deflate_chunks(src.data_ptr(), nbytes, self.chunk, None, None, None, n, (FLAG_FINAL if final else 0) | (FLAG_DICT if one_stream else 0),
                                               level, self.slots.data_ptr(), self.stride, self.out_len.data_ptr(), s), "deflate")
         if self.with_crc and nbytes > 0:
             check(self.lib.mz_cuda_crc32_segments(src.data_ptr(), nbytes, self.chunk, None, None, n, self.residue.data_ptr(),

@@ -55,6 +55,8 @@ constexpr int DF_STAGE_WORDS = DF_UNIT / 4 + 64;
 constexpr int DF_HDR_WORDS = 96;
 
 constexpr uint32_t DF_FLAG_FINAL = 1u; /* chunk ends the stream: BFINAL on its last block, no sync marker */
+constexpr uint32_t DF_FLAG_DICT = 2u;  /* the 32 KiB in front of the chunk (same buffer) belong to the same DEFLATE stream: the chunk may refer back
+                                        * into them. Only the history variant of the kernel (levels 6-9) looks at it. */
 
 /* shared-memory carve-up (bytes); two CTAs per SM: <= 113 KiB each */
 constexpr int DF_OFF_IN = 0;
@@ -76,6 +78,16 @@ constexpr int DF_OFF_SINK = DF_OFF_MISC + 32 * 4 + 16;       /* u32[32]: one wor
 constexpr int DF_SMEM_BYTES = DF_OFF_SINK + 32 * 4;
 constexpr uint32_t DF_ZERO_SYM = 286;                        /* literal/length symbol that never occurs: its table entries are all zero */
 static_assert(DF_HASH_ENTRIES * 4 <= DF_STAGE_WORDS * 4, "hash fits the staging region");
+/* The history variant (template parameter HIST, levels 6-9): the previous 32 KiB -- the chunk's first unit, or with DF_FLAG_DICT the
+ * bytes in front of the chunk -- stay resident in FRONT of the unit (offsets -32768 .. -1 relative to the standard carve-up, which is
+ * unchanged) and the hash table, now 2^14 keys that survive from unit to unit, lies BEHIND it instead of under the bit staging:
+ * 32 KiB + DF_SMEM_BYTES + 64 KiB = 208 KiB, one CTA per SM. Positions in the keys and candidates are relative to the start of the
+ * previous unit (0 .. 65535). */
+constexpr int DFH_PREV = 32768;
+constexpr int DFH_HASH_BITS = 14;
+constexpr int DFH_OFF_HASH = (DF_SMEM_BYTES + 15) & ~15;
+constexpr int DFH_SMEM_BYTES = DFH_PREV + DFH_OFF_HASH + (4 << DFH_HASH_BITS);
+static_assert(DFH_SMEM_BYTES <= 227 * 1024, "shared memory budget of the history variant");
 static_assert(DF_SMEM_BYTES <= 113 * 1024, "shared memory budget for two CTAs per SM");
 
 enum { MISC_CHUNK = 3, MISC_CARRY = 8 /* 4 words */ };
@@ -441,13 +453,14 @@ __device__ __forceinline__ uint32_t extend_match8(const Smem &sm, uint32_t c, ui
     return len < maxlen ? len : maxlen;
 }
 
+template <bool HIST>
 __device__ __forceinline__ uint32_t hash_addr(uint32_t v) { /* byte offset of the key of 4-byte value v */
-    return DF_OFF_HASH + (((v * 2654435761u) >> (32 - DF_HASH_BITS)) << 2);
+    return (HIST ? DFH_OFF_HASH : DF_OFF_HASH) + (((v * 2654435761u) >> (32 - (HIST ? DFH_HASH_BITS : DF_HASH_BITS))) << 2);
 }
 
 /* span record (two words, parked in the token region during the parse):
- *   A = j0 | (L0 - 3) << 3 | c0 << 11 | (lit & 63) << 26      first match: start offset, length, candidate position
- *   B = j1 | (L1 - 3) << 3 | c1 << 11 | (lit >> 6) << 26      second match; (L - 3) == 0 means none
+ *   A = j0 | (L0 - 3) << 3 | (d0 - 1) << 11 | (lit & 63) << 26      first match: start offset, length, distance - 1
+ *   B = j1 | (L1 - 3) << 3 | (d1 - 1) << 11 | (lit >> 6) << 26      second match; (L - 3) == 0 means none
  * lit = the span's positions coded as literals. */
 __device__ __forceinline__ uint32_t rec_len(uint32_t r) { uint32_t l = (r >> 3) & 255u; return l ? l + 3 : 0u; }
 
@@ -475,7 +488,7 @@ __device__ __forceinline__ void span_classify(const Smem &sm, uint32_t A, uint32
         const bool strad = L != 0 && j < crel && end > crel;
         const uint32_t rem = end - crel;
         const uint32_t Lf = kept ? L : ((strad && rem >= 3) ? rem : 0u);
-        const uint32_t d1 = q0 + j - ((R >> 11) & 0x7fffu) - 1u;
+        const uint32_t d1 = (R >> 11) & 0x7fffu;
         M[r] = Lf ? (0x80000000u | ((kept ? j : cr8) & 7u) | ((Lf - 3) << 4) | (d1 << 12)) : 0u;
         ex = (strad && rem < 3) ? rem : ex;
     }
@@ -549,9 +562,11 @@ __device__ __forceinline__ uint32_t nth_parked(const uint32_t (&bm)[DF_NBATCH], 
 }
 
 /* ---- the kernel ------------------------------------------------------------------------------- */
-template <int STRIDE, bool LAZY>
-__global__ void __launch_bounds__(DF_THREADS, 2) deflate_chunks_kernel(DeflateParams P) {
-    MZ_DYN_SMEM(smem);
+template <int STRIDE, bool LAZY, bool HIST = false>
+__global__ void __launch_bounds__(DF_THREADS, HIST ? 1 : 2) deflate_chunks_kernel(DeflateParams P) {
+    MZ_DYN_SMEM(smem_raw);
+    uint8_t *const smem = smem_raw + (HIST ? DFH_PREV : 0); /* the standard carve-up; the history variant keeps the previous unit in front of it */
+    constexpr uint32_t CUR = HIST ? (uint32_t)DFH_PREV : 0u; /* position of the unit's byte 0 as keys and candidates count it */
     uint8_t *s_in = smem + DF_OFF_IN;
     uint32_t *s_stage = (uint32_t *)(smem + DF_OFF_STAGE);
     uint32_t *s_hist_ll = (uint32_t *)(smem + DF_OFF_HIST);
@@ -612,8 +627,10 @@ __global__ void __launch_bounds__(DF_THREADS, 2) deflate_chunks_kernel(DeflatePa
             off = (uint64_t)chunk * P.chunk_size;
             uint64_t rem = P.total_len - off;
             len = rem < P.chunk_size ? (uint32_t)rem : P.chunk_size;
-            flags = P.flags ? P.flags[chunk] : (chunk == P.nchunks - 1 ? P.last_flags : 0u);
+            /* last_flags: FINAL belongs to the last chunk; DICT says the whole buffer is one stream, so it holds for every chunk */
+            flags = P.flags ? P.flags[chunk] : ((chunk == P.nchunks - 1 ? P.last_flags & ~DF_FLAG_DICT : 0u) | (P.last_flags & DF_FLAG_DICT));
         }
+        const bool dict = HIST && (flags & DF_FLAG_DICT) && off >= (uint64_t)DFH_PREV;
         uint8_t *gout = P.out + (uint64_t)chunk * P.slot_stride;
 
         uint32_t flushed = 0; /* bytes of this chunk already in global memory (multiple of 16) */
@@ -660,8 +677,32 @@ __global__ void __launch_bounds__(DF_THREADS, 2) deflate_chunks_kernel(DeflatePa
             }
             for (uint32_t i = len16 + tid; i < ulen; i += DF_THREADS) s_in[i] = gin[i];
             for (uint32_t i = ulen + tid; i < ((ulen + 63) & ~15u) + 16 && i < DF_UNIT + 64; i += DF_THREADS) s_in[i] = 0; /* zero pad */
-            if (P.level != 0)
-                for (uint32_t i = tid; i < DF_HASH_ENTRIES / 4; i += DF_THREADS) sm.st128(DF_OFF_HASH + i * 16, ~0u, ~0u, ~0u, ~0u);
+            if (P.level != 0) {
+                if (!HIST) {
+                    for (uint32_t i = tid; i < DF_HASH_ENTRIES / 4; i += DF_THREADS) sm.st128(DF_OFF_HASH + i * 16, ~0u, ~0u, ~0u, ~0u);
+                } else if (u == 0) {
+                    for (uint32_t i = tid; i < (1u << DFH_HASH_BITS) / 4; i += DF_THREADS) sm.st128(DFH_OFF_HASH + i * 16, ~0u, ~0u, ~0u, ~0u);
+                    if (dict) { /* the 32 KiB in front of the chunk become the previous unit */
+                        const uint8_t *gp = P.in + off - DFH_PREV;
+                        if ((((uintptr_t)gp) & 15) == 0) {
+                            for (uint32_t i = tid * 16; i < (uint32_t)DFH_PREV; i += DF_THREADS * 16) *(uint4 *)(smem - DFH_PREV + i) = ldg_stream((const uint4 *)(gp + i));
+                        } else {
+                            for (uint32_t i = tid; i < (uint32_t)DFH_PREV; i += DF_THREADS) smem[(int)i - DFH_PREV] = gp[i];
+                        }
+                    }
+                } else {
+                    /* the table lives on: what was the current unit is the previous one now (position - 32768, batch age + 8);
+                     * what pointed into the unit before that is too far away and goes */
+                    for (uint32_t i = tid; i < (1u << DFH_HASH_BITS) / 4; i += DF_THREADS) {
+                        uint4 e = *(const uint4 *)(smem + DFH_OFF_HASH + i * 16);
+                        e.x = (e.x != ~0u && (e.x & 0xffffu) >= (uint32_t)DFH_PREV) ? e.x + 0x78000u : ~0u;
+                        e.y = (e.y != ~0u && (e.y & 0xffffu) >= (uint32_t)DFH_PREV) ? e.y + 0x78000u : ~0u;
+                        e.z = (e.z != ~0u && (e.z & 0xffffu) >= (uint32_t)DFH_PREV) ? e.z + 0x78000u : ~0u;
+                        e.w = (e.w != ~0u && (e.w & 0xffffu) >= (uint32_t)DFH_PREV) ? e.w + 0x78000u : ~0u;
+                        *(uint4 *)(smem + DFH_OFF_HASH + i * 16) = e;
+                    }
+                }
+            }
 #ifndef MZ_EMU
             if (bulk) {
                 mbar_wait(s_bar, bar_phase);
@@ -669,6 +710,22 @@ __global__ void __launch_bounds__(DF_THREADS, 2) deflate_chunks_kernel(DeflatePa
             }
 #endif
             __syncthreads();
+            if (HIST && P.level != 0 && u == 0 && dict) {
+                /* insert the dictionary's positions: keys (15 - batch) << 16 | position, older than anything the unit will add */
+#pragma unroll 1
+                for (uint32_t b = 0; b < (uint32_t)DF_NBATCH; b++) {
+                    const uint32_t p0 = b * DF_BATCH + tid * DF_SPAN;
+                    const uint2 x = sm.ld64((uint32_t)(DF_OFF_IN - DFH_PREV) + p0);
+                    const uint32_t y = sm.ld32((uint32_t)(DF_OFF_IN - DFH_PREV) + p0 + 8); /* (the last span reads into the unit: loaded above) */
+                    const uint32_t key0 = ((15u - b) << 16) | p0;
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const uint32_t v = j == 0 ? x.x : (j < 4 ? __funnelshift_r(x.x, x.y, 8 * j) : (j == 4 ? x.y : __funnelshift_r(x.y, y, 8 * (j - 4))));
+                        sm.red_min32(hash_addr<true>(v), key0 + j);
+                    }
+                }
+                __syncthreads();
+            }
 
             uint32_t fF[DF_NBATCH], fA[DF_NBATCH];
             bool stored = (P.level == 0);
@@ -693,13 +750,13 @@ __global__ void __launch_bounds__(DF_THREADS, 2) deflate_chunks_kernel(DeflatePa
                     }
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
-                        ha[j] = hash_addr(v[j]);
+                        ha[j] = hash_addr<HIST>(v[j]);
                         if (j % STRIDE == 0) lc[j] = sm.ld32(ha[j]); /* key of the latest earlier batch that holds this hash */
                     }
                     const uint32_t nvalid = ulen > q0 ? (ulen - q0 < 8 ? ulen - q0 : 8u) : 0u;
                     __syncthreads();
                     {
-                        const uint32_t key0 = ((uint32_t)(DF_NBATCH - 1 - b) << 16) | q0;
+                        const uint32_t key0 = ((uint32_t)(DF_NBATCH - 1 - b) << 16) | (CUR + q0);
 #pragma unroll
                         for (int j = 0; j < 8; j++) sm.red_min32(ha[j], (uint32_t)j < nvalid ? key0 + j : 0xffffffffu);
                     }
@@ -711,14 +768,17 @@ __global__ void __launch_bounds__(DF_THREADS, 2) deflate_chunks_kernel(DeflatePa
                             continue;
                         }
                         const uint32_t cn = sm.ld32(ha[j]) & 0xffffu;
-                        const uint32_t c = cn < q0 + j ? cn : (lc[j] & 0xffffu);
-                        const uint32_t ca = DF_OFF_IN + (c & ~3u);
+                        const uint32_t pq = CUR + q0 + j; /* my position as the keys count it */
+                        const uint32_t c = cn < pq ? cn : (lc[j] & 0xffffu);
+                        const uint32_t ca = DF_OFF_IN - CUR + (c & ~3u);
                         const uint32_t w0 = sm.ld32(ca), w1 = sm.ld32(ca + 4), w2 = sm.ld32(ca + 8);
                         const uint32_t s = c << 3;
                         const uint32_t x0 = __funnelshift_r(w0, w1, s) ^ v[j];
                         const uint32_t x1 = __funnelshift_r(w1, w2, s) ^ v[j + 4];
-                        const uint32_t l = (c < q0 + j && x0 == 0) ? 4u + ((uint32_t)__clz((int)__brev(x1)) >> 3) : 0u;
-                        lc[j] = l | (c << 4);
+                        /* (history variant: a candidate more than 32768 back is out of DEFLATE's reach) */
+                        const bool reach = c < pq && (!HIST || c >= q0 + j);
+                        const uint32_t l = (reach && x0 == 0) ? 4u + ((uint32_t)__clz((int)__brev(x1)) >> 3) : 0u;
+                        lc[j] = l | ((pq - c - 1u) << 4); /* length | distance - 1 */
                     }
                     if (q0 + 16 > ulen) { /* unit tail: the zero padding must not be matched */
 #pragma unroll
@@ -779,7 +839,7 @@ __global__ void __launch_bounds__(DF_THREADS, 2) deflate_chunks_kernel(DeflatePa
                             const uint2 r = sm.ld64(DF_OFF_REC + sidx * 8);
                             const bool second = (r.y & 0x03ffffffu) != 0;
                             const uint32_t w = second ? r.y : r.x, last = w & 0x03ffffffu;
-                            const uint32_t j = last & 7u, c = (last >> 11) & 0x7fffu, q = sidx * DF_SPAN + j;
+                            const uint32_t j = last & 7u, q = sidx * DF_SPAN + j, c = q - ((last >> 11) & 0x7fffu) - 1u; /* (wraps below 0: into the previous unit) */
                             uint32_t maxlen = ulen - q;
                             maxlen = maxlen < 258 ? maxlen : 258u;
                             const uint32_t l = extend_match8(sm, c, q, maxlen);
@@ -1067,6 +1127,8 @@ __global__ void __launch_bounds__(DF_THREADS, 2) deflate_chunks_kernel(DeflatePa
                 if (tid < 4) s_misc[MISC_CARRY + tid] = (n16 * 4 + tid < used_words) ? s_stage[n16 * 4 + tid] : 0u;
                 bitpos -= n16 * 128;
                 flushed += n16 * 16;
+                if (HIST && u + 1 < nunits) /* this unit is the next one's history */
+                    for (uint32_t i = tid; i < (uint32_t)DF_UNIT / 16; i += DF_THREADS) *(uint4 *)(smem - DFH_PREV + i * 16) = *(const uint4 *)(s_in + i * 16);
                 __syncthreads();
             }
         }
@@ -1101,6 +1163,8 @@ __global__ void __launch_bounds__(DF_THREADS, 2) deflate_chunks_kernel(DeflatePa
  * inserted), 2..3 = every position, 4..9 = every position + one-step lazy evaluation */
 __host__ __device__ inline int deflate_stride_for_level(int level) { return level <= 1 ? 2 : 1; }
 __host__ __device__ inline bool deflate_lazy_for_level(int level) { return level >= 4; }
+/* 6..9: the history variant (previous 32 KiB as a dictionary, 2^14-key table that survives from unit to unit, one CTA per SM) */
+__host__ __device__ inline bool deflate_hist_for_level(int level) { return level >= 6; }
 
 } // namespace mzc
 #endif

@@ -93,6 +93,7 @@ int32_t get_ctx(DeviceCtx **out) {
             CK(cudaFuncSetAttribute(deflate_chunks_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_SMEM_BYTES));
             CK(cudaFuncSetAttribute(deflate_chunks_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_SMEM_BYTES));
             CK(cudaFuncSetAttribute(deflate_chunks_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DF_SMEM_BYTES));
+            CK(cudaFuncSetAttribute(deflate_chunks_kernel<1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DFH_SMEM_BYTES));
             CK(cudaFuncSetAttribute(crc32_segments_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CRC_SMEM_BYTES));
             CK(cudaFuncSetAttribute(inflate_streams_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, INF_SMEM_BYTES));
             CK(cudaFuncSetAttribute(inflate_spec_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SPEC_RESOLVE_SMEM));
@@ -373,8 +374,12 @@ int32_t mz_cuda_deflate_chunks(const void *d_in, uint64_t total_len, uint32_t ch
         MZ_LAUNCH((deflate_chunks_kernel<2, false>), dim3(grid), dim3(DF_THREADS), DF_SMEM_BYTES, (cudaStream_t)stream, P);
     else if (!deflate_lazy_for_level(level))
         MZ_LAUNCH((deflate_chunks_kernel<1, false>), dim3(grid), dim3(DF_THREADS), DF_SMEM_BYTES, (cudaStream_t)stream, P);
-    else
+    else if (!deflate_hist_for_level(level))
         MZ_LAUNCH((deflate_chunks_kernel<1, true>), dim3(grid), dim3(DF_THREADS), DF_SMEM_BYTES, (cudaStream_t)stream, P);
+    else { /* the history variant: 208 KiB of shared memory, one CTA per SM */
+        const uint32_t grid1 = nchunks < (uint32_t)c->sm_count ? nchunks : (uint32_t)c->sm_count;
+        MZ_LAUNCH((deflate_chunks_kernel<1, true, true>), dim3(grid1), dim3(DF_THREADS), DFH_SMEM_BYTES, (cudaStream_t)stream, P);
+    }
     CK(cudaGetLastError());
     return MZ_OK;
 }

@@ -571,7 +571,7 @@ static int32_t cu_submit(mz_stream_cuda *cu, cu_slot *s, const uint8_t *src, siz
     if (err == MZ_OK)
         err = mz_cuda_event_record(s->ev_h2d, s->stream);
     if (err == MZ_OK)
-        err = mz_cuda_deflate_chunks(s->d_in, n, CU_CHUNK, NULL, NULL, NULL, nchunks, final ? MZ_CUDA_FLAG_FINAL : 0, lvl, s->d_slots,
+        err = mz_cuda_deflate_chunks(s->d_in, n, CU_CHUNK, NULL, NULL, NULL, nchunks, (final ? MZ_CUDA_FLAG_FINAL : 0) | MZ_CUDA_FLAG_DICT /* one stream: chunks see the 32 KiB before them */, lvl, s->d_slots,
                                      w->slot_stride, s->d_out_len, s->stream);
     if (err == MZ_OK)
         err = mz_cuda_concat(s->d_slots, w->slot_stride, s->d_out_len, nchunks, s->d_offsets, s->d_out, s->stream);

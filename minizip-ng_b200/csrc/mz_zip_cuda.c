@@ -184,7 +184,7 @@ static void *zc_prepare(void *arg) {
             const uint32_t n = left > (int64_t)ZC_CHUNK ? ZC_CHUNK : (uint32_t)left;
             b->h_off[nch] = pos + (uint64_t)k * ZC_CHUNK;
             b->h_len[nch] = n;
-            b->h_flags[nch] = k + 1 == c ? 1u : 0u; /* BFINAL on the entry's last chunk */
+            b->h_flags[nch] = (k + 1 == c ? 1u : 0u) | (k > 0 ? 2u : 0u); /* BFINAL on the entry's last chunk; later chunks of an entry may refer back into the one before (MZ_CUDA_FLAG_DICT) */
             left -= n;
             nch++;
         }
@@ -618,7 +618,7 @@ static void *za_prepare(void *arg) {
             const uint32_t n = left > (int64_t)ZC_CHUNK ? ZC_CHUNK : (uint32_t)left;
             b->h_off[nch] = pos + (uint64_t)k * ZC_CHUNK;
             b->h_len[nch] = n;
-            b->h_flags[nch] = k + 1 == c ? 1u : 0u;
+            b->h_flags[nch] = (k + 1 == c ? 1u : 0u) | (k > 0 ? 2u : 0u); /* FINAL | DICT, as above */
             left -= n;
             nch++;
         }

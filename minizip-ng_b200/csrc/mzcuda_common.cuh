@@ -51,20 +51,20 @@ struct Smem {
 #ifdef MZ_EMU
     uint8_t *b;
     __device__ __forceinline__ void init(uint8_t *base) { b = base; }
-    __device__ __forceinline__ uint32_t ld32(uint32_t off) const { return *(const uint32_t *)(b + off); }
-    __device__ __forceinline__ uint32_t ld16(uint32_t off) const { return *(const uint16_t *)(b + off); }
-    __device__ __forceinline__ uint32_t ld8(uint32_t off) const { return b[off]; }
-    __device__ __forceinline__ void st32(uint32_t off, uint32_t v) const { *(uint32_t *)(b + off) = v; }
-    __device__ __forceinline__ void st16(uint32_t off, uint32_t v) const { *(uint16_t *)(b + off) = (uint16_t)v; }
-    __device__ __forceinline__ void red_or32(uint32_t off, uint32_t v) const { *(uint32_t *)(b + off) |= v; }
-    __device__ __forceinline__ void red_add32(uint32_t off, uint32_t v) const { *(uint32_t *)(b + off) += v; }
-    __device__ __forceinline__ void red_min32(uint32_t off, uint32_t v) const { uint32_t *p = (uint32_t *)(b + off); if (v < *p) *p = v; }
+    __device__ __forceinline__ uint32_t ld32(uint32_t off) const { return *(const uint32_t *)(b + (int32_t)off); }
+    __device__ __forceinline__ uint32_t ld16(uint32_t off) const { return *(const uint16_t *)(b + (int32_t)off); }
+    __device__ __forceinline__ uint32_t ld8(uint32_t off) const { return b[(int32_t)off]; }
+    __device__ __forceinline__ void st32(uint32_t off, uint32_t v) const { *(uint32_t *)(b + (int32_t)off) = v; }
+    __device__ __forceinline__ void st16(uint32_t off, uint32_t v) const { *(uint16_t *)(b + (int32_t)off) = (uint16_t)v; }
+    __device__ __forceinline__ void red_or32(uint32_t off, uint32_t v) const { *(uint32_t *)(b + (int32_t)off) |= v; }
+    __device__ __forceinline__ void red_add32(uint32_t off, uint32_t v) const { *(uint32_t *)(b + (int32_t)off) += v; }
+    __device__ __forceinline__ void red_min32(uint32_t off, uint32_t v) const { uint32_t *p = (uint32_t *)(b + (int32_t)off); if (v < *p) *p = v; }
     __device__ __forceinline__ void st16_if(bool p, uint32_t off, uint32_t v) const { if (p) st16(off, v); }
     __device__ __forceinline__ void red_add32_if(bool p, uint32_t off, uint32_t v) const { if (p) red_add32(off, v); }
     __device__ __forceinline__ void red_or32_if(bool p, uint32_t off, uint32_t v) const { if (p) red_or32(off, v); }
-    __device__ __forceinline__ uint2 ld64(uint32_t off) const { return *(const uint2 *)(b + off); }
-    __device__ __forceinline__ void st64(uint32_t off, uint32_t x, uint32_t y) const { *(uint2 *)(b + off) = make_uint2(x, y); }
-    __device__ __forceinline__ void st128(uint32_t off, uint32_t x, uint32_t y, uint32_t z, uint32_t w) const { *(uint4 *)(b + off) = make_uint4(x, y, z, w); }
+    __device__ __forceinline__ uint2 ld64(uint32_t off) const { return *(const uint2 *)(b + (int32_t)off); }
+    __device__ __forceinline__ void st64(uint32_t off, uint32_t x, uint32_t y) const { *(uint2 *)(b + (int32_t)off) = make_uint2(x, y); }
+    __device__ __forceinline__ void st128(uint32_t off, uint32_t x, uint32_t y, uint32_t z, uint32_t w) const { *(uint4 *)(b + (int32_t)off) = make_uint4(x, y, z, w); }
     /* absolute forms: addr() folds the window base into a region base once, the *_a accessors then take that address as it is */
     __device__ __forceinline__ uint32_t addr(uint32_t off) const { return off; }
     __device__ __forceinline__ uint32_t ld32_a(uint32_t a) const { return ld32(a); }

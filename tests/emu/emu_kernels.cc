@@ -58,7 +58,8 @@ int64_t emu_deflate(const uint8_t *in, uint64_t len, uint32_t chunk_size, int le
     if (grid == 0 || grid > nchunks) grid = nchunks;
     if (deflate_stride_for_level(level) == 2) MZ_LAUNCH((deflate_chunks_kernel<2, false>), dim3(grid), dim3(DF_THREADS), DF_SMEM_BYTES, 0, P);
     else if (!deflate_lazy_for_level(level)) MZ_LAUNCH((deflate_chunks_kernel<1, false>), dim3(grid), dim3(DF_THREADS), DF_SMEM_BYTES, 0, P);
-    else MZ_LAUNCH((deflate_chunks_kernel<1, true>), dim3(grid), dim3(DF_THREADS), DF_SMEM_BYTES, 0, P);
+    else if (!deflate_hist_for_level(level)) MZ_LAUNCH((deflate_chunks_kernel<1, true>), dim3(grid), dim3(DF_THREADS), DF_SMEM_BYTES, 0, P);
+    else MZ_LAUNCH((deflate_chunks_kernel<1, true, true>), dim3(grid), dim3(DF_THREADS), DFH_SMEM_BYTES, 0, P);
     MZ_LAUNCH(scan_lengths_kernel, dim3(1), dim3(SCAN_THREADS), 0, 0, (const uint32_t *)out_len.data(), nchunks, (uint64_t)0, offs.data());
     if (offs[nchunks] > dst_cap) return -5;
     MZ_LAUNCH(gather_slots_kernel, dim3(nchunks < 8 ? nchunks : 8), dim3(GATHER_THREADS), 0, 0, (const uint8_t *)sl, stride,

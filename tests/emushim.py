@@ -28,7 +28,8 @@ class EmuLib:
         out = C.create_string_buffer(cap)
         nch = max(1, (len(data) + chunk - 1) // chunk)
         lens = (C.c_uint32 * nch)()
-        n = self.lib.emu_deflate(data, len(data), chunk, level, 1 if final else 0, out, cap, grid, lens)
+        flags = final if (isinstance(final, int) and not isinstance(final, bool)) else (1 if final else 0)  # 1 = FINAL, 2 = DICT (one stream: chunks may refer back)
+        n = self.lib.emu_deflate(data, len(data), chunk, level, flags, out, cap, grid, lens)
         if n < 0:
             raise ValueError(n)
         return out.raw[:n], list(lens)

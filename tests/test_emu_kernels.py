@@ -54,6 +54,31 @@ def test_emu_deflate_size_sweep(emu):
     assert zlib.decompress(comp, -15) == rep and len(comp) < 10_000
 
 
+def test_emu_deflate_history_variant(emu, orc):
+    """levels 6-9 (the kernel's history variant): the second unit of a chunk refers back into the first; with the DICT flag (the buffer
+    is ONE stream) a chunk also refers back into the 32 KiB before it. Every stream must inflate to its input (zlib and the oracle),
+    the output with history must not be larger than without, and distances never exceed 32768 (zlib would reject the stream)."""
+    text = datagen.text_like(460_001, 23)
+    for data in (text, datagen.mixed(300_000, 24), (datagen.text_like(40_000, 25) * 12)[:333_333], bytes(200_000), datagen.random_bytes(150_000, 26),
+                 text[:32768], text[:32769], text[:65536], text[:65537], text[:98304 + 5]):
+        sizes = {}
+        for level, flags in ((3, 1), (6, 1), (6, 3), (9, 3)):
+            comp, lens = emu.deflate(data, level=level, final=flags)
+            assert zlib.decompress(comp, -15) == data, (len(data), level, flags)
+            err, out, cons = orc.inflate(comp, len(data) + 8)
+            assert err == 0 and out == data and cons == len(comp)
+            sizes[(level, flags)] = len(comp)
+        if len(data) > 100_000 and data[:64] != bytes(64):
+            assert sizes[(6, 3)] <= sizes[(6, 1)] <= sizes[(3, 1)] * 1.002, sizes
+    # a period longer than a unit: only the history can find it (distance 40 000 is out of reach, 30 000 is not)
+    for period, reachable in ((30_000, True), (40_000, False)):
+        blockdata = datagen.random_bytes(period, 27)
+        data = (blockdata * 6)[:170_000]
+        comp, _ = emu.deflate(data, level=6, final=3)
+        assert zlib.decompress(comp, -15) == data
+        assert (len(comp) < 0.5 * len(data)) == reachable, (period, len(comp))
+
+
 def test_emu_deflate_ratio_sane(emu):
     data = datagen.text_like(1 << 18, 9)
     comp, _ = emu.deflate(data, level=1)

@@ -129,6 +129,31 @@ def test_deflate_batch_roundtrip(cu, torch_cuda, orc, kind, level):
             assert crc == orc.crc32(0, data)
 
 
+def test_deflate_history_variant_on_gpu(cu, torch_cuda, orc):
+    """levels 6-9 = the kernel's history variant (208 KiB of shared memory, one CTA per SM): independent chunks and one-stream mode
+    (MZ_CUDA_FLAG_DICT); same checks as on the emulator (tests/test_emu_kernels.py), bigger inputs"""
+    p, lib, _ = cu
+    import datagen
+    for data in (datagen.text_like(3_000_001, 31), datagen.mixed(2_000_000, 32), bytes(1_000_000), datagen.random_bytes(700_000, 33),
+                 (datagen.random_bytes(30_000, 34) * 40)[:1_100_000]):
+        n = len(data)
+        t = _dev(torch_cuda, data)
+        sizes = {}
+        for level, one in ((3, False), (6, False), (6, True), (9, True)):
+            b = p.DeflateBatch(n)
+            k = b.compress(t, n, level=level, final=True, one_stream=one)
+            joined, crc = b.result(k)
+            comp = bytes(joined.cpu().numpy().tobytes())
+            assert zlib.decompress(comp, -15) == data, (n, level, one)
+            err, out, cons = orc.inflate(comp, n + 8)
+            assert err == 0 and out == data and cons == len(comp)
+            assert crc == orc.crc32(0, data)
+            sizes[(level, one)] = len(comp)
+        if data[:64] != bytes(64):
+            assert sizes[(6, True)] <= sizes[(6, False)] <= sizes[(3, False)] * 1.002, sizes
+    assert sizes[(6, True)] < 0.1 * n  # the 30 000-byte period is only visible through the history
+
+
 def test_deflate_empty_stream_bytes(cu, torch_cuda):
     p, lib, _ = cu
     b = p.DeflateBatch(1)

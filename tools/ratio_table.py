@@ -17,10 +17,10 @@ sets = {"bench text (tests/support/textgen)": textgen.host(n, seed=1),
         "C4 mix (70 % text, 20 % records, 10 % random)": (datagen.mixed(8 << 20, seed=3) * (n // (8 << 20) + 1))[:n]}
 
 
-def ours(data, level):
+def ours(data, level, one_stream=False):
     src = torch.from_numpy(np.frombuffer(data, dtype=np.uint8).copy()).cuda()
     b = pkg.DeflateBatch(len(data))
-    k = b.compress(src, len(data), level=level, final=True)
+    k = b.compress(src, len(data), level=level, final=True, one_stream=one_stream)
     joined, crc = b.result(k)
     return bytes(joined.cpu().numpy().tobytes()), crc
 
@@ -36,12 +36,13 @@ def zl(data, level, chunk=None):
     return t
 
 
-print("| data (%d MiB) | level | ours | zlib whole stream | zlib 64 KiB chunks | ours / zlib whole | identical on re-run |" % mib)
-print("|---|---|---|---|---|---|---|")
+print("| data (%d MiB) | level | ours, independent 64 KiB chunks | ours, one stream (MZ_CUDA_FLAG_DICT) | zlib whole stream | zlib 64 KiB chunks | ours one stream / zlib whole | ours chunks / zlib chunks | identical on re-run |" % mib)
+print("|---|---|---|---|---|---|---|---|---|")
 for name, data in sets.items():
     for level in (1, 2, 6, 9):
         c1, crc = ours(data, level)
         c2, _ = ours(data, level)
-        assert zlib.decompress(c1, -15) == data and (crc & 0xffffffff) == zlib.crc32(data)
+        c3, _ = ours(data, level, one_stream=True)
+        assert zlib.decompress(c1, -15) == data and (crc & 0xffffffff) == zlib.crc32(data) and zlib.decompress(c3, -15) == data
         zw, zc = zl(data, level), zl(data, level, 65536)
-        print("| %s | %d | %.4f | %.4f | %.4f | %.3f | %s |" % (name, level, len(c1) / n, zw / n, zc / n, len(c1) / zw, "yes" if c1 == c2 else "NO"))
+        print("| %s | %d | %.4f | %.4f | %.4f | %.4f | %.3f | %.3f | %s |" % (name, level, len(c1) / n, len(c3) / n, zw / n, zc / n, len(c3) / zw, len(c1) / zc, "yes" if c1 == c2 else "NO"))
