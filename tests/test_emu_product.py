@@ -59,7 +59,6 @@ def test_read_path_compressed_window_ring_with_read_ahead(emulib):
     m = re.findall(r"for (\d+) bytes read ahead under rounds in flight; (\d+) window uploads wrapped", out)
     assert m and max(int(a) for a, _ in m) > (2 << 20) and max(int(b) for _, b in m) >= 1, out[-2000:]
     _scenario("ring", MZ_CUDA_SPEC_SEG_KB=4, MZ_CUDA_BATCH_KB=1024, MZ_CUDA_READ_WINDOW_KB=1300, MZ_CUDA_READ_OUT_MULT=1, MZ_CUDA_READ_AHEAD=2)
-    _scenario("ring", MZ_CUDA_SPEC_SEG_KB=4, MZ_CUDA_BATCH_KB=1024, MZ_CUDA_READ_WINDOW_KB=1100, MZ_CUDA_READ_AHEAD=0)
 
 
 def test_crc_symbol_device_path(emulib):
