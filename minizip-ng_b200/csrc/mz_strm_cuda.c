@@ -291,6 +291,7 @@ typedef struct mz_stream_cuda_s {
     size_t cin_len;     /* bytes in the window (what the kernels see: d_cin[0 .. cin_len)) */
     size_t cin_off;     /* where the window starts in the ring ws->h_cin */
     size_t ahead_len;   /* bytes read from base beyond the window (behind it in the ring), not yet uploaded */
+    int8_t verify_copy; /* MZ_CUDA_VERIFY_COPY=1: compare every copy into the caller's buffer with its source (debug aid) */
     int8_t ahead_force; /* MZ_CUDA_READ_AHEAD=2: read ahead whether or not the round is still running (tests: on the emulator it never is) */
     uint64_t win_base;  /* output offset of byte 0 of the window being decoded into */
     int dwin, lwin;     /* which window (0 = ws->d_win, 1 = ws->d_win2) is decoded into / delivered from */
@@ -384,7 +385,7 @@ static void cu_copy_out(uint8_t *dst, const uint8_t *src, size_t n) {
         return;
     }
     g_cp.parts = g_cp.n + 1;
-    g_cp.part = ((n / (size_t)g_cp.parts) + 4095) & ~(size_t)4095;
+    g_cp.part = (((n + (size_t)g_cp.parts - 1) / (size_t)g_cp.parts) + 4095) & ~(size_t)4095; /* parts * part >= n: round the quotient UP first */
     g_cp.total = n;
     g_cp.dst = dst;
     g_cp.src = src;
@@ -475,6 +476,7 @@ int32_t mz_stream_cuda_open(void *stream, const char *path, int32_t mode) {
     cu->cin_base = 0;
     cu->cin_len = 0;
     cu->cin_off = cu->ahead_len = 0;
+    cu->verify_copy = getenv("MZ_CUDA_VERIFY_COPY") != NULL;
     {
         const char *ra = getenv("MZ_CUDA_READ_AHEAD"); /* 0 = off, 1 = while a round is in flight (default), 2 = always (tests) */
         cu->ahead_force = ra ? (ra[0] == '2' ? 1 : (ra[0] == '0' ? -1 : 0)) : 0;
@@ -1391,6 +1393,14 @@ int32_t mz_stream_cuda_read(void *stream, void *buf, int32_t size) {
             if (k > (size_t)(size - done))
                 k = (size_t)(size - done);
             CU_TIMED(cu, t_copy, cu_copy_out(out + done, cu->ws->h_dec + cu->dec_base + cu->dec_pos, k));
+            if (cu->verify_copy && memcmp(out + done, cu->ws->h_dec + cu->dec_base + cu->dec_pos, k) != 0) { /* MZ_CUDA_VERIFY_COPY: debug aid */
+                size_t bad = 0;
+                while (bad < k && out[done + bad] == cu->ws->h_dec[cu->dec_base + cu->dec_pos + bad])
+                    bad++;
+                fprintf(stderr, "mz_strm_cuda: VERIFY_COPY mismatch: %zu bytes at output %lld, first bad byte +%zu (dec_base %zu dec_pos %zu dec_len %zu)\n", k,
+                        (long long)(cu->total_out + done), bad, cu->dec_base, cu->dec_pos, cu->dec_len);
+                memcpy(out + done, cu->ws->h_dec + cu->dec_base + cu->dec_pos, k);
+            }
             cu->dec_pos += k;
             done += (int32_t)k;
             continue;

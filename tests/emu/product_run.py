@@ -113,7 +113,8 @@ def scenario_ring():
     or not a round is in flight -- on the emulator a launch has always finished): many wraps of a small ring, the trailer found
     across a wrap, TOTAL_IN_MAX honoured by the read-ahead (bytes behind the member are never touched), truncation reported"""
     text = datagen.text_like(8_000_000, 21) + datagen.random_bytes(400_000, 5) + datagen.text_like(4_000_000, 22)
-    for level, rsize in ((6, 300_000), (1, 65536)):
+    # 262146 = 4 * 65536 + 2: a copy the helper threads split into four 64 KiB slices -- plus two bytes that belong to the last one
+    for level, rsize in ((6, 262146), (1, 65536)):
         comp = gz(text, level, 31)
         assert len(comp) > (4 << 20)
         out, info = tl.decompress(CREATE, comp, len(text), window_bits=31, read_size=rsize)
