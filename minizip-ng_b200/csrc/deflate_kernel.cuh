@@ -842,8 +842,29 @@ __global__ void __launch_bounds__(DF_THREADS, HIST ? 1 : 2) deflate_chunks_kerne
                             const uint32_t j = last & 7u, q = sidx * DF_SPAN + j, c = q - ((last >> 11) & 0x7fffu) - 1u; /* (wraps below 0: into the previous unit) */
                             uint32_t maxlen = ulen - q;
                             maxlen = maxlen < 258 ? maxlen : 258u;
-                            const uint32_t l = extend_match8(sm, c, q, maxlen);
-                            sm.st32(DF_OFF_REC + sidx * 8 + (second ? 4u : 0u), (w & ~(255u << 3)) | ((l - 3) << 3));
+                            /* Runs and short periods (zeros, 16- and 32-bit fill patterns): the table's candidate is the FIRST occurrence of
+                             * the 8 bytes in an earlier batch, thousands of positions back -- 11 to 13 distance extra bits per match where
+                             * the same bytes lie 1..4 positions back for none. Take the nearest such source if it carries at least as far. */
+                            uint32_t cn = c;
+                            if (q >= 4) {
+                                const uint32_t a0 = sm.ld32u(DF_OFF_IN, q), a1 = sm.ld32u(DF_OFF_IN, q + 4);
+#pragma unroll
+                                for (int pp = 4; pp >= 1; pp--)
+                                    if (a0 == sm.ld32u(DF_OFF_IN, q - pp) && a1 == sm.ld32u(DF_OFF_IN, q - pp + 4)) cn = q - pp;
+                            }
+                            uint32_t l = 0, cb = c;
+                            if (cn != c) {
+                                l = extend_match8(sm, cn, q, maxlen);
+                                cb = cn;
+                            }
+                            if (l < 64u && l < maxlen) { /* (a near source that runs this far is good enough: skip the second walk) */
+                                const uint32_t lf = extend_match8(sm, c, q, maxlen);
+                                if (lf > l) {
+                                    l = lf;
+                                    cb = c;
+                                }
+                            }
+                            sm.st32(DF_OFF_REC + sidx * 8 + (second ? 4u : 0u), (w & ~((255u << 3) | (0x7fffu << 11))) | ((l - 3) << 3) | ((q - cb - 1u) << 11));
                             sm.st16(DF_OFF_SPN + sidx * 2, (j << 9) | (j + l));
                         }
                     }
