@@ -842,20 +842,29 @@ __global__ void __launch_bounds__(DF_THREADS, HIST ? 1 : 2) deflate_chunks_kerne
                             const uint32_t j = last & 7u, q = sidx * DF_SPAN + j, c = q - ((last >> 11) & 0x7fffu) - 1u; /* (wraps below 0: into the previous unit) */
                             uint32_t maxlen = ulen - q;
                             maxlen = maxlen < 258 ? maxlen : 258u;
-                            /* Runs and short periods (zeros, 16- and 32-bit fill patterns): the table's candidate is the FIRST occurrence of
-                             * the 8 bytes in an earlier batch, thousands of positions back -- 11 to 13 distance extra bits per match where
-                             * the same bytes lie 1..4 positions back for none. Take the nearest such source if it carries at least as far. */
-                            uint32_t cn = c;
+                            /* Runs and short periods (zeros, 16- / 24- / 32-bit fill patterns): the table's candidate is the FIRST occurrence
+                             * of the 8 bytes in an earlier batch, thousands of positions back -- 11 to 13 distance extra bits per match
+                             * where the same bytes lie 1..4 positions back for none. The 8 bytes at q themselves say whether that can
+                             * be (period 4, 2 or 1: both words equal; period 3: the bytes 3 further on repeat the first word), so text
+                             * pays two loads and two compares here; then the nearest such source is taken if it carries at least as far. */
+                            uint32_t l = 0, cb = c;
                             if (q >= 4) {
                                 const uint32_t a0 = sm.ld32u(DF_OFF_IN, q), a1 = sm.ld32u(DF_OFF_IN, q + 4);
-#pragma unroll
-                                for (int pp = 4; pp >= 1; pp--)
-                                    if (a0 == sm.ld32u(DF_OFF_IN, q - pp) && a1 == sm.ld32u(DF_OFF_IN, q - pp + 4)) cn = q - pp;
-                            }
-                            uint32_t l = 0, cb = c;
-                            if (cn != c) {
-                                l = extend_match8(sm, cn, q, maxlen);
-                                cb = cn;
+                                const bool p4 = a0 == a1, p3 = __funnelshift_r(a0, a1, 24) == a0;
+                                if (p4 || p3) {
+                                    uint32_t cn = c;
+                                    if (p4) {
+                                        if (a0 == sm.ld32u(DF_OFF_IN, q - 4)) cn = q - 4;
+                                        if (a0 == sm.ld32u(DF_OFF_IN, q - 2)) cn = q - 2;
+                                        if (a0 == sm.ld32u(DF_OFF_IN, q - 1)) cn = q - 1;
+                                    } else if (a0 == sm.ld32u(DF_OFF_IN, q - 3)) {
+                                        cn = q - 3;
+                                    }
+                                    if (cn != c) {
+                                        l = extend_match8(sm, cn, q, maxlen);
+                                        cb = cn;
+                                    }
+                                }
                             }
                             if (l < 64u && l < maxlen) { /* (a near source that runs this far is good enough: skip the second walk) */
                                 const uint32_t lf = extend_match8(sm, c, q, maxlen);
