@@ -28,6 +28,9 @@ data = datagen.mixed(260_000, 7) + datagen.random_bytes(3_000, 1)
 for level in (1, 6):
     comp, _ = emu.deflate(data, level=level)
     assert zlib.decompress(comp, -15) == data
+for d2, flags in ((data, 3), (bytes(70_000), 1), ((b"\x01\x00\x00" * 30_000)[:80_001], 3), (datagen.text_like(150_000, 8), 3)):
+    comp, _ = emu.deflate(d2, level=6, final=flags)  # the history variant: one stream (DICT), runs and short periods (near sources in M0)
+    assert zlib.decompress(comp, -15) == d2
 comp, _ = emu.deflate(b"", level=1)
 assert zlib.decompress(comp, -15) == b""
 for n in (0, 1, 5, 4097, 70_000):

@@ -83,3 +83,4 @@ def test_host_paths_under_sanitizers(emulib):
     _scenario("read", MZ_CUDA_SPEC=1, MZ_CUDA_SPEC_SEG_KB=4, MZ_CUDA_BATCH_KB=1024, **san)
     _scenario("long", MZ_CUDA_SPEC_SEG_KB=4, MZ_CUDA_BATCH_KB=1024, MZ_CUDA_READ_WINDOW_KB=2048, **san)
     _scenario("long", MZ_CUDA_SPEC_SEG_KB=4, MZ_CUDA_BATCH_KB=1024, MZ_CUDA_READ_WINDOW_KB=1100, MZ_CUDA_READ_OUT_MULT=1, **san)
+    _scenario("ring", MZ_CUDA_SPEC_SEG_KB=4, MZ_CUDA_BATCH_KB=1024, MZ_CUDA_READ_WINDOW_KB=1100, MZ_CUDA_READ_AHEAD=2, **san)
