@@ -845,8 +845,8 @@ __global__ void __launch_bounds__(DF_THREADS, HIST ? 1 : 2) deflate_chunks_kerne
                             /* Runs and short periods (zeros, 16- / 24- / 32-bit fill patterns): the table's candidate is the FIRST occurrence
                              * of the 8 bytes in an earlier batch, thousands of positions back -- 11 to 13 distance extra bits per match
                              * where the same bytes lie 1..4 positions back for none. The 8 bytes at q themselves say whether that can
-                             * be (period 4, 2 or 1: both words equal; period 3: the bytes 3 further on repeat the first word), so text
-                             * pays two loads and two compares here; then the nearest such source is taken if it carries at least as far. */
+                             * be (period 4, 2 or 1: both words equal -- then one word 4, 2 or 1 back settles all 8 bytes; period 3: the bytes
+                             * 3 further on repeat the first word -- then both words are compared), so text pays two loads and two compares here; then the nearest such source is taken if it carries at least as far. */
                             uint32_t l = 0, cb = c;
                             if (q >= 4) {
                                 const uint32_t a0 = sm.ld32u(DF_OFF_IN, q), a1 = sm.ld32u(DF_OFF_IN, q + 4);
@@ -857,10 +857,26 @@ __global__ void __launch_bounds__(DF_THREADS, HIST ? 1 : 2) deflate_chunks_kerne
                                         if (a0 == sm.ld32u(DF_OFF_IN, q - 4)) cn = q - 4;
                                         if (a0 == sm.ld32u(DF_OFF_IN, q - 2)) cn = q - 2;
                                         if (a0 == sm.ld32u(DF_OFF_IN, q - 1)) cn = q - 1;
-                                    } else if (a0 == sm.ld32u(DF_OFF_IN, q - 3)) {
-                                        cn = q - 3;
+                                    } else if (a0 == sm.ld32u(DF_OFF_IN, q - 3) && a1 == sm.ld32u(DF_OFF_IN, q + 1)) {
+                                        cn = q - 3; /* (the pre-test saw 7 bytes of the period; extend_match8 relies on all 8) */
                                     }
                                     if (cn != c) {
+                                        /* Inside such a run EVERY span holds this match, and the cover would cut each down to the 64
+                                         * bytes its thread adds (507 matches for 32 KiB of zeros). Only the anchors keep theirs -- the
+                                         * run's first span (the 8 bytes in front of it do not continue the period) and every 32nd span
+                                         * (a match of 258 reaches the next one); the others give the match back: its positions count as
+                                         * literals again (emitted only if, against expectation, nothing covers them) and no walk is
+                                         * spent on them. */
+                                        const uint32_t pd = q - cn;
+                                        if (q >= 12u && (sidx & 31u) != 0u && sm.ld32u(DF_OFF_IN, q - 8) == sm.ld32u(DF_OFF_IN, q - 8 - pd) &&
+                                            sm.ld32u(DF_OFF_IN, q - 4) == sm.ld32u(DF_OFF_IN, q - 4 - pd)) {
+                                            const uint32_t left = ulen - sidx * DF_SPAN, nval = left < 8u ? left : 8u;
+                                            const uint32_t lit = ((r.x >> 26) | ((r.y >> 26) << 6) | (0xffu << j)) & ((1u << nval) - 1u);
+                                            const uint32_t mA = second ? (r.x & 0x03ffffffu) : 0u; /* an earlier, short match of the span stays */
+                                            sm.st64(DF_OFF_REC + sidx * 8, mA | ((lit & 63u) << 26), (lit >> 6) << 26);
+                                            sm.st16(DF_OFF_SPN + sidx * 2, mA ? ((mA & 7u) << 9) | ((mA & 7u) + rec_len(mA)) : 0u);
+                                            continue;
+                                        }
                                         l = extend_match8(sm, cn, q, maxlen);
                                         cb = cn;
                                     }

@@ -60,3 +60,18 @@ def mixed(n_bytes, seed=3):
         total += ln
         i += 1
     return b"".join(parts)[:n_bytes]
+
+
+def near_period_traps(seed=5, sites=400):
+    """Sites where 7 of the 8 bytes at a position continue a period of 3 ("abc" + "abcabcaZ") and the same 8 bytes occurred earlier
+    followed by a different byte, so the table's match is exactly 8 long: a near-source rule that trusts 7 bytes of the period would
+    claim an 8-byte match at distance 3 whose last byte is wrong (found by tests/emu/fuzz_kernels.py, round 2)."""
+    import random
+    rng = random.Random(seed)
+    out = bytearray(random_bytes(6000, seed + 1))
+    for k in range(sites):
+        a, b, c, z = (rng.randrange(256) for _ in range(4))
+        blk = bytes([a, b, c, a, b, c, a, z])
+        out += random_bytes(rng.randrange(5, 40), 100 + k) + blk + bytes([rng.randrange(256)]) + random_bytes(rng.randrange(5, 300), 900 + k)
+        out += bytes([a, b, c]) + blk + bytes([rng.randrange(256)]) + random_bytes(rng.randrange(5, 40), 1900 + k)
+    return bytes(out)

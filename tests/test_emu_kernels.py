@@ -79,6 +79,23 @@ def test_emu_deflate_history_variant(emu, orc):
         assert (len(comp) < 0.5 * len(data)) == reachable, (period, len(comp))
 
 
+def test_emu_deflate_runs_and_near_sources(emu, orc):
+    """the M0 pass: runs and short periods take a source 1..4 positions back and only the anchors of a run keep their match; the
+    traps of datagen.near_period_traps must not be mistaken for such sources; ratios on runs stay in zlib-1's neighbourhood"""
+    traps = datagen.near_period_traps()
+    cases = [traps, bytes(200_000), (b"abc" * 70_000)[:200_001], b"".join(bytes([i & 255]) * (5 + 13 * i % 700) for i in range(900)),
+             b"".join(datagen.random_bytes(37, i) + bytes(3000 + 17 * i) for i in range(60)), b"".join((i // 7).to_bytes(4, "little") for i in range(60_000)),
+             bytes(7) + b"x" + bytes(9) + b"y" * 11 + bytes(300), traps[:32768] + bytes(40_000) + traps[:20_000]]
+    for data in cases:
+        for level, flags in ((1, 1), (3, 1), (6, 1), (9, 3)):
+            comp, _ = emu.deflate(data, level=level, final=flags)
+            assert zlib.decompress(comp, -15) == data, (len(data), level, flags)
+            err, out, cons = orc.inflate(comp, len(data) + 8)
+            assert err == 0 and out == data and cons == len(comp)
+    comp, _ = emu.deflate(bytes(1 << 20), level=1)
+    assert len(comp) < (1 << 20) * 0.006  # 32 KiB of zeros: ~130 bytes (zlib level 1: 0.0044)
+
+
 def test_emu_deflate_ratio_sane(emu):
     data = datagen.text_like(1 << 18, 9)
     comp, _ = emu.deflate(data, level=1)

@@ -154,6 +154,26 @@ def test_deflate_history_variant_on_gpu(cu, torch_cuda, orc):
     assert sizes[(6, True)] < 0.1 * n  # the 30 000-byte period is only visible through the history
 
 
+def test_deflate_runs_and_near_sources_on_gpu(cu, torch_cuda, orc):
+    """same inputs as tests/test_emu_kernels.py::test_emu_deflate_runs_and_near_sources, on the device"""
+    p, lib, _ = cu
+    import datagen
+    traps = datagen.near_period_traps()
+    cases = [traps, bytes(2_000_000), (b"abc" * 700_000)[:2_000_001], b"".join(bytes([i & 255]) * (5 + 13 * i % 700) for i in range(3000)),
+             b"".join(datagen.random_bytes(37, i) + bytes(3000 + 17 * i) for i in range(200)), traps[:32768] + bytes(40_000) + traps[:20_000]]
+    for data in cases:
+        n = len(data)
+        t = _dev(torch_cuda, data)
+        for level, one in ((1, False), (3, False), (6, False), (9, True)):
+            b = p.DeflateBatch(n)
+            k = b.compress(t, n, level=level, final=True, one_stream=one)
+            joined, crc = b.result(k)
+            comp = bytes(joined.cpu().numpy().tobytes())
+            assert zlib.decompress(comp, -15) == data, (n, level, one)
+            assert crc == orc.crc32(0, data)
+    assert len(comp) < 0.5 * n
+
+
 def test_deflate_empty_stream_bytes(cu, torch_cuda):
     p, lib, _ = cu
     b = p.DeflateBatch(1)
