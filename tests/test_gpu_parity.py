@@ -171,7 +171,8 @@ def test_deflate_runs_and_near_sources_on_gpu(cu, torch_cuda, orc):
             comp = bytes(joined.cpu().numpy().tobytes())
             assert zlib.decompress(comp, -15) == data, (n, level, one)
             assert crc == orc.crc32(0, data)
-    assert len(comp) < 0.5 * n
+            if data[:4096] == bytes(4096) and data[-4096:] == bytes(4096):
+                assert len(comp) < 0.006 * n  # zeros: ~130 bytes per 32 KiB (zlib level 1: 0.0044)
 
 
 def test_deflate_empty_stream_bytes(cu, torch_cuda):
