@@ -112,13 +112,17 @@ def scenario_ring():
     """the compressed window as a ring with read-ahead (MZ_CUDA_READ_AHEAD=2: bytes are pulled from base behind the window whether
     or not a round is in flight -- on the emulator a launch has always finished): many wraps of a small ring, the trailer found
     across a wrap, TOTAL_IN_MAX honoured by the read-ahead (bytes behind the member are never touched), truncation reported"""
-    text = datagen.text_like(8_000_000, 21) + datagen.random_bytes(400_000, 5) + datagen.text_like(4_000_000, 22)
+    small = os.environ.get("MZ_TEST_RING_SMALL") == "1"  # (the sanitizer run: no wrap, but the read-ahead accounting under ASan)
+    text = (datagen.text_like(2_000_000, 21) + datagen.random_bytes(200_000, 5) + datagen.text_like(1_000_000, 22)) if small else \
+           (datagen.text_like(4_500_000, 21) + datagen.random_bytes(300_000, 5) + datagen.text_like(2_000_000, 22))
     # 262146 = 4 * 65536 + 2: a copy the helper threads split into four 64 KiB slices -- plus two bytes that belong to the last one
     for level, rsize in ((6, 262146), (1, 65536)):
         comp = gz(text, level, 31)
-        assert len(comp) > (4 << 20)
+        assert len(comp) > ((1 << 20) if small else (5 << 19))
         out, info = tl.decompress(CREATE, comp, len(text), window_bits=31, read_size=rsize)
         assert info["read"] == len(text) and out == text and info["total_in"] == len(comp) and info["close"] == 0, info
+        if level == 1:
+            continue  # (the variations below once, on the level-6 member)
         junk = comp + datagen.random_bytes(1_500_000, 6)
         out, info = tl.decompress(CREATE, junk, len(text), window_bits=31, read_size=rsize, total_in_max=len(comp))
         assert out == text and info["total_in"] == len(comp) and info["base_tell"] == len(comp) and info["close"] == 0, info

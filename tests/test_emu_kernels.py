@@ -290,6 +290,17 @@ def test_emu_sha256_known_answers_and_every_padding_case(emu):
         assert g == hashlib.sha256(m).digest()
 
 
+def test_emu_fuzzers_short(emu):
+    """a short, seeded turn of the two randomized differential runs (tests/emu/fuzz_kernels.py: every kernel against zlib;
+    tests/emu/fuzz_deflate.py: the deflate kernel at random levels, with and without the one-stream flag, over runs and periods).
+    Run them longer by hand after touching a kernel: the period-3 bug of round 2 took 277 iterations to show."""
+    import sys
+    emu_dir = os.path.join(HERE, "emu")
+    for script, seed, secs in (("fuzz_kernels.py", 20260923, 15), ("fuzz_deflate.py", 7, 10)):
+        r = subprocess.run([sys.executable, os.path.join(emu_dir, script), str(seed), str(secs)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
+        assert r.returncode == 0 and b"fails 0" in r.stdout, r.stdout[-2000:]
+
+
 def test_emu_kernels_under_sanitizers():
     """the same kernel sources built with AddressSanitizer + UBSan: out-of-bounds global accesses, shifts by >= 32,
     signed overflow ... in the deflate, CRC, inflate and K6 kernels abort the run"""
