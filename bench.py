@@ -253,7 +253,7 @@ def host_text_sample(nbytes, seed=99):
 
 WORKLOADS = {
     "c1": "C1: CRC-32 of a 64 MiB buffer via mz_crypt_crc32_update",
-    "c2": "C2: minigzip-style deflate level %(level)d (gzip framing) of a %(mib)d MiB synthetic text buffer",
+    "c2": "C2: minigzip-style deflate level %(level)d (gzip framing) of a %(mib)d MiB synthetic text buffer, one stream (64 KiB chunks that may refer back 32 KiB: MZ_CUDA_FLAG_DICT)",
     "c3": "C3: inflate one %(gib).2f GiB multi-block .gz member (zlib level 6 blocks) through the stream read() call",
     "c4": "C4: zip of %(entries)d x 64 KiB entries, per-entry deflate level %(level)d + CRC-32",
     "c5": "C5: %(gib).2f GiB enwik-style buffer, independent 64 KiB chunks, DEFLATE level %(level)d + CRC-32 per chunk + fold + join",
