@@ -350,6 +350,19 @@ def test_stream_read_sizes_and_windows(cu, read_size, monkeypatch):
         assert info["total_in"] == len(comp) and info["total_out"] == n
 
 
+def test_stream_read_parallel_copy_slices(cu):
+    """reads big enough for the helper threads (>= 256 KiB) whose size is NOT a multiple of the thread count while a quarter of it IS a
+    multiple of 4 KiB: the slice rounding that lost the last n mod 4 bytes in round 2 (262146 = 4 * 65536 + 2, 1048579 = 4 * 262144 + 3)"""
+    p, lib, tl = cu
+    data = datagen.mixed(6_000_000, 91)
+    co = zlib.compressobj(6, zlib.DEFLATED, 31)
+    comp = co.compress(data) + co.flush()
+    for read_size in (262146, 1048579, 786433):
+        out, info = tl.decompress(lib.mz_stream_cuda_create, comp, len(data), window_bits=31, read_size=read_size)
+        assert info["read"] == len(data) and out == data, (read_size, info)
+        assert info["total_in"] == len(comp) and info["close"] == 0
+
+
 def test_stream_read_errors(cu, golden):
     """Error taxonomy observed from the reference: truncated -> -5, bad trailer / wrong framing -> -3, sticky, close -> -112."""
     p, lib, tl = cu
