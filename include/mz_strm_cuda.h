@@ -55,7 +55,7 @@ void mz_stream_cuda_delete(void **stream);
 void *mz_stream_cuda_get_interface(void);
 
 /* Replacement for mz_crypt.c:35. Calls below MZ_CUDA_CRC_MIN_BYTES (default 1 MiB, environment
- * override) are answered by a 10-line host table loop: the reference calls this with 1-byte
+ * override) are answered on the host (PCLMULQDQ folding on x86-64, a table loop elsewhere): the reference calls this with 1-byte
  * (mz_strm_pkcrypt.c:79,86) and <=64 KiB (mz_zip.c:2049,2064) buffers for which a PCIe round trip is
  * absurd; anything larger goes to the GPU kernel. */
 uint32_t mz_crypt_crc32_update(uint32_t value, const uint8_t *buf, int32_t size);

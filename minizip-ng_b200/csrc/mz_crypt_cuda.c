@@ -12,9 +12,10 @@
  * Tiny buffers do not go to the GPU: the reference calls this once per byte from the PKWARE key schedule
  * (mz_strm_pkcrypt.c:79,86) and once per <=64 KiB from the zip entry loop (mz_zip.c:2049,2064); a PCIe
  * round trip per call would be absurd, so calls below MZ_CUDA_CRC_MIN_BYTES (default 1 MiB) are answered
- * on the host by a slice-by-16 table loop (the table-driven form of mz_crypt.c:81-90, 16 bytes per step so
- * that the zip path is not slower than with zlib's crc32). That loop is the only host arithmetic in the
- * product and it is stated here, in DESIGN.md and in include/mz_strm_cuda.h.
+ * on the host: by carry-less-multiplication folding where the CPU has PCLMULQDQ (64 bytes and more: ~17 GB/s per
+ * core on 64 KiB calls, zlib 1.3's crc32: 3.8), else and for the tails by a slice-by-16 table loop (the table-driven
+ * form of mz_crypt.c:81-90). This is the only host arithmetic in the product and it is stated here, in DESIGN.md
+ * and in include/mz_strm_cuda.h.
  */
 #include <pthread.h>
 #include <stdio.h>
@@ -45,9 +46,85 @@ static inline uint32_t ld32le(const uint8_t *p) {
     return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
 }
 
+/* ---- host path on x86-64 with carry-less multiplication: fold 64 bytes per step --------------------------------
+ * (V. Gopal et al., "Fast CRC Computation for Generic Polynomials Using PCLMULQDQ Instruction", Intel 2009, the bit-reflected
+ * variant.) The message is a polynomial over GF(2); 128-bit pieces A, B of it that lie T bits apart satisfy
+ * A x^T + B = (A_hi x^(T+64) mod P) + (A_lo x^T mod P) + B (mod P), two PCLMULQDQ per 16 bytes instead of 16 table lookups.
+ * The constants are k(n) = bitreflect32(x^n mod P) << 1 for P = 0x104C11DB7 (the shift makes up for the reflected product being
+ * one bit short): fold across 512 bits k(4*128+32), k(4*128-32); across 128 bits k(128+32), k(128-32); 128 -> 64 bits k(64);
+ * Barrett reduction with mu' = bitreflect33(floor(x^64 / P)) and P' = bitreflect33(P). tests/test_abi_cpu.py re-derives them.
+ * Used for calls of 64 bytes and more when the CPU has PCLMULQDQ + SSE4.1 (zlib 1.3's braided loop: ~3.8 GB/s per core here;
+ * the table loop below: ~3.0; this: the memory stream). */
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+#define MZ_HAVE_CLMUL_PATH 1
+static int g_clmul_ok;
+static pthread_once_t g_cpu_once = PTHREAD_ONCE_INIT;
+static void cpu_init(void) {
+    __builtin_cpu_init();
+    const char *off = getenv("MZ_CUDA_CRC_NO_CLMUL"); /* tests: keep the table loop covered on machines that have the instruction */
+    g_clmul_ok = __builtin_cpu_supports("pclmul") && __builtin_cpu_supports("sse4.1") && !(off && off[0] == '1');
+}
+
+#define CL_FOLD(x, k, d)                                             \
+    do {                                                             \
+        const __m128i lo_ = _mm_clmulepi64_si128((x), (k), 0x00);    \
+        (x) = _mm_clmulepi64_si128((x), (k), 0x11);                  \
+        (x) = _mm_xor_si128(_mm_xor_si128((x), lo_), (d));           \
+    } while (0)
+
+/* state in, state out (the inverted running value); len >= 64 and a multiple of 16 */
+__attribute__((target("pclmul,sse4.1"))) static uint32_t crc_clmul(uint32_t c, const uint8_t *buf, size_t len) {
+    const __m128i k512 = _mm_set_epi64x(0x01c6e41596ll, 0x0154442bd4ll); /* {k(4*128+32), k(4*128-32)} */
+    const __m128i k128 = _mm_set_epi64x(0x00ccaa009ell, 0x01751997d0ll); /* {k(128+32), k(128-32)} */
+    const __m128i k64 = _mm_set_epi64x(0, 0x0163cd6124ll);               /* k(64) */
+    const __m128i pmu = _mm_set_epi64x(0x01f7011641ll, 0x01db710641ll);  /* {P', mu'} */
+    const __m128i mask32 = _mm_setr_epi32(~0, 0, ~0, 0);
+    __m128i a = _mm_loadu_si128((const __m128i *)(buf + 0)), b = _mm_loadu_si128((const __m128i *)(buf + 16));
+    __m128i d = _mm_loadu_si128((const __m128i *)(buf + 32)), e = _mm_loadu_si128((const __m128i *)(buf + 48));
+    a = _mm_xor_si128(a, _mm_cvtsi32_si128((int)c));
+    buf += 64;
+    len -= 64;
+    while (len >= 64) { /* four independent chains, 512 bits apart */
+        CL_FOLD(a, k512, _mm_loadu_si128((const __m128i *)(buf + 0)));
+        CL_FOLD(b, k512, _mm_loadu_si128((const __m128i *)(buf + 16)));
+        CL_FOLD(d, k512, _mm_loadu_si128((const __m128i *)(buf + 32)));
+        CL_FOLD(e, k512, _mm_loadu_si128((const __m128i *)(buf + 48)));
+        buf += 64;
+        len -= 64;
+    }
+    CL_FOLD(a, k128, b); /* the four chains into one, 128 bits apart each */
+    CL_FOLD(a, k128, d);
+    CL_FOLD(a, k128, e);
+    while (len >= 16) {
+        CL_FOLD(a, k128, _mm_loadu_si128((const __m128i *)buf));
+        buf += 16;
+        len -= 16;
+    }
+    /* 128 -> 64 bits: the low half times x^(64+32), then the low 32 bits of what is left times x^64 */
+    __m128i t = _mm_clmulepi64_si128(a, k128, 0x10);
+    a = _mm_xor_si128(_mm_srli_si128(a, 8), t);
+    t = _mm_srli_si128(a, 4);
+    a = _mm_xor_si128(_mm_clmulepi64_si128(_mm_and_si128(a, mask32), k64, 0x00), t);
+    /* Barrett: 64 -> 32 bits */
+    t = _mm_and_si128(_mm_clmulepi64_si128(_mm_and_si128(a, mask32), pmu, 0x10), mask32);
+    a = _mm_xor_si128(a, _mm_clmulepi64_si128(t, pmu, 0x00));
+    return (uint32_t)_mm_extract_epi32(a, 1);
+}
+#endif
+
 static uint32_t crc_small(uint32_t value, const uint8_t *buf, size_t size) {
     pthread_once(&g_tab_once, tab_init);
     uint32_t c = ~value;
+#ifdef MZ_HAVE_CLMUL_PATH
+    pthread_once(&g_cpu_once, cpu_init);
+    if (g_clmul_ok && size >= 64) {
+        const size_t n = size & ~(size_t)15;
+        c = crc_clmul(c, buf, n);
+        buf += n;
+        size -= n;
+    }
+#endif
     while (size >= 16) {
         const uint32_t a = ld32le(buf) ^ c, b = ld32le(buf + 4), d = ld32le(buf + 8), e = ld32le(buf + 12);
         c = g_tab[15][a & 0xFF] ^ g_tab[14][(a >> 8) & 0xFF] ^ g_tab[13][(a >> 16) & 0xFF] ^ g_tab[12][a >> 24] ^

@@ -97,6 +97,54 @@ def test_small_crc_calls_match_reference_semantics(built, orc):
     assert lib.mz_crypt_crc32_update(5, None, 0) == 5
 
 
+def test_host_crc_paths_and_clmul_constants(built, orc):
+    """Calls below the GPU threshold: the carry-less-multiplication path (x86-64 with PCLMULQDQ; 64 bytes and more) and the table
+    loop must both give zlib's value for every length, alignment and start value; the folding constants written into
+    mz_crypt_cuda.c are re-derived here from the polynomial (k(n) = bitreflect32(x^n mod P) << 1, mu', P')."""
+    import random
+    import subprocess
+    import sys
+    P = 0x104C11DB7
+
+    def xpow(n):
+        r = 1
+        for _ in range(n):
+            r <<= 1
+            if r >> 32:
+                r ^= P
+        return r
+
+    def refl(v, bits):
+        return int(bin(v)[2:].zfill(bits)[::-1], 2)
+
+    num, q = 1 << 64, 0
+    for i in range(64, 31, -1):
+        if (num >> i) & 1:
+            q |= 1 << (i - 32)
+            num ^= P << (i - 32)
+    want = {"k512": (refl(xpow(4 * 128 + 32), 32) << 1, refl(xpow(4 * 128 - 32), 32) << 1), "k128": (refl(xpow(128 + 32), 32) << 1, refl(xpow(128 - 32), 32) << 1),
+            "k64": (refl(xpow(64), 32) << 1, 0), "pmu": (refl(P, 33), refl(q, 33))}
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "minizip-ng_b200", "csrc", "mz_crypt_cuda.c")).read()
+    for name, (lo, hi) in want.items():
+        m = re.search(r"const __m128i %s = _mm_set_epi64x\((0x[0-9a-f]+|0)(?:ll)?, (0x[0-9a-f]+)ll\)" % name, src)
+        assert m and int(m.group(1), 16) == hi and int(m.group(2), 16) == lo, (name, hex(lo), hex(hi), m and m.groups())
+    # both host paths against zlib (a child process each: the choice is latched at the first call)
+    code = r"""
+import ctypes as C, os, random, sys, zlib
+lib = C.CDLL(sys.argv[1]); lib.mz_crypt_crc32_update.restype = C.c_uint32; lib.mz_crypt_crc32_update.argtypes = [C.c_uint32, C.c_void_p, C.c_int32]
+rng = random.Random(int(sys.argv[2])); data = bytes(rng.randrange(256) for _ in range(200000)); buf = C.create_string_buffer(data, len(data) + 64)
+for it in range(6000):
+    a = rng.randrange(0, 64); n = rng.choice([rng.randrange(0, 400), rng.randrange(0, 150000), 63, 64, 65, 79, 80, 81, 127, 128, 129, 4096, 65535])
+    n = min(n, len(data) - a); v0 = rng.choice([0, 0xffffffff, rng.randrange(1 << 32)])
+    assert lib.mz_crypt_crc32_update(v0, C.byref(buf, a), n) == zlib.crc32(data[a:a + n], v0), (a, n, v0)
+print("host crc ok")
+"""
+    p = _pkg(built)
+    for env in ({}, {"MZ_CUDA_CRC_NO_CLMUL": "1"}):
+        r = subprocess.run([sys.executable, "-c", code, p.LIB_PATH, "7"], env=dict(os.environ, **env), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=300)
+        assert r.returncode == 0 and b"host crc ok" in r.stdout, r.stdout[-2000:]
+
+
 def test_crc_combine_host_arithmetic(built, orc):
     p = _pkg(built)
     lib = p.load()
