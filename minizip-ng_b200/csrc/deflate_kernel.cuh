@@ -757,8 +757,11 @@ __global__ void __launch_bounds__(DF_THREADS, HIST ? 1 : 2) deflate_chunks_kerne
                     __syncthreads();
                     {
                         const uint32_t key0 = ((uint32_t)(DF_NBATCH - 1 - b) << 16) | (CUR + q0);
+                        /* positions at or behind the end of the unit (zero padding, stale bytes) are inserted as well: they lie behind
+                         * every valid position, so they never win a bucket a valid position of this batch hashes to, are never
+                         * "before" anybody, and no batch follows a short unit -- cheaper than a select per key */
 #pragma unroll
-                        for (int j = 0; j < 8; j++) sm.red_min32(ha[j], (uint32_t)j < nvalid ? key0 + j : 0xffffffffu);
+                        for (int j = 0; j < 8; j++) sm.red_min32(ha[j], key0 + j);
                     }
                     __syncthreads();
 #pragma unroll
